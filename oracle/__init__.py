@@ -1,0 +1,147 @@
+"""oracle/ -- TEST INFRASTRUCTURE ONLY.
+
+CPU checkers for the Sprintz hot path:
+
+* ``Oracle``  : our plain-C restatement (oracle/sprintz_oracle.c -> oracle/liboracle.so)
+* ``Ref``     : the UNMODIFIED reference compiled from /root/reference by oracle/Makefile
+                (oracle/_ref/libsprintz_ref.so; prebuilt, travels to the GPU box)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / ``--impl reference`` legs may
+import this package.  The product package (sprintz_b200/) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "liboracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libsprintz_ref.so")
+
+DELTA, XFF = 0, 1
+SLACK = 4096  # the reference reads/writes past buffer ends; give every buffer slack
+
+
+def build(ref: bool = True) -> None:
+    """(Re)build liboracle.so and, if /root/reference is present, oracle/_ref."""
+    subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
+    if ref:
+        subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+
+
+def _as_u8(a: np.ndarray) -> np.ndarray:
+    return np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+
+
+class _Codec:
+    """numpy-level wrapper shared by Oracle and Ref. Streams are returned as exact-length uint8 arrays."""
+
+    name = "?"
+
+    def max_bytes(self, esz: int, n: int, ndims: int) -> int:
+        d = max(1, ndims)
+        hb = 3 if esz == 1 else 4
+        H = (2 * d * hb + 7) // 8
+        return 8 + n * esz + (n // (16 * d) + 2) * H + 16
+
+    def compress(self, predictor: int, x: np.ndarray, ndims: int, write_size: bool = True):
+        raise NotImplementedError
+
+    def decompress(self, predictor: int, esz: int, stream: np.ndarray, n_out: int):
+        raise NotImplementedError
+
+
+class Oracle(_Codec):
+    name = "oracle"
+
+    def __init__(self):
+        if not os.path.exists(ORACLE_SO):
+            build(ref=False)
+        L = C.CDLL(ORACLE_SO)
+        L.oracle_compress.restype = C.c_int64
+        L.oracle_compress.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p,
+                                      C.c_uint16, C.c_int, C.POINTER(C.c_uint64)]
+        L.oracle_decompress.restype = C.c_int64
+        L.oracle_decompress.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.oracle_decompress_raw.restype = C.c_int64
+        L.oracle_decompress_raw.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                            C.c_uint16, C.c_uint32, C.c_uint16]
+        self.L = L
+
+    def compress(self, predictor, x, ndims, write_size=True):
+        """-> (stream bytes [exact true length], returned element count)"""
+        esz = x.dtype.itemsize
+        src = _as_u8(x)
+        n = x.size
+        buf = np.zeros(self.max_bytes(esz, n, ndims) + SLACK, np.uint8)
+        nb = C.c_uint64(0)
+        ret = self.L.oracle_compress(predictor, esz, src.ctypes.data, n, buf.ctypes.data,
+                                     ndims, int(write_size), C.byref(nb))
+        return buf[: nb.value].copy(), int(ret)
+
+    def decompress(self, predictor, esz, stream, n_out):
+        src = np.concatenate([_as_u8(stream), np.zeros(SLACK, np.uint8)])
+        out = np.full((n_out + 64) * esz + SLACK, 0xAA, np.uint8)
+        ret = self.L.oracle_decompress(predictor, esz, src.ctypes.data, out.ctypes.data)
+        dt = np.uint8 if esz == 1 else np.uint16
+        return out[: n_out * esz].view(dt).copy(), int(ret)
+
+    def decompress_raw(self, predictor, esz, stream, n_out, ndims, ngroups, rem):
+        src = np.concatenate([_as_u8(stream), np.zeros(SLACK, np.uint8)])
+        out = np.full((n_out + 64) * esz + SLACK, 0xAA, np.uint8)
+        ret = self.L.oracle_decompress_raw(predictor, esz, src.ctypes.data, out.ctypes.data,
+                                           ndims, ngroups, rem)
+        dt = np.uint8 if esz == 1 else np.uint16
+        return out[: n_out * esz].view(dt).copy(), int(ret)
+
+
+class Ref(_Codec):
+    name = "reference"
+
+    def __init__(self):
+        if not os.path.exists(REF_SO):
+            raise FileNotFoundError(
+                f"{REF_SO} missing: run `make -C oracle ref` where /root/reference exists")
+        L = C.CDLL(REF_SO)
+        L.ref_compress.restype = C.c_int64
+        L.ref_compress.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p,
+                                   C.c_uint16, C.c_int]
+        L.ref_decompress.restype = C.c_int64
+        L.ref_decompress.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_compress_chunks.restype = C.c_double
+        L.ref_compress_chunks.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64,
+                                          C.c_uint16, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
+        L.ref_decompress_chunks.restype = C.c_double
+        L.ref_decompress_chunks.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64,
+                                            C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]
+        self.L = L
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(REF_SO)
+
+    def compress(self, predictor, x, ndims, write_size=True):
+        """-> (stream bytes [ret*esz bytes, + 1 possibly-dropped byte for 16b], returned element count).
+
+        The reference reports floor(bytes/2) for 16-bit streams, so the buffer is
+        pre-zeroed and we return ret*esz + (esz-1) bytes; callers compare the first ret*esz bytes
+        and treat the extra byte separately."""
+        esz = x.dtype.itemsize
+        n = x.size
+        src = np.concatenate([_as_u8(x), np.zeros(SLACK, np.uint8)])
+        buf = np.zeros(self.max_bytes(esz, n, ndims) + SLACK, np.uint8)
+        ret = int(self.L.ref_compress(predictor, esz, src.ctypes.data, n, buf.ctypes.data,
+                                      ndims, int(write_size)))
+        if ret < 0:
+            return buf[:0].copy(), ret
+        return buf[: ret * esz + (esz - 1)].copy(), ret
+
+    def decompress(self, predictor, esz, stream, n_out):
+        src = np.concatenate([_as_u8(stream), np.zeros(SLACK, np.uint8)])
+        out = np.full((n_out + 64) * esz + SLACK, 0xAA, np.uint8)
+        ret = self.L.ref_decompress(predictor, esz, src.ctypes.data, out.ctypes.data)
+        dt = np.uint8 if esz == 1 else np.uint16
+        return out[: n_out * esz].view(dt).copy(), int(ret)

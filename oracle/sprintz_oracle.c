@@ -1,0 +1,416 @@
+/* oracle/sprintz_oracle.c -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * Plain-C, scalar, portable restatement of the reference Sprintz codec hot path:
+ *   sprintz_{compress,decompress}_{delta,xff}_{8b,16b}      (sprintz.h:16-32, sprintz.cpp:92-251)
+ * which dispatch on ndims (sprintz.cpp:69-85) to
+ *   compress_rowmajor_delta_rle           sprintz_delta_rle.cpp:54-404     (high-dim)
+ *   compress_rowmajor_delta_rle_lowdim    sprintz_delta_lowdim.cpp:38-384  (8b: D<=4, 16b: D<=2)
+ *   compress_rowmajor_xff_rle             sprintz_xff_rle.cpp:60-555       (high-dim FIRE)
+ *   compress_rowmajor_xff_rle_lowdim      sprintz_xff_lowdim.cpp:43-400    (low-dim FIRE)
+ * and the matching decoders (sprintz_delta_rle.cpp:417-772, sprintz_delta_lowdim.cpp:397-794,
+ * sprintz_xff_rle.cpp:568-1179, sprintz_xff_lowdim.cpp:413-1119).
+ *
+ * It is written from the *behaviour* of that code, not from its
+ * structure: the reference encoder is a goto-driven state machine over pext'ed stripes and
+ * the reference decoders are AVX2; this file is a slot-oriented bit-stream writer/reader.
+ *
+ * PINNING.  The reference ships no golden compressed bytes (its tests are round-trips,
+ * test/compress_testing.hpp:23-51).  This restatement is therefore pinned against the
+ * reference itself: oracle/_ref/libsprintz_ref.so is the unmodified reference compiled from
+ * /root/reference by oracle/Makefile, and tests/test_oracle_vs_ref.py + the committed
+ * fixtures under tests/golden/ (generated from that library by tests/golden/make_golden.py)
+ * require byte-identical streams, identical return values and identical decoded integers.
+ *
+ * Known deliberate difference: the reference's 16-bit high-dim FIRE *decoder* mis-builds the
+ * filter coefficients inside run slots (sprintz_xff_rle.cpp:892-929 vs the correct :1073-1081,
+ * SURVEY.md section 8a row D4).  This decoder is the true inverse of the (bit-exact) encoder.
+ */
+#include "sprintz_oracle.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+#define BLOCK_SZ 8
+#define MAX_RUN_NBLOCKS 0x7fff          /* sprintz_delta_rle.cpp:68 */
+#define MIN_DATA_SIZE (8 * BLOCK_SZ * 2) /* sprintz_delta_rle.cpp:71 -> 128 elements */
+
+typedef struct {
+    int w;      /* element bits: 8 | 16 */
+    int esz;    /* element bytes */
+    int hb;     /* header field bits: 3 | 4   (sprintz_delta_rle.cpp:61) */
+    int cb;     /* FIRE counter bits: 16 | 32 (util.h:39-47) */
+    int fire;   /* 0 delta, 1 xff */
+    int low;    /* low-dim variant? (sprintz.cpp:69-85) */
+    int D;
+    uint32_t H; /* header bytes per group */
+} cfg_t;
+
+typedef struct {
+    uint32_t* prev_val;   /* [D] */
+    int32_t*  prev_delta; /* [D] */
+    int32_t*  counter;    /* [D] */
+} state_t;
+
+static int64_t sx(int64_t v, int bits)   /* wrap to signed `bits`-bit */
+{
+    uint64_t m = (bits == 64) ? ~0ull : ((1ull << bits) - 1);
+    uint64_t u = (uint64_t)v & m;
+    if (u >> (bits - 1)) u |= ~m;
+    return (int64_t)u;
+}
+
+static int bitlength(uint32_t x) { int n = 0; while (x) { n++; x >>= 1; } return n; }
+
+static cfg_t make_cfg(int predictor, int elem_sz, int D)
+{
+    cfg_t c;
+    c.esz = elem_sz; c.w = 8 * elem_sz;
+    c.hb = (elem_sz == 1) ? 3 : 4;
+    c.cb = (elem_sz == 1) ? 16 : 32;
+    c.fire = predictor != 0;
+    c.low = (elem_sz == 1) ? (D <= 4) : (D <= 2);
+    c.D = D;
+    c.H = (uint32_t)((2u * (uint32_t)D * (uint32_t)c.hb + 7u) / 8u);
+    return c;
+}
+
+static uint32_t load_elem(const uint8_t* p, uint64_t idx, int esz)
+{
+    return esz == 1 ? p[idx] : (uint32_t)p[2 * idx] | ((uint32_t)p[2 * idx + 1] << 8);
+}
+static void store_elem(uint8_t* p, uint64_t idx, int esz, uint32_t v)
+{
+    if (esz == 1) { p[idx] = (uint8_t)v; }
+    else { p[2 * idx] = (uint8_t)v; p[2 * idx + 1] = (uint8_t)(v >> 8); }
+}
+
+/* FIRE coefficient from the counter.
+ * high-dim: (int16_t)((counter >> (1 + w-4)) << (w-4))      sprintz_xff_rle.cpp:209-217
+ * low-dim : counter >> 1, counter_t wide (no truncation)     sprintz_xff_lowdim.cpp:38-39,170-173 */
+static int32_t fire_coef(const cfg_t* c, int32_t counter)
+{
+    if (c->low) return (int32_t)sx((int64_t)counter >> 1, c->cb);
+    int sh = c->w - 4;
+    return (int32_t)sx(((int64_t)counter >> (1 + sh)) * (1ll << sh), 16);
+}
+
+/* prediction = (int_t)(((counter_t)prev_delta * coef) >> w); the product is an `int`
+ * in the reference, i.e. wraps at 32 bits (sprintz_xff_rle.cpp:225). */
+static int32_t fire_predict(const cfg_t* c, int32_t prev_delta, int32_t coef)
+{
+    int64_t prod = sx((int64_t)prev_delta * (int64_t)coef, 32);
+    return (int32_t)sx(prod >> c->w, c->w);
+}
+
+/* bits -> nbits with the variant's promotion rule.
+ * 8b (all variants) : 7 -> 8                          bitpack.h:72-93, sprintz_delta_lowdim.cpp:172-173
+ * 16b high-dim      : low byte rule 7->8, and if the high byte is used n = 8 + rule(high)
+ *                     (so 15 -> 16)                  sprintz_delta_rle.cpp:177-187
+ * 16b low-dim       : only 15 -> 16                   sprintz_delta_lowdim.cpp:172-173 */
+static int nbits_rule(const cfg_t* c, uint32_t mask)
+{
+    int n = bitlength(mask);
+    if (c->low) { if (n == c->w - 1) n = c->w; return n; }
+    if (c->w == 8) { if (n == 7) n = 8; return n; }
+    if (mask >> 8) { int u = bitlength(mask >> 8); if (u == 7) u = 8; return 8 + u; }
+    if (n == 7) n = 8;
+    return n;
+}
+
+/* One block (8 rows x D) of forecasting + zigzag + per-dim width.
+ * delta: sprintz_delta_rle.cpp:161-201; FIRE: sprintz_xff_rle.cpp:197-298.
+ * zz is [8][D] row-major. Returns sum of nbits. */
+static uint32_t encode_block(const cfg_t* c, state_t* st, const uint8_t* src, uint64_t first_elem,
+                             uint32_t* zz, uint8_t* nbits)
+{
+    const int D = c->D, w = c->w;
+    const uint32_t wmask = (1u << w) - 1u;
+    uint32_t total = 0;
+    for (int d = 0; d < D; d++) {
+        int32_t coef = c->fire ? fire_coef(c, st->counter[d]) : 0;
+        uint32_t mask = 0, pv = st->prev_val[d];
+        int32_t pd = st->prev_delta[d], gs = 0;
+        for (int r = 0; r < BLOCK_SZ; r++) {
+            uint32_t v = load_elem(src, first_elem + (uint64_t)r * D + d, c->esz);
+            int32_t delta = (int32_t)sx((int64_t)v - (int64_t)pv, w);
+            int32_t err = delta;
+            if (c->fire) {
+                int32_t pred = fire_predict(c, pd, coef);
+                err = (int32_t)sx((int64_t)delta - pred, w);
+                if (r & 1) {  /* learning_downsample = 2: odd rows only (sprintz_xff_rle.cpp:240) */
+                    int32_t g = (err == 0) ? 0 : (err < 0 ? (int32_t)sx(-(int64_t)pd, w) : pd); /* util.h:63-68 */
+                    gs = (int32_t)sx((int64_t)gs + g, w);
+                }
+            }
+            uint32_t z = (((uint32_t)err << 1) ^ (uint32_t)(err >> (w - 1))) & wmask; /* bitpack.h:302 */
+            zz[r * D + d] = z;
+            mask |= z;
+            pv = v; pd = delta;
+        }
+        st->prev_val[d] = pv; st->prev_delta[d] = pd;
+        if (c->fire)  /* counter += grad_sum >> 2, counter_t wraps (sprintz_xff_rle.cpp:273-275) */
+            st->counter[d] = (int32_t)sx((int64_t)st->counter[d] + (gs >> 2), c->cb);
+        nbits[d] = (uint8_t)nbits_rule(c, mask);
+        total += nbits[d];
+    }
+    return total;
+}
+
+/* ---- little-endian LSB-first bit writer / reader over a byte buffer ---- */
+static void put_bits(uint8_t* base, uint64_t bitpos, uint32_t v, int n)
+{
+    for (int i = 0; i < n; i++) {
+        if ((v >> i) & 1u) base[(bitpos + i) >> 3] |= (uint8_t)(1u << ((bitpos + i) & 7));
+    }
+}
+static uint32_t get_bits(const uint8_t* base, uint64_t bitpos, int n)
+{
+    uint32_t v = 0;
+    for (int i = 0; i < n; i++)
+        v |= (uint32_t)((base[(bitpos + i) >> 3] >> ((bitpos + i) & 7)) & 1u) << i;
+    return v;
+}
+
+typedef struct {
+    uint8_t* dest;      /* write cursor */
+    uint8_t* hdr;       /* current group's header */
+    uint32_t nslots;
+    uint32_t ngroups;
+} emitter_t;
+
+static void begin_slot(const cfg_t* c, emitter_t* e)
+{
+    if ((e->nslots & 1u) == 0) {           /* a new pair of slots == a new group */
+        e->hdr = e->dest;
+        memset(e->hdr, 0, c->H);
+        e->dest += c->H;
+        e->ngroups++;
+    }
+}
+
+/* run slot: header fields all zero, payload = 1 or 2 length bytes (sprintz_delta_rle.cpp:238-245) */
+static void emit_run(const cfg_t* c, emitter_t* e, uint32_t run)
+{
+    begin_slot(c, e);
+    *e->dest++ = (uint8_t)((run & 0x7f) | (run > 0x7f ? 0x80 : 0));
+    if (run > 0x7f) *e->dest++ = (uint8_t)(run >> 7);
+    e->nslots++;
+}
+
+/* data slot: header nibbles + packed payload.
+ * high-dim payload: 8 rows, each the D fields LSB-first, byte padded (sprintz_delta_rle.cpp:204-212,345-381)
+ * low-dim payload : per dim its 8 fields LSB-first == nbits[d] bytes (sprintz_delta_lowdim.cpp:306-356) */
+static void emit_data(const cfg_t* c, emitter_t* e, const uint32_t* zz, const uint8_t* nbits, uint32_t total)
+{
+    const int D = c->D;
+    begin_slot(c, e);
+    uint32_t s = e->nslots & 1u;
+    for (int d = 0; d < D; d++) {
+        uint32_t field = nbits[d] - (nbits[d] == c->w);   /* w stored as w-1 (sprintz_delta_rle.cpp:199) */
+        put_bits(e->hdr, (uint64_t)(s * (uint32_t)D + (uint32_t)d) * c->hb, field, c->hb);
+    }
+    if (c->low) {
+        memset(e->dest, 0, total);
+        uint64_t bit = 0;
+        for (int d = 0; d < D; d++)
+            for (int r = 0; r < BLOCK_SZ; r++) { put_bits(e->dest, bit, zz[r * D + d], nbits[d]); bit += nbits[d]; }
+        e->dest += total;
+    } else {
+        uint32_t row_bytes = (total + 7) / 8;
+        memset(e->dest, 0, (size_t)row_bytes * BLOCK_SZ);
+        for (int r = 0; r < BLOCK_SZ; r++) {
+            uint64_t bit = (uint64_t)r * row_bytes * 8;
+            for (int d = 0; d < D; d++) { put_bits(e->dest, bit, zz[r * D + d], nbits[d]); bit += nbits[d]; }
+        }
+        e->dest += (size_t)row_bytes * BLOCK_SZ;
+    }
+    e->nslots++;
+}
+
+static void write_meta(uint8_t* p, uint16_t ndims, uint32_t ngroups, uint16_t rem)  /* format.h:35-45 */
+{
+    p[0] = (uint8_t)ngroups; p[1] = (uint8_t)(ngroups >> 8); p[2] = (uint8_t)(ngroups >> 16); p[3] = (uint8_t)(ngroups >> 24);
+    p[4] = (uint8_t)rem; p[5] = (uint8_t)(rem >> 8);
+    p[6] = (uint8_t)ndims; p[7] = (uint8_t)(ndims >> 8);
+}
+
+int64_t oracle_compress(int predictor, int elem_sz, const void* src_, uint32_t len, void* dest_,
+                        uint16_t ndims, int write_size, uint64_t* true_nbytes)
+{
+    if (ndims == 0) return -1;                 /* sprintz.cpp:71 */
+    const uint8_t* src = (const uint8_t*)src_;
+    uint8_t* const orig = (uint8_t*)dest_;
+    cfg_t c = make_cfg(predictor, elem_sz, ndims);
+    const int D = c.D;
+    const int64_t B = (int64_t)BLOCK_SZ * D, G = 2 * B, L = len;
+    uint8_t* dest = orig;
+
+    if (len < MIN_DATA_SIZE) {                 /* sprintz_delta_rle.cpp:101-109 */
+        if (write_size) { write_meta(dest, ndims, 0, (uint16_t)len); dest += 8; }
+        memcpy(dest, src, (size_t)len * c.esz);
+        dest += (size_t)len * c.esz;
+        if (true_nbytes) *true_nbytes = (uint64_t)(dest - orig);
+        return (int64_t)(dest - orig) / c.esz;
+    }
+    if (write_size) dest += 8;
+
+    state_t st;
+    st.prev_val = (uint32_t*)calloc(D, sizeof(uint32_t));
+    st.prev_delta = (int32_t*)calloc(D, sizeof(int32_t));
+    st.counter = (int32_t*)calloc(D, sizeof(int32_t));
+    uint32_t* zz = (uint32_t*)malloc(sizeof(uint32_t) * BLOCK_SZ * D);
+    uint8_t* nbits = (uint8_t*)malloc(D);
+
+    /* continue-run test: `<` for delta and all low-dim codecs, `<=` for high-dim FIRE
+     * (sprintz_delta_rle.cpp:226, sprintz_delta_lowdim.cpp:190, sprintz_xff_lowdim.cpp:234
+     *  vs sprintz_xff_rle.cpp:362) */
+    const int strict = !(c.fire && !c.low);
+
+    emitter_t e; e.dest = dest; e.hdr = NULL; e.nslots = 0; e.ngroups = 0;
+    int64_t i = 0;          /* next block index */
+    uint32_t run = 0;
+    int outer = 1;          /* next block read is gated by the outer-loop test (sprintz_delta_rle.cpp:138) */
+    int64_t tail;
+    for (;;) {
+        if (outer && i * B > L - G) { tail = i * B; break; }
+        uint32_t total = encode_block(&c, &st, src, (uint64_t)(i * B), zz, nbits);
+        int zero = (total == 0);
+    again:
+        if (zero && run < MAX_RUN_NBLOCKS) {
+            run++; i++;
+            if (strict ? (i * B < L - G) : (i * B <= L - G)) { outer = 0; continue; }
+            /* not enough data to finish the group: flush the run, pad the pair (:249-252) */
+            emit_run(&c, &e, run); run = 0;
+            if (e.nslots & 1u) { *e.dest++ = 0; e.nslots++; }
+            tail = i * B; break;
+        }
+        if (run > 0) {      /* a run just ended (:263-312) */
+            emit_run(&c, &e, run); run = 0;
+            if (zero) goto again;              /* only when the run hit MAX_RUN_NBLOCKS (:305-308) */
+        }
+        emit_data(&c, &e, zz, nbits, total);
+        i++;
+        outer = ((e.nslots & 1u) == 0);
+    }
+    dest = e.dest;
+
+    uint32_t remaining = (uint32_t)(L - tail);
+    /* low-dim truncates the tail length itself to u16, high-dim only its stored copy
+     * (sprintz_delta_lowdim.cpp:376-381 vs sprintz_delta_rle.cpp:398-402) */
+    uint32_t copy_len = c.low ? (uint16_t)remaining : remaining;
+    if (write_size) write_meta(orig, ndims, e.ngroups, (uint16_t)remaining);
+    memcpy(dest, src + (size_t)tail * c.esz, (size_t)copy_len * c.esz);
+    dest += (size_t)copy_len * c.esz;
+
+    free(st.prev_val); free(st.prev_delta); free(st.counter); free(zz); free(nbits);
+    if (true_nbytes) *true_nbytes = (uint64_t)(dest - orig);
+    return (int64_t)(dest - orig) / c.esz;      /* pointer difference in int_t units */
+}
+
+/* ------------------------------------------------------------------ decode */
+
+int64_t oracle_decompress_raw(int predictor, int elem_sz, const void* src_, void* dest_,
+                              uint16_t ndims, uint32_t ngroups, uint16_t remaining_len)
+{
+    const uint8_t* src = (const uint8_t*)src_;
+    uint8_t* out = (uint8_t*)dest_;
+    if (ngroups == 0 && remaining_len < MIN_DATA_SIZE) {   /* sprintz_xff_rle.cpp:623-629 */
+        memcpy(out, src, (size_t)remaining_len * elem_sz);
+        return remaining_len;
+    }
+    if (ndims == 0) return 0;                              /* sprintz_delta_rle.cpp:475-478 */
+    cfg_t c = make_cfg(predictor, elem_sz, ndims);
+    const int D = c.D, w = c.w;
+    const uint32_t wmask = (1u << w) - 1u;
+
+    state_t st;
+    st.prev_val = (uint32_t*)calloc(D, sizeof(uint32_t));
+    st.prev_delta = (int32_t*)calloc(D, sizeof(int32_t));
+    st.counter = (int32_t*)calloc(D, sizeof(int32_t));
+    uint8_t* nbits = (uint8_t*)malloc(D);
+    int32_t* gs = (int32_t*)malloc(sizeof(int32_t) * D);
+    int32_t* coef = (int32_t*)malloc(sizeof(int32_t) * D);
+
+    uint64_t o = 0;     /* output element cursor */
+    for (uint32_t g = 0; g < ngroups; g++) {
+        const uint8_t* hdr = src; src += c.H;
+        for (uint32_t s = 0; s < 2; s++) {
+            uint32_t total = 0;
+            for (int d = 0; d < D; d++) {
+                uint32_t f = get_bits(hdr, (uint64_t)(s * (uint32_t)D + (uint32_t)d) * c.hb, c.hb);
+                nbits[d] = (uint8_t)(f == (uint32_t)(w - 1) ? (uint32_t)w : f);
+                total += nbits[d];
+            }
+            if (total == 0) {   /* run slot (sprintz_delta_rle.cpp:640-667, sprintz_xff_rle.cpp:828-958) */
+                uint32_t n = src[0] & 0x7f;
+                if (src[0] & 0x80) { n |= (uint32_t)src[1] << 7; src += 2; } else { src += 1; }
+                for (int d = 0; d < D; d++) coef[d] = c.fire ? fire_coef(&c, st.counter[d]) : 0;
+                for (uint64_t r = 0; r < (uint64_t)n * BLOCK_SZ; r++) {
+                    for (int d = 0; d < D; d++) {
+                        if (c.fire) {   /* free-run the predictor with err = 0; counters untouched */
+                            int32_t pred = fire_predict(&c, st.prev_delta[d], coef[d]);
+                            st.prev_delta[d] = pred;
+                            st.prev_val[d] = (st.prev_val[d] + (uint32_t)pred) & wmask;
+                        }
+                        store_elem(out, o + (uint64_t)d, c.esz, st.prev_val[d]);
+                    }
+                    o += (uint64_t)D;
+                }
+                continue;
+            }
+            uint32_t row_bytes = (total + 7) / 8;
+            for (int d = 0; d < D; d++) { gs[d] = 0; coef[d] = c.fire ? fire_coef(&c, st.counter[d]) : 0; }
+            uint64_t colbit = 0;    /* low-dim: start bit of dim d's column */
+            uint32_t rowoff = 0;    /* high-dim: bit offset of dim d inside a row */
+            for (int d = 0; d < D; d++) {
+                for (int r = 0; r < BLOCK_SZ; r++) {
+                    uint64_t bit = c.low ? colbit + (uint64_t)r * nbits[d]
+                                         : (uint64_t)r * row_bytes * 8 + rowoff;
+                    uint32_t u = get_bits(src, bit, nbits[d]);
+                    int32_t err = (int32_t)sx((int64_t)((u >> 1) ^ (0u - (u & 1u))), w);   /* bitpack.h:303 */
+                    int32_t delta = err;
+                    if (c.fire) {
+                        int32_t pd = st.prev_delta[d];
+                        int32_t pred = fire_predict(&c, pd, coef[d]);
+                        delta = (int32_t)sx((int64_t)err + pred, w);
+                        if (r & 1) {
+                            int32_t gr = (err == 0) ? 0 : (err < 0 ? (int32_t)sx(-(int64_t)pd, w) : pd);
+                            gs[d] = (int32_t)sx((int64_t)gs[d] + gr, w);
+                        }
+                    }
+                    st.prev_delta[d] = delta;
+                    st.prev_val[d] = (st.prev_val[d] + (uint32_t)delta) & wmask;
+                    store_elem(out, o + (uint64_t)r * D + d, c.esz, st.prev_val[d]);
+                }
+                if (c.fire) st.counter[d] = (int32_t)sx((int64_t)st.counter[d] + (gs[d] >> 2), c.cb);
+                colbit += (uint64_t)BLOCK_SZ * nbits[d];
+                rowoff += nbits[d];
+            }
+            src += c.low ? total : row_bytes * BLOCK_SZ;
+            o += (uint64_t)BLOCK_SZ * D;
+        }
+    }
+    memcpy(out + o * c.esz, src, (size_t)remaining_len * c.esz);
+    o += remaining_len;
+
+    free(st.prev_val); free(st.prev_delta); free(st.counter); free(nbits); free(gs); free(coef);
+    return (int64_t)o;
+}
+
+int64_t oracle_decompress(int predictor, int elem_sz, const void* src_, void* dest)
+{
+    const uint8_t* p = (const uint8_t*)src_;      /* format.h:47-62 */
+    uint32_t ngroups = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+    uint16_t rem = (uint16_t)(p[4] | (p[5] << 8));
+    uint16_t ndims = (uint16_t)(p[6] | (p[7] << 8));
+    return oracle_decompress_raw(predictor, elem_sz, p + 8, dest, ndims, ngroups, rem);
+}
+
+uint64_t oracle_max_compressed_bytes(int elem_sz, uint64_t len, uint16_t ndims)
+{
+    uint64_t D = ndims ? ndims : 1;
+    uint64_t hb = (elem_sz == 1) ? 3 : 4;
+    uint64_t H = (2 * D * hb + 7) / 8;
+    uint64_t nblocks = len / (8 * D);
+    return 8 + len * (uint64_t)elem_sz + (nblocks / 2 + 2) * H + 16;
+}

@@ -1,0 +1,44 @@
+/* oracle/sprintz_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Plain-C scalar restatement of the reference Sprintz codec path
+ * (dblalock/sprintz cpp/Compress, sprintz.h:16-32).  See sprintz_oracle.c for the
+ * per-function reference citations and for how the restatement is pinned.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may use this library; the product (sprintz_b200/) never links or loads it.
+ */
+#ifndef SPRINTZ_ORACLE_H
+#define SPRINTZ_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* predictor: 0 = delta, 1 = xff (FIRE).  elem_sz: 1 or 2 bytes.
+ * `len` and the return value are ELEMENT counts, exactly like the reference
+ * (for elem_sz == 2 the return is floor(bytes/2), sprintz_delta_lowdim.cpp:380-383).
+ * *true_nbytes (optional) receives the exact byte length of the stream.
+ * Returns -1 for ndims == 0 (sprintz.cpp:69-76). */
+int64_t oracle_compress(int predictor, int elem_sz, const void* src, uint32_t len,
+                        void* dest, uint16_t ndims, int write_size,
+                        uint64_t* true_nbytes);
+
+/* Decodes a stream that starts with the 8-byte RLE metadata (format.h:35-62).
+ * Returns the number of elements written. Never writes past that count. */
+int64_t oracle_decompress(int predictor, int elem_sz, const void* src, void* dest);
+
+/* 5-argument form for streams written with write_size == 0
+ * (sprintz_delta.h:52-90, sprintz_xff.h:47-83). */
+int64_t oracle_decompress_raw(int predictor, int elem_sz, const void* src, void* dest,
+                              uint16_t ndims, uint32_t ngroups, uint16_t remaining_len);
+
+/* Worst-case stream size in bytes for `len` elements (our own bound, used by tests
+ * to size buffers; the reference has no capacity arguments). */
+uint64_t oracle_max_compressed_bytes(int elem_sz, uint64_t len, uint16_t ndims);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
