@@ -1,0 +1,139 @@
+/* sprintz_b200.h -- C ABI of the B200-native Sprintz encode/decode path.
+ *
+ * This library replaces ONE path of dblalock/sprintz: the codec entry points of
+ * cpp/Compress/sprintz.h:16-32 (sprintz_{compress,decompress}_{delta,xff}_{8b,16b}) and the kernels
+ * behind them (sprintz_delta_rle.cpp, sprintz_delta_lowdim.cpp, sprintz_xff_rle.cpp,
+ * sprintz_xff_lowdim.cpp).  Every stream it writes is byte-identical to the reference's output for the
+ * same input, and every stream the reference writes decodes to the same integers.
+ *
+ * Three layers, all plain C (pointers + sizes; no torch / C++ types):
+ *   1. reference drop-ins on HOST buffers        spz_{compress,decompress}_{delta,xff}_{8b,16b}
+ *   2. single-stream calls on DEVICE buffers     spz_compress_dev / spz_decompress_dev
+ *   3. the chunked FRAME (the throughput path)   spz_frame_*  -- a long stream cut into chunks, each chunk
+ *      an independent reference stream, plus a chunk directory from a device-wide exclusive scan.
+ *
+ * There is no CPU fallback: every call runs CUDA kernels on the current device and fails with
+ * SPZ_E_CUDA if it cannot.  `len` and element-count returns are in ELEMENTS, as in the reference.
+ */
+#ifndef SPRINTZ_B200_H
+#define SPRINTZ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPZ_DELTA 0   /* sprintz_*_delta_*  */
+#define SPZ_XFF   1   /* sprintz_*_xff_*  (FIRE) */
+
+#define SPZ_OK            0
+#define SPZ_E_ARG        -1   /* the reference's own error return (ndims == 0, sprintz.cpp:71) */
+#define SPZ_E_CUDA       -2   /* CUDA runtime / launch failure (see spz_last_error) */
+#define SPZ_E_CAPACITY   -3   /* destination or workspace too small */
+#define SPZ_E_STREAM     -4   /* malformed stream (ndims mismatch, overrun) */
+#define SPZ_E_UNSUPPORTED -5  /* ndims > SPZ_MAX_NDIMS */
+
+#define SPZ_MAX_NDIMS 1024
+#define SPZ_FRAME_MAGIC 0x315a5053u   /* "SPZ1" */
+
+typedef void* spz_stream_t;           /* a cudaStream_t (0 = default stream) */
+
+/* per-chunk record (device memory, 16 bytes) */
+typedef struct spz_chunk_meta {
+    uint32_t nbytes;      /* encoder: exact stream length in bytes | decoder: bytes consumed */
+    uint32_t ngroups;     /* format.h:35-45 */
+    uint32_t remaining;   /* encoder: trailing raw elements | decoder (streams with metadata): elements produced */
+    uint32_t status;      /* 0 ok; 1 ndims mismatch; 2 capacity overflow */
+} spz_chunk_meta;
+
+/* 64-byte frame header (little endian), followed by u64 chunk_off[nchunks+1], u32 chunk_nbytes[nchunks],
+ * padding to 16, then the chunk streams (each starting 16-byte aligned at payload_off + chunk_off[c]). */
+typedef struct spz_frame_header {
+    uint32_t magic;
+    uint16_t version;
+    uint8_t  elem_sz;
+    uint8_t  predictor;
+    uint32_t ndims;
+    uint32_t chunk_rows;
+    uint64_t len;            /* total elements */
+    uint64_t nchunks;
+    uint64_t payload_off;    /* byte offset of the first chunk stream inside the frame */
+    uint64_t payload_bytes;  /* sum of 16-byte-rounded chunk stream sizes */
+    uint64_t frame_bytes;    /* payload_off + payload_bytes + 16 bytes of read slack */
+    uint64_t reserved;
+} spz_frame_header;
+
+const char* spz_version(void);
+const char* spz_last_error(void);    /* thread-local description of the last SPZ_E_CUDA */
+
+/* ---------------------------------------------------------------- 1. reference drop-ins (host buffers)
+ * Same arguments, return values and stream bytes as sprintz.h:16-32 (the C++ default `write_size=true`
+ * becomes an explicit int).  Each call copies the input to the GPU, runs the single-stream kernel (one
+ * team of lanes: FIRE and the stream parse are serial by construction) and copies the
+ * result back.  Like the reference there are no capacity arguments: `dest` must hold
+ * spz_max_compressed_bytes() bytes (compress) / the decoded length (decompress; no overrun past it,
+ * unlike the reference's 32-byte vector stores). */
+int64_t spz_compress_delta_8b (const uint8_t*  src, uint32_t len, int8_t*  dest, uint16_t ndims, int write_size);
+int64_t spz_decompress_delta_8b(const int8_t*  src, uint8_t*  dest);
+int64_t spz_compress_xff_8b   (const uint8_t*  src, uint32_t len, int8_t*  dest, uint16_t ndims, int write_size);
+int64_t spz_decompress_xff_8b (const int8_t*  src, uint8_t*  dest);
+int64_t spz_compress_delta_16b(const uint16_t* src, uint32_t len, int16_t* dest, uint16_t ndims, int write_size);
+int64_t spz_decompress_delta_16b(const int16_t* src, uint16_t* dest);
+int64_t spz_compress_xff_16b  (const uint16_t* src, uint32_t len, int16_t* dest, uint16_t ndims, int write_size);
+int64_t spz_decompress_xff_16b(const int16_t* src, uint16_t* dest);
+
+/* generic forms of the above; *true_nbytes (optional) = exact stream length (the 16-bit return value is
+ * floor(bytes/2), sprintz_delta_lowdim.cpp:380-383) */
+int64_t spz_compress_host(int predictor, int elem_sz, const void* src, uint32_t len, void* dest,
+                          uint16_t ndims, int write_size, uint64_t* true_nbytes);
+int64_t spz_decompress_host(int predictor, int elem_sz, const void* src, void* dest);
+/* 5-argument decoders for streams written with write_size == 0 (sprintz_delta.h:52-90, sprintz_xff.h:47-83) */
+int64_t spz_decompress_raw_host(int predictor, int elem_sz, const void* src, void* dest,
+                                uint16_t ndims, uint32_t ngroups, uint16_t remaining_len);
+
+/* worst-case stream size in bytes for `len` elements (multiple of 16) */
+uint64_t spz_max_compressed_bytes(int elem_sz, uint64_t len, uint16_t ndims);
+/* walks a host stream's group headers: exact stream length in bytes and decoded element count */
+int spz_measure_stream(int elem_sz, const void* src, int has_meta, uint16_t ndims, uint32_t ngroups,
+                       uint16_t remaining_len, uint64_t* stream_bytes, uint64_t* decoded_elems);
+
+/* ---------------------------------------------------------------- 2. single stream, device buffers
+ * d_dest must hold spz_max_compressed_bytes(); d_meta (1 record) receives sizes. Asynchronous on `stream`. */
+int spz_compress_dev(int predictor, int elem_sz, const void* d_src, uint32_t len, uint16_t ndims,
+                     int write_size, void* d_dest, spz_chunk_meta* d_meta, spz_stream_t stream);
+/* has_meta == 0: d_meta->ngroups / ->remaining are inputs. d_src needs 8 readable bytes past the stream. */
+int spz_decompress_dev(int predictor, int elem_sz, const void* d_src, int has_meta, uint16_t ndims,
+                       void* d_dest, uint64_t dest_cap_elems, spz_chunk_meta* d_meta, spz_stream_t stream);
+
+/* ---------------------------------------------------------------- 3. chunked frame
+ * chunk c covers elements [c*chunk_rows*ndims, (c+1)*chunk_rows*ndims) and is encoded exactly as the
+ * reference encodes that slice. chunk_rows should be a multiple of 16 (whole groups). */
+uint64_t spz_frame_nchunks(uint64_t len, uint16_t ndims, uint32_t chunk_rows);
+uint64_t spz_frame_max_bytes(int elem_sz, uint64_t len, uint16_t ndims, uint32_t chunk_rows);
+uint64_t spz_frame_workspace_bytes(int elem_sz, uint64_t len, uint16_t ndims, uint32_t chunk_rows);
+
+/* Device buffers, asynchronous on `stream`. *d_frame_bytes (device, optional) receives the frame size. */
+int spz_frame_encode_dev(int predictor, int elem_sz, const void* d_src, uint64_t len, uint16_t ndims,
+                         uint32_t chunk_rows, void* d_frame, uint64_t frame_cap,
+                         void* d_work, uint64_t work_bytes, uint64_t* d_frame_bytes, spz_stream_t stream);
+/* d_status (device, optional, nchunks records) receives per-chunk decode status. */
+int spz_frame_decode_dev(int predictor, int elem_sz, const void* d_frame, uint64_t len, uint16_t ndims,
+                         uint32_t chunk_rows, void* d_dest, uint64_t dest_cap_elems,
+                         spz_chunk_meta* d_status, spz_stream_t stream);
+/* synchronous copy of the 64-byte header from a device frame */
+int spz_frame_read_header(const void* d_frame, spz_frame_header* out, spz_stream_t stream);
+
+/* Host buffers: H2D -> kernels -> D2H inside the call (pinned host memory makes the copies asynchronous).
+ * Returns frame bytes (compress) / elements (decompress), or a negative SPZ_E_* code. */
+int64_t spz_frame_compress_host(int predictor, int elem_sz, const void* src, uint64_t len, uint16_t ndims,
+                                uint32_t chunk_rows, void* frame, uint64_t frame_cap);
+int64_t spz_frame_decompress_host(const void* frame, uint64_t frame_bytes, void* dest, uint64_t dest_cap_elems);
+
+/* releases the cached device workspaces of the host-buffer entry points */
+void spz_release_workspaces(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPRINTZ_B200_H */

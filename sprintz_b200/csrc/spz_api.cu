@@ -1,0 +1,428 @@
+// spz_api.cu -- the C ABI (include/sprintz_b200.h) over the CUDA kernels.
+//
+// Host-side mirror of the reference's operator interface for this path: sprintz.h:16-32 (the eight
+// compress/decompress entry points) and the ndims dispatch of sprintz.cpp:69-85 (which happens inside
+// launch_encode / launch_decode).  No CPU codec lives here: the only host-side stream logic is
+// spz_measure_stream(), which walks group headers to learn how many bytes to copy because the reference
+// signatures carry no sizes.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <mutex>
+
+#include "spz_common.cuh"
+#include "../../include/sprintz_b200.h"
+
+namespace spz {
+cudaError_t launch_encode(int elem_sz, int predictor, EncParams p, cudaStream_t stream);
+cudaError_t launch_decode(int elem_sz, int predictor, DecParams p, cudaStream_t stream);
+cudaError_t launch_scan_sizes(const ChunkMeta* meta, uint64_t nchunks, uint64_t* chunk_off, uint32_t* chunk_nbytes,
+                              unsigned long long* tile_state, unsigned int* ticket,
+                              spz_frame_header* hdr, const spz_frame_header& hdr_in, uint64_t* d_frame_bytes,
+                              cudaStream_t stream);
+cudaError_t launch_gather(const uint8_t* slots, uint64_t slot_stride, uint64_t nchunks, const uint64_t* chunk_off,
+                          const uint32_t* chunk_nbytes, uint8_t* payload, cudaStream_t stream);
+uint64_t scan_tiles(uint64_t nchunks);
+}  // namespace spz
+
+using namespace spz;
+
+static thread_local char g_err[256] = "";
+
+static int cuda_fail(cudaError_t e, const char* where)
+{
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return SPZ_E_CUDA;
+}
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(e__, #call); } while (0)
+
+static inline uint64_t align16(uint64_t x) { return (x + 15ull) & ~15ull; }
+static inline bool valid_codec(int predictor, int elem_sz)
+{
+    return (predictor == 0 || predictor == 1) && (elem_sz == 1 || elem_sz == 2);
+}
+
+extern "C" const char* spz_version(void) { return "sprintz_b200 0.1 (sm_100a)"; }
+extern "C" const char* spz_last_error(void) { return g_err; }
+
+extern "C" uint64_t spz_max_compressed_bytes(int elem_sz, uint64_t len, uint16_t ndims)
+{
+    const uint64_t D = ndims ? ndims : 1;
+    const uint64_t hb = elem_sz == 1 ? 3 : 4;
+    const uint64_t H = (2 * D * hb + 7) / 8;
+    const uint64_t nblocks = len / (8 * D);
+    return align16(8 + len * (uint64_t)elem_sz + (nblocks / 2 + 2) * H + 16) + 16;
+}
+
+// ------------------------------------------------------------------ layout of a frame
+
+struct FrameLayout {
+    uint64_t nchunks, chunk_len, off_dir, off_sizes, payload_off;
+};
+static FrameLayout frame_layout(uint64_t len, uint16_t ndims, uint32_t chunk_rows)
+{
+    FrameLayout f;
+    f.chunk_len = (uint64_t)chunk_rows * ndims;
+    f.nchunks = len == 0 ? 1 : (len + f.chunk_len - 1) / f.chunk_len;
+    f.off_dir = sizeof(spz_frame_header);
+    f.off_sizes = f.off_dir + 8 * (f.nchunks + 1);
+    f.payload_off = align16(f.off_sizes + 4 * f.nchunks);
+    return f;
+}
+
+extern "C" uint64_t spz_frame_nchunks(uint64_t len, uint16_t ndims, uint32_t chunk_rows)
+{
+    if (ndims == 0 || chunk_rows == 0) return 0;
+    return frame_layout(len, ndims, chunk_rows).nchunks;
+}
+
+static uint64_t slot_stride_of(int elem_sz, uint64_t chunk_len, uint16_t ndims)
+{
+    return spz_max_compressed_bytes(elem_sz, chunk_len, ndims);
+}
+
+extern "C" uint64_t spz_frame_max_bytes(int elem_sz, uint64_t len, uint16_t ndims, uint32_t chunk_rows)
+{
+    if (ndims == 0 || chunk_rows == 0) return 0;
+    const FrameLayout f = frame_layout(len, ndims, chunk_rows);
+    return f.payload_off + f.nchunks * slot_stride_of(elem_sz, f.chunk_len, ndims) + 16;
+}
+
+// workspace = [tile_state | ticket | meta | slots]
+struct WorkLayout { uint64_t off_state, off_ticket, off_meta, off_slots, slot_stride, total; };
+static WorkLayout work_layout(int elem_sz, uint64_t len, uint16_t ndims, uint32_t chunk_rows)
+{
+    const FrameLayout f = frame_layout(len, ndims, chunk_rows);
+    WorkLayout w;
+    w.off_state = 0;
+    w.off_ticket = align16(8 * scan_tiles(f.nchunks));
+    w.off_meta = w.off_ticket + 16;
+    w.off_slots = align16(w.off_meta + sizeof(ChunkMeta) * f.nchunks);
+    w.slot_stride = slot_stride_of(elem_sz, f.chunk_len < len || len == 0 ? f.chunk_len : len, ndims);
+    w.total = w.off_slots + f.nchunks * w.slot_stride + 16;
+    return w;
+}
+
+extern "C" uint64_t spz_frame_workspace_bytes(int elem_sz, uint64_t len, uint16_t ndims, uint32_t chunk_rows)
+{
+    if (ndims == 0 || chunk_rows == 0) return 0;
+    return work_layout(elem_sz, len, ndims, chunk_rows).total;
+}
+
+// ------------------------------------------------------------------ device entry points
+
+extern "C" int spz_compress_dev(int predictor, int elem_sz, const void* d_src, uint32_t len, uint16_t ndims,
+                                int write_size, void* d_dest, spz_chunk_meta* d_meta, spz_stream_t stream)
+{
+    if (!valid_codec(predictor, elem_sz) || ndims == 0) return SPZ_E_ARG;
+    if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
+    EncParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = (const uint8_t*)d_src; p.dst = (uint8_t*)d_dest; p.meta = (ChunkMeta*)d_meta;
+    p.len = len; p.chunk_len = len ? len : 1; p.nchunks = 1; p.slot_stride = 0;
+    p.ndims = ndims; p.write_size = write_size ? 1 : 0;
+    CK(launch_encode(elem_sz, predictor, p, (cudaStream_t)stream));
+    return SPZ_OK;
+}
+
+extern "C" int spz_decompress_dev(int predictor, int elem_sz, const void* d_src, int has_meta, uint16_t ndims,
+                                  void* d_dest, uint64_t dest_cap_elems, spz_chunk_meta* d_meta, spz_stream_t stream)
+{
+    if (!valid_codec(predictor, elem_sz) || ndims == 0) return SPZ_E_ARG;
+    if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
+    if (!has_meta && !d_meta) return SPZ_E_ARG;
+    DecParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = (const uint8_t*)d_src; p.offsets = nullptr; p.dst = (uint8_t*)d_dest; p.meta = (ChunkMeta*)d_meta;
+    p.len = dest_cap_elems; p.chunk_len = dest_cap_elems ? dest_cap_elems : 1; p.nchunks = 1; p.slot_stride = 0;
+    p.dst_cap = dest_cap_elems; p.ndims = ndims; p.has_meta = has_meta ? 1 : 0;
+    CK(launch_decode(elem_sz, predictor, p, (cudaStream_t)stream));
+    return SPZ_OK;
+}
+
+extern "C" int spz_frame_encode_dev(int predictor, int elem_sz, const void* d_src, uint64_t len, uint16_t ndims,
+                                    uint32_t chunk_rows, void* d_frame, uint64_t frame_cap,
+                                    void* d_work, uint64_t work_bytes, uint64_t* d_frame_bytes, spz_stream_t stream_)
+{
+    if (!valid_codec(predictor, elem_sz) || ndims == 0 || chunk_rows == 0) return SPZ_E_ARG;
+    if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const FrameLayout f = frame_layout(len, ndims, chunk_rows);
+    if (f.chunk_len > 0xffffffffull) return SPZ_E_ARG;           // a chunk is one reference stream: uint32_t len
+    const WorkLayout w = work_layout(elem_sz, len, ndims, chunk_rows);
+    if (work_bytes < w.total) return SPZ_E_CAPACITY;
+    if (frame_cap < spz_frame_max_bytes(elem_sz, len, ndims, chunk_rows)) return SPZ_E_CAPACITY;
+
+    uint8_t* work = (uint8_t*)d_work;
+    uint8_t* frame = (uint8_t*)d_frame;
+    CK(cudaMemsetAsync(work, 0, w.off_meta, stream));             // scan tile states + ticket
+
+    EncParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = (const uint8_t*)d_src; p.dst = work + w.off_slots; p.meta = (ChunkMeta*)(work + w.off_meta);
+    p.len = len; p.chunk_len = f.chunk_len; p.nchunks = f.nchunks; p.slot_stride = w.slot_stride;
+    p.ndims = ndims; p.write_size = 1;
+    CK(launch_encode(elem_sz, predictor, p, stream));
+
+    spz_frame_header h;
+    memset(&h, 0, sizeof(h));
+    h.magic = SPZ_FRAME_MAGIC; h.version = 1; h.elem_sz = (uint8_t)elem_sz; h.predictor = (uint8_t)predictor;
+    h.ndims = ndims; h.chunk_rows = chunk_rows; h.len = len; h.nchunks = f.nchunks; h.payload_off = f.payload_off;
+    uint64_t* chunk_off = (uint64_t*)(frame + f.off_dir);
+    uint32_t* chunk_nbytes = (uint32_t*)(frame + f.off_sizes);
+    CK(launch_scan_sizes(p.meta, f.nchunks, chunk_off, chunk_nbytes,
+                         (unsigned long long*)(work + w.off_state), (unsigned int*)(work + w.off_ticket),
+                         (spz_frame_header*)frame, h, d_frame_bytes, stream));
+    CK(launch_gather(work + w.off_slots, w.slot_stride, f.nchunks, chunk_off, chunk_nbytes,
+                     frame + f.payload_off, stream));
+    return SPZ_OK;
+}
+
+extern "C" int spz_frame_decode_dev(int predictor, int elem_sz, const void* d_frame, uint64_t len, uint16_t ndims,
+                                    uint32_t chunk_rows, void* d_dest, uint64_t dest_cap_elems,
+                                    spz_chunk_meta* d_status, spz_stream_t stream)
+{
+    if (!valid_codec(predictor, elem_sz) || ndims == 0 || chunk_rows == 0) return SPZ_E_ARG;
+    if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
+    if (dest_cap_elems < len) return SPZ_E_CAPACITY;
+    const FrameLayout f = frame_layout(len, ndims, chunk_rows);
+    const uint8_t* frame = (const uint8_t*)d_frame;
+    DecParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = frame + f.payload_off; p.offsets = (const uint64_t*)(frame + f.off_dir);
+    p.dst = (uint8_t*)d_dest; p.meta = (ChunkMeta*)d_status;
+    p.len = len; p.chunk_len = f.chunk_len; p.nchunks = f.nchunks; p.dst_cap = len;
+    p.ndims = ndims; p.has_meta = 1;
+    CK(launch_decode(elem_sz, predictor, p, (cudaStream_t)stream));
+    return SPZ_OK;
+}
+
+extern "C" int spz_frame_read_header(const void* d_frame, spz_frame_header* out, spz_stream_t stream)
+{
+    CK(cudaMemcpyAsync(out, d_frame, sizeof(*out), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return out->magic == SPZ_FRAME_MAGIC ? SPZ_OK : SPZ_E_STREAM;
+}
+
+// ------------------------------------------------------------------ host-buffer entry points
+
+namespace {
+// Cached device buffers for the host-pointer calls (grown on demand, guarded by one mutex: the
+// reference is re-entrant, so are we, but concurrent host calls serialise on the device anyway).
+struct DevCache {
+    std::mutex mu;
+    void* buf[3] = {nullptr, nullptr, nullptr};
+    uint64_t cap[3] = {0, 0, 0};
+    cudaStream_t stream = nullptr;
+    cudaError_t ensure(int i, uint64_t bytes)
+    {
+        if (cap[i] >= bytes) return cudaSuccess;
+        if (buf[i]) { cudaFree(buf[i]); buf[i] = nullptr; cap[i] = 0; }
+        uint64_t want = bytes + (bytes >> 3) + 4096;
+        cudaError_t e = cudaMalloc(&buf[i], want);
+        if (e == cudaSuccess) cap[i] = want;
+        return e;
+    }
+    cudaError_t get_stream(cudaStream_t* s)
+    {
+        if (!stream) { cudaError_t e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking); if (e != cudaSuccess) return e; }
+        *s = stream; return cudaSuccess;
+    }
+    void release()
+    {
+        for (int i = 0; i < 3; i++) { if (buf[i]) cudaFree(buf[i]); buf[i] = nullptr; cap[i] = 0; }
+        if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+    }
+};
+DevCache g_cache;
+}  // namespace
+
+extern "C" void spz_release_workspaces(void)
+{
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    g_cache.release();
+}
+
+extern "C" int spz_measure_stream(int elem_sz, const void* src_, int has_meta, uint16_t ndims, uint32_t ngroups,
+                                  uint16_t remaining_len, uint64_t* stream_bytes, uint64_t* decoded_elems)
+{
+    const uint8_t* src = (const uint8_t*)src_;
+    uint64_t pos = 0;
+    if (has_meta) {
+        ngroups = (uint32_t)src[0] | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16) | ((uint32_t)src[3] << 24);
+        remaining_len = (uint16_t)(src[4] | (src[5] << 8));
+        ndims = (uint16_t)(src[6] | (src[7] << 8));
+        pos = 8;
+    }
+    uint64_t elems = 0;
+    if (!(ngroups == 0 && remaining_len < kMinDataSize)) {
+        if (ndims == 0) return SPZ_E_ARG;
+        const uint32_t D = ndims, w = 8u * elem_sz, hb = elem_sz == 1 ? 3 : 4;
+        const bool low = elem_sz == 1 ? (D <= 4) : (D <= 2);
+        const uint32_t H = (2 * D * hb + 7) / 8;
+        for (uint32_t g = 0; g < ngroups; g++) {
+            const uint8_t* hdr = src + pos;
+            pos += H;
+            for (uint32_t s = 0; s < 2; s++) {
+                uint32_t total = 0;
+                for (uint32_t d = 0; d < D; d++) {
+                    const uint32_t bit = (s * D + d) * hb;
+                    uint32_t f = (((uint32_t)hdr[bit >> 3] | ((uint32_t)hdr[(bit >> 3) + 1] << 8)) >> (bit & 7)) & ((1u << hb) - 1);
+                    total += (f == w - 1) ? w : f;
+                }
+                if (total == 0) {
+                    uint32_t n = src[pos] & 0x7f;
+                    if (src[pos] & 0x80) { n |= (uint32_t)src[pos + 1] << 7; pos += 2; } else pos += 1;
+                    elems += (uint64_t)n * 8 * D;
+                } else {
+                    pos += low ? total : 8ull * ((total + 7) / 8);
+                    elems += 8ull * D;
+                }
+            }
+        }
+    }
+    pos += (uint64_t)remaining_len * elem_sz;
+    elems += remaining_len;
+    if (stream_bytes) *stream_bytes = pos;
+    if (decoded_elems) *decoded_elems = elems;
+    return SPZ_OK;
+}
+
+extern "C" int64_t spz_compress_host(int predictor, int elem_sz, const void* src, uint32_t len, void* dest,
+                                     uint16_t ndims, int write_size, uint64_t* true_nbytes)
+{
+    if (ndims == 0) { printf("Received invalid ndims %d\n", (int)ndims); return -1; }   // sprintz.cpp:71
+    if (!valid_codec(predictor, elem_sz)) return SPZ_E_ARG;
+    if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    cudaStream_t st;
+    CK(g_cache.get_stream(&st));
+    const uint64_t in_bytes = (uint64_t)len * elem_sz;
+    const uint64_t out_cap = spz_max_compressed_bytes(elem_sz, len, ndims);
+    CK(g_cache.ensure(0, in_bytes + 16));
+    CK(g_cache.ensure(1, out_cap + 16));
+    CK(g_cache.ensure(2, 64));
+    if (in_bytes) CK(cudaMemcpyAsync(g_cache.buf[0], src, in_bytes, cudaMemcpyHostToDevice, st));
+    int rc = spz_compress_dev(predictor, elem_sz, g_cache.buf[0], len, ndims, write_size, g_cache.buf[1],
+                              (spz_chunk_meta*)g_cache.buf[2], st);
+    if (rc != SPZ_OK) return rc;
+    spz_chunk_meta m;
+    CK(cudaMemcpyAsync(&m, g_cache.buf[2], sizeof(m), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (m.status != 0) return SPZ_E_CAPACITY;
+    CK(cudaMemcpyAsync(dest, g_cache.buf[1], m.nbytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (true_nbytes) *true_nbytes = m.nbytes;
+    return (int64_t)(m.nbytes / (uint32_t)elem_sz);    // pointer difference in int_t units
+}
+
+static int64_t decompress_host_impl(int predictor, int elem_sz, const void* src, void* dest, int has_meta,
+                                    uint16_t ndims, uint32_t ngroups, uint16_t remaining_len)
+{
+    if (!valid_codec(predictor, elem_sz)) return SPZ_E_ARG;
+    uint64_t sbytes = 0, elems = 0;
+    if (has_meta) {
+        const uint8_t* s8 = (const uint8_t*)src;
+        ngroups = (uint32_t)s8[0] | ((uint32_t)s8[1] << 8) | ((uint32_t)s8[2] << 16) | ((uint32_t)s8[3] << 24);
+        remaining_len = (uint16_t)(s8[4] | (s8[5] << 8));
+        ndims = (uint16_t)(s8[6] | (s8[7] << 8));
+    }
+    const bool raw = (ngroups == 0 && remaining_len < kMinDataSize);
+    if (ndims == 0 && !raw) return 0;                              // sprintz_delta_rle.cpp:475-478
+    if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
+    int rc = spz_measure_stream(elem_sz, src, has_meta, ndims, ngroups, remaining_len, &sbytes, &elems);
+    if (rc != SPZ_OK) return rc;
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    cudaStream_t st;
+    CK(g_cache.get_stream(&st));
+    CK(g_cache.ensure(0, sbytes + 32));
+    CK(g_cache.ensure(1, elems * elem_sz + 16));
+    CK(g_cache.ensure(2, 64));
+    CK(cudaMemcpyAsync(g_cache.buf[0], src, sbytes, cudaMemcpyHostToDevice, st));
+    spz_chunk_meta m;
+    memset(&m, 0, sizeof(m));
+    m.ngroups = ngroups; m.remaining = remaining_len;
+    CK(cudaMemcpyAsync(g_cache.buf[2], &m, sizeof(m), cudaMemcpyHostToDevice, st));
+    rc = spz_decompress_dev(predictor, elem_sz, g_cache.buf[0], has_meta, ndims ? ndims : 1, g_cache.buf[1], elems,
+                            (spz_chunk_meta*)g_cache.buf[2], st);
+    if (rc != SPZ_OK) return rc;
+    CK(cudaMemcpyAsync(&m, g_cache.buf[2], sizeof(m), cudaMemcpyDeviceToHost, st));
+    if (elems) CK(cudaMemcpyAsync(dest, g_cache.buf[1], elems * elem_sz, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (m.status != 0) return SPZ_E_STREAM;
+    return (int64_t)elems;
+}
+
+extern "C" int64_t spz_decompress_host(int predictor, int elem_sz, const void* src, void* dest)
+{
+    return decompress_host_impl(predictor, elem_sz, src, dest, 1, 0, 0, 0);
+}
+extern "C" int64_t spz_decompress_raw_host(int predictor, int elem_sz, const void* src, void* dest,
+                                           uint16_t ndims, uint32_t ngroups, uint16_t remaining_len)
+{
+    return decompress_host_impl(predictor, elem_sz, src, dest, 0, ndims, ngroups, remaining_len);
+}
+
+// the eight reference-named entry points (sprintz.h:16-32)
+extern "C" int64_t spz_compress_delta_8b(const uint8_t* s, uint32_t n, int8_t* d, uint16_t nd, int ws) { return spz_compress_host(SPZ_DELTA, 1, s, n, d, nd, ws, nullptr); }
+extern "C" int64_t spz_decompress_delta_8b(const int8_t* s, uint8_t* d) { return spz_decompress_host(SPZ_DELTA, 1, s, d); }
+extern "C" int64_t spz_compress_xff_8b(const uint8_t* s, uint32_t n, int8_t* d, uint16_t nd, int ws) { return spz_compress_host(SPZ_XFF, 1, s, n, d, nd, ws, nullptr); }
+extern "C" int64_t spz_decompress_xff_8b(const int8_t* s, uint8_t* d) { return spz_decompress_host(SPZ_XFF, 1, s, d); }
+extern "C" int64_t spz_compress_delta_16b(const uint16_t* s, uint32_t n, int16_t* d, uint16_t nd, int ws) { return spz_compress_host(SPZ_DELTA, 2, s, n, d, nd, ws, nullptr); }
+extern "C" int64_t spz_decompress_delta_16b(const int16_t* s, uint16_t* d) { return spz_decompress_host(SPZ_DELTA, 2, s, d); }
+extern "C" int64_t spz_compress_xff_16b(const uint16_t* s, uint32_t n, int16_t* d, uint16_t nd, int ws) { return spz_compress_host(SPZ_XFF, 2, s, n, d, nd, ws, nullptr); }
+extern "C" int64_t spz_decompress_xff_16b(const int16_t* s, uint16_t* d) { return spz_decompress_host(SPZ_XFF, 2, s, d); }
+
+// ------------------------------------------------------------------ frame, host buffers
+
+extern "C" int64_t spz_frame_compress_host(int predictor, int elem_sz, const void* src, uint64_t len, uint16_t ndims,
+                                           uint32_t chunk_rows, void* frame, uint64_t frame_cap)
+{
+    if (!valid_codec(predictor, elem_sz) || ndims == 0 || chunk_rows == 0) return SPZ_E_ARG;
+    if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    cudaStream_t st;
+    CK(g_cache.get_stream(&st));
+    const uint64_t in_bytes = len * (uint64_t)elem_sz;
+    const uint64_t fmax = spz_frame_max_bytes(elem_sz, len, ndims, chunk_rows);
+    const uint64_t wbytes = spz_frame_workspace_bytes(elem_sz, len, ndims, chunk_rows);
+    CK(g_cache.ensure(0, in_bytes + 16));
+    CK(g_cache.ensure(1, fmax + 16));
+    CK(g_cache.ensure(2, wbytes + 16));
+    if (in_bytes) CK(cudaMemcpyAsync(g_cache.buf[0], src, in_bytes, cudaMemcpyHostToDevice, st));
+    int rc = spz_frame_encode_dev(predictor, elem_sz, g_cache.buf[0], len, ndims, chunk_rows, g_cache.buf[1],
+                                  g_cache.cap[1], g_cache.buf[2], g_cache.cap[2], nullptr, st);
+    if (rc != SPZ_OK) return rc;
+    spz_frame_header h;
+    rc = spz_frame_read_header(g_cache.buf[1], &h, st);
+    if (rc != SPZ_OK) return rc;
+    if (h.frame_bytes > frame_cap) return SPZ_E_CAPACITY;
+    CK(cudaMemcpyAsync(frame, g_cache.buf[1], h.frame_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return (int64_t)h.frame_bytes;
+}
+
+extern "C" int64_t spz_frame_decompress_host(const void* frame, uint64_t frame_bytes, void* dest, uint64_t dest_cap_elems)
+{
+    if (frame_bytes < sizeof(spz_frame_header)) return SPZ_E_STREAM;
+    spz_frame_header h;
+    memcpy(&h, frame, sizeof(h));
+    if (h.magic != SPZ_FRAME_MAGIC || h.frame_bytes > frame_bytes || !valid_codec(h.predictor, h.elem_sz) ||
+        h.ndims == 0 || h.ndims > SPZ_MAX_NDIMS || h.chunk_rows == 0) return SPZ_E_STREAM;
+    if (dest_cap_elems < h.len) return SPZ_E_CAPACITY;
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    cudaStream_t st;
+    CK(g_cache.get_stream(&st));
+    const uint64_t nchunks = h.nchunks;
+    CK(g_cache.ensure(0, h.len * h.elem_sz + 16));
+    CK(g_cache.ensure(1, h.frame_bytes + 32));
+    CK(g_cache.ensure(2, sizeof(spz_chunk_meta) * nchunks + 16));
+    CK(cudaMemcpyAsync(g_cache.buf[1], frame, h.frame_bytes, cudaMemcpyHostToDevice, st));
+    int rc = spz_frame_decode_dev(h.predictor, h.elem_sz, g_cache.buf[1], h.len, (uint16_t)h.ndims, h.chunk_rows,
+                                  g_cache.buf[0], h.len, nullptr, st);
+    if (rc != SPZ_OK) return rc;
+    if (h.len) CK(cudaMemcpyAsync(dest, g_cache.buf[0], h.len * h.elem_sz, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return (int64_t)h.len;
+}

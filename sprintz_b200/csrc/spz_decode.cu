@@ -1,0 +1,226 @@
+// spz_decode.cu -- Sprintz decode kernels for sm_100a.
+//
+// One team of lanes decodes one chunk == one complete reference stream (the inverse of spz_encode.cu;
+// replaces sprintz_decompress_{delta,xff}_{8b,16b}, sprintz.cpp:110-129,232-251):
+//
+//   header   lane-per-dim extraction of the 3/4-bit width fields + team prefix sum -> bit offsets
+//            (replaces the pdep/sad/pshufb header unpack, sprintz_delta_rle.cpp:537-617)
+//   unpack   per lane: two aligned 32-bit loads + funnel shift + mask (replaces the pdep hot loop :672-701)
+//   predict  per lane serial recurrence over the 8 rows: zigzag^-1, delta | FIRE (replaces :704-736 and
+//            sprintz_xff_rle.cpp:1012-1128); FIRE's floor-multiply makes this serial in rows *and* blocks,
+//            so parallelism comes from chunks x dims
+//   runs     delta: repeat the previous row; FIRE: free-run the predictor with err = 0
+//            (sprintz_delta_rle.cpp:640-667, sprintz_xff_rle.cpp:828-958 -- but with the *correct*
+//            coefficients)
+#include "spz_common.cuh"
+
+namespace spz {
+
+template <int W, bool FIRE, bool LOW>
+__global__ void __launch_bounds__(kThreads) spz_decode_kernel(const DecParams p)
+{
+    typedef typename Traits<W>::uint_t uint_t;
+    constexpr int ESZ = W / 8;
+    constexpr int HB = Traits<W>::HB;
+    constexpr int CB = Traits<W>::CB;
+    constexpr uint32_t WMASK = (1u << W) - 1u;
+
+    extern __shared__ __align__(16) uint8_t smem[];
+
+    const int lane = threadIdx.x & 31;
+    const int TEAM = (int)p.team;
+    const int DPL = (int)p.dpl;
+    const int D = (int)p.ndims;
+    const int t = lane & (TEAM - 1);
+    const int team_in_cta = (int)(threadIdx.x / TEAM);
+    const uint64_t c = (uint64_t)blockIdx.x * p.teams_per_cta + team_in_cta;
+    if (c >= p.nchunks) return;
+    const uint32_t tmask = team_mask_of(lane, TEAM);
+    const int Dp = TEAM * DPL;
+
+    // ---- per-team shared memory: predictor state + the current slot's widths / bit offsets
+    int32_t* s_pv = reinterpret_cast<int32_t*>(smem + (size_t)team_in_cta * p.team_smem);
+    int32_t* s_pd = s_pv + Dp;
+    int32_t* s_ct = s_pd + Dp;
+    uint32_t* s_fo = reinterpret_cast<uint32_t*>(s_ct + Dp);   // [Dp] (bit offset << 8) | width
+    for (int k = 0; k < DPL; k++) {
+        s_pv[k * TEAM + t] = 0; s_pd[k * TEAM + t] = 0; s_ct[k * TEAM + t] = 0;
+    }
+
+    const uint8_t* __restrict__ stream = p.src + (p.offsets ? p.offsets[c] : c * p.slot_stride);
+    const uint64_t first = c * p.chunk_len;
+    uint_t* __restrict__ out = reinterpret_cast<uint_t*>(p.dst) + first;
+    // elements this chunk may write
+    const uint64_t cap = (first >= p.dst_cap) ? 0 :
+        ((p.dst_cap - first < p.chunk_len) ? (p.dst_cap - first) : p.chunk_len);
+
+    uint32_t ngroups, remaining, status = kStatusOk;
+    uint64_t pos = 0;                   // byte cursor in the stream (team-uniform)
+    if (p.has_meta) {                   // format.h:47-62
+        ngroups = (uint32_t)stream[0] | ((uint32_t)stream[1] << 8) | ((uint32_t)stream[2] << 16) | ((uint32_t)stream[3] << 24);
+        remaining = (uint32_t)stream[4] | ((uint32_t)stream[5] << 8);
+        const uint32_t nd = (uint32_t)stream[6] | ((uint32_t)stream[7] << 8);
+        if (nd != (uint32_t)D) status = kStatusBadDims;
+        pos = 8;
+    } else {
+        ngroups = p.meta[c].ngroups;
+        remaining = p.meta[c].remaining & 0xffffu;
+    }
+
+    uint64_t o = 0;                     // output element cursor (team-uniform)
+    const uint32_t H = (2u * (uint32_t)D * HB + 7u) >> 3;
+    const uint64_t B = (uint64_t)kBlockRows * D;
+
+    if (status == kStatusOk && !(ngroups == 0 && remaining < kMinDataSize)) {
+        for (uint32_t g = 0; g < ngroups && status == kStatusOk; g++) {
+            const uint8_t* hdr = stream + pos;
+            pos += H;
+            for (uint32_t s = 0; s < 2; s++) {
+                // ---- widths of this slot: field (s*D + d) of the group header, prefix-summed over dims
+                uint32_t total = 0;
+                for (int k = 0; k < DPL; k++) {
+                    const int d = k * TEAM + t;
+                    uint32_t n = 0;
+                    if (d < D) {
+                        const uint32_t f = load_bits32(hdr, (s * (uint32_t)D + (uint32_t)d) * HB) & ((1u << HB) - 1u);
+                        n = (f == (uint32_t)(W - 1)) ? (uint32_t)W : f;
+                    }
+                    const uint32_t incl = team_incl_scan(n, t, TEAM, tmask);
+                    s_fo[d] = ((total + incl - n) << 8) | n;
+                    total += team_last(incl, TEAM, tmask);
+                }
+
+                if (total == 0) {
+                    // ---- run slot (sprintz_delta_rle.cpp:640-667)
+                    uint32_t nrun = stream[pos] & 0x7f;
+                    if (stream[pos] & 0x80) { nrun |= (uint32_t)stream[pos + 1] << 7; pos += 2; } else { pos += 1; }
+                    const uint64_t nrows = (uint64_t)nrun * kBlockRows;
+                    if (o + nrows * D > cap) { status = kStatusOverflow; break; }
+                    for (int k = 0; k < DPL; k++) {
+                        const int d = k * TEAM + t;
+                        if (d < D) {
+                            uint32_t pv = (uint32_t)s_pv[d];
+                            uint_t* op = out + o + d;
+                            if (FIRE) {
+                                int32_t pd = s_pd[d];
+                                const int32_t coef = fire_coef<W, LOW>(s_ct[d]);
+                                for (uint64_t r = 0; r < nrows; r++) {
+                                    pd = fire_predict<W>(pd, coef);        // err == 0  ->  delta == prediction
+                                    pv = (pv + (uint32_t)pd) & WMASK;
+                                    op[r * D] = (uint_t)pv;
+                                }
+                                s_pd[d] = pd;
+                                s_pv[d] = (int32_t)pv;
+                            } else {
+                                for (uint64_t r = 0; r < nrows; r++) op[r * D] = (uint_t)pv;
+                            }
+                        }
+                    }
+                    o += nrows * D;
+                    continue;
+                }
+
+                // ---- data slot
+                if (o + B > cap) { status = kStatusOverflow; break; }
+                const uint32_t row_bytes = (total + 7u) >> 3;
+                const uint8_t* pay = stream + pos;
+                for (int k = 0; k < DPL; k++) {
+                    const int d = k * TEAM + t;
+                    if (d < D) {
+                        const uint32_t fo = s_fo[d];
+                        const uint32_t n = fo & 0xffu, off = fo >> 8;
+                        const uint32_t fmask = (n >= 32) ? 0xffffffffu : ((1u << n) - 1u);
+                        // high-dim: row r's field at bit r*row_bytes*8 + off; low-dim: column at byte `off`, field r at r*n
+                        const uint32_t bit0 = LOW ? off * 8u : off;
+                        const uint32_t stride = LOW ? n : row_bytes * 8u;
+                        uint32_t u[kBlockRows];
+#pragma unroll
+                        for (int r = 0; r < kBlockRows; r++) u[r] = load_bits32(pay, bit0 + (uint32_t)r * stride) & fmask;
+
+                        uint32_t pv = (uint32_t)s_pv[d];
+                        int32_t pd = 0, coef = 0, gs = 0;
+                        if (FIRE) { pd = s_pd[d]; coef = fire_coef<W, LOW>(s_ct[d]); }
+                        uint_t* op = out + o + d;
+#pragma unroll
+                        for (int r = 0; r < kBlockRows; r++) {
+                            const int32_t err = zigzag_dec<W>(u[r]);
+                            int32_t delta = err;
+                            if (FIRE) {
+                                delta = sx<W>(err + fire_predict<W>(pd, coef));
+                                if (r & 1) gs += fire_grad<W>(err, pd);
+                            }
+                            pd = delta;
+                            pv = (pv + (uint32_t)delta) & WMASK;
+                            op[r * D] = (uint_t)pv;
+                        }
+                        s_pv[d] = (int32_t)pv;
+                        if (FIRE) {
+                            s_pd[d] = pd;
+                            s_ct[d] = sx<CB>(s_ct[d] + (sx<W>(gs) >> 2));
+                        }
+                    }
+                }
+                pos += LOW ? total : row_bytes * kBlockRows;
+                o += B;
+            }
+        }
+    }
+
+    // ---- trailing raw elements (also the whole stream when it was stored raw)
+    if (status == kStatusOk) {
+        if (o + remaining > cap) {
+            status = kStatusOverflow;
+        } else {
+            const uint8_t* tsrc = stream + pos;
+            uint8_t* tdst = reinterpret_cast<uint8_t*>(out + o);
+            const uint32_t nb = remaining * ESZ;
+            for (uint32_t b = t; b < nb; b += TEAM) tdst[b] = tsrc[b];
+            o += remaining;
+        }
+    }
+    if (t == 0 && p.meta) {
+        p.meta[c].status = status;
+        if (p.has_meta) { p.meta[c].nbytes = (uint32_t)(pos + (uint64_t)remaining * ESZ); p.meta[c].ngroups = ngroups; p.meta[c].remaining = (uint32_t)o; }
+    }
+}
+
+// ------------------------------------------------------------------ launch
+
+template <int W, bool FIRE, bool LOW>
+static cudaError_t launch_one(const DecParams& p, uint32_t grid, size_t smem, cudaStream_t stream)
+{
+    cudaError_t e = cudaFuncSetAttribute(spz_decode_kernel<W, FIRE, LOW>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    spz_decode_kernel<W, FIRE, LOW><<<grid, p.teams_per_cta * p.team, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+static inline uint32_t pow2_ceil(uint32_t x) { uint32_t p = 1; while (p < x) p <<= 1; return p; }
+
+cudaError_t launch_decode(int elem_sz, int predictor, DecParams p, cudaStream_t stream)
+{
+    const bool low = elem_sz == 1 ? (p.ndims <= 4) : (p.ndims <= 2);
+    p.team = p.ndims >= 32 ? 32 : pow2_ceil(p.ndims);
+    p.dpl = (p.ndims + p.team - 1) / p.team;
+    p.team_smem = (4u * 4u * p.team * p.dpl + 15u) & ~15u;
+    uint32_t teams_per_cta = kThreads / p.team;
+    while (teams_per_cta > 1 && (size_t)teams_per_cta * p.team_smem > 200 * 1024) teams_per_cta >>= 1;
+    p.teams_per_cta = teams_per_cta;
+    const size_t smem = (size_t)teams_per_cta * p.team_smem;
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    const uint64_t grid64 = (p.nchunks + teams_per_cta - 1) / teams_per_cta;
+    if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
+    const uint32_t grid = (uint32_t)grid64;
+#define SPZ_GO(Wv, Fv, Lv) return launch_one<Wv, Fv, Lv>(p, grid, smem, stream)
+    if (elem_sz == 1) {
+        if (predictor) { if (low) SPZ_GO(8, true, true); else SPZ_GO(8, true, false); }
+        else           { if (low) SPZ_GO(8, false, true); else SPZ_GO(8, false, false); }
+    } else {
+        if (predictor) { if (low) SPZ_GO(16, true, true); else SPZ_GO(16, true, false); }
+        else           { if (low) SPZ_GO(16, false, true); else SPZ_GO(16, false, false); }
+    }
+#undef SPZ_GO
+}
+
+}  // namespace spz
