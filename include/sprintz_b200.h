@@ -130,6 +130,11 @@ int64_t spz_frame_compress_host(int predictor, int elem_sz, const void* src, uin
                                 uint32_t chunk_rows, void* frame, uint64_t frame_cap);
 int64_t spz_frame_decompress_host(const void* frame, uint64_t frame_bytes, void* dest, uint64_t dest_cap_elems);
 
+/* Optional timing of spz_frame_encode_dev's launches with CUDA events on the call's stream (up to 64 calls
+ * between enable and collect). ms3 = summed milliseconds of {codec kernel, directory scan, compaction}. */
+int spz_profile_enable(int on);
+int spz_profile_collect(float* ms3, int* ncalls);
+
 /* releases the cached device workspaces of the host-buffer entry points */
 void spz_release_workspaces(void);
 

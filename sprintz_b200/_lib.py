@@ -60,6 +60,8 @@ SYMBOLS = {
     "spz_frame_read_header": (_i, [_vp, C.POINTER(FrameHeader), _vp]),
     "spz_frame_compress_host": (_i64, [_i, _i, _vp, _u64, _u16, _u32, _vp, _u64]),
     "spz_frame_decompress_host": (_i64, [_vp, _u64, _vp, _u64]),
+    "spz_profile_enable": (_i, [_i]),
+    "spz_profile_collect": (_i, [C.POINTER(C.c_float), C.POINTER(_i)]),
     "spz_release_workspaces": (None, []),
 }
 

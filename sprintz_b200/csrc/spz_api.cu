@@ -43,6 +43,52 @@ static inline bool valid_codec(int predictor, int elem_sz)
     return (predictor == 0 || predictor == 1) && (elem_sz == 1 || elem_sz == 2);
 }
 
+// ------------------------------------------------------------------ optional per-kernel timing of the frame encoder
+// bench.py needs the codec kernel's own duration (roofline), separate from scan + compaction. When enabled,
+// spz_frame_encode_dev records CUDA events on its stream around each launch; nothing is synchronised
+// until spz_profile_collect().
+namespace {
+constexpr int kProfSlots = 64;
+struct Profile {
+    bool on = false;
+    int n = 0;
+    cudaEvent_t ev[kProfSlots][4];
+    bool made = false;
+} g_prof;
+}  // namespace
+
+extern "C" int spz_profile_enable(int on)
+{
+    if (on && !g_prof.made) {
+        for (int i = 0; i < kProfSlots; i++)
+            for (int j = 0; j < 4; j++) CK(cudaEventCreate(&g_prof.ev[i][j]));
+        g_prof.made = true;
+    }
+    g_prof.on = on != 0;
+    g_prof.n = 0;
+    return SPZ_OK;
+}
+
+// sums (ms) over the recorded frame-encode calls: [0] codec kernel, [1] directory scan, [2] compaction
+extern "C" int spz_profile_collect(float* ms3, int* ncalls)
+{
+    ms3[0] = ms3[1] = ms3[2] = 0.f;
+    const int n = g_prof.n < kProfSlots ? g_prof.n : kProfSlots;
+    for (int i = 0; i < n; i++) {
+        CK(cudaEventSynchronize(g_prof.ev[i][3]));
+        for (int j = 0; j < 3; j++) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, g_prof.ev[i][j], g_prof.ev[i][j + 1]));
+            ms3[j] += ms;
+        }
+    }
+    if (ncalls) *ncalls = n;
+    g_prof.n = 0;
+    return SPZ_OK;
+}
+#define PROF_MARK(j) do { if (g_prof.on && g_prof.n < kProfSlots) CK(cudaEventRecord(g_prof.ev[g_prof.n][j], stream)); } while (0)
+#define PROF_NEXT() do { if (g_prof.on && g_prof.n < kProfSlots) g_prof.n++; } while (0)
+
 extern "C" const char* spz_version(void) { return "sprintz_b200 0.1 (sm_100a)"; }
 extern "C" const char* spz_last_error(void) { return g_err; }
 
@@ -163,7 +209,9 @@ extern "C" int spz_frame_encode_dev(int predictor, int elem_sz, const void* d_sr
     p.src = (const uint8_t*)d_src; p.dst = work + w.off_slots; p.meta = (ChunkMeta*)(work + w.off_meta);
     p.len = len; p.chunk_len = f.chunk_len; p.nchunks = f.nchunks; p.slot_stride = w.slot_stride;
     p.ndims = ndims; p.write_size = 1;
+    PROF_MARK(0);
     CK(launch_encode(elem_sz, predictor, p, stream));
+    PROF_MARK(1);
 
     spz_frame_header h;
     memset(&h, 0, sizeof(h));
@@ -174,8 +222,11 @@ extern "C" int spz_frame_encode_dev(int predictor, int elem_sz, const void* d_sr
     CK(launch_scan_sizes(p.meta, f.nchunks, chunk_off, chunk_nbytes,
                          (unsigned long long*)(work + w.off_state), (unsigned int*)(work + w.off_ticket),
                          (spz_frame_header*)frame, h, d_frame_bytes, stream));
+    PROF_MARK(2);
     CK(launch_gather(work + w.off_slots, w.slot_stride, f.nchunks, chunk_off, chunk_nbytes,
                      frame + f.payload_off, stream));
+    PROF_MARK(3);
+    PROF_NEXT();
     return SPZ_OK;
 }
 
