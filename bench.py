@@ -223,14 +223,20 @@ def run_ours(args, cfg, cfg_name):
     frame_bytes = int(hdr.frame_bytes)
     ratio = raw / payload
 
+    # clocks are sampled from the start of warm-up to the end of the timed region (the timed region alone can
+    # be shorter than one nvidia-smi period); warm-up is extended until a few samples under load exist
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(warm):
         codec.decode(codec.encode(x), out)
+    t_w = time.time()
+    while len(sampler.lines) < 3 and time.time() - t_w < 4.0:
+        codec.decode(codec.encode(x), out)
+        torch.cuda.synchronize()
     barrier()
 
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps + 1)]
     L.spz_profile_enable(1)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
     ev[0].record()
     for i in range(steps):

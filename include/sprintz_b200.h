@@ -102,9 +102,11 @@ int spz_measure_stream(int elem_sz, const void* src, int has_meta, uint16_t ndim
  * d_dest must hold spz_max_compressed_bytes(); d_meta (1 record) receives sizes. Asynchronous on `stream`. */
 int spz_compress_dev(int predictor, int elem_sz, const void* d_src, uint32_t len, uint16_t ndims,
                      int write_size, void* d_dest, spz_chunk_meta* d_meta, spz_stream_t stream);
-/* has_meta == 0: d_meta->ngroups / ->remaining are inputs. d_src needs 8 readable bytes past the stream. */
-int spz_decompress_dev(int predictor, int elem_sz, const void* d_src, int has_meta, uint16_t ndims,
-                       void* d_dest, uint64_t dest_cap_elems, spz_chunk_meta* d_meta, spz_stream_t stream);
+/* has_meta == 0: d_meta->ngroups / ->remaining are inputs.  src_bytes = readable bytes at d_src; it must
+ * cover the stream plus 8 bytes (the kernels read whole aligned words / 16-byte units, never past it). */
+int spz_decompress_dev(int predictor, int elem_sz, const void* d_src, uint64_t src_bytes, int has_meta,
+                       uint16_t ndims, void* d_dest, uint64_t dest_cap_elems, spz_chunk_meta* d_meta,
+                       spz_stream_t stream);
 
 /* ---------------------------------------------------------------- 3. chunked frame
  * chunk c covers elements [c*chunk_rows*ndims, (c+1)*chunk_rows*ndims) and is encoded exactly as the
@@ -117,9 +119,10 @@ uint64_t spz_frame_workspace_bytes(int elem_sz, uint64_t len, uint16_t ndims, ui
 int spz_frame_encode_dev(int predictor, int elem_sz, const void* d_src, uint64_t len, uint16_t ndims,
                          uint32_t chunk_rows, void* d_frame, uint64_t frame_cap,
                          void* d_work, uint64_t work_bytes, uint64_t* d_frame_bytes, spz_stream_t stream);
-/* d_status (device, optional, nchunks records) receives per-chunk decode status. */
-int spz_frame_decode_dev(int predictor, int elem_sz, const void* d_frame, uint64_t len, uint16_t ndims,
-                         uint32_t chunk_rows, void* d_dest, uint64_t dest_cap_elems,
+/* frame_bytes = readable bytes at d_frame (the frame size, or the buffer's capacity).
+ * d_status (device, optional, nchunks records) receives per-chunk decode status. */
+int spz_frame_decode_dev(int predictor, int elem_sz, const void* d_frame, uint64_t frame_bytes, uint64_t len,
+                         uint16_t ndims, uint32_t chunk_rows, void* d_dest, uint64_t dest_cap_elems,
                          spz_chunk_meta* d_status, spz_stream_t stream);
 /* synchronous copy of the 64-byte header from a device frame */
 int spz_frame_read_header(const void* d_frame, spz_frame_header* out, spz_stream_t stream);

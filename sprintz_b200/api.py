@@ -132,7 +132,7 @@ def decompress_dev(predictor: int, esz: int, stream, ndims: int, n_out: int):
     src[: stream.numel()] = stream
     out = torch.empty(n_out, dtype=torch.uint8 if esz == 1 else torch.int16, device=stream.device)
     meta = torch.zeros(4, dtype=torch.int32, device=stream.device)
-    check(lib().spz_decompress_dev(predictor, esz, src.data_ptr(), 1, ndims, out.data_ptr(), n_out,
+    check(lib().spz_decompress_dev(predictor, esz, src.data_ptr(), src.numel(), 1, ndims, out.data_ptr(), n_out,
                                    meta.data_ptr(), _stream_ptr()), "spz_decompress_dev")
     m = meta.cpu().numpy().view(np.uint32)
     if int(m[3]) != 0:
@@ -203,8 +203,8 @@ class FrameCodec:
 
     def decode(self, frame: Frame, out):
         assert out.numel() >= self.len and out.element_size() == self.elem_sz and out.is_cuda
-        check(lib().spz_frame_decode_dev(frame.predictor, frame.elem_sz, frame.buf.data_ptr(), frame.len,
-                                         frame.ndims, frame.chunk_rows, out.data_ptr(), out.numel(),
+        check(lib().spz_frame_decode_dev(frame.predictor, frame.elem_sz, frame.buf.data_ptr(), frame.buf.numel(),
+                                         frame.len, frame.ndims, frame.chunk_rows, out.data_ptr(), out.numel(),
                                          self.status.data_ptr(), _stream_ptr()), "spz_frame_decode_dev")
         return out
 

@@ -172,8 +172,9 @@ extern "C" int spz_compress_dev(int predictor, int elem_sz, const void* d_src, u
     return SPZ_OK;
 }
 
-extern "C" int spz_decompress_dev(int predictor, int elem_sz, const void* d_src, int has_meta, uint16_t ndims,
-                                  void* d_dest, uint64_t dest_cap_elems, spz_chunk_meta* d_meta, spz_stream_t stream)
+extern "C" int spz_decompress_dev(int predictor, int elem_sz, const void* d_src, uint64_t src_bytes, int has_meta,
+                                  uint16_t ndims, void* d_dest, uint64_t dest_cap_elems, spz_chunk_meta* d_meta,
+                                  spz_stream_t stream)
 {
     if (!valid_codec(predictor, elem_sz) || ndims == 0) return SPZ_E_ARG;
     if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
@@ -183,6 +184,7 @@ extern "C" int spz_decompress_dev(int predictor, int elem_sz, const void* d_src,
     p.src = (const uint8_t*)d_src; p.offsets = nullptr; p.dst = (uint8_t*)d_dest; p.meta = (ChunkMeta*)d_meta;
     p.len = dest_cap_elems; p.chunk_len = dest_cap_elems ? dest_cap_elems : 1; p.nchunks = 1; p.slot_stride = 0;
     p.dst_cap = dest_cap_elems; p.ndims = ndims; p.has_meta = has_meta ? 1 : 0;
+    p.src_end = (const uint8_t*)d_src + src_bytes;
     CK(launch_decode(elem_sz, predictor, p, (cudaStream_t)stream));
     return SPZ_OK;
 }
@@ -230,9 +232,9 @@ extern "C" int spz_frame_encode_dev(int predictor, int elem_sz, const void* d_sr
     return SPZ_OK;
 }
 
-extern "C" int spz_frame_decode_dev(int predictor, int elem_sz, const void* d_frame, uint64_t len, uint16_t ndims,
-                                    uint32_t chunk_rows, void* d_dest, uint64_t dest_cap_elems,
-                                    spz_chunk_meta* d_status, spz_stream_t stream)
+extern "C" int spz_frame_decode_dev(int predictor, int elem_sz, const void* d_frame, uint64_t frame_bytes,
+                                    uint64_t len, uint16_t ndims, uint32_t chunk_rows, void* d_dest,
+                                    uint64_t dest_cap_elems, spz_chunk_meta* d_status, spz_stream_t stream)
 {
     if (!valid_codec(predictor, elem_sz) || ndims == 0 || chunk_rows == 0) return SPZ_E_ARG;
     if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
@@ -245,6 +247,8 @@ extern "C" int spz_frame_decode_dev(int predictor, int elem_sz, const void* d_fr
     p.dst = (uint8_t*)d_dest; p.meta = (ChunkMeta*)d_status;
     p.len = len; p.chunk_len = f.chunk_len; p.nchunks = f.nchunks; p.dst_cap = len;
     p.ndims = ndims; p.has_meta = 1;
+    if (frame_bytes < f.payload_off + 16) return SPZ_E_STREAM;
+    p.src_end = frame + frame_bytes;
     CK(launch_decode(elem_sz, predictor, p, (cudaStream_t)stream));
     return SPZ_OK;
 }
@@ -395,8 +399,8 @@ static int64_t decompress_host_impl(int predictor, int elem_sz, const void* src,
     memset(&m, 0, sizeof(m));
     m.ngroups = ngroups; m.remaining = remaining_len;
     CK(cudaMemcpyAsync(g_cache.buf[2], &m, sizeof(m), cudaMemcpyHostToDevice, st));
-    rc = spz_decompress_dev(predictor, elem_sz, g_cache.buf[0], has_meta, ndims ? ndims : 1, g_cache.buf[1], elems,
-                            (spz_chunk_meta*)g_cache.buf[2], st);
+    rc = spz_decompress_dev(predictor, elem_sz, g_cache.buf[0], sbytes + 16, has_meta, ndims ? ndims : 1,
+                            g_cache.buf[1], elems, (spz_chunk_meta*)g_cache.buf[2], st);
     if (rc != SPZ_OK) return rc;
     CK(cudaMemcpyAsync(&m, g_cache.buf[2], sizeof(m), cudaMemcpyDeviceToHost, st));
     if (elems) CK(cudaMemcpyAsync(dest, g_cache.buf[1], elems * elem_sz, cudaMemcpyDeviceToHost, st));
@@ -470,8 +474,8 @@ extern "C" int64_t spz_frame_decompress_host(const void* frame, uint64_t frame_b
     CK(g_cache.ensure(1, h.frame_bytes + 32));
     CK(g_cache.ensure(2, sizeof(spz_chunk_meta) * nchunks + 16));
     CK(cudaMemcpyAsync(g_cache.buf[1], frame, h.frame_bytes, cudaMemcpyHostToDevice, st));
-    int rc = spz_frame_decode_dev(h.predictor, h.elem_sz, g_cache.buf[1], h.len, (uint16_t)h.ndims, h.chunk_rows,
-                                  g_cache.buf[0], h.len, nullptr, st);
+    int rc = spz_frame_decode_dev(h.predictor, h.elem_sz, g_cache.buf[1], h.frame_bytes, h.len, (uint16_t)h.ndims,
+                                  h.chunk_rows, g_cache.buf[0], h.len, nullptr, st);
     if (rc != SPZ_OK) return rc;
     if (h.len) CK(cudaMemcpyAsync(dest, g_cache.buf[0], h.len * h.elem_sz, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

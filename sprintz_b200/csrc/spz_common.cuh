@@ -68,6 +68,9 @@ struct DecParams {
     uint32_t        has_meta;  // 1: each stream starts with the 8-byte metadata
     uint32_t        team_smem;
     uint32_t        teams_per_cta;
+    const uint8_t*  src_end;   // one past the last readable byte of the source buffer (fast path only)
+    uint32_t        ring_cap;  // fast path: bytes of the per-team input ring (power of two)
+    uint32_t        out_cap;   // fast path: bytes of the per-team output staging
 };
 
 template <int W> struct Traits;
@@ -153,6 +156,49 @@ __device__ __forceinline__ uint32_t load_bits32(const uint8_t* base, uint32_t bi
     uint32_t sh = (uint32_t)((a & 3) << 3) + (bit & 7);
     uint32_t w0 = wp[0], w1 = wp[1];
     return __funnelshift_r(w0, w1, sh);
+}
+
+// ------------------------------------------------------------------ shared-memory output staging
+// One team's output bytes are staged in shared memory and leave for HBM as 128-bit stores.  buf[0]
+// corresponds to the 16-byte aligned global address gdst; the first `skip` bytes (non-zero only before the
+// first flush after (re)initialisation) lie before the region this team owns and are never written.
+struct OutStage {
+    uint8_t* buf;
+    uint8_t* gdst;
+    uint32_t cur;
+    uint32_t skip;
+    __device__ __forceinline__ void init(uint8_t* smem_buf, uint8_t* gptr)
+    {
+        const uint32_t mis = (uint32_t)((uintptr_t)gptr & 15);
+        buf = smem_buf; gdst = gptr - mis; skip = mis; cur = mis;
+    }
+};
+
+__device__ __forceinline__ void stage_flush(OutStage& o, bool final_flush, int t, int team, uint32_t tmask)
+{
+    __syncwarp(tmask);
+    const uint32_t hi = final_flush ? o.cur : (o.cur & ~15u);
+    const uint32_t lo = o.skip;
+    if (hi > lo) {
+        uint32_t a = (lo + 15u) & ~15u;
+        if (a > hi) a = hi;
+        for (uint32_t b = lo + t; b < a; b += team) o.gdst[b] = o.buf[b];            // unaligned head
+        const uint4* s4 = reinterpret_cast<const uint4*>(o.buf);
+        uint4* g4 = reinterpret_cast<uint4*>(o.gdst);
+        for (uint32_t u = (a >> 4) + t; u < (hi >> 4); u += team) g4[u] = s4[u];    // 128-bit body
+        uint32_t tb = hi & ~15u;
+        if (tb < a) tb = a;
+        for (uint32_t b = tb + t; b < hi; b += team) o.gdst[b] = o.buf[b];           // tail (final only)
+        __syncwarp(tmask);
+        if (!final_flush) {
+            const uint32_t rem = o.cur - hi;        // < 16, and hi >= 16: source and dest cannot overlap
+            for (uint32_t b = t; b < rem; b += team) o.buf[b] = o.buf[hi + b];
+            o.gdst += hi;
+            o.cur = rem;
+            o.skip = 0;
+            __syncwarp(tmask);
+        }
+    }
 }
 
 }  // namespace spz

@@ -198,8 +198,14 @@ static cudaError_t launch_one(const DecParams& p, uint32_t grid, size_t smem, cu
 
 static inline uint32_t pow2_ceil(uint32_t x) { uint32_t p = 1; while (p < x) p <<= 1; return p; }
 
+cudaError_t launch_decode_hd(int elem_sz, int predictor, DecParams p, cudaStream_t stream);
+
 cudaError_t launch_decode(int elem_sz, int predictor, DecParams p, cudaStream_t stream)
 {
+    {   // fast path for high-dim shapes; the generic kernel below covers everything else
+        const cudaError_t e = launch_decode_hd(elem_sz, predictor, p, stream);
+        if (e != cudaErrorNotSupported) return e;
+    }
     const bool low = elem_sz == 1 ? (p.ndims <= 4) : (p.ndims <= 2);
     p.team = p.ndims >= 32 ? 32 : pow2_ceil(p.ndims);
     p.dpl = (p.ndims + p.team - 1) / p.team;

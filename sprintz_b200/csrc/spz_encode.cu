@@ -18,42 +18,6 @@ namespace spz {
 
 namespace {
 
-// Shared-memory staging of one team's output stream. buf[0] corresponds to the 16-byte aligned global
-// address gdst; the first `skip` bytes (only non-zero before the first flush) lie before the stream start.
-struct OutStage {
-    uint8_t* buf;
-    uint8_t* gdst;
-    uint32_t cur;
-    uint32_t skip;
-};
-
-__device__ __forceinline__ void stage_flush(OutStage& o, bool final_flush, int t, int team, uint32_t tmask)
-{
-    __syncwarp(tmask);
-    const uint32_t hi = final_flush ? o.cur : (o.cur & ~15u);
-    const uint32_t lo = o.skip;
-    if (hi > lo) {
-        uint32_t a = (lo + 15u) & ~15u;
-        if (a > hi) a = hi;
-        for (uint32_t b = lo + t; b < a; b += team) o.gdst[b] = o.buf[b];            // unaligned head
-        const uint4* s4 = reinterpret_cast<const uint4*>(o.buf);
-        uint4* g4 = reinterpret_cast<uint4*>(o.gdst);
-        for (uint32_t u = (a >> 4) + t; u < (hi >> 4); u += team) g4[u] = s4[u];    // 128-bit body
-        uint32_t tb = hi & ~15u;
-        if (tb < a) tb = a;
-        for (uint32_t b = tb + t; b < hi; b += team) o.gdst[b] = o.buf[b];           // tail (final only)
-        __syncwarp(tmask);
-        if (!final_flush) {
-            const uint32_t rem = o.cur - hi;        // < 16, and hi >= 16: source and dest cannot overlap
-            for (uint32_t b = t; b < rem; b += team) o.buf[b] = o.buf[hi + b];
-            o.gdst += hi;
-            o.cur = rem;
-            o.skip = 0;
-            __syncwarp(tmask);
-        }
-    }
-}
-
 // Serial LSB-first bit packer used by one lane for one row (or the header). Writes to shared memory
 // at an arbitrary byte address: the first and last words go out as bytes, the middle as aligned words.
 struct BitPacker {
@@ -142,14 +106,9 @@ __global__ void __launch_bounds__(kThreads) spz_encode_kernel(const EncParams p)
     const uint32_t meta_bytes = p.write_size ? 8u : 0u;
 
     OutStage o;
-    {
-        const uint32_t mis = (uint32_t)((uintptr_t)gstream & 15);
-        o.buf = s_out;
-        o.gdst = gstream - mis;
-        o.skip = mis;
-        o.cur = mis + meta_bytes;
-        if (t == 0) for (uint32_t b = 0; b < meta_bytes; b++) s_out[mis + b] = 0;   // placeholder
-    }
+    o.init(s_out, gstream);
+    if (t == 0) for (uint32_t b = 0; b < meta_bytes; b++) s_out[o.cur + b] = 0;      // metadata placeholder
+    o.cur += meta_bytes;
     uint64_t stream_bytes = meta_bytes;     // bytes emitted so far (team-uniform)
     uint32_t ngroups = 0, nslots = 0, run = 0;
     uint32_t hdr_off = 0;                   // staging offset of the current group's header

@@ -93,6 +93,12 @@ spz_scan_sizes_kernel(const ChunkMeta* __restrict__ meta, uint64_t nchunks,
     if (tile == last_tile && threadIdx.x == 0) {
         const unsigned long long total = tile_excl + block_total;
         chunk_off[nchunks] = total;
+        // zero the alignment gap between the size table and the payload so frames are deterministic
+        {
+            uint8_t* gap = reinterpret_cast<uint8_t*>(chunk_nbytes + nchunks);
+            uint8_t* pay = reinterpret_cast<uint8_t*>(hdr) + hdr_in.payload_off;
+            while (gap < pay) *gap++ = 0;
+        }
         spz_frame_header h = hdr_in;
         h.payload_bytes = total;
         h.frame_bytes = h.payload_off + total + 16;
