@@ -1,14 +1,22 @@
 // spz_decode_hd.cu -- fast high-dim decode kernels (compile-time team size / dims-per-lane).
 //
 // Same work decomposition as spz_decode.cu (one team of lanes per chunk, lane-per-dim serial recurrence),
-// rebuilt around the memory system after the first ncu pass showed the generic kernel L1TEX-bound:
+// rebuilt after two ncu passes:
+//   pass 1 (generic kernel): L1TEX-bound -- every field cost two global loads that touched one line per team.
+//   pass 2 (first fast kernel): INT32-ALU-pipe bound (72 %) + ~6 instructions of MATCH/VOTE per sub-warp sync.
 //
+// What this version does about it:
 //   input    the compressed stream is pulled through a per-team shared-memory ring with coalesced 128-bit
-//            loads issued one fill ahead (register double buffering); field extraction is then two LDS of
-//            words the whole team shares (broadcast) + one funnel shift
-//   state    prev value / prev delta / FIRE counter live in registers (DPL is a template parameter)
+//            loads issued one fill ahead (register double buffering); a field is two broadcast LDS + one
+//            funnel shift
+//   sync     the kernel is WARP-SYNCHRONOUS: the 32/TEAM teams of a warp step through their chunks group by
+//            group in lock-step, per-team differences (fewer groups, run slots, errors) are predicates, so
+//            every shuffle / __syncwarp uses the full mask (one instruction, no convergence test)
+//   pipes    INT32 ALU and FMA pipes are both half rate on sm_100; the recurrence is phrased so they share
+//            the work: prev_delta is kept left-aligned (delta << (32-W)) so the FIRE prediction is one
+//            IMAD.HI, the W-bit wrap is one IMAD.SHL, and the gradient sum wraps for free in the top bits
 //   headers  both slots of a group are parsed at once; the two prefix sums share one packed shuffle scan
-//   output   decoded rows are staged in shared memory and leave as 128-bit coalesced stores
+//   output   decoded rows are staged in a double-buffered shared tile and leave as 128-bit coalesced stores
 //
 // Reference behaviour restated: sprintz_delta_rle.cpp:417-772, sprintz_xff_rle.cpp:568-1179 (high-dim only;
 // the low-dim column-major variants stay on the generic kernel).
@@ -16,52 +24,49 @@
 
 namespace spz {
 
-namespace {
+constexpr unsigned kFull = 0xffffffffu;
 
-__device__ __forceinline__ uint4 ldg_v4(const uint8_t* p)
-{
-    return __ldg(reinterpret_cast<const uint4*>(p));
-}
-
-}  // namespace
-
-template <int W, bool FIRE, int TEAM, int DPL>
+template <int W, bool FIRE, int TEAM, int DPL, bool FULLD>
 __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams p)
 {
     typedef typename Traits<W>::uint_t uint_t;
     constexpr int ESZ = W / 8;
     constexpr int HB = Traits<W>::HB;
     constexpr int CB = Traits<W>::CB;
+    constexpr int UP = 32 - W;                      // left-alignment shift of W-bit signed values
     constexpr uint32_t FILL = TEAM * 16;            // bytes one ring fill brings in
     constexpr uint32_t FMASK = (1u << HB) - 1u;
+    constexpr int TEAMS_PER_WARP = 32 / TEAM;
 
     extern __shared__ __align__(16) uint8_t smem[];
 
     const int lane = threadIdx.x & 31;
     const int t = lane & (TEAM - 1);
     const int team_in_cta = (int)(threadIdx.x / TEAM);
-    const uint64_t c = (uint64_t)blockIdx.x * p.teams_per_cta + team_in_cta;
-    if (c >= p.nchunks) return;
-    const uint32_t tmask = team_mask_of(lane, TEAM);
-    const int D = (int)p.ndims;
+    const uint64_t c64 = (uint64_t)blockIdx.x * (kThreads / TEAM) + team_in_cta;
+    const bool valid = c64 < p.nchunks;
+    const uint64_t c = valid ? c64 : 0;            // invalid teams shadow chunk 0 but never store
+    const int D = FULLD ? TEAM * DPL : (int)p.ndims;
 
     uint8_t* const ring = smem + (size_t)team_in_cta * p.team_smem;     // ring_cap bytes + 16 mirror bytes
-    uint8_t* const obuf = ring + p.ring_cap + 16;
     const uint32_t RCAP = p.ring_cap;
     const uint32_t RMASK = RCAP - 1u;
+    uint8_t* const obuf0 = ring + RCAP + 16;                            // two output tiles of out_cap bytes
+    const uint32_t OCAP = p.out_cap;
 
-    // ---- input: absolute byte offsets are relative to `abase`, the 16-byte aligned-down stream start
+    // ---- input: byte offsets are relative to `abase`, the 16-byte aligned-down stream start
     const uint8_t* const gstream = p.src + (p.offsets ? p.offsets[c] : c * p.slot_stride);
     const uint32_t mis_in = (uint32_t)((uintptr_t)gstream & 15);
     const uint8_t* const abase = gstream - mis_in;
-    const uint64_t limit = (uint64_t)(p.src_end - abase);               // readable bytes from abase
-    uint64_t wr = 0;                                                    // bytes of the stream staged so far
+    const uint64_t lim64 = (uint64_t)(p.src_end - abase);
+    const uint32_t limit = lim64 > 0xfffffff0ull ? 0xfffffff0u : (uint32_t)lim64;   // readable bytes from abase
+    uint32_t wr = 0;                                // stream bytes staged so far (team-uniform)
     uint4 nxt;
 
     auto prefetch = [&]() {
-        const uint64_t o = wr + (uint64_t)t * 16;
-        if (o + 16 <= limit) {
-            nxt = ldg_v4(abase + o);
+        const uint32_t o = wr + (uint32_t)t * 16u;
+        if (o + 16u <= limit) {
+            nxt = __ldg(reinterpret_cast<const uint4*>(abase + o));
         } else {
             uint32_t w[4] = {0, 0, 0, 0};
             for (uint32_t b = 0; b < 16; b++)
@@ -69,16 +74,20 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
             nxt = make_uint4(w[0], w[1], w[2], w[3]);
         }
     };
-    // make stream bytes [.., need_end) available in the ring (team-uniform)
-    auto ensure = [&](uint64_t need_end) {
-        while (wr < need_end) {
-            const uint32_t ro = ((uint32_t)wr + (uint32_t)t * 16u) & RMASK;
-            *reinterpret_cast<uint4*>(ring + ro) = nxt;
-            if (ro == 0) *reinterpret_cast<uint4*>(ring + RCAP) = nxt;      // mirror: word reads may run 4 bytes past the end
-            wr += FILL;
-            prefetch();
+    // Make stream bytes [.., need_end) available in the ring. Called at warp-uniform points; teams that do
+    // not need a fill idle through it.
+    auto ensure = [&](uint32_t need_end, bool on) {
+        while (__any_sync(kFull, on && wr < need_end)) {
+            __syncwarp();                            // readers of the bytes about to be overwritten are done
+            if (on && wr < need_end) {
+                const uint32_t ro = (wr + (uint32_t)t * 16u) & RMASK;
+                *reinterpret_cast<uint4*>(ring + ro) = nxt;
+                if (ro == 0) *reinterpret_cast<uint4*>(ring + RCAP) = nxt;  // mirror: word reads run 4 bytes past the end
+                wr += FILL;
+                prefetch();
+            }
+            __syncwarp();
         }
-        __syncwarp(tmask);
     };
     // 32-bit window at ring-relative bit position `bit` (may exceed the ring: masked)
     auto ring_bits = [&](uint32_t bit) -> uint32_t {
@@ -87,27 +96,58 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
         const uint32_t w1 = *reinterpret_cast<const uint32_t*>(ring + bo + 4);
         return __funnelshift_r(w0, w1, bit);
     };
-    auto ring_byte = [&](uint64_t at) -> uint32_t { return ring[(uint32_t)at & RMASK]; };
+    auto ring_byte = [&](uint32_t at) -> uint32_t { return ring[at & RMASK]; };
 
     // ---- output
     const uint64_t first = c * p.chunk_len;
     uint_t* const out = reinterpret_cast<uint_t*>(p.dst) + first;
-    const uint64_t cap = (first >= p.dst_cap) ? 0 :
+    const uint64_t cap64 = (!valid || first >= p.dst_cap) ? 0 :
         ((p.dst_cap - first < p.chunk_len) ? (p.dst_cap - first) : p.chunk_len);
-    OutStage os;
-    os.init(obuf, reinterpret_cast<uint8_t*>(out));
+    const uint32_t cap = cap64 > 0xffffffffull ? 0xffffffffu : (uint32_t)cap64;
+    // Output staging: tile `ob` holds bytes for the 16-byte aligned global address gdst; the first `skip`
+    // bytes precede this chunk's region. Two tiles alternate so a flush needs a single barrier.
+    uint8_t* ob = obuf0;
+    uint8_t* gdst;
+    uint32_t ocur, oskip;
+    {
+        const uint32_t mis = (uint32_t)((uintptr_t)out & 15);
+        gdst = reinterpret_cast<uint8_t*>(out) - mis; ocur = mis; oskip = mis;
+    }
+    // Writes staged bytes [oskip, hi) to HBM; hi = whole 16-byte units unless `final_flush`. The remainder
+    // moves to the other tile, which becomes current.
+    auto flush = [&](bool on, bool final_flush) {
+        __syncwarp();
+        if (on) {
+            const uint32_t hi = final_flush ? ocur : (ocur & ~15u);
+            if (hi > oskip) {
+                uint32_t a = (oskip + 15u) & ~15u;
+                if (a > hi) a = hi;
+                for (uint32_t b = oskip + t; b < a; b += TEAM) gdst[b] = ob[b];
+                const uint4* s4 = reinterpret_cast<const uint4*>(ob);
+                uint4* g4 = reinterpret_cast<uint4*>(gdst);
+                for (uint32_t u = (a >> 4) + t; u < (hi >> 4); u += TEAM) g4[u] = s4[u];
+                uint32_t tb = hi & ~15u;
+                if (tb < a) tb = a;
+                for (uint32_t b = tb + t; b < hi; b += TEAM) gdst[b] = ob[b];
+                uint8_t* nb = (ob == obuf0) ? obuf0 + OCAP : obuf0;
+                const uint32_t rem = ocur - hi;
+                for (uint32_t b = t; b < rem; b += TEAM) nb[b] = ob[hi + b];
+                ob = nb; gdst += hi; ocur = rem; oskip = 0;
+            }
+        }
+    };
 
-    // ---- predictor state (registers)
+    // ---- predictor state (registers); prev_delta is kept left-aligned: pdh = prev_delta << (32-W)
     uint32_t pv[DPL];
-    int32_t pd[DPL], ct[DPL];
+    int32_t pdh[DPL], ct[DPL];
 #pragma unroll
-    for (int k = 0; k < DPL; k++) { pv[k] = 0; pd[k] = 0; ct[k] = 0; }
+    for (int k = 0; k < DPL; k++) { pv[k] = 0; pdh[k] = 0; ct[k] = 0; }
 
     prefetch();
-    uint64_t pos = mis_in;              // absolute consume offset (team-uniform)
-    uint32_t ngroups, remaining, status = kStatusOk;
+    uint32_t pos = mis_in;              // consume offset from abase (team-uniform)
+    uint32_t ngroups = 0, remaining = 0, status = kStatusOk;
     if (p.has_meta) {                   // format.h:47-62
-        ensure(pos + 8);
+        ensure(pos + 8, true);
         ngroups = ring_byte(pos) | (ring_byte(pos + 1) << 8) | (ring_byte(pos + 2) << 16) | (ring_byte(pos + 3) << 24);
         remaining = ring_byte(pos + 4) | (ring_byte(pos + 5) << 8);
         const uint32_t nd = ring_byte(pos + 6) | (ring_byte(pos + 7) << 8);
@@ -117,126 +157,148 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
         ngroups = p.meta[c].ngroups;
         remaining = p.meta[c].remaining & 0xffffu;
     }
+    if (!valid || status != kStatusOk) ngroups = 0;
 
-    uint64_t o = 0;                     // output element cursor (team-uniform)
+    uint32_t o = 0;                     // output element cursor (team-uniform)
     const uint32_t H = (2u * (uint32_t)D * HB + 7u) >> 3;
     const uint32_t B = (uint32_t)kBlockRows * D;
     const uint32_t max_group = H + 2u * B * ESZ;
     const uint32_t row_out = (uint32_t)D * ESZ;         // output bytes per row
 
-    if (status == kStatusOk && !(ngroups == 0 && remaining < kMinDataSize)) {
-        for (uint32_t g = 0; g < ngroups; g++) {
-            __syncwarp(tmask);          // everyone is done reading the previous group before the ring advances
-            ensure(pos + max_group + 8);
+    const uint32_t gmax = __reduce_max_sync(kFull, ngroups);
+    for (uint32_t g = 0; g < gmax; g++) {
+        const bool act = g < ngroups && status == kStatusOk;
+        ensure(pos + max_group + 8, act);
 
-            // ---- both slots' widths: fields (s*D + d), prefix sums over dims share one packed scan
-            const uint32_t hbit = ((uint32_t)pos & RMASK) * 8u;
-            uint32_t nn[DPL], offs[DPL];
-            uint32_t carry = 0;
+        // ---- both slots' widths: fields (s*D + d); the prefix sums over dims share one packed scan
+        const uint32_t hbit = (pos & RMASK) * 8u;
+        uint32_t nn[DPL], offs[DPL];
+        uint32_t carry = 0;
 #pragma unroll
-            for (int k = 0; k < DPL; k++) {
-                const int d = k * TEAM + t;
-                uint32_t packed = 0;
-                if (d < D) {
-                    const uint32_t f0 = ring_bits(hbit + (uint32_t)d * HB) & FMASK;
-                    const uint32_t f1 = ring_bits(hbit + (uint32_t)(D + d) * HB) & FMASK;
-                    const uint32_t n0 = (f0 == (uint32_t)(W - 1)) ? (uint32_t)W : f0;
-                    const uint32_t n1 = (f1 == (uint32_t)(W - 1)) ? (uint32_t)W : f1;
-                    packed = n0 | (n1 << 16);
-                }
-                uint32_t incl = packed;
-#pragma unroll
-                for (int s = 1; s < TEAM; s <<= 1) {
-                    const uint32_t y = __shfl_up_sync(tmask, incl, s, TEAM);
-                    if (t >= s) incl += y;
-                }
-                nn[k] = packed;
-                offs[k] = carry + incl - packed;
-                carry += __shfl_sync(tmask, incl, TEAM - 1, TEAM);
+        for (int k = 0; k < DPL; k++) {
+            const int d = k * TEAM + t;
+            uint32_t packed = 0;
+            if (FULLD || d < D) {
+                const uint32_t f0 = ring_bits(hbit + (uint32_t)d * HB) & FMASK;
+                const uint32_t f1 = ring_bits(hbit + (uint32_t)(D + d) * HB) & FMASK;
+                const uint32_t n0 = (f0 == (uint32_t)(W - 1)) ? (uint32_t)W : f0;
+                const uint32_t n1 = (f1 == (uint32_t)(W - 1)) ? (uint32_t)W : f1;
+                packed = n0 | (n1 << 16);
             }
-            pos += H;
+            uint32_t incl = packed;
+#pragma unroll
+            for (int s = 1; s < TEAM; s <<= 1) {
+                const uint32_t y = __shfl_up_sync(kFull, incl, s, TEAM);
+                if (t >= s) incl += y;
+            }
+            nn[k] = packed;
+            offs[k] = carry + incl - packed;
+            carry += __shfl_sync(kFull, incl, TEAM - 1, TEAM);
+        }
+        if (act) pos += H;
 
 #pragma unroll 1
-            for (uint32_t s = 0; s < 2; s++) {
-                const uint32_t sh16 = 16u * s;
-                const uint32_t total = (carry >> sh16) & 0xffffu;
-                if (total == 0) {
-                    // ---- run slot (sprintz_delta_rle.cpp:640-667): rare, handled without the staging buffer
+        for (uint32_t s = 0; s < 2; s++) {
+            const uint32_t sh16 = 16u * s;
+            const uint32_t total = (carry >> sh16) & 0xffffu;
+            const bool is_run = act && status == kStatusOk && total == 0;
+            if (__any_sync(kFull, is_run)) {
+                // ---- run slot (sprintz_delta_rle.cpp:640-667): rare; the whole warp walks through it, teams
+                // without a run idle. Staged bytes leave first, then rows are stored directly.
+                uint32_t nrows = 0;
+                if (is_run) {
                     uint32_t nrun = ring_byte(pos) & 0x7f;
                     if (ring_byte(pos) & 0x80) { nrun |= ring_byte(pos + 1) << 7; pos += 2; } else { pos += 1; }
-                    const uint64_t nrows = (uint64_t)nrun * kBlockRows;
-                    if (o + nrows * D > cap) { status = kStatusOverflow; break; }
-                    stage_flush(os, true, t, TEAM, tmask);
+                    nrows = nrun * kBlockRows;
+                    if ((uint64_t)o + (uint64_t)nrows * D > cap) { status = kStatusOverflow; nrows = 0; }
+                }
+                const bool go = is_run && status == kStatusOk;
+                flush(go, true);
+                if (go) {
 #pragma unroll
                     for (int k = 0; k < DPL; k++) {
                         const int d = k * TEAM + t;
-                        if (d < D) {
+                        if (FULLD || d < D) {
                             uint_t* op = out + o + d;
                             if (FIRE) {
-                                const int32_t coef = fire_coef<W, false>(ct[k]);
-                                for (uint64_t r = 0; r < nrows; r++) {
-                                    pd[k] = fire_predict<W>(pd[k], coef);      // err == 0  ->  delta == prediction
-                                    pv[k] += (uint32_t)pd[k];
-                                    op[r * D] = (uint_t)pv[k];
+                                const int32_t coefs = (int32_t)((uint32_t)fire_coef<W, false>(ct[k]) << W);
+                                for (uint32_t r = 0; r < nrows; r++) {
+                                    // err == 0 -> delta == prediction = (prev_delta * coef) >> W, wrapped to W bits
+                                    const int32_t pred = __mulhi(pdh[k], coefs) >> W;
+                                    pdh[k] = (int32_t)((uint32_t)pred << UP);
+                                    pv[k] += (uint32_t)pred;
+                                    op[(size_t)r * D] = (uint_t)pv[k];
                                 }
                             } else {
-                                for (uint64_t r = 0; r < nrows; r++) op[r * D] = (uint_t)pv[k];
+                                for (uint32_t r = 0; r < nrows; r++) op[(size_t)r * D] = (uint_t)pv[k];
                             }
                         }
                     }
                     o += nrows * D;
-                    __syncwarp(tmask);
-                    os.init(obuf, reinterpret_cast<uint8_t*>(out + o));
-                    continue;
+                    const uint32_t mis = (uint32_t)((uintptr_t)(out + o) & 15);
+                    gdst = reinterpret_cast<uint8_t*>(out + o) - mis; ocur = mis; oskip = mis;
                 }
+            }
 
-                // ---- data slot
-                if (o + B > cap) { status = kStatusOverflow; break; }
+            // ---- data slot
+            bool data = act && status == kStatusOk && total != 0;
+            if (data && o + B > cap) { status = kStatusOverflow; data = false; }
+            if (data) {
                 const uint32_t row_bits = ((total + 7u) >> 3) * 8u;
-                const uint32_t pbit = ((uint32_t)pos & RMASK) * 8u;
+                const uint32_t pbit = (pos & RMASK) * 8u;
+                uint8_t* const obase = ob + ocur + (uint32_t)t * ESZ;
 #pragma unroll
                 for (int k = 0; k < DPL; k++) {
                     const int d = k * TEAM + t;
-                    if (d < D) {
+                    if (FULLD || d < D) {
                         const uint32_t n = (nn[k] >> sh16) & 0xffffu;
                         const uint32_t fmask = (1u << n) - 1u;
+                        const uint32_t hmask = fmask >> 1;         // magnitude bits of the zigzag code
+                        const uint32_t smask = fmask & 1u;         // its sign bit (0 when the field is empty)
                         uint32_t bit = pbit + ((offs[k] >> sh16) & 0xffffu);
-                        uint32_t u[kBlockRows];
+                        uint32_t x[kBlockRows];
 #pragma unroll
-                        for (int r = 0; r < kBlockRows; r++) { u[r] = ring_bits(bit) & fmask; bit += row_bits; }
+                        for (int r = 0; r < kBlockRows; r++) { x[r] = ring_bits(bit); bit += row_bits; }
 
-                        int32_t coef = 0, gs = 0;
-                        if (FIRE) coef = fire_coef<W, false>(ct[k]);
-                        uint8_t* ob = os.buf + os.cur + (uint32_t)d * ESZ;
+                        int32_t coefs = 0, gsh = 0;
+                        if (FIRE) coefs = (int32_t)((uint32_t)fire_coef<W, false>(ct[k]) << W);
+                        uint8_t* op = obase + (uint32_t)(k * TEAM) * ESZ;
 #pragma unroll
                         for (int r = 0; r < kBlockRows; r++) {
-                            const int32_t err = (int32_t)((u[r] >> 1) ^ (0u - (u[r] & 1u)));    // zigzag^-1 (bitpack.h:303)
+                            // zigzag^-1 (bitpack.h:303) fused with the field mask
+                            const uint32_t sgn = x[r] & smask;                                   // 1 iff err < 0
+                            const int32_t err = (int32_t)(((x[r] >> 1) & hmask) ^ (0u - sgn));
                             int32_t delta = err;
                             if (FIRE) {
-                                delta = sx<W>(err + fire_predict<W>(pd[k], coef));
-                                if (r & 1) gs += fire_grad<W>(err, pd[k]);
+                                if (r & 1) {
+                                    // icopysign(err, prev_delta) (util.h:63-68), accumulated left-aligned so the
+                                    // int_t wrap of grad_sum is the natural 32-bit wrap
+                                    const int32_t nz = (int32_t)min((uint32_t)err, 1u);      // err != 0
+                                    gsh += pdh[k] * (nz - 2 * (int32_t)sgn * nz);
+                                }
+                                // prediction = (prev_delta * coef) >> W (sprintz_xff_rle.cpp:225); exact: pdh*coefs = prod << 32
+                                delta = err + (__mulhi(pdh[k], coefs) >> W);
+                                pdh[k] = (int32_t)((uint32_t)delta << UP);       // wraps delta to W bits
                             }
-                            pd[k] = delta;
                             pv[k] += (uint32_t)delta;
-                            *reinterpret_cast<uint_t*>(ob) = (uint_t)pv[k];
-                            ob += row_out;
+                            *reinterpret_cast<uint_t*>(op) = (uint_t)pv[k];
+                            op += row_out;
                         }
-                        if (FIRE) ct[k] = sx<CB>(ct[k] + (sx<W>(gs) >> 2));
+                        if (FIRE) ct[k] = sx<CB>(ct[k] + ((gsh >> UP) >> 2));     // sprintz_xff_rle.cpp:273-275
                     }
                 }
                 pos += (row_bits >> 3) * kBlockRows;
-                os.cur += B * ESZ;
+                ocur += B * ESZ;
                 o += B;
             }
-            if (status != kStatusOk) break;
-            stage_flush(os, false, t, TEAM, tmask);
         }
+        flush(act, false);
     }
-    stage_flush(os, true, t, TEAM, tmask);
+    flush(valid, true);
 
     // ---- trailing raw elements (also the whole stream when it was stored raw)
-    if (status == kStatusOk) {
-        if (o + remaining > cap) {
+    if (valid && status == kStatusOk) {
+        if ((uint64_t)o + remaining > cap) {
             status = kStatusOverflow;
         } else {
             const uint8_t* tsrc = abase + pos;
@@ -246,25 +308,25 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
             o += remaining;
         }
     }
-    if (t == 0 && p.meta) {
+    if (valid && t == 0 && p.meta) {
         p.meta[c].status = status;
         if (p.has_meta) {
-            p.meta[c].nbytes = (uint32_t)(pos - mis_in + (uint64_t)remaining * ESZ);
+            p.meta[c].nbytes = pos - mis_in + remaining * ESZ;
             p.meta[c].ngroups = ngroups;
-            p.meta[c].remaining = (uint32_t)o;
+            p.meta[c].remaining = o;
         }
     }
 }
 
 // ------------------------------------------------------------------ launch
 
-template <int W, bool FIRE, int TEAM, int DPL>
+template <int W, bool FIRE, int TEAM, int DPL, bool FULLD>
 static cudaError_t launch_hd(const DecParams& p, uint32_t grid, size_t smem, cudaStream_t stream)
 {
-    cudaError_t e = cudaFuncSetAttribute(spz_decode_hd_kernel<W, FIRE, TEAM, DPL>,
+    cudaError_t e = cudaFuncSetAttribute(spz_decode_hd_kernel<W, FIRE, TEAM, DPL, FULLD>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    spz_decode_hd_kernel<W, FIRE, TEAM, DPL><<<grid, p.teams_per_cta * TEAM, smem, stream>>>(p);
+    spz_decode_hd_kernel<W, FIRE, TEAM, DPL, FULLD><<<grid, kThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -276,16 +338,19 @@ cudaError_t launch_decode_hd(int elem_sz, int predictor, DecParams p, cudaStream
 {
     const bool low = elem_sz == 1 ? (p.ndims <= 4) : (p.ndims <= 2);
     if (low || p.ndims > 128 || p.src_end == nullptr) return cudaErrorNotSupported;
+    // 32-bit stream / output offsets inside one chunk
+    if (p.chunk_len * (uint64_t)elem_sz > 0x70000000ull) return cudaErrorNotSupported;
     const uint32_t team = p.ndims >= 32 ? 32 : pow2_ceil(p.ndims);
     const uint32_t dpl = (p.ndims + team - 1) / team;
+    const bool fulld = (team * dpl == p.ndims);
     const uint32_t hb = elem_sz == 1 ? 3 : 4;
     const uint32_t H = (2 * p.ndims * hb + 7) / 8;
     const uint32_t max_group = H + 2 * 8 * p.ndims * elem_sz;
     p.team = team; p.dpl = dpl;
     p.ring_cap = pow2_ceil(max_group + 8 + team * 16);
     p.out_cap = (16 + 2 * 8 * p.ndims * elem_sz + 16 + 15) & ~15u;
-    p.team_smem = p.ring_cap + 16 + p.out_cap;
-    uint32_t teams_per_cta = kThreads / team;
+    p.team_smem = p.ring_cap + 16 + 2 * p.out_cap;
+    const uint32_t teams_per_cta = kThreads / team;
     p.teams_per_cta = teams_per_cta;
     const size_t smem = (size_t)teams_per_cta * p.team_smem;
     if (smem > 200 * 1024) return cudaErrorNotSupported;
@@ -293,8 +358,9 @@ cudaError_t launch_decode_hd(int elem_sz, int predictor, DecParams p, cudaStream
     if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
     const uint32_t grid = (uint32_t)grid64;
 
-#define SPZ_HD(Wv, Tv, Dv) \
-    return predictor ? launch_hd<Wv, true, Tv, Dv>(p, grid, smem, stream) : launch_hd<Wv, false, Tv, Dv>(p, grid, smem, stream)
+#define SPZ_HD2(Wv, Tv, Dv, Fv) \
+    return predictor ? launch_hd<Wv, true, Tv, Dv, Fv>(p, grid, smem, stream) : launch_hd<Wv, false, Tv, Dv, Fv>(p, grid, smem, stream)
+#define SPZ_HD(Wv, Tv, Dv) do { if (fulld) { SPZ_HD2(Wv, Tv, Dv, true); } else { SPZ_HD2(Wv, Tv, Dv, false); } } while (0)
     if (elem_sz == 1) {
         if (team == 8) SPZ_HD(8, 8, 1);
         if (team == 16) SPZ_HD(8, 16, 1);
@@ -312,6 +378,7 @@ cudaError_t launch_decode_hd(int elem_sz, int predictor, DecParams p, cudaStream
         if (dpl == 4) SPZ_HD(16, 32, 4);
     }
 #undef SPZ_HD
+#undef SPZ_HD2
     return cudaErrorNotSupported;
 }
 

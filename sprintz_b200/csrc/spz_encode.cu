@@ -365,8 +365,14 @@ static void enc_layout(int elem_sz, bool low, EncParams& p)
     p.team_smem = off + cap;
 }
 
+cudaError_t launch_encode_hd(int elem_sz, int predictor, EncParams p, cudaStream_t stream);
+
 cudaError_t launch_encode(int elem_sz, int predictor, EncParams p, cudaStream_t stream)
 {
+    {   // fast path for high-dim shapes; the generic kernel below covers everything else
+        const cudaError_t e = launch_encode_hd(elem_sz, predictor, p, stream);
+        if (e != cudaErrorNotSupported) return e;
+    }
     const bool low = elem_sz == 1 ? (p.ndims <= 4) : (p.ndims <= 2);
     p.team = p.ndims >= 32 ? 32 : pow2_ceil(p.ndims);
     p.dpl = (p.ndims + p.team - 1) / p.team;
