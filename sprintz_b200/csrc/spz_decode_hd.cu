@@ -118,21 +118,29 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
     auto flush = [&](bool on, bool final_flush) {
         __syncwarp();
         if (on) {
-            const uint32_t hi = final_flush ? ocur : (ocur & ~15u);
-            if (hi > oskip) {
-                uint32_t a = (oskip + 15u) & ~15u;
-                if (a > hi) a = hi;
-                for (uint32_t b = oskip + t; b < a; b += TEAM) gdst[b] = ob[b];
+            uint8_t* const nb = (ob == obuf0) ? obuf0 + OCAP : obuf0;
+            if (oskip == 0u && (ocur & 15u) == 0u) {
+                // common case: the chunk's output is 16-byte aligned, a group is a whole number of units
                 const uint4* s4 = reinterpret_cast<const uint4*>(ob);
                 uint4* g4 = reinterpret_cast<uint4*>(gdst);
-                for (uint32_t u = (a >> 4) + t; u < (hi >> 4); u += TEAM) g4[u] = s4[u];
-                uint32_t tb = hi & ~15u;
-                if (tb < a) tb = a;
-                for (uint32_t b = tb + t; b < hi; b += TEAM) gdst[b] = ob[b];
-                uint8_t* nb = (ob == obuf0) ? obuf0 + OCAP : obuf0;
-                const uint32_t rem = ocur - hi;
-                for (uint32_t b = t; b < rem; b += TEAM) nb[b] = ob[hi + b];
-                ob = nb; gdst += hi; ocur = rem; oskip = 0;
+                for (uint32_t u = t; u < (ocur >> 4); u += TEAM) g4[u] = s4[u];
+                ob = nb; gdst += ocur; ocur = 0;
+            } else {
+                const uint32_t hi = final_flush ? ocur : (ocur & ~15u);
+                if (hi > oskip) {
+                    uint32_t a = (oskip + 15u) & ~15u;
+                    if (a > hi) a = hi;
+                    for (uint32_t b = oskip + t; b < a; b += TEAM) gdst[b] = ob[b];
+                    const uint4* s4 = reinterpret_cast<const uint4*>(ob);
+                    uint4* g4 = reinterpret_cast<uint4*>(gdst);
+                    for (uint32_t u = (a >> 4) + t; u < (hi >> 4); u += TEAM) g4[u] = s4[u];
+                    uint32_t tb = hi & ~15u;
+                    if (tb < a) tb = a;
+                    for (uint32_t b = tb + t; b < hi; b += TEAM) gdst[b] = ob[b];
+                    const uint32_t rem = ocur - hi;
+                    for (uint32_t b = t; b < rem; b += TEAM) nb[b] = ob[hi + b];
+                    ob = nb; gdst += hi; ocur = rem; oskip = 0;
+                }
             }
         }
     };
@@ -197,10 +205,68 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
         }
         if (act) pos += H;
 
+        // One data slot: unpack + inverse predictor for my dims, rows staged at ob + ocur.
+        auto data_slot = [&](uint32_t sh16, uint32_t total) {
+            const uint32_t row_bits = ((total + 7u) >> 3) * 8u;
+            const uint32_t pbit = (pos & RMASK) * 8u;
+            uint8_t* const obase = ob + ocur + (uint32_t)t * ESZ;
+#pragma unroll
+            for (int k = 0; k < DPL; k++) {
+                const int d = k * TEAM + t;
+                if (FULLD || d < D) {
+                    const uint32_t n = (nn[k] >> sh16) & 0xffffu;
+                    const uint32_t fmask = (1u << n) - 1u;
+                    const uint32_t hmask = fmask >> 1;         // magnitude bits of the zigzag code
+                    const uint32_t smask = fmask & 1u;         // its sign bit (0 when the field is empty)
+                    uint32_t bit = pbit + ((offs[k] >> sh16) & 0xffffu);
+                    uint32_t x[kBlockRows];
+#pragma unroll
+                    for (int r = 0; r < kBlockRows; r++) { x[r] = ring_bits(bit); bit += row_bits; }
+
+                    int32_t coefs = 0, gsh = 0;
+                    if (FIRE) coefs = (int32_t)((uint32_t)fire_coef<W, false>(ct[k]) << W);
+                    uint8_t* op = obase + (uint32_t)(k * TEAM) * ESZ;
+#pragma unroll
+                    for (int r = 0; r < kBlockRows; r++) {
+                        // zigzag^-1 (bitpack.h:303) fused with the field mask
+                        const uint32_t sgn = x[r] & smask;                                   // 1 iff err < 0
+                        const int32_t err = (int32_t)(((x[r] >> 1) & hmask) ^ (0u - sgn));
+                        int32_t delta = err;
+                        if (FIRE) {
+                            if (r & 1) {
+                                // icopysign(err, prev_delta) (util.h:63-68), accumulated left-aligned so the
+                                // int_t wrap of grad_sum is the natural 32-bit wrap
+                                if (sgn) gsh -= pdh[k]; else if (err != 0) gsh += pdh[k];
+                            }
+                            // prediction = (prev_delta * coef) >> W (sprintz_xff_rle.cpp:225); exact: pdh*coefs = prod << 32
+                            delta = err + (__mulhi(pdh[k], coefs) >> W);
+                            pdh[k] = (int32_t)((uint32_t)delta << UP);       // wraps delta to W bits
+                        }
+                        pv[k] += (uint32_t)delta;
+                        *reinterpret_cast<uint_t*>(op) = (uint_t)pv[k];
+                        op += row_out;
+                    }
+                    if (FIRE) ct[k] = sx<CB>(ct[k] + ((gsh >> UP) >> 2));     // sprintz_xff_rle.cpp:273-275
+                }
+            }
+            pos += (row_bits >> 3) * kBlockRows;
+            ocur += B * ESZ;
+            o += B;
+        };
+
+        const uint32_t tot0 = carry & 0xffffu, tot1 = carry >> 16;
+        // Fast path: every team of the warp has two data slots that fit.
+        if (__all_sync(kFull, act && tot0 != 0u && tot1 != 0u && o + 2u * B <= cap)) {
+            data_slot(0u, tot0);
+            data_slot(16u, tot1);
+            flush(true, false);
+            continue;
+        }
+
 #pragma unroll 1
         for (uint32_t s = 0; s < 2; s++) {
             const uint32_t sh16 = 16u * s;
-            const uint32_t total = (carry >> sh16) & 0xffffu;
+            const uint32_t total = s ? tot1 : tot0;
             const bool is_run = act && status == kStatusOk && total == 0;
             if (__any_sync(kFull, is_run)) {
                 // ---- run slot (sprintz_delta_rle.cpp:640-667): rare; the whole warp walks through it, teams
@@ -243,54 +309,7 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
             // ---- data slot
             bool data = act && status == kStatusOk && total != 0;
             if (data && o + B > cap) { status = kStatusOverflow; data = false; }
-            if (data) {
-                const uint32_t row_bits = ((total + 7u) >> 3) * 8u;
-                const uint32_t pbit = (pos & RMASK) * 8u;
-                uint8_t* const obase = ob + ocur + (uint32_t)t * ESZ;
-#pragma unroll
-                for (int k = 0; k < DPL; k++) {
-                    const int d = k * TEAM + t;
-                    if (FULLD || d < D) {
-                        const uint32_t n = (nn[k] >> sh16) & 0xffffu;
-                        const uint32_t fmask = (1u << n) - 1u;
-                        const uint32_t hmask = fmask >> 1;         // magnitude bits of the zigzag code
-                        const uint32_t smask = fmask & 1u;         // its sign bit (0 when the field is empty)
-                        uint32_t bit = pbit + ((offs[k] >> sh16) & 0xffffu);
-                        uint32_t x[kBlockRows];
-#pragma unroll
-                        for (int r = 0; r < kBlockRows; r++) { x[r] = ring_bits(bit); bit += row_bits; }
-
-                        int32_t coefs = 0, gsh = 0;
-                        if (FIRE) coefs = (int32_t)((uint32_t)fire_coef<W, false>(ct[k]) << W);
-                        uint8_t* op = obase + (uint32_t)(k * TEAM) * ESZ;
-#pragma unroll
-                        for (int r = 0; r < kBlockRows; r++) {
-                            // zigzag^-1 (bitpack.h:303) fused with the field mask
-                            const uint32_t sgn = x[r] & smask;                                   // 1 iff err < 0
-                            const int32_t err = (int32_t)(((x[r] >> 1) & hmask) ^ (0u - sgn));
-                            int32_t delta = err;
-                            if (FIRE) {
-                                if (r & 1) {
-                                    // icopysign(err, prev_delta) (util.h:63-68), accumulated left-aligned so the
-                                    // int_t wrap of grad_sum is the natural 32-bit wrap
-                                    const int32_t nz = (int32_t)min((uint32_t)err, 1u);      // err != 0
-                                    gsh += pdh[k] * (nz - 2 * (int32_t)sgn * nz);
-                                }
-                                // prediction = (prev_delta * coef) >> W (sprintz_xff_rle.cpp:225); exact: pdh*coefs = prod << 32
-                                delta = err + (__mulhi(pdh[k], coefs) >> W);
-                                pdh[k] = (int32_t)((uint32_t)delta << UP);       // wraps delta to W bits
-                            }
-                            pv[k] += (uint32_t)delta;
-                            *reinterpret_cast<uint_t*>(op) = (uint_t)pv[k];
-                            op += row_out;
-                        }
-                        if (FIRE) ct[k] = sx<CB>(ct[k] + ((gsh >> UP) >> 2));     // sprintz_xff_rle.cpp:273-275
-                    }
-                }
-                pos += (row_bits >> 3) * kBlockRows;
-                ocur += B * ESZ;
-                o += B;
-            }
+            if (data) data_slot(sh16, total);
         }
         flush(act, false);
     }

@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(kThreads) spz_encode_hd_kernel(const EncParams
     constexpr int NCL = Dp / CL;                    // clusters per row
     constexpr int NVEC = DPL * ESZ;                 // 16-byte vectors per lane per 16-row group (upper bound)
     constexpr uint32_t ZS = ((((uint32_t)Dp * ESZ + 3u) >> 2) | 1u) * 4u;   // zz tile row stride (odd #words)
+    constexpr bool HFAST = FULLD && TEAM >= 8;      // D % 8 == 0: header bytes are owned by octets of dims
 
     extern __shared__ __align__(16) uint8_t smem[];
 
@@ -105,21 +106,35 @@ __global__ void __launch_bounds__(kThreads) spz_encode_hd_kernel(const EncParams
     auto flush = [&](bool on, bool final_flush) {
         __syncwarp();
         if (on) {
-            const uint32_t hi = final_flush ? ocur : (ocur & ~15u);
-            if (hi > oskip) {
-                uint32_t a = (oskip + 15u) & ~15u;
-                if (a > hi) a = hi;
-                for (uint32_t b = oskip + t; b < a; b += TEAM) gdst[b] = ob[b];
+            uint8_t* const nb = (ob == stage0) ? stage0 + OCAP : stage0;
+            if (!final_flush && oskip == 0u) {
+                // common case: whole 16-byte units leave, the (<16 byte) remainder moves to the other tile
+                const uint32_t hi = ocur & ~15u;
                 const uint4* s4 = reinterpret_cast<const uint4*>(ob);
                 uint4* g4 = reinterpret_cast<uint4*>(gdst);
-                for (uint32_t u = (a >> 4) + t; u < (hi >> 4); u += TEAM) g4[u] = s4[u];
-                uint32_t tb = hi & ~15u;
-                if (tb < a) tb = a;
-                for (uint32_t b = tb + t; b < hi; b += TEAM) gdst[b] = ob[b];
-                uint8_t* nb = (ob == stage0) ? stage0 + OCAP : stage0;
+                for (uint32_t u = t; u < (hi >> 4); u += TEAM) g4[u] = s4[u];
                 const uint32_t rem = ocur - hi;
-                for (uint32_t b = t; b < rem; b += TEAM) nb[b] = ob[hi + b];
-                ob = nb; gdst += hi; ocur = rem; oskip = 0;
+                if ((uint32_t)t < rem) nb[t] = ob[hi + t];
+                if (TEAM < 16 && (uint32_t)t + TEAM < rem) nb[t + TEAM] = ob[hi + t + TEAM];
+                if (TEAM < 8 && (uint32_t)t + 2 * TEAM < rem) { nb[t + 2 * TEAM] = ob[hi + t + 2 * TEAM]; }
+                if (TEAM < 8 && (uint32_t)t + 3 * TEAM < rem) { nb[t + 3 * TEAM] = ob[hi + t + 3 * TEAM]; }
+                ob = nb; gdst += hi; ocur = rem;
+            } else {
+                const uint32_t hi = final_flush ? ocur : (ocur & ~15u);
+                if (hi > oskip) {
+                    uint32_t a = (oskip + 15u) & ~15u;
+                    if (a > hi) a = hi;
+                    for (uint32_t b = oskip + t; b < a; b += TEAM) gdst[b] = ob[b];
+                    const uint4* s4 = reinterpret_cast<const uint4*>(ob);
+                    uint4* g4 = reinterpret_cast<uint4*>(gdst);
+                    for (uint32_t u = (a >> 4) + t; u < (hi >> 4); u += TEAM) g4[u] = s4[u];
+                    uint32_t tb = hi & ~15u;
+                    if (tb < a) tb = a;
+                    for (uint32_t b = tb + t; b < hi; b += TEAM) gdst[b] = ob[b];
+                    const uint32_t rem = ocur - hi;
+                    for (uint32_t b = t; b < rem; b += TEAM) nb[b] = ob[hi + b];
+                    ob = nb; gdst += hi; ocur = rem; oskip = 0;
+                }
             }
         }
     };
@@ -144,9 +159,10 @@ __global__ void __launch_bounds__(kThreads) spz_encode_hd_kernel(const EncParams
     bool on = valid && L >= (int64_t)kMinDataSize;
     const bool strict = !FIRE;              // `<` vs `<=` in the continue-run test (high-dim: sprintz_xff_rle.cpp:362)
 
-    // Group finished: bit-emit the pending data blocks, gather the header, flush. Warp-uniform call.
+    // Group finished: bit-emit the pending data blocks, (generic shapes: gather the header), flush.
+    // Warp-uniform call.
     auto close_group = [&](bool gc) {
-        if (gc) {
+        if (!HFAST && gc) {
 #pragma unroll
             for (int k = 0; k < DPL; k++) {
                 const int d = k * TEAM + t;
@@ -156,51 +172,110 @@ __global__ void __launch_bounds__(kThreads) spz_encode_hd_kernel(const EncParams
         }
         __syncwarp();
         if (gc) {
-            // ---- row jobs: job j -> (pending entry j>>3, row j&7)
+            // ---- row jobs: job j -> (pending entry j>>3, row j&7). Rows are emitted byte by byte (4 at a time):
+            // no alignment cases, no branches besides the flush predicate.
             for (uint32_t j = t; j < pend * 8u; j += TEAM) {
                 const uint32_t e = j >> 3, r = j & 7u;
                 const uint32_t half = e ? pe_half1 : pe_half0;
                 const uint32_t rb = e ? pe_rb1 : pe_rb0;
-                const uint32_t dst = (e ? pe_off1 : pe_off0) + r * rb;
+                uint8_t* dstp = ob + (e ? pe_off1 : pe_off0) + r * rb;
                 const uint_t* zrow = reinterpret_cast<const uint_t*>(s_zz + (half * 8u + r) * ZS);
-                const uint32_t* mul = s_mul + half * Dp;
+                const uint4* mul4 = reinterpret_cast<const uint4*>(s_mul + half * Dp);
                 const uint8_t* cw = s_cw + half * Dp;
-                uint32_t a = dst & 3u;               // bytes of the first word that belong to someone else
-                uint32_t wp = dst - a;
                 uint64_t acc = 0;
-                uint32_t pos = 8u * a;
+                uint32_t pos = 0;
 #pragma unroll 2
                 for (int q = 0; q < NCL; q++) {
-                    uint32_t qv = 0;
-#pragma unroll
-                    for (int jj = 0; jj < CL; jj++) qv += (uint32_t)zrow[q * CL + jj] * mul[q * CL + jj];
-                    acc += (uint64_t)qv * (uint64_t)(1u << pos);        // fields are disjoint: add == or
+                    uint32_t qv;
+                    if (CL == 4) {
+                        const uint4 m = mul4[q];
+                        qv = (uint32_t)zrow[q * 4] * m.x + (uint32_t)zrow[q * 4 + 1] * m.y +
+                             (uint32_t)zrow[q * 4 + 2] * m.z + (uint32_t)zrow[q * 4 + 3] * m.w;
+                    } else {
+                        const uint2 m = reinterpret_cast<const uint2*>(mul4)[q];
+                        qv = (uint32_t)zrow[q * 2] * m.x + (uint32_t)zrow[q * 2 + 1] * m.y;
+                    }
+                    const uint32_t p2 = 1u << pos;
+                    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(qv), "r"(p2));   // fields are disjoint: add == or
                     pos += cw[q * CL];
                     if (pos >= 32u) {
                         const uint32_t wv = (uint32_t)acc;
-                        if (a) { for (uint32_t b = a; b < 4u; b++) ob[wp + b] = (uint8_t)(wv >> (8u * b)); a = 0; }
-                        else *reinterpret_cast<uint32_t*>(ob + wp) = wv;
-                        wp += 4u; acc >>= 32; pos -= 32u;
+                        dstp[0] = (uint8_t)wv; dstp[1] = (uint8_t)(wv >> 8); dstp[2] = (uint8_t)(wv >> 16); dstp[3] = (uint8_t)(wv >> 24);
+                        dstp += 4; acc >>= 32; pos -= 32u;
                     }
                 }
-                const uint32_t nbts = (pos + 7u) >> 3;
-                for (uint32_t b = a; b < nbts; b++) ob[wp + b] = (uint8_t)(acc >> (8u * b));
+                const uint32_t wv = (uint32_t)acc;      // < 32 bits left
+                if (pos > 0u)  dstp[0] = (uint8_t)wv;
+                if (pos > 8u)  dstp[1] = (uint8_t)(wv >> 8);
+                if (pos > 16u) dstp[2] = (uint8_t)(wv >> 16);
+                if (pos > 24u) dstp[3] = (uint8_t)(wv >> 24);
             }
-            // ---- header words: lane j gathers the nibbles overlapping bits [32j, 32j+32) of the group header
-            const uint32_t nfields = 2u * (uint32_t)D;
-            for (uint32_t j = t; j * 4u < H; j += TEAM) {
-                const uint32_t f_lo = (32u * j) / HB;
-                uint32_t f_hi = (32u * j + 31u) / HB;
-                if (f_hi > nfields - 1u) f_hi = nfields - 1u;
-                const int32_t sh0 = (int32_t)(f_lo * HB) - (int32_t)(32u * j);     // in (-HB, 0]
-                uint32_t w = (uint32_t)s_hf[f_lo] >> (uint32_t)(-sh0);
-                for (uint32_t f = f_lo + 1u; f <= f_hi; f++) w |= (uint32_t)s_hf[f] << (f * HB - 32u * j);
-                for (uint32_t b = 0; b < 4u; b++)
-                    if (4u * j + b < H) ob[hdr_off + 4u * j + b] = (uint8_t)(w >> (8u * b));
+            if (!HFAST) {
+                // ---- header words: lane j gathers the nibbles overlapping bits [32j, 32j+32) of the group header
+                const uint32_t nfields = 2u * (uint32_t)D;
+                for (uint32_t j = t; j * 4u < H; j += TEAM) {
+                    const uint32_t f_lo = (32u * j) / HB;
+                    uint32_t f_hi = (32u * j + 31u) / HB;
+                    if (f_hi > nfields - 1u) f_hi = nfields - 1u;
+                    const int32_t sh0 = (int32_t)(f_lo * HB) - (int32_t)(32u * j);     // in (-HB, 0]
+                    uint32_t w = (uint32_t)s_hf[f_lo] >> (uint32_t)(-sh0);
+                    for (uint32_t f = f_lo + 1u; f <= f_hi; f++) w |= (uint32_t)s_hf[f] << (f * HB - 32u * j);
+                    for (uint32_t b = 0; b < 4u; b++)
+                        if (4u * j + b < H) ob[hdr_off + 4u * j + b] = (uint8_t)(w >> (8u * b));
+                }
             }
             pend = 0;
         }
         flush(gc, false);
+    };
+
+    // One slot of the open group (team-predicated by the caller).
+    auto emit_slot = [&](uint32_t act, uint32_t run_len, const uint32_t (&fh)[DPL], uint32_t row_bytes) -> bool {
+        const uint32_t sl = nslots & 1u;
+        if (sl == 0u) {
+            hdr_off = ocur; ocur += H; sbytes += H; ngroups++;
+        }
+        if (act == ACT_RUN) {       // zero header fields + 1..2 length bytes (sprintz_delta_rle.cpp:238-245)
+            const uint32_t two = run_len > 0x7fu ? 1u : 0u;
+            if (t == 0) {
+                ob[ocur] = (uint8_t)((run_len & 0x7fu) | (two << 7));
+                if (two) ob[ocur + 1] = (uint8_t)(run_len >> 7);
+            }
+            ocur += 1u + two; sbytes += 1u + two;
+        } else if (act == ACT_PAD) {
+            if (t == 0) ob[ocur] = 0;
+            ocur += 1u; sbytes += 1u;
+        } else {                    // data slot: payload bytes are produced at group end
+            if (pend == 0u) { pe_half0 = wh; pe_off0 = ocur; pe_rb0 = row_bytes; }
+            else            { pe_half1 = wh; pe_off1 = ocur; pe_rb1 = row_bytes; }
+            pend++;
+            if (!HFAST) {
+#pragma unroll
+                for (int k = 0; k < DPL; k++) { if (sl == 0u) hf0[k] = fh[k]; else hf1[k] = fh[k]; }
+            }
+            ocur += kBlockRows * row_bytes; sbytes += kBlockRows * row_bytes;
+            wh ^= 1u; blk++;
+        }
+        nslots++;
+        return (nslots & 1u) == 0u;
+    };
+    // HFAST shapes write a slot's header bytes as soon as the slot is emitted: D is a multiple of 8, so every 8
+    // dims own 3 (8-bit) / 4 (16-bit) whole header bytes and an xor-butterfly over the octet assembles them; run
+    // and pad slots write zeros. Called at a warp-uniform point: `doit` = my team emitted a slot, `isdata` = it
+    // was a data slot, `sl` = its index in the group.
+    auto emit_header_fast = [&](bool doit, bool isdata, uint32_t sl, uint32_t hoff, const uint32_t (&fh)[DPL]) {
+#pragma unroll
+        for (int k = 0; k < DPL; k++) {
+            uint32_t v = isdata ? (fh[k] << (HB * (t & 7))) : 0u;
+            v |= __shfl_xor_sync(kFullE, v, 1);
+            v |= __shfl_xor_sync(kFullE, v, 2);
+            v |= __shfl_xor_sync(kFullE, v, 4);
+            const uint32_t bidx = (uint32_t)(t & 7);
+            if (doit && bidx < (uint32_t)HB) {
+                const uint32_t byte0 = ((sl * (uint32_t)D + (uint32_t)((k * TEAM + t) & ~7)) * HB) >> 3;
+                ob[hoff + byte0 + bidx] = (uint8_t)(v >> (8u * bidx));
+            }
+        }
     };
 
     prefetch(0);
@@ -253,8 +328,7 @@ __global__ void __launch_bounds__(kThreads) spz_encode_hd_kernel(const EncParams
                     const uint32_t zz = (((uint32_t)eh >> (UP - 1)) ^ (uint32_t)(eh >> 31)) & WMASK;
                     if (FIRE && (r & 1)) {
                         // grad_sum += icopysign(err, prev_delta) (util.h:63-68), left-aligned so it wraps like int_t
-                        const int32_t fac = (int32_t)min(zz, 1u) - 2 * (int32_t)(zz & 1u);
-                        gsh += dprev * fac;
+                        if (eh > 0) gsh += dprev; else if (eh < 0) gsh -= dprev;
                     }
                     mask |= zz;
                     *reinterpret_cast<uint_t*>(zcol + (uint32_t)r * ZS) = (uint_t)zz;
@@ -294,7 +368,17 @@ __global__ void __launch_bounds__(kThreads) spz_encode_hd_kernel(const EncParams
         const bool zero = (total == 0);
         const uint32_t row_bytes = (total + 7u) >> 3;
 
-        // ================= control: per-team action generator, executed in lock-step passes
+        // ================= control
+        // Fast path: every live team has a plain data block (no run open, block not all-zero).
+        if (__all_sync(kFullE, !on || (!zero && run == 0u))) {
+            bool gc = false;
+            const uint32_t sl = nslots & 1u;
+            if (on) { gc = emit_slot(ACT_DATA, 0u, fh, row_bytes); outer = gc; }
+            if (HFAST) emit_header_fast(on, on, sl, hdr_off, fh);
+            if (__any_sync(kFullE, gc)) close_group(gc);
+            continue;
+        }
+        // General case: per-team action generator (run slot / pad / data slot), executed in lock-step passes.
         // st: 0 = block just read; 1 = run flushed because the data ran out, maybe pad; 2 = finished; 3 = block consumed
         uint32_t st = on ? 0u : 3u;
         for (;;) {
@@ -318,32 +402,12 @@ __global__ void __launch_bounds__(kThreads) spz_encode_hd_kernel(const EncParams
             if (!__any_sync(kFullE, act != ACT_NONE)) break;
 
             bool gc = false;
+            const uint32_t sl = nslots & 1u;
             if (act != ACT_NONE) {
-                const uint32_t s = nslots & 1u;
-                if (s == 0u) { hdr_off = ocur; ocur += H; sbytes += H; ngroups++; }
-                if (act == ACT_RUN) {       // zero header fields + 1..2 length bytes (sprintz_delta_rle.cpp:238-245)
-                    const uint32_t two = run_len > 0x7fu ? 1u : 0u;
-                    if (t == 0) {
-                        ob[ocur] = (uint8_t)((run_len & 0x7fu) | (two << 7));
-                        if (two) ob[ocur + 1] = (uint8_t)(run_len >> 7);
-                    }
-                    ocur += 1u + two; sbytes += 1u + two;
-                } else if (act == ACT_PAD) {
-                    if (t == 0) ob[ocur] = 0;
-                    ocur += 1u; sbytes += 1u;
-                } else {                    // data slot: payload bytes are produced at group end
-                    if (pend == 0u) { pe_half0 = wh; pe_off0 = ocur; pe_rb0 = row_bytes; }
-                    else            { pe_half1 = wh; pe_off1 = ocur; pe_rb1 = row_bytes; }
-                    pend++;
-#pragma unroll
-                    for (int k = 0; k < DPL; k++) { if (s == 0u) hf0[k] = fh[k]; else hf1[k] = fh[k]; }
-                    ocur += kBlockRows * row_bytes; sbytes += kBlockRows * row_bytes;
-                    wh ^= 1u; blk++;
-                }
-                nslots++;
-                gc = (nslots & 1u) == 0u;
+                gc = emit_slot(act, run_len, fh, row_bytes);
                 if (act == ACT_DATA) outer = gc;
             }
+            if (HFAST) emit_header_fast(act != ACT_NONE, act == ACT_DATA, sl, hdr_off, fh);
             if (__any_sync(kFullE, gc)) close_group(gc);
         }
     }
