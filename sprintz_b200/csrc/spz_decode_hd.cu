@@ -48,10 +48,16 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
     const uint64_t c = valid ? c64 : 0;            // invalid teams shadow chunk 0 but never store
     const int D = FULLD ? TEAM * DPL : (int)p.ndims;
 
-    uint8_t* const ring = smem + (size_t)team_in_cta * p.team_smem;     // ring_cap bytes + 16 mirror bytes
+    // team_smem is a multiple of ring_cap, so the ring's offset inside the CTA's dynamic shared memory is
+    // ring_cap-aligned and "wrap + add base" is a single LOP3: (byte & mask) | ring_off
+    const uint32_t ring_off = (uint32_t)team_in_cta * p.team_smem;
+    uint8_t* const ring = smem + ring_off;                              // ring_cap bytes + 16 mirror bytes
     const uint32_t RCAP = p.ring_cap;
     const uint32_t RMASK = RCAP - 1u;
-    uint8_t* const obuf0 = ring + RCAP + 16;                            // two output tiles of out_cap bytes
+    const uint32_t WMASK4 = RMASK & ~3u;
+    // two output tiles of out_cap bytes; skewed by 32 B per team of the warp so the lock-step teams' row stores
+    // land in different banks (team regions are ring_cap-aligned, i.e. bank-aligned)
+    uint8_t* const obuf0 = ring + RCAP + 16 + (uint32_t)(team_in_cta % TEAMS_PER_WARP) * 32u;
     const uint32_t OCAP = p.out_cap;
 
     // ---- input: byte offsets are relative to `abase`, the 16-byte aligned-down stream start
@@ -91,9 +97,16 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
     };
     // 32-bit window at ring-relative bit position `bit` (may exceed the ring: masked)
     auto ring_bits = [&](uint32_t bit) -> uint32_t {
-        const uint32_t bo = (bit >> 3) & (RMASK & ~3u);
-        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(ring + bo);
-        const uint32_t w1 = *reinterpret_cast<const uint32_t*>(ring + bo + 4);
+        const uint32_t bo = ((bit >> 3) & WMASK4) | ring_off;
+        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(smem + bo);
+        const uint32_t w1 = *reinterpret_cast<const uint32_t*>(smem + bo + 4);
+        return __funnelshift_r(w0, w1, bit);
+    };
+    // same, with the byte position tracked separately by the caller (byte == bit >> 3): saves the shift
+    auto ring_bits2 = [&](uint32_t bit, uint32_t byte) -> uint32_t {
+        const uint32_t bo = (byte & WMASK4) | ring_off;
+        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(smem + bo);
+        const uint32_t w1 = *reinterpret_cast<const uint32_t*>(smem + bo + 4);
         return __funnelshift_r(w0, w1, bit);
     };
     auto ring_byte = [&](uint32_t at) -> uint32_t { return ring[at & RMASK]; };
@@ -119,8 +132,14 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
         __syncwarp();
         if (on) {
             uint8_t* const nb = (ob == obuf0) ? obuf0 + OCAP : obuf0;
-            if (oskip == 0u && (ocur & 15u) == 0u) {
-                // common case: the chunk's output is 16-byte aligned, a group is a whole number of units
+            if (FULLD && oskip == 0u && ocur == (uint32_t)(2 * kBlockRows * TEAM * DPL * ESZ)) {
+                // common case: aligned output, exactly one group staged = DPL*ESZ 16-byte units per lane
+                const uint4* s4 = reinterpret_cast<const uint4*>(ob);
+                uint4* g4 = reinterpret_cast<uint4*>(gdst);
+#pragma unroll
+                for (int j = 0; j < DPL * ESZ; j++) g4[t + j * TEAM] = s4[t + j * TEAM];
+                ob = nb; gdst += ocur; ocur = 0;
+            } else if (oskip == 0u && (ocur & 15u) == 0u) {
                 const uint4* s4 = reinterpret_cast<const uint4*>(ob);
                 uint4* g4 = reinterpret_cast<uint4*>(gdst);
                 for (uint32_t u = t; u < (ocur >> 4); u += TEAM) g4[u] = s4[u];
@@ -207,7 +226,8 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
 
         // One data slot: unpack + inverse predictor for my dims, rows staged at ob + ocur.
         auto data_slot = [&](uint32_t sh16, uint32_t total) {
-            const uint32_t row_bits = ((total + 7u) >> 3) * 8u;
+            const uint32_t row_bytes = (total + 7u) >> 3;
+            const uint32_t row_bits = row_bytes * 8u;
             const uint32_t pbit = (pos & RMASK) * 8u;
             uint8_t* const obase = ob + ocur + (uint32_t)t * ESZ;
 #pragma unroll
@@ -219,24 +239,28 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
                     const uint32_t hmask = fmask >> 1;         // magnitude bits of the zigzag code
                     const uint32_t smask = fmask & 1u;         // its sign bit (0 when the field is empty)
                     uint32_t bit = pbit + ((offs[k] >> sh16) & 0xffffu);
+                    uint32_t byte = bit >> 3;
                     uint32_t x[kBlockRows];
 #pragma unroll
-                    for (int r = 0; r < kBlockRows; r++) { x[r] = ring_bits(bit); bit += row_bits; }
+                    for (int r = 0; r < kBlockRows; r++) { x[r] = ring_bits2(bit, byte); bit += row_bits; byte += row_bytes; }
 
                     int32_t coefs = 0, gsh = 0;
                     if (FIRE) coefs = (int32_t)((uint32_t)fire_coef<W, false>(ct[k]) << W);
                     uint8_t* op = obase + (uint32_t)(k * TEAM) * ESZ;
 #pragma unroll
                     for (int r = 0; r < kBlockRows; r++) {
-                        // zigzag^-1 (bitpack.h:303) fused with the field mask
-                        const uint32_t sgn = x[r] & smask;                                   // 1 iff err < 0
-                        const int32_t err = (int32_t)(((x[r] >> 1) & hmask) ^ (0u - sgn));
+                        // zigzag^-1 (bitpack.h:303) fused with the field mask, phrased as multiply-adds so the FMA
+                        // pipe shares the work: err = h*(1-2b) - b with b = sign bit, h = magnitude bits
+                        const int32_t b = (int32_t)(x[r] & smask);
+                        const int32_t h = (int32_t)((x[r] >> 1) & hmask);
+                        const int32_t sg = 1 - 2 * b;                                        // +1 / -1
+                        const int32_t err = h * sg - b;
                         int32_t delta = err;
                         if (FIRE) {
                             if (r & 1) {
                                 // icopysign(err, prev_delta) (util.h:63-68), accumulated left-aligned so the
-                                // int_t wrap of grad_sum is the natural 32-bit wrap
-                                if (sgn) gsh -= pdh[k]; else if (err != 0) gsh += pdh[k];
+                                // int_t wrap of grad_sum is the natural 32-bit wrap; err != 0 <=> (h | b) != 0
+                                if ((h | b) != 0) gsh += pdh[k] * sg;
                             }
                             // prediction = (prev_delta * coef) >> W (sprintz_xff_rle.cpp:225); exact: pdh*coefs = prod << 32
                             delta = err + (__mulhi(pdh[k], coefs) >> W);
@@ -249,7 +273,7 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
                     if (FIRE) ct[k] = sx<CB>(ct[k] + ((gsh >> UP) >> 2));     // sprintz_xff_rle.cpp:273-275
                 }
             }
-            pos += (row_bits >> 3) * kBlockRows;
+            pos += row_bytes * kBlockRows;
             ocur += B * ESZ;
             o += B;
         };
@@ -368,7 +392,7 @@ cudaError_t launch_decode_hd(int elem_sz, int predictor, DecParams p, cudaStream
     p.team = team; p.dpl = dpl;
     p.ring_cap = pow2_ceil(max_group + 8 + team * 16);
     p.out_cap = (16 + 2 * 8 * p.ndims * elem_sz + 16 + 15) & ~15u;
-    p.team_smem = p.ring_cap + 16 + 2 * p.out_cap;
+    p.team_smem = ((p.ring_cap + 16 + 2 * p.out_cap + 128 + p.ring_cap - 1) / p.ring_cap) * p.ring_cap;
     const uint32_t teams_per_cta = kThreads / team;
     p.teams_per_cta = teams_per_cta;
     const size_t smem = (size_t)teams_per_cta * p.team_smem;
