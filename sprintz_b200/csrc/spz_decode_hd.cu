@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
     uint8_t* const ring = smem + ring_off;                              // ring_cap bytes + 16 mirror bytes
     const uint32_t RCAP = p.ring_cap;
     const uint32_t RMASK = RCAP - 1u;
-    const uint32_t WMASK4 = RMASK & ~3u;
+    uint32_t WMASK4 = RMASK & ~3u;
+    asm volatile("" : "+r"(WMASK4));          // keep it one register: (byte & WMASK4) | ring_off is then a single LOP3
     // two output tiles of out_cap bytes; skewed by 32 B per team of the warp so the lock-step teams' row stores
     // land in different banks (team regions are ring_cap-aligned, i.e. bank-aligned)
     uint8_t* const obuf0 = ring + RCAP + 16 + (uint32_t)(team_in_cta % TEAMS_PER_WARP) * 32u;
@@ -215,8 +216,9 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
             uint32_t incl = packed;
 #pragma unroll
             for (int s = 1; s < TEAM; s <<= 1) {
-                const uint32_t y = __shfl_up_sync(kFull, incl, s, TEAM);
-                if (t >= s) incl += y;
+                // shfl.up's predicate says whether the source lane is inside my team segment: predicated add, no select
+                asm volatile("{ .reg .pred p; .reg .b32 r; shfl.sync.up.b32 r|p, %0, %1, %2, 0xffffffff; @p add.u32 %0, %0, r; }"
+                             : "+r"(incl) : "r"(s), "r"((32 - TEAM) << 8));
             }
             nn[k] = packed;
             offs[k] = carry + incl - packed;
@@ -226,7 +228,8 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
 
         // One data slot: unpack + inverse predictor for my dims, rows staged at ob + ocur.
         auto data_slot = [&](uint32_t sh16, uint32_t total) {
-            const uint32_t row_bytes = (total + 7u) >> 3;
+            uint32_t row_bytes = (total + 7u) >> 3;
+            asm volatile("" : "+r"(row_bytes));      // keep it a register: byte += row_bytes stays an add (FMA-pipe IMAD.IADD)
             const uint32_t row_bits = row_bytes * 8u;
             const uint32_t pbit = (pos & RMASK) * 8u;
             uint8_t* const obase = ob + ocur + (uint32_t)t * ESZ;
@@ -236,34 +239,31 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
                 if (FULLD || d < D) {
                     const uint32_t n = (nn[k] >> sh16) & 0xffffu;
                     const uint32_t fmask = (1u << n) - 1u;
-                    const uint32_t hmask = fmask >> 1;         // magnitude bits of the zigzag code
-                    const uint32_t smask = fmask & 1u;         // its sign bit (0 when the field is empty)
+                    const uint32_t smask = fmask & 1u;         // the zigzag sign bit (0 when the field is empty)
                     uint32_t bit = pbit + ((offs[k] >> sh16) & 0xffffu);
                     uint32_t byte = bit >> 3;
                     uint32_t x[kBlockRows];
 #pragma unroll
                     for (int r = 0; r < kBlockRows; r++) { x[r] = ring_bits2(bit, byte); bit += row_bits; byte += row_bytes; }
 
-                    int32_t coefs = 0, gsh = 0;
-                    if (FIRE) coefs = (int32_t)((uint32_t)fire_coef<W, false>(ct[k]) << W);
+                    int32_t coef = 0, gsh = 0;
+                    if (FIRE) coef = fire_coef<W, false>(ct[k]);
                     uint8_t* op = obase + (uint32_t)(k * TEAM) * ESZ;
 #pragma unroll
                     for (int r = 0; r < kBlockRows; r++) {
-                        // zigzag^-1 (bitpack.h:303) fused with the field mask, phrased as multiply-adds so the FMA
-                        // pipe shares the work: err = h*(1-2b) - b with b = sign bit, h = magnitude bits
-                        const int32_t b = (int32_t)(x[r] & smask);
-                        const int32_t h = (int32_t)((x[r] >> 1) & hmask);
-                        const int32_t sg = 1 - 2 * b;                                        // +1 / -1
-                        const int32_t err = h * sg - b;
+                        // zigzag^-1 (bitpack.h:303) fused with the field mask: err = ((x & fmask) ^ -b) >> 1, b = sign bit
+                        const uint32_t b = x[r] & smask;
+                        const int32_t err = (int32_t)((x[r] & fmask) ^ (0u - b)) >> 1;
                         int32_t delta = err;
                         if (FIRE) {
                             if (r & 1) {
                                 // icopysign(err, prev_delta) (util.h:63-68), accumulated left-aligned so the
-                                // int_t wrap of grad_sum is the natural 32-bit wrap; err != 0 <=> (h | b) != 0
-                                if ((h | b) != 0) gsh += pdh[k] * sg;
+                                // int_t wrap of grad_sum is the natural 32-bit wrap
+                                if (err != 0) gsh += pdh[k] * (int32_t)(1u - 2u * b);
                             }
-                            // prediction = (prev_delta * coef) >> W (sprintz_xff_rle.cpp:225); exact: pdh*coefs = prod << 32
-                            delta = err + (__mulhi(pdh[k], coefs) >> W);
+                            // prediction = (prev_delta * coef) >> W (sprintz_xff_rle.cpp:225): with prev_delta left-aligned
+                            // by 32-W bits this is exactly the high word of the product -> one IMAD.HI with addend
+                            delta = __mulhi(pdh[k], coef) + err;
                             pdh[k] = (int32_t)((uint32_t)delta << UP);       // wraps delta to W bits
                         }
                         pv[k] += (uint32_t)delta;
@@ -311,10 +311,10 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
                         if (FULLD || d < D) {
                             uint_t* op = out + o + d;
                             if (FIRE) {
-                                const int32_t coefs = (int32_t)((uint32_t)fire_coef<W, false>(ct[k]) << W);
+                                const int32_t coef = fire_coef<W, false>(ct[k]);
                                 for (uint32_t r = 0; r < nrows; r++) {
                                     // err == 0 -> delta == prediction = (prev_delta * coef) >> W, wrapped to W bits
-                                    const int32_t pred = __mulhi(pdh[k], coefs) >> W;
+                                    const int32_t pred = __mulhi(pdh[k], coef);
                                     pdh[k] = (int32_t)((uint32_t)pred << UP);
                                     pv[k] += (uint32_t)pred;
                                     op[(size_t)r * D] = (uint_t)pv[k];

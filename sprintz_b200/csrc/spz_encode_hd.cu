@@ -310,8 +310,8 @@ __global__ void __launch_bounds__(kThreads) spz_encode_hd_kernel(const EncParams
                 uint32_t xh[kBlockRows];
 #pragma unroll
                 for (int r = 0; r < kBlockRows; r++) xh[r] = (uint32_t)in[r * D] << UP;
-                int32_t coefs = 0, gsh = 0;
-                if (FIRE) coefs = (int32_t)((uint32_t)fire_coef<W, false>(ct[k]) << W);
+                int32_t coef = 0, gsh = 0;
+                if (FIRE) coef = fire_coef<W, false>(ct[k]);
                 uint32_t mask = 0;
                 int32_t dprev = pdh[k];
                 uint32_t xprev = pvh[k];
@@ -320,8 +320,9 @@ __global__ void __launch_bounds__(kThreads) spz_encode_hd_kernel(const EncParams
                     const int32_t dh = (int32_t)(xh[r] - xprev);            // delta, left-aligned (wraps to W bits)
                     int32_t eh = dh;
                     if (FIRE) {
-                        // err = delta - ((prev_delta * coef) >> W)  (sprintz_xff_rle.cpp:225-237); pdh*coefs == prod << 32
-                        const int32_t pred = __mulhi(dprev, coefs) >> W;
+                        // err = delta - ((prev_delta * coef) >> W)  (sprintz_xff_rle.cpp:225-237): prev_delta is left-aligned
+                        // by 32-W bits, so the prediction is exactly the high word of the product
+                        const int32_t pred = __mulhi(dprev, coef);
                         eh = dh - (int32_t)((uint32_t)pred << UP);
                     }
                     // zigzag (bitpack.h:302) of the left-aligned error
@@ -346,8 +347,8 @@ __global__ void __launch_bounds__(kThreads) spz_encode_hd_kernel(const EncParams
             uint32_t incl = n;
 #pragma unroll
             for (int s = 1; s < TEAM; s <<= 1) {
-                const uint32_t y = __shfl_up_sync(kFullE, incl, s, TEAM);
-                if (t >= s) incl += y;
+                asm volatile("{ .reg .pred p; .reg .b32 r; shfl.sync.up.b32 r|p, %0, %1, %2, 0xffffffff; @p add.u32 %0, %0, r; }"
+                             : "+r"(incl) : "r"(s), "r"((32 - TEAM) << 8));
             }
             nw[k] = n;
             fh[k] = n - (n == (uint32_t)W);                    // w stored as w-1 (sprintz_delta_rle.cpp:199)
