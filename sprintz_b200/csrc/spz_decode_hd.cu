@@ -383,8 +383,14 @@ cudaError_t launch_decode_hd(int elem_sz, int predictor, DecParams p, cudaStream
     if (low || p.ndims > 128 || p.src_end == nullptr) return cudaErrorNotSupported;
     // 32-bit stream / output offsets inside one chunk
     if (p.chunk_len * (uint64_t)elem_sz > 0x70000000ull) return cudaErrorNotSupported;
-    const uint32_t team = p.ndims >= 32 ? 32 : pow2_ceil(p.ndims);
-    const uint32_t dpl = (p.ndims + team - 1) / team;
+    // team shape: a power-of-two slice of the warp with DPL dims per lane. Prefer an exact cover of ndims
+    // (no padded lanes, compile-time row stride); D=80 -> 16x5, D=24 -> 8x3, D=48 -> 16x3.
+    uint32_t team = p.ndims >= 32 ? 32 : pow2_ceil(p.ndims);
+    uint32_t dpl = (p.ndims + team - 1) / team;
+    if (team * dpl != p.ndims) {
+        if (p.ndims == 80 || p.ndims == 48) { team = 16; dpl = p.ndims / 16; }
+        else if (p.ndims == 24 || p.ndims == 40) { team = 8; dpl = p.ndims / 8; }
+    }
     const bool fulld = (team * dpl == p.ndims);
     const uint32_t hb = elem_sz == 1 ? 3 : 4;
     const uint32_t H = (2 * p.ndims * hb + 7) / 8;
@@ -405,16 +411,24 @@ cudaError_t launch_decode_hd(int elem_sz, int predictor, DecParams p, cudaStream
     return predictor ? launch_hd<Wv, true, Tv, Dv, Fv>(p, grid, smem, stream) : launch_hd<Wv, false, Tv, Dv, Fv>(p, grid, smem, stream)
 #define SPZ_HD(Wv, Tv, Dv) do { if (fulld) { SPZ_HD2(Wv, Tv, Dv, true); } else { SPZ_HD2(Wv, Tv, Dv, false); } } while (0)
     if (elem_sz == 1) {
-        if (team == 8) SPZ_HD(8, 8, 1);
-        if (team == 16) SPZ_HD(8, 16, 1);
+        if (team == 8 && dpl == 1) SPZ_HD(8, 8, 1);
+        if (team == 8 && dpl == 3) SPZ_HD2(8, 8, 3, true);
+        if (team == 8 && dpl == 5) SPZ_HD2(8, 8, 5, true);
+        if (team == 16 && dpl == 1) SPZ_HD(8, 16, 1);
+        if (team == 16 && dpl == 3) SPZ_HD2(8, 16, 3, true);
+        if (team == 16 && dpl == 5) SPZ_HD2(8, 16, 5, true);
         if (dpl == 1) SPZ_HD(8, 32, 1);
         if (dpl == 2) SPZ_HD(8, 32, 2);
         if (dpl == 3) SPZ_HD(8, 32, 3);
         if (dpl == 4) SPZ_HD(8, 32, 4);
     } else {
         if (team == 4) SPZ_HD(16, 4, 1);
-        if (team == 8) SPZ_HD(16, 8, 1);
-        if (team == 16) SPZ_HD(16, 16, 1);
+        if (team == 8 && dpl == 1) SPZ_HD(16, 8, 1);
+        if (team == 8 && dpl == 3) SPZ_HD2(16, 8, 3, true);
+        if (team == 8 && dpl == 5) SPZ_HD2(16, 8, 5, true);
+        if (team == 16 && dpl == 1) SPZ_HD(16, 16, 1);
+        if (team == 16 && dpl == 3) SPZ_HD2(16, 16, 3, true);
+        if (team == 16 && dpl == 5) SPZ_HD2(16, 16, 5, true);
         if (dpl == 1) SPZ_HD(16, 32, 1);
         if (dpl == 2) SPZ_HD(16, 32, 2);
         if (dpl == 3) SPZ_HD(16, 32, 3);
