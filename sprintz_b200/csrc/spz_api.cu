@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <mutex>
+#include <vector>
 
 #include "spz_common.cuh"
 #include "../../include/sprintz_b200.h"
@@ -19,6 +20,7 @@ cudaError_t launch_encode(int elem_sz, int predictor, EncParams p, cudaStream_t 
 cudaError_t launch_decode(int elem_sz, int predictor, DecParams p, cudaStream_t stream);
 cudaError_t launch_scan_sizes(const ChunkMeta* meta, uint64_t nchunks, uint64_t* chunk_off, uint32_t* chunk_nbytes,
                               unsigned long long* tile_state, unsigned int* ticket,
+                              const unsigned long long* base_in, unsigned long long* total_out, int is_last,
                               spz_frame_header* hdr, const spz_frame_header& hdr_in, uint64_t* d_frame_bytes,
                               cudaStream_t stream);
 cudaError_t launch_gather(const uint8_t* slots, uint64_t slot_stride, uint64_t nchunks, const uint64_t* chunk_off,
@@ -223,7 +225,7 @@ extern "C" int spz_frame_encode_dev(int predictor, int elem_sz, const void* d_sr
     uint32_t* chunk_nbytes = (uint32_t*)(frame + f.off_sizes);
     CK(launch_scan_sizes(p.meta, f.nchunks, chunk_off, chunk_nbytes,
                          (unsigned long long*)(work + w.off_state), (unsigned int*)(work + w.off_ticket),
-                         (spz_frame_header*)frame, h, d_frame_bytes, stream));
+                         nullptr, nullptr, 1, (spz_frame_header*)frame, h, d_frame_bytes, stream));
     PROF_MARK(2);
     CK(launch_gather(work + w.off_slots, w.slot_stride, f.nchunks, chunk_off, chunk_nbytes,
                      frame + f.payload_off, stream));
@@ -293,10 +295,12 @@ struct DevCache {
 DevCache g_cache;
 }  // namespace
 
+static void release_pipe();
 extern "C" void spz_release_workspaces(void)
 {
     std::lock_guard<std::mutex> lk(g_cache.mu);
     g_cache.release();
+    release_pipe();
 }
 
 extern "C" int spz_measure_stream(int elem_sz, const void* src_, int has_meta, uint16_t ndims, uint32_t ngroups,
@@ -430,54 +434,202 @@ extern "C" int64_t spz_compress_xff_16b(const uint16_t* s, uint32_t n, int16_t* 
 extern "C" int64_t spz_decompress_xff_16b(const int16_t* s, uint16_t* d) { return spz_decompress_host(SPZ_XFF, 2, s, d); }
 
 // ------------------------------------------------------------------ frame, host buffers
+//
+// Both calls are software pipelines over SLABS of whole chunks on three streams (upload / kernels /
+// download), so the PCIe transfers of neighbouring slabs overlap in both directions and with the kernels:
+//   compress : H2D raw slab k+1 | encode + directory scan + compaction of slab k | D2H payload of slab k-1
+//   decompress: H2D payload slab k+1 | decode slab k | D2H decoded slab k-1
+// The chunk streams and the directory are exactly those of spz_frame_encode_dev (the scan carries the running
+// payload offset from slab to slab). With pageable host memory the copies serialise inside the driver but stay
+// correct; pinned host buffers make them asynchronous.
 
-extern "C" int64_t spz_frame_compress_host(int predictor, int elem_sz, const void* src, uint64_t len, uint16_t ndims,
-                                           uint32_t chunk_rows, void* frame, uint64_t frame_cap)
+namespace {
+constexpr uint64_t kSlabBytes = 64ull << 20;     // raw bytes per pipeline slab
+
+struct Pipe {
+    cudaStream_t up = nullptr, run = nullptr, down = nullptr;
+    static constexpr int kMaxSlabs = 4096;
+    cudaEvent_t ev_up[kMaxSlabs], ev_run[kMaxSlabs];
+    int nev = 0;
+    unsigned long long* h_tot = nullptr;          // pinned: running payload offset after each slab
+    cudaError_t init(int nslabs)
+    {
+        cudaError_t e;
+        if (!up) {
+            if ((e = cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking)) != cudaSuccess) return e;
+            if ((e = cudaStreamCreateWithFlags(&run, cudaStreamNonBlocking)) != cudaSuccess) return e;
+            if ((e = cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking)) != cudaSuccess) return e;
+            if ((e = cudaMallocHost(&h_tot, sizeof(unsigned long long) * kMaxSlabs)) != cudaSuccess) return e;
+        }
+        for (; nev < nslabs; nev++) {
+            if ((e = cudaEventCreateWithFlags(&ev_up[nev], cudaEventDisableTiming)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&ev_run[nev], cudaEventDisableTiming)) != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+    void release()
+    {
+        for (int i = 0; i < nev; i++) { cudaEventDestroy(ev_up[i]); cudaEventDestroy(ev_run[i]); }
+        nev = 0;
+        if (up) { cudaStreamDestroy(up); cudaStreamDestroy(run); cudaStreamDestroy(down); up = run = down = nullptr; }
+        if (h_tot) { cudaFreeHost(h_tot); h_tot = nullptr; }
+    }
+};
+Pipe g_pipe;
+}  // namespace
+
+extern "C" int64_t spz_frame_compress_host(int predictor, int elem_sz, const void* src_, uint64_t len, uint16_t ndims,
+                                           uint32_t chunk_rows, void* frame_, uint64_t frame_cap)
 {
     if (!valid_codec(predictor, elem_sz) || ndims == 0 || chunk_rows == 0) return SPZ_E_ARG;
     if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
     std::lock_guard<std::mutex> lk(g_cache.mu);
-    cudaStream_t st;
-    CK(g_cache.get_stream(&st));
+    const uint8_t* src = (const uint8_t*)src_;
+    uint8_t* hframe = (uint8_t*)frame_;
+    const FrameLayout f = frame_layout(len, ndims, chunk_rows);
+    if (f.chunk_len > 0xffffffffull) return SPZ_E_ARG;
+    const WorkLayout w = work_layout(elem_sz, len, ndims, chunk_rows);
     const uint64_t in_bytes = len * (uint64_t)elem_sz;
     const uint64_t fmax = spz_frame_max_bytes(elem_sz, len, ndims, chunk_rows);
-    const uint64_t wbytes = spz_frame_workspace_bytes(elem_sz, len, ndims, chunk_rows);
+    const uint64_t chunk_bytes = f.chunk_len * elem_sz;
+    uint64_t slab_chunks = kSlabBytes / (chunk_bytes ? chunk_bytes : 1);
+    if (slab_chunks == 0) slab_chunks = 1;
+    uint64_t nslabs = (f.nchunks + slab_chunks - 1) / slab_chunks;
+    if (nslabs > (uint64_t)Pipe::kMaxSlabs) { slab_chunks = (f.nchunks + Pipe::kMaxSlabs - 1) / Pipe::kMaxSlabs; nslabs = (f.nchunks + slab_chunks - 1) / slab_chunks; }
+    const uint64_t tiles_per_slab = scan_tiles(slab_chunks);
+    // workspace: per-slab scan states + tickets + running totals, then meta + slots as in work_layout
+    const uint64_t off_state = 0;
+    const uint64_t off_ticket = align16(8 * tiles_per_slab * nslabs);
+    const uint64_t off_tot = align16(off_ticket + 4 * nslabs);
+    const uint64_t off_meta = align16(off_tot + 8 * (nslabs + 1));
+    const uint64_t off_slots = align16(off_meta + sizeof(ChunkMeta) * f.nchunks);
+    const uint64_t wtotal = off_slots + f.nchunks * w.slot_stride + 16;
+    CK(g_pipe.init((int)nslabs));
     CK(g_cache.ensure(0, in_bytes + 16));
     CK(g_cache.ensure(1, fmax + 16));
-    CK(g_cache.ensure(2, wbytes + 16));
-    if (in_bytes) CK(cudaMemcpyAsync(g_cache.buf[0], src, in_bytes, cudaMemcpyHostToDevice, st));
-    int rc = spz_frame_encode_dev(predictor, elem_sz, g_cache.buf[0], len, ndims, chunk_rows, g_cache.buf[1],
-                                  g_cache.cap[1], g_cache.buf[2], g_cache.cap[2], nullptr, st);
-    if (rc != SPZ_OK) return rc;
+    CK(g_cache.ensure(2, wtotal + 16));
+    uint8_t* d_in = (uint8_t*)g_cache.buf[0];
+    uint8_t* d_frame = (uint8_t*)g_cache.buf[1];
+    uint8_t* work = (uint8_t*)g_cache.buf[2];
+    if (frame_cap < f.payload_off + 16) return SPZ_E_CAPACITY;
+
+    CK(cudaMemsetAsync(work, 0, off_meta, g_pipe.run));
     spz_frame_header h;
-    rc = spz_frame_read_header(g_cache.buf[1], &h, st);
-    if (rc != SPZ_OK) return rc;
-    if (h.frame_bytes > frame_cap) return SPZ_E_CAPACITY;
-    CK(cudaMemcpyAsync(frame, g_cache.buf[1], h.frame_bytes, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    return (int64_t)h.frame_bytes;
+    memset(&h, 0, sizeof(h));
+    h.magic = SPZ_FRAME_MAGIC; h.version = 1; h.elem_sz = (uint8_t)elem_sz; h.predictor = (uint8_t)predictor;
+    h.ndims = ndims; h.chunk_rows = chunk_rows; h.len = len; h.nchunks = f.nchunks; h.payload_off = f.payload_off;
+    uint64_t* chunk_off = (uint64_t*)(d_frame + f.off_dir);
+    uint32_t* chunk_nbytes = (uint32_t*)(d_frame + f.off_sizes);
+    unsigned long long* d_tot = (unsigned long long*)(work + off_tot);     // d_tot[k] = payload offset before slab k
+    ChunkMeta* meta = (ChunkMeta*)(work + off_meta);
+
+    uint64_t copied = 0;        // payload bytes already on their way to the host
+    int rc_cap = SPZ_OK;
+    for (uint64_t k = 0; k <= nslabs; k++) {
+        if (k < nslabs) {
+            const uint64_t c0 = k * slab_chunks;
+            const uint64_t nc = (c0 + slab_chunks <= f.nchunks) ? slab_chunks : (f.nchunks - c0);
+            const uint64_t e0 = c0 * f.chunk_len;
+            const uint64_t ne = (e0 + nc * f.chunk_len <= len) ? nc * f.chunk_len : (len - e0);
+            if (ne) CK(cudaMemcpyAsync(d_in + e0 * elem_sz, src + e0 * elem_sz, ne * elem_sz, cudaMemcpyHostToDevice, g_pipe.up));
+            CK(cudaEventRecord(g_pipe.ev_up[k], g_pipe.up));
+            CK(cudaStreamWaitEvent(g_pipe.run, g_pipe.ev_up[k], 0));
+            EncParams p;
+            memset(&p, 0, sizeof(p));
+            p.src = d_in + e0 * elem_sz; p.dst = work + off_slots + c0 * w.slot_stride; p.meta = meta + c0;
+            p.len = ne; p.chunk_len = f.chunk_len; p.nchunks = nc; p.slot_stride = w.slot_stride;
+            p.ndims = ndims; p.write_size = 1;
+            CK(launch_encode(elem_sz, predictor, p, g_pipe.run));
+            CK(launch_scan_sizes(meta + c0, nc, chunk_off + c0, chunk_nbytes + c0,
+                                 (unsigned long long*)(work + off_state) + k * tiles_per_slab,
+                                 (unsigned int*)(work + off_ticket) + k, d_tot + k, d_tot + k + 1,
+                                 k + 1 == nslabs, (spz_frame_header*)d_frame, h, nullptr, g_pipe.run));
+            CK(launch_gather(work + off_slots + c0 * w.slot_stride, w.slot_stride, nc, chunk_off + c0, chunk_nbytes + c0,
+                             d_frame + f.payload_off, g_pipe.run));
+            CK(cudaMemcpyAsync(&g_pipe.h_tot[k], d_tot + k + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, g_pipe.run));
+            CK(cudaEventRecord(g_pipe.ev_run[k], g_pipe.run));
+        }
+        if (k >= 1) {       // slab k-1 is compacted: its payload range can leave while slab k runs
+            CK(cudaEventSynchronize(g_pipe.ev_run[k - 1]));
+            const uint64_t upto = g_pipe.h_tot[k - 1];
+            if (f.payload_off + upto + 16 > frame_cap) { rc_cap = SPZ_E_CAPACITY; break; }
+            CK(cudaStreamWaitEvent(g_pipe.down, g_pipe.ev_run[k - 1], 0));
+            if (upto > copied)
+                CK(cudaMemcpyAsync(hframe + f.payload_off + copied, d_frame + f.payload_off + copied, upto - copied,
+                                   cudaMemcpyDeviceToHost, g_pipe.down));
+            copied = upto;
+        }
+    }
+    if (rc_cap != SPZ_OK) { cudaDeviceSynchronize(); return rc_cap; }
+    // header + directory (written by the last slab's scan) and the 16 bytes of read slack
+    CK(cudaMemcpyAsync(hframe, d_frame, f.payload_off, cudaMemcpyDeviceToHost, g_pipe.down));
+    CK(cudaStreamSynchronize(g_pipe.down));
+    CK(cudaStreamSynchronize(g_pipe.run));
+    memset(hframe + f.payload_off + copied, 0, 16);
+    return (int64_t)(f.payload_off + copied + 16);
 }
 
-extern "C" int64_t spz_frame_decompress_host(const void* frame, uint64_t frame_bytes, void* dest, uint64_t dest_cap_elems)
+extern "C" int64_t spz_frame_decompress_host(const void* frame_, uint64_t frame_bytes, void* dest_, uint64_t dest_cap_elems)
 {
     if (frame_bytes < sizeof(spz_frame_header)) return SPZ_E_STREAM;
+    const uint8_t* hframe = (const uint8_t*)frame_;
+    uint8_t* dest = (uint8_t*)dest_;
     spz_frame_header h;
-    memcpy(&h, frame, sizeof(h));
+    memcpy(&h, hframe, sizeof(h));
     if (h.magic != SPZ_FRAME_MAGIC || h.frame_bytes > frame_bytes || !valid_codec(h.predictor, h.elem_sz) ||
         h.ndims == 0 || h.ndims > SPZ_MAX_NDIMS || h.chunk_rows == 0) return SPZ_E_STREAM;
     if (dest_cap_elems < h.len) return SPZ_E_CAPACITY;
+    const FrameLayout f = frame_layout(h.len, (uint16_t)h.ndims, h.chunk_rows);
+    if (f.nchunks != h.nchunks || f.payload_off != h.payload_off || h.frame_bytes < f.payload_off + 16) return SPZ_E_STREAM;
+    const uint64_t* hoff = (const uint64_t*)(hframe + f.off_dir);      // the directory is readable on the host
     std::lock_guard<std::mutex> lk(g_cache.mu);
-    cudaStream_t st;
-    CK(g_cache.get_stream(&st));
-    const uint64_t nchunks = h.nchunks;
-    CK(g_cache.ensure(0, h.len * h.elem_sz + 16));
+    const int esz = h.elem_sz;
+    const uint64_t chunk_bytes = f.chunk_len * esz;
+    uint64_t slab_chunks = kSlabBytes / (chunk_bytes ? chunk_bytes : 1);
+    if (slab_chunks == 0) slab_chunks = 1;
+    uint64_t nslabs = (f.nchunks + slab_chunks - 1) / slab_chunks;
+    if (nslabs > (uint64_t)Pipe::kMaxSlabs) { slab_chunks = (f.nchunks + Pipe::kMaxSlabs - 1) / Pipe::kMaxSlabs; nslabs = (f.nchunks + slab_chunks - 1) / slab_chunks; }
+    CK(g_pipe.init((int)nslabs));
+    CK(g_cache.ensure(0, h.len * esz + 16));
     CK(g_cache.ensure(1, h.frame_bytes + 32));
-    CK(g_cache.ensure(2, sizeof(spz_chunk_meta) * nchunks + 16));
-    CK(cudaMemcpyAsync(g_cache.buf[1], frame, h.frame_bytes, cudaMemcpyHostToDevice, st));
-    int rc = spz_frame_decode_dev(h.predictor, h.elem_sz, g_cache.buf[1], h.frame_bytes, h.len, (uint16_t)h.ndims,
-                                  h.chunk_rows, g_cache.buf[0], h.len, nullptr, st);
-    if (rc != SPZ_OK) return rc;
-    if (h.len) CK(cudaMemcpyAsync(dest, g_cache.buf[0], h.len * h.elem_sz, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(g_cache.ensure(2, sizeof(spz_chunk_meta) * f.nchunks + 16));
+    uint8_t* d_out = (uint8_t*)g_cache.buf[0];
+    uint8_t* d_frame = (uint8_t*)g_cache.buf[1];
+    spz_chunk_meta* d_status = (spz_chunk_meta*)g_cache.buf[2];
+    if (hoff[f.nchunks] + f.payload_off + 16 > h.frame_bytes) return SPZ_E_STREAM;
+
+    // header + directory first (small), then payload slabs
+    CK(cudaMemcpyAsync(d_frame, hframe, f.payload_off, cudaMemcpyHostToDevice, g_pipe.up));
+    for (uint64_t k = 0; k < nslabs; k++) {
+        const uint64_t c0 = k * slab_chunks;
+        const uint64_t nc = (c0 + slab_chunks <= f.nchunks) ? slab_chunks : (f.nchunks - c0);
+        const uint64_t b0 = hoff[c0], b1 = hoff[c0 + nc] + (k + 1 == nslabs ? 16 : 0);
+        if (b1 < b0 || f.payload_off + b1 > h.frame_bytes) return SPZ_E_STREAM;
+        CK(cudaMemcpyAsync(d_frame + f.payload_off + b0, hframe + f.payload_off + b0, b1 - b0, cudaMemcpyHostToDevice, g_pipe.up));
+        CK(cudaEventRecord(g_pipe.ev_up[k], g_pipe.up));
+        CK(cudaStreamWaitEvent(g_pipe.run, g_pipe.ev_up[k], 0));
+        const uint64_t e0 = c0 * f.chunk_len;
+        const uint64_t ne = (e0 + nc * f.chunk_len <= h.len) ? nc * f.chunk_len : (h.len - e0);
+        DecParams p;
+        memset(&p, 0, sizeof(p));
+        p.src = d_frame + f.payload_off; p.offsets = (const uint64_t*)(d_frame + f.off_dir) + c0;
+        p.dst = d_out + e0 * esz; p.meta = (ChunkMeta*)(d_status + c0);
+        p.len = ne; p.chunk_len = f.chunk_len; p.nchunks = nc; p.dst_cap = ne;
+        p.ndims = h.ndims; p.has_meta = 1;
+        p.src_end = d_frame + f.payload_off + b1;
+        CK(launch_decode(esz, h.predictor, p, g_pipe.run));
+        CK(cudaEventRecord(g_pipe.ev_run[k], g_pipe.run));
+        CK(cudaStreamWaitEvent(g_pipe.down, g_pipe.ev_run[k], 0));
+        if (ne) CK(cudaMemcpyAsync(dest + e0 * esz, d_out + e0 * esz, ne * esz, cudaMemcpyDeviceToHost, g_pipe.down));
+    }
+    // per-chunk status: any failure fails the call
+    static thread_local std::vector<spz_chunk_meta> hst;
+    hst.resize(f.nchunks);
+    CK(cudaStreamWaitEvent(g_pipe.down, g_pipe.ev_run[nslabs - 1], 0));
+    CK(cudaMemcpyAsync(hst.data(), d_status, sizeof(spz_chunk_meta) * f.nchunks, cudaMemcpyDeviceToHost, g_pipe.down));
+    CK(cudaStreamSynchronize(g_pipe.down));
+    for (uint64_t c = 0; c < f.nchunks; c++) if (hst[c].status != 0) return SPZ_E_STREAM;
     return (int64_t)h.len;
 }
+
+static void release_pipe() { g_pipe.release(); }

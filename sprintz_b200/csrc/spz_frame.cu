@@ -16,12 +16,16 @@ constexpr unsigned long long kFlagAgg = 1ull << 62;
 constexpr unsigned long long kFlagPrefix = 2ull << 62;
 constexpr unsigned long long kValMask = (1ull << 62) - 1;
 
-// Single-pass exclusive scan (decoupled look-back) of the 16-byte-rounded chunk sizes.
+// Single-pass exclusive scan (decoupled look-back) of the 16-byte-rounded chunk sizes of one *segment* of
+// `nchunks` consecutive chunks (the whole frame, or one slab of the pipelined host path). All pointers are
+// already shifted to the segment's first chunk. *base_in (optional) is the payload offset at which the
+// segment starts, *total_out receives the offset after it; the last segment also writes the frame header.
 // tile_state[] and *ticket must be zero on entry.
 __global__ void __launch_bounds__(kScanThreads)
 spz_scan_sizes_kernel(const ChunkMeta* __restrict__ meta, uint64_t nchunks,
                       uint64_t* __restrict__ chunk_off, uint32_t* __restrict__ chunk_nbytes,
                       unsigned long long* tile_state, unsigned int* ticket,
+                      const unsigned long long* base_in, unsigned long long* total_out, int is_last,
                       spz_frame_header* hdr, spz_frame_header hdr_in, uint64_t* d_frame_bytes)
 {
     __shared__ unsigned int s_tile;
@@ -82,7 +86,7 @@ spz_scan_sizes_kernel(const ChunkMeta* __restrict__ meta, uint64_t nchunks,
         s_excl = excl;
     }
     __syncthreads();
-    const unsigned long long tile_excl = s_excl;
+    const unsigned long long tile_excl = s_excl + (base_in ? *base_in : 0ull);
 #pragma unroll
     for (int j = 0; j < kScanItems; j++) {
         const uint64_t idx = base + j;
@@ -93,17 +97,18 @@ spz_scan_sizes_kernel(const ChunkMeta* __restrict__ meta, uint64_t nchunks,
     if (tile == last_tile && threadIdx.x == 0) {
         const unsigned long long total = tile_excl + block_total;
         chunk_off[nchunks] = total;
-        // zero the alignment gap between the size table and the payload so frames are deterministic
-        {
+        if (total_out) *total_out = total;
+        if (is_last) {
+            // zero the alignment gap between the size table and the payload so frames are deterministic
             uint8_t* gap = reinterpret_cast<uint8_t*>(chunk_nbytes + nchunks);
             uint8_t* pay = reinterpret_cast<uint8_t*>(hdr) + hdr_in.payload_off;
             while (gap < pay) *gap++ = 0;
+            spz_frame_header h = hdr_in;
+            h.payload_bytes = total;
+            h.frame_bytes = h.payload_off + total + 16;
+            *hdr = h;
+            if (d_frame_bytes) *d_frame_bytes = h.frame_bytes;
         }
-        spz_frame_header h = hdr_in;
-        h.payload_bytes = total;
-        h.frame_bytes = h.payload_off + total + 16;
-        *hdr = h;
-        if (d_frame_bytes) *d_frame_bytes = h.frame_bytes;
     }
 }
 
@@ -140,12 +145,14 @@ spz_gather_kernel(const uint8_t* __restrict__ slots, uint64_t slot_stride, uint6
 
 cudaError_t launch_scan_sizes(const ChunkMeta* meta, uint64_t nchunks, uint64_t* chunk_off, uint32_t* chunk_nbytes,
                               unsigned long long* tile_state, unsigned int* ticket,
+                              const unsigned long long* base_in, unsigned long long* total_out, int is_last,
                               spz_frame_header* hdr, const spz_frame_header& hdr_in, uint64_t* d_frame_bytes,
                               cudaStream_t stream)
 {
     const uint64_t tiles = (nchunks + kScanTile - 1) / kScanTile;
     spz_scan_sizes_kernel<<<(unsigned)tiles, kScanThreads, 0, stream>>>(meta, nchunks, chunk_off, chunk_nbytes,
-                                                                      tile_state, ticket, hdr, hdr_in, d_frame_bytes);
+                                                                      tile_state, ticket, base_in, total_out, is_last,
+                                                                      hdr, hdr_in, d_frame_bytes);
     return cudaGetLastError();
 }
 
