@@ -174,7 +174,7 @@ def run_reference(args, cfg, cfg_name):
                          "roundtrip_ok": res["roundtrip_ok"]},
         "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line, args.real_stdout)
     return 0
 
 
@@ -341,13 +341,30 @@ def run_ours(args, cfg, cfg_name):
             line["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference",
                                     "sample": f"unavailable: {type(e).__name__}: {e}"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line, args.real_stdout)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
 def main():
+    # Only the JSON line may reach stdout (NCCL / torchrun print banners there): park fd 1 on stderr until the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        return _main(real_stdout)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+
+
+def emit(line, real_stdout):
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
+
+def _main(real_stdout):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -365,6 +382,7 @@ def main():
     if args.bytes_mb:
         cfg["nbytes"] = args.bytes_mb << 20
         cfg["desc"] += f" [size overridden to {args.bytes_mb} MiB]"
+    args.real_stdout = real_stdout
     if args.impl == "reference":
         return run_reference(args, cfg, args.config)
     return run_ours(args, cfg, args.config)
