@@ -71,6 +71,7 @@ struct DecParams {
     const uint8_t*  src_end;   // one past the last readable byte of the source buffer (fast path only)
     uint32_t        ring_cap;  // fast path: bytes of the per-team input ring (power of two)
     uint32_t        out_cap;   // fast path: bytes of the per-team output staging
+    uint32_t        ring_mask4;// fast path: (ring_cap - 1) & ~3, as a kernel constant so wrap+base is one LOP3
 };
 
 template <int W> struct Traits;

@@ -54,8 +54,10 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
     uint8_t* const ring = smem + ring_off;                              // ring_cap bytes + 16 mirror bytes
     const uint32_t RCAP = p.ring_cap;
     const uint32_t RMASK = RCAP - 1u;
-    uint32_t WMASK4 = RMASK & ~3u;
-    asm volatile("" : "+r"(WMASK4));          // keep it one register: (byte & WMASK4) | ring_off is then a single LOP3
+    // teams of a warp run in lock-step at similar stream positions and their rings are bank-aligned: store
+    // stream byte x at ring position (x + skew) so their word reads fall into different banks
+    const uint32_t skew = (uint32_t)(team_in_cta % TEAMS_PER_WARP) * 32u;
+#define WMASK4 (p.ring_mask4)          /* constant-bank operand: (byte & mask) | ring_off is a single LOP3 */
     // two output tiles of out_cap bytes; skewed by 32 B per team of the warp so the lock-step teams' row stores
     // land in different banks (team regions are ring_cap-aligned, i.e. bank-aligned)
     uint8_t* const obuf0 = ring + RCAP + 16 + (uint32_t)(team_in_cta % TEAMS_PER_WARP) * 32u;
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
         while (__any_sync(kFull, on && wr < need_end)) {
             __syncwarp();                            // readers of the bytes about to be overwritten are done
             if (on && wr < need_end) {
-                const uint32_t ro = (wr + (uint32_t)t * 16u) & RMASK;
+                const uint32_t ro = (wr + skew + (uint32_t)t * 16u) & RMASK;
                 *reinterpret_cast<uint4*>(ring + ro) = nxt;
                 if (ro == 0) *reinterpret_cast<uint4*>(ring + RCAP) = nxt;  // mirror: word reads run 4 bytes past the end
                 wr += FILL;
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
         const uint32_t w1 = *reinterpret_cast<const uint32_t*>(smem + bo + 4);
         return __funnelshift_r(w0, w1, bit);
     };
-    auto ring_byte = [&](uint32_t at) -> uint32_t { return ring[at & RMASK]; };
+    auto ring_byte = [&](uint32_t at) -> uint32_t { return ring[(at + skew) & RMASK]; };
 
     // ---- output
     const uint64_t first = c * p.chunk_len;
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
         ensure(pos + max_group + 8, act);
 
         // ---- both slots' widths: fields (s*D + d); the prefix sums over dims share one packed scan
-        const uint32_t hbit = (pos & RMASK) * 8u;
+        const uint32_t hbit = ((pos + skew) & RMASK) * 8u;
         uint32_t nn[DPL], offs[DPL];
         uint32_t carry = 0;
 #pragma unroll
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
             uint32_t row_bytes = (total + 7u) >> 3;
             asm volatile("" : "+r"(row_bytes));      // keep it a register: byte += row_bytes stays an add (FMA-pipe IMAD.IADD)
             const uint32_t row_bits = row_bytes * 8u;
-            const uint32_t pbit = (pos & RMASK) * 8u;
+            const uint32_t pbit = ((pos + skew) & RMASK) * 8u;
             uint8_t* const obase = ob + ocur + (uint32_t)t * ESZ;
 #pragma unroll
             for (int k = 0; k < DPL; k++) {
@@ -361,6 +363,8 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
     }
 }
 
+#undef WMASK4
+
 // ------------------------------------------------------------------ launch
 
 template <int W, bool FIRE, int TEAM, int DPL, bool FULLD>
@@ -397,6 +401,7 @@ cudaError_t launch_decode_hd(int elem_sz, int predictor, DecParams p, cudaStream
     const uint32_t max_group = H + 2 * 8 * p.ndims * elem_sz;
     p.team = team; p.dpl = dpl;
     p.ring_cap = pow2_ceil(max_group + 8 + team * 16);
+    p.ring_mask4 = (p.ring_cap - 1u) & ~3u;
     p.out_cap = (16 + 2 * 8 * p.ndims * elem_sz + 16 + 15) & ~15u;
     p.team_smem = ((p.ring_cap + 16 + 2 * p.out_cap + 128 + p.ring_cap - 1) / p.ring_cap) * p.ring_cap;
     const uint32_t teams_per_cta = kThreads / team;

@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(kThreads) spz_encode_hd_kernel(const EncParams
 
     // ---- output staging (double buffered)
     uint8_t* ob = stage0;
+    uint32_t ob_sel = 0;                    // which of the two staging tiles is current
     uint8_t* gdst;
     uint32_t ocur, oskip;
     {
@@ -106,7 +107,8 @@ __global__ void __launch_bounds__(kThreads) spz_encode_hd_kernel(const EncParams
     auto flush = [&](bool on, bool final_flush) {
         __syncwarp();
         if (on) {
-            uint8_t* const nb = (ob == stage0) ? stage0 + OCAP : stage0;
+            ob_sel ^= 1u;
+            uint8_t* const nb = stage0 + ob_sel * OCAP;
             if (!final_flush && oskip == 0u) {
                 // common case: whole 16-byte units leave, the (<16 byte) remainder moves to the other tile
                 const uint32_t hi = ocur & ~15u;
@@ -134,13 +136,14 @@ __global__ void __launch_bounds__(kThreads) spz_encode_hd_kernel(const EncParams
                     const uint32_t rem = ocur - hi;
                     for (uint32_t b = t; b < rem; b += TEAM) nb[b] = ob[hi + b];
                     ob = nb; gdst += hi; ocur = rem; oskip = 0;
+                } else {
+                    ob_sel ^= 1u;           // nothing left: stay on the current tile
                 }
             }
         }
     };
     if (t == 0) for (uint32_t b = 0; b < meta_bytes; b++) ob[ocur + b] = 0;     // metadata placeholder
     ocur += meta_bytes;
-    uint32_t sbytes = meta_bytes;           // stream bytes emitted so far (team-uniform)
 
     // ---- predictor state (registers), values left-aligned: xh = x << (32-W)
     uint32_t pvh[DPL];
@@ -158,6 +161,10 @@ __global__ void __launch_bounds__(kThreads) spz_encode_hd_kernel(const EncParams
     bool outer = true;
     bool on = valid && L >= (int64_t)kMinDataSize;
     const bool strict = !FIRE;              // `<` vs `<=` in the continue-run test (high-dim: sprintz_xff_rle.cpp:362)
+    // blk*B <= L-G  <=>  blk <= last_start ; blk*B < L-G  <=>  blk <= last_strict   (both -1 when L < G)
+    const int32_t last_start = (L >= G) ? (int32_t)((L - G) / B) : -1;
+    const int32_t last_strict = (L > G) ? (int32_t)((L - G - 1) / B) : -1;
+    const int32_t last_cont = strict ? last_strict : last_start;
 
     // Group finished: bit-emit the pending data blocks, (generic shapes: gather the header), flush.
     // Warp-uniform call.
@@ -233,7 +240,7 @@ __global__ void __launch_bounds__(kThreads) spz_encode_hd_kernel(const EncParams
     auto emit_slot = [&](uint32_t act, uint32_t run_len, const uint32_t (&fh)[DPL], uint32_t row_bytes) -> bool {
         const uint32_t sl = nslots & 1u;
         if (sl == 0u) {
-            hdr_off = ocur; ocur += H; sbytes += H; ngroups++;
+            hdr_off = ocur; ocur += H; ngroups++;
         }
         if (act == ACT_RUN) {       // zero header fields + 1..2 length bytes (sprintz_delta_rle.cpp:238-245)
             const uint32_t two = run_len > 0x7fu ? 1u : 0u;
@@ -241,10 +248,10 @@ __global__ void __launch_bounds__(kThreads) spz_encode_hd_kernel(const EncParams
                 ob[ocur] = (uint8_t)((run_len & 0x7fu) | (two << 7));
                 if (two) ob[ocur + 1] = (uint8_t)(run_len >> 7);
             }
-            ocur += 1u + two; sbytes += 1u + two;
+            ocur += 1u + two;
         } else if (act == ACT_PAD) {
             if (t == 0) ob[ocur] = 0;
-            ocur += 1u; sbytes += 1u;
+            ocur += 1u;
         } else {                    // data slot: payload bytes are produced at group end
             if (pend == 0u) { pe_half0 = wh; pe_off0 = ocur; pe_rb0 = row_bytes; }
             else            { pe_half1 = wh; pe_off1 = ocur; pe_rb1 = row_bytes; }
@@ -253,7 +260,7 @@ __global__ void __launch_bounds__(kThreads) spz_encode_hd_kernel(const EncParams
 #pragma unroll
                 for (int k = 0; k < DPL; k++) { if (sl == 0u) hf0[k] = fh[k]; else hf1[k] = fh[k]; }
             }
-            ocur += kBlockRows * row_bytes; sbytes += kBlockRows * row_bytes;
+            ocur += kBlockRows * row_bytes;
             wh ^= 1u; blk++;
         }
         nslots++;
@@ -280,12 +287,12 @@ __global__ void __launch_bounds__(kThreads) spz_encode_hd_kernel(const EncParams
 
     prefetch(0);
     for (uint32_t it = 0;; it++) {
-        if (on && outer && (int64_t)blk * B > L - G) { tail = (int64_t)blk * B; on = false; }
+        if (on && outer && (int32_t)blk > last_start) { tail = (int64_t)blk * B; on = false; }
         if (!__any_sync(kFullE, on)) break;
 
         // ---- stage the next 16 input rows (every other block)
-        __syncwarp();
         if ((it & 1u) == 0) {
+            __syncwarp();                           // phase-1 readers of the previous 16 rows are done
             if (on) {
 #pragma unroll
                 for (int j = 0; j < NVEC; j++) {
@@ -294,8 +301,8 @@ __global__ void __launch_bounds__(kThreads) spz_encode_hd_kernel(const EncParams
                 }
                 prefetch((it >> 1) + 1u);
             }
+            __syncwarp();
         }
-        __syncwarp();
 
         // ================= phase 1: lane-per-dim forecasting of this block
         uint32_t nw[DPL], fh[DPL], offs[DPL], incls[DPL];
@@ -387,8 +394,7 @@ __global__ void __launch_bounds__(kThreads) spz_encode_hd_kernel(const EncParams
             if (st == 0u) {
                 if (zero && run < kMaxRun) {
                     run++; blk++;
-                    const int64_t pnext = (int64_t)blk * B;
-                    if (strict ? (pnext < L - G) : (pnext <= L - G)) { outer = false; st = 3u; }
+                    if ((int32_t)blk <= last_cont) { outer = false; st = 3u; }
                     else { act = ACT_RUN; run_len = run; run = 0; st = 1u; }    // not enough data to finish the group
                 } else if (run > 0) {
                     act = ACT_RUN; run_len = run; run = 0;                      // a run just ended; re-evaluate this block
@@ -422,9 +428,10 @@ __global__ void __launch_bounds__(kThreads) spz_encode_hd_kernel(const EncParams
             const uint32_t space = OCAP - ocur;
             const uint32_t take = left < space ? left : space;
             for (uint32_t b = t; b < take; b += TEAM) ob[ocur + b] = tsrc[done + b];
-            ocur += take; done += take; left -= take; sbytes += take;
+            ocur += take; done += take; left -= take;
             flush(left > 0, false);
         }
+        const uint32_t sbytes = (uint32_t)((gdst + ocur) - gstream);      // exact stream length
         flush(valid, true);
         __syncwarp();
         if (valid && t == 0) {
