@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(kThreads) spz_encode_hd_kernel(const EncParams
     uint8_t* const s_hf = s_cw + 2 * Dp;                                // [2*Dp]  header nibbles of the open group
     uint8_t* const stage0 = sm + p.out_off;                             // two staging tiles of out_cap bytes
     const uint32_t OCAP = p.out_cap;
+    const uint32_t max_group_bytes = ((2u * (FULLD ? (uint32_t)Dp : p.ndims) * HB + 7u) >> 3) + 2u * kBlockRows * (FULLD ? (uint32_t)Dp : p.ndims) * ESZ + 4u;
 
     // ---- this chunk
     const uint64_t first = c * p.chunk_len;
@@ -233,7 +234,9 @@ __global__ void __launch_bounds__(kThreads) spz_encode_hd_kernel(const EncParams
             }
             pend = 0;
         }
-        flush(gc, false);
+        // several groups accumulate in the staging tile; it leaves for HBM when the next group might not fit
+        const bool need = gc && ocur + max_group_bytes + 16u > OCAP;
+        if (__any_sync(kFullE, need)) flush(need, false);
     };
 
     // One slot of the open group (team-predicated by the caller).
@@ -497,8 +500,13 @@ cudaError_t launch_encode_hd(int elem_sz, int predictor, EncParams p, cudaStream
     p.tile_off = off;                                       // s_mul, s_cw, s_hf
     off += up16(2 * Dp * 4 + 2 * Dp + 2 * Dp);
     p.out_off = off;
-    p.out_cap = up16(32 + H + 2 * 8 * p.ndims * elem_sz + 4 + 16);
-    if (p.out_cap < 256) p.out_cap = 256;
+    {
+        const uint32_t grp = H + 2 * 8 * p.ndims * elem_sz + 4;
+        uint32_t ngrp = 4;
+        while (ngrp > 1 && ngrp * grp > 1536) ngrp--;           // keep the two tiles small enough for 8 CTAs/SM
+        p.out_cap = up16(32 + ngrp * grp + 16);
+        if (p.out_cap < 256) p.out_cap = 256;
+    }
     p.team_smem = off + 2 * p.out_cap;
     const uint32_t teams_per_cta = kThreads / team;
     p.teams_per_cta = teams_per_cta;
