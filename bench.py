@@ -48,6 +48,16 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(cfg_name, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture of this config (or None)."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)["configs"][cfg_name][kernel]["traffic"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -298,9 +308,12 @@ def run_ours(args, cfg, cfg_name):
     alg_bytes = raw * (1.0 + 1.0 / ratio)               # N*(1 + 1/r), both directions
     dom_is_dec = t_dec_kernel >= t_enc_kernel
     dom_t = t_dec_kernel if dom_is_dec else t_enc_kernel
-    roof = lambda t: {"bound": "hbm", "achieved": alg_bytes / t / 1e9, "peak": peak, "unit": "GB/s",  # noqa: E731
-                      "frac": alg_bytes / t / 1e9 / peak, "traffic": None,
-                      "alg_bytes_per_launch": alg_bytes, "ms_per_launch": 1e3 * t, "peak_source": peak_src}
+    full_size = not args.bytes_mb
+    roof = lambda t, kern: {"bound": "hbm", "achieved": alg_bytes / t / 1e9, "peak": peak, "unit": "GB/s",  # noqa: E731
+                            "frac": alg_bytes / t / 1e9 / peak,
+                            "traffic": ncu_traffic(cfg_name, kern) if full_size else None,
+                            "alg_bytes_per_launch": alg_bytes, "ms_per_launch": 1e3 * t, "peak_source": peak_src,
+                            "kernel": kern}
 
     value = world * raw * steps / t_total / 1e9
     line = {
@@ -313,8 +326,9 @@ def run_ours(args, cfg, cfg_name):
                    "l2": "inputs (>= 1 GiB) exceed the 126 MB L2; no explicit flush",
                    "parallelism": f"chunk-sharded x{world}, no data-path collective"},
         "encode_gbs": world * raw * steps / t_enc_m / 1e9, "decode_gbs": world * raw * steps / t_dec_m / 1e9,
-        "roofline": dict(roof(dom_t), kernel="spz_decode_kernel" if dom_is_dec else "spz_encode_kernel"),
-        "roofline_decode": roof(t_dec_kernel), "roofline_encode": roof(t_enc_kernel),
+        "roofline": roof(dom_t, "spz_decode_hd_kernel" if dom_is_dec else "spz_encode_hd_kernel"),
+        "roofline_decode": roof(t_dec_kernel, "spz_decode_hd_kernel"),
+        "roofline_encode": roof(t_enc_kernel, "spz_encode_hd_kernel"),
         "encode_breakdown_ms": {"codec_kernel": 1e3 * t_enc_kernel, "directory_scan": 1e3 * t_scan,
                                 "compaction": 1e3 * t_gather},
         "e2e": {"value": world * raw * e2e_steps / t_e2e / 1e9, "unit": "GB/s",
