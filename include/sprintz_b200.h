@@ -138,6 +138,12 @@ int64_t spz_frame_decompress_host(const void* frame, uint64_t frame_bytes, void*
 int spz_profile_enable(int on);
 int spz_profile_collect(float* ms3, int* ncalls);
 
+/* Kernel family used by the codec launches: 0 = automatic (lane-per-octet kernels for frames with many chunks of
+ * 8 / 16 dims, team-per-chunk kernels otherwise), 1 = team kernels only, 2 = lane kernels whenever the shape
+ * allows (testing: exercises them on small inputs). All families are CUDA and produce identical bytes.
+ * Returns the previous setting. */
+int spz_set_kernel_path(int path);
+
 /* releases the cached device workspaces of the host-buffer entry points */
 void spz_release_workspaces(void);
 

@@ -62,6 +62,7 @@ SYMBOLS = {
     "spz_frame_decompress_host": (_i64, [_vp, _u64, _vp, _u64]),
     "spz_profile_enable": (_i, [_i]),
     "spz_profile_collect": (_i, [C.POINTER(C.c_float), C.POINTER(_i)]),
+    "spz_set_kernel_path": (_i, [_i]),
     "spz_release_workspaces": (None, []),
 }
 

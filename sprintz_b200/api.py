@@ -24,10 +24,16 @@ __all__ = [
     "sprintz_decompress_xff_8b", "sprintz_compress_delta_16b", "sprintz_decompress_delta_16b",
     "sprintz_compress_xff_16b", "sprintz_decompress_xff_16b",
     "Frame", "frame_encode", "frame_decode", "frame_compress_host", "frame_decompress_host",
-    "compress_dev", "decompress_dev",
+    "compress_dev", "decompress_dev", "set_kernel_path",
 ]
 
 _UDT = {1: np.uint8, 2: np.uint16}
+
+
+def set_kernel_path(path: int) -> int:
+    """0 = automatic, 1 = team-per-chunk kernels only, 2 = lane-per-octet kernels whenever the shape allows
+    (include/sprintz_b200.h: spz_set_kernel_path).  Returns the previous setting."""
+    return int(lib().spz_set_kernel_path(int(path)))
 
 
 def max_compressed_bytes(esz: int, n: int, ndims: int) -> int:

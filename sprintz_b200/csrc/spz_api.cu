@@ -26,6 +26,8 @@ cudaError_t launch_scan_sizes(const ChunkMeta* meta, uint64_t nchunks, uint64_t*
 cudaError_t launch_gather(const uint8_t* slots, uint64_t slot_stride, uint64_t nchunks, const uint64_t* chunk_off,
                           const uint32_t* chunk_nbytes, uint8_t* payload, cudaStream_t stream);
 uint64_t scan_tiles(uint64_t nchunks);
+void set_force_path(int v);
+int get_force_path();
 }  // namespace spz
 
 using namespace spz;
@@ -90,6 +92,13 @@ extern "C" int spz_profile_collect(float* ms3, int* ncalls)
 }
 #define PROF_MARK(j) do { if (g_prof.on && g_prof.n < kProfSlots) CK(cudaEventRecord(g_prof.ev[g_prof.n][j], stream)); } while (0)
 #define PROF_NEXT() do { if (g_prof.on && g_prof.n < kProfSlots) g_prof.n++; } while (0)
+
+extern "C" int spz_set_kernel_path(int path)
+{
+    const int old = get_force_path();
+    if (path >= 0 && path <= 2) set_force_path(path);
+    return old;
+}
 
 extern "C" const char* spz_version(void) { return "sprintz_b200 0.1 (sm_100a)"; }
 extern "C" const char* spz_last_error(void) { return g_err; }

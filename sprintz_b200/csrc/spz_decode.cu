@@ -199,9 +199,14 @@ static cudaError_t launch_one(const DecParams& p, uint32_t grid, size_t smem, cu
 static inline uint32_t pow2_ceil(uint32_t x) { uint32_t p = 1; while (p < x) p <<= 1; return p; }
 
 cudaError_t launch_decode_hd(int elem_sz, int predictor, DecParams p, cudaStream_t stream);
+cudaError_t launch_decode_lane(int elem_sz, int predictor, DecParams p, cudaStream_t stream);
 
 cudaError_t launch_decode(int elem_sz, int predictor, DecParams p, cudaStream_t stream)
 {
+    {   // throughput path: frames with many chunks of 8 / 16 dims (spz_decode_lane.cu)
+        const cudaError_t e = launch_decode_lane(elem_sz, predictor, p, stream);
+        if (e != cudaErrorNotSupported) return e;
+    }
     {   // fast path for high-dim shapes; the generic kernel below covers everything else
         const cudaError_t e = launch_decode_hd(elem_sz, predictor, p, stream);
         if (e != cudaErrorNotSupported) return e;

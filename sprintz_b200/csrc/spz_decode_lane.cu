@@ -1,0 +1,356 @@
+// spz_decode_lane.cu -- "lane-per-octet" decode kernels: the throughput path for frames of many chunks.
+//
+// The team kernels (spz_decode_hd.cu) spread one chunk over 8..32 lanes and pay ~180 warp instructions of
+// cooperative bookkeeping per group (header scan shuffles, ring barriers, staged flush); ncu showed them
+// instruction-issue bound at ~27 thread instructions per sample with 44 % of those being that overhead
+// (profiles/r1_final_ncu_summary.csv).  When a frame has tens of thousands of chunks there is no need to
+// cooperate at all: here ONE lane owns 8 consecutive dims of one chunk (ndims = 8: a lane per chunk,
+// ndims = 16: two lanes per chunk) and is a plain scalar decoder, so there are no shuffles, votes or barriers
+// and every per-group cost is paid once per 8 dims x 16 rows.
+//
+//   input    each lane pulls the chunk's stream through a private 128-byte ring in shared memory with
+//            32-byte (one sector) loads issued one fill ahead.  The ring is word-interleaved across the warp
+//            (word i of lane L lives at row i, column L), so a lane only ever touches its own bank: field
+//            reads at lane-specific bit positions are conflict-free by construction.  A 33rd row mirrors row 0
+//            so the two-word window never has to wrap.
+//            Loads run one fill ahead in registers and four fills ahead as an L2 prefetch.
+//   unpack   a lane's 8 fields of a row are CONTIGUOUS bits (<= 64 for 8-bit, 2 x <= 64 for 16-bit): three ring
+//            words + two funnel shifts give the aligned 64-bit segment, then every field is "mask the low bits,
+//            shift the segment right by its width" -- 2 shifts per field instead of an address computation,
+//            two LDS and a funnel shift per field
+//   predict  zigzag^-1 and delta | FIRE entirely in the left-aligned domain: m = u ^ -(u & 1) is 2*err, so
+//            prev_delta<<(32-W) = (mulhi(prev_delta<<, coef) << (32-W)) + (m << (31-W)) and the running value
+//            accumulates left-aligned too (natural W-bit wrap, PRMT picks the high halves on output); the 8
+//            dims of a lane are independent -> instruction-level parallelism instead of occupancy
+//   output   a lane owns 8 consecutive elements of every row: packed with PRMT and stored as one 64/128-bit
+//            store per row (two rows per store when ndims * esz == 8); lanes of a chunk fill whole sectors
+//   runs / tail / errors   plain divergent scalar code, as in the reference's decoder
+//
+// Reference behaviour restated: sprintz_delta_rle.cpp:417-772, sprintz_xff_rle.cpp:568-1179 (high-dim).
+#include "spz_common.cuh"
+
+namespace spz {
+
+constexpr int kLaneThreads = 128;
+#ifndef SPZ_LANE_MINB
+#define SPZ_LANE_MINB 4
+#endif
+constexpr uint32_t kLaneWarpSmem = 8192;      // 33 rows x 128 B used; the stride keeps "row | lane" an OR
+
+template <int W, bool FIRE, int D>
+__global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_kernel(const DecParams p)
+{
+    typedef typename Traits<W>::uint_t uint_t;
+    constexpr int ESZ = W / 8;
+    constexpr int HB = Traits<W>::HB;
+    constexpr int CB = Traits<W>::CB;
+    constexpr int UP = 32 - W;
+    constexpr int NP = D / 8;                       // lanes per chunk
+    constexpr uint32_t FMASK = (1u << HB) - 1u;
+    constexpr uint32_t H = (2u * D * HB + 7u) / 8u; // header bytes per group
+    constexpr uint32_t B = 8u * D;                  // elements per block
+    constexpr uint32_t LB = 8u * ESZ;               // bytes a lane owns in every row
+    constexpr uint32_t ROWB = (uint32_t)D * ESZ;    // bytes per row
+    static_assert(D % 8 == 0 && D <= 16, "lane kernels cover ndims 8 and 16");
+
+    __shared__ __align__(16) uint8_t smem[(kLaneThreads / 32) * kLaneWarpSmem];
+
+    const uint64_t gtid = (uint64_t)blockIdx.x * kLaneThreads + threadIdx.x;
+    const uint64_t c = gtid / NP;
+    const uint32_t part = (uint32_t)(gtid % NP);
+    if (c >= p.nchunks) return;                     // lanes never cooperate: early exit is safe
+    const uint32_t rboff = (threadIdx.x >> 5) * kLaneWarpSmem + (threadIdx.x & 31) * 4u;
+
+    // ---- input ring
+    const uint8_t* const gstream = p.src + (p.offsets ? p.offsets[c] : c * p.slot_stride);
+    const uint32_t mis = (uint32_t)((uintptr_t)gstream & 31);
+    const uint8_t* base32 = gstream - mis;
+    asm volatile("" : "+l"(base32));                // keep the pointer in registers (no rematerialisation per fill)
+    const uint64_t span = (uint64_t)(p.src_end - base32);               // readable bytes from base32
+    const uint32_t limit = span > 0xfffffff0ull ? 0xfffffff0u : (uint32_t)span;
+    const uint32_t lim = (limit - 1u) & ~31u;       // last 32-byte block that still holds a readable byte
+    uint32_t filled = 0;                            // stream bytes staged so far (multiple of 32)
+    uint32_t nx[8];                                 // the next 32 stream bytes, loaded one fill ahead
+    auto load_next = [&]() {
+        const uint32_t o = filled < lim ? filled : lim;
+        // one 256-bit load == one sector per lane (sm_100: LDG.E.256)
+        asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(nx[0]), "=r"(nx[1]), "=r"(nx[2]), "=r"(nx[3]), "=r"(nx[4]), "=r"(nx[5]), "=r"(nx[6]), "=r"(nx[7])
+                     : "l"(base32 + o));
+    };
+    auto fill = [&]() {
+        const uint32_t so = ((filled << 5) & 0xC00u) | rboff;
+#pragma unroll
+        for (int j = 0; j < 8; j++) *reinterpret_cast<uint32_t*>(smem + so + j * 128) = nx[j];
+        if ((filled & 96u) == 0u) {                  // once per trip around the ring
+            // rows 32, 33 mirror rows 0, 1: a 3-word read never wraps
+            *reinterpret_cast<uint32_t*>(smem + rboff + 32 * 128) = nx[0];
+            *reinterpret_cast<uint32_t*>(smem + rboff + 33 * 128) = nx[1];
+        }
+        {   // the register prefetch below runs one fill ahead; an L1 prefetch two fills further ahead lets it hit L1
+            const uint32_t o = filled + 96u < lim ? filled + 96u : lim;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(base32 + o));
+        }
+        filled += 32u;
+        load_next();
+    };
+    // 32-bit window of the stream at bit position `bit` (relative to base32)
+    auto window = [&](uint32_t bit) -> uint32_t {
+        const uint32_t a = ((bit << 2) & 0xF80u) | rboff;
+        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(smem + a);
+        const uint32_t w1 = *reinterpret_cast<const uint32_t*>(smem + a + 128);
+        return __funnelshift_r(w0, w1, bit);
+    };
+    // aligned 64-bit segment of the stream starting at bit position `bit`
+    auto segment = [&](uint32_t bit, uint32_t& lo, uint32_t& hi) {
+        const uint32_t a = ((bit << 2) & 0xF80u) | rboff;
+        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(smem + a);
+        const uint32_t w1 = *reinterpret_cast<const uint32_t*>(smem + a + 128);
+        const uint32_t w2 = *reinterpret_cast<const uint32_t*>(smem + a + 256);
+        lo = __funnelshift_r(w0, w1, bit);
+        hi = __funnelshift_r(w1, w2, bit);
+    };
+    // Every consumer takes at most 32 bytes between two calls, so one fill restores "48 bytes ahead"
+    // (a unit of <= 32 bytes plus the 12-byte reach of a 3-word read from its last byte).
+    auto ensure = [&](uint32_t bit) { if (filled - (bit >> 3) < 48u) fill(); };
+
+    load_next();
+    fill(); fill(); fill();
+
+    // ---- output
+    const uint64_t first = c * p.chunk_len;
+    uint_t* const out = reinterpret_cast<uint_t*>(p.dst) + first;
+    const uint64_t cap64 = first >= p.dst_cap ? 0 : ((p.dst_cap - first < p.chunk_len) ? (p.dst_cap - first) : p.chunk_len);
+    const uint32_t cap = cap64 > 0xffffffffull ? 0xffffffffu : (uint32_t)cap64;
+    uint8_t* orow = reinterpret_cast<uint8_t*>(out) + part * LB;        // my bytes of the next row to write
+
+    uint32_t pvh[8];                                // running values, left-aligned (value << (32-W))
+    int32_t pdh[8], ct[8];                          // previous deltas (left-aligned), FIRE counters
+#pragma unroll
+    for (int j = 0; j < 8; j++) { pvh[j] = 0; pdh[j] = 0; ct[j] = 0; }
+    uint32_t held0 = 0, held1 = 0;                  // even row of a pair when a row is only 8 bytes (NP == 1, W == 8)
+
+    // my 8 values of one row -> HBM
+    auto store_row = [&](uint32_t r) {
+        if (W == 16) {
+            uint4 v;
+            v.x = __byte_perm(pvh[0], pvh[1], 0x7632); v.y = __byte_perm(pvh[2], pvh[3], 0x7632);
+            v.z = __byte_perm(pvh[4], pvh[5], 0x7632); v.w = __byte_perm(pvh[6], pvh[7], 0x7632);
+            *reinterpret_cast<uint4*>(orow) = v;
+            orow += ROWB;
+        } else {
+            const uint32_t a = __byte_perm(pvh[0], pvh[1], 0x0073), b = __byte_perm(pvh[2], pvh[3], 0x0073);
+            const uint32_t e = __byte_perm(pvh[4], pvh[5], 0x0073), f = __byte_perm(pvh[6], pvh[7], 0x0073);
+            const uint32_t w0 = __byte_perm(a, b, 0x5410), w1 = __byte_perm(e, f, 0x5410);
+            if (NP == 1) {                           // rows are 8 bytes: rows r, r+1 form one 16-byte store
+                if ((r & 1u) == 0u) { held0 = w0; held1 = w1; }
+                else { *reinterpret_cast<uint4*>(orow) = make_uint4(held0, held1, w0, w1); orow += 2 * ROWB; }
+            } else {
+                *reinterpret_cast<uint2*>(orow) = make_uint2(w0, w1);
+                orow += ROWB;
+            }
+        }
+    };
+
+    uint32_t pos = mis * 8u;                         // bit cursor relative to base32
+    uint32_t ngroups = 0, remaining = 0, status = kStatusOk;
+    if (p.has_meta) {                                // format.h:47-62
+        ngroups = window(pos);
+        const uint32_t w1 = window(pos + 32u);
+        remaining = w1 & 0xffffu;
+        if ((w1 >> 16) != (uint32_t)D) status = kStatusBadDims;
+        pos += 64u;
+        ensure(pos);
+    } else {
+        ngroups = p.meta[c].ngroups;
+        remaining = p.meta[c].remaining & 0xffffu;
+    }
+    if (status != kStatusOk) ngroups = 0;
+
+    uint32_t o = 0;                                  // output element cursor of the chunk
+#pragma unroll 1
+    for (uint32_t g = 0; g < ngroups; g++) {
+        if ((pos >> 3) > limit) { status = kStatusTruncated; break; }
+        const uint32_t hbit = pos;
+        pos += H * 8u;
+        // both slots' header words are read before the ring moves on
+        uint32_t mine[2], sum_before[2], total[2];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            mine[s] = window(hbit + (uint32_t)(s * D) * HB + part * (8u * HB));
+            uint32_t before = 0, all = 0;
+#pragma unroll
+            for (int q = 0; q < NP; q++) {
+                const uint32_t fw = (NP == 1) ? mine[s] : window(hbit + (uint32_t)(s * D + q * 8) * HB);
+                // sum of the 8 widths of octet q: sum of the fields + the number of fields equal to W-1 (stored W)
+                uint32_t sum;
+                if (HB == 4) {
+                    const uint32_t e = (fw & 0x0f0f0f0fu) + ((fw >> 4) & 0x0f0f0f0fu);      // 4 byte lanes, each <= 30
+                    uint32_t full = fw & (fw >> 1); full &= full >> 2;                      // bit 0 of a nibble: nibble == 15
+                    sum = ((e * 0x01010101u) >> 24) + (uint32_t)__popc(full & 0x11111111u);
+                } else {
+                    const uint32_t x = fw & 0x00ffffffu;
+                    const uint32_t e = (x & 0007070707u) + ((x >> 3) & 0007070707u);        // 4 six-bit lanes, each <= 14
+                    const uint32_t full = x & (x >> 1) & (x >> 2) & 0011111111u;            // bit 0 of a field: field == 7
+                    sum = (((e * 0x00041041u) >> 18) & 63u) + (uint32_t)__popc(full);
+                }
+                all += sum;
+                if ((uint32_t)q < part) before += sum;
+            }
+            sum_before[s] = before; total[s] = all;
+        }
+        ensure(pos);
+
+#pragma unroll 1
+        for (int s = 0; s < 2; s++) {
+            const uint32_t tot = s ? total[1] : total[0];
+            if (tot == 0u) {
+                // ---- run slot (sprintz_delta_rle.cpp:640-667, sprintz_xff_rle.cpp:828-958)
+                const uint32_t rb = window(pos);
+                uint32_t nrun = rb & 0x7fu;
+                if (rb & 0x80u) { nrun |= ((rb >> 8) & 0xffu) << 7; pos += 16u; } else { pos += 8u; }
+                ensure(pos);
+                if ((uint64_t)o + (uint64_t)nrun * B > cap) { status = kStatusOverflow; break; }
+                int32_t coef[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) coef[j] = FIRE ? fire_coef<W, false>(ct[j]) : 0;
+#pragma unroll 1
+                for (uint32_t b = 0; b < nrun; b++) {
+#pragma unroll
+                    for (uint32_t r = 0; r < 8; r++) {
+                        if (FIRE) {
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                // err == 0 -> delta == prediction = (prev_delta * coef) >> W, wrapped to W bits
+                                const int32_t pred = __mulhi(pdh[j], coef[j]);
+                                pdh[j] = (int32_t)((uint32_t)pred << UP);
+                                pvh[j] += (uint32_t)pdh[j];
+                            }
+                        }
+                        store_row(r);
+                    }
+                }
+                o += nrun * B;
+                continue;
+            }
+
+            // ---- data slot
+            if (o + B > cap) { status = kStatusOverflow; break; }
+            const uint32_t fw = s ? mine[1] : mine[0];
+            uint32_t nb[8], fm[8];
+            int32_t coef[8], gsh[8];
+            const uint32_t offA = s ? sum_before[1] : sum_before[0];   // bit offset of my first dim inside a row
+            uint32_t offB = offA;                                      // ... of my fifth dim (16-bit: second segment)
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t f = (fw >> (j * HB)) & FMASK;
+                const uint32_t n = f + (f == (uint32_t)(W - 1) ? 1u : 0u);
+                nb[j] = n;
+                if (j < 4) offB += n;
+                fm[j] = (1u << n) - 1u;
+                coef[j] = FIRE ? fire_coef<W, false>(ct[j]) : 0;
+                gsh[j] = 0;
+            }
+            const uint32_t row_bits = ((tot + 7u) >> 3) * 8u;
+            uint32_t rowbit = pos;
+#pragma unroll
+            for (uint32_t r = 0; r < 8; r++) {
+                uint32_t lo, hi;
+                segment(rowbit + offA, lo, hi);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    if (W == 16 && j == 4) segment(rowbit + offB, lo, hi);
+                    // zigzag^-1 (bitpack.h:303) in doubled form: m = u ^ -(u & 1) == 2 * err (bit 0 is always clear)
+                    const uint32_t u = lo & fm[j];
+                    const uint32_t sgn = 0u - (u & 1u);
+                    const uint32_t m = u ^ sgn;
+                    if (j != 7 && !(W == 16 && j == 3)) { lo = __funnelshift_r(lo, hi, nb[j]); hi >>= nb[j]; }
+                    if (FIRE) {
+                        if (r & 1u) {
+                            // icopysign(err, prev_delta) (util.h:63-68), accumulated left-aligned so the int_t wrap
+                            // of grad_sum is the natural 32-bit wrap
+                            if (m != 0u) gsh[j] += (int32_t)(((uint32_t)pdh[j] ^ sgn) - sgn);
+                        }
+                        // prediction = (prev_delta * coef) >> W (sprintz_xff_rle.cpp:225): prev_delta is left-aligned
+                        // by 32-W bits, so this is the high word of the product; delta = prediction + err, and
+                        // (delta << UP) = (prediction << UP) + (m << (UP-1)) wraps to W bits by itself
+                        const int32_t th = __mulhi(pdh[j], coef[j]);
+                        pdh[j] = (int32_t)(((uint32_t)th << UP) + (m << (UP - 1)));
+                        pvh[j] += (uint32_t)pdh[j];
+                    } else {
+                        pvh[j] += m << (UP - 1);
+                    }
+                }
+                store_row(r);
+                rowbit += row_bits;
+                ensure(rowbit);
+            }
+            pos = rowbit;
+            if (FIRE) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) ct[j] = sx<CB>(ct[j] + ((gsh[j] >> UP) >> 2));   // sprintz_xff_rle.cpp:273-275
+            }
+            o += B;
+        }
+        if (status != kStatusOk) break;
+    }
+
+    // ---- trailing raw elements (also the whole stream when it was stored raw)
+    if (status == kStatusOk) {
+        if ((uint64_t)o + remaining > cap) {
+            status = kStatusOverflow;
+        } else {
+            const uint8_t* tsrc = base32 + (pos >> 3);
+            uint8_t* tdst = reinterpret_cast<uint8_t*>(out + o);
+            const uint32_t nb = remaining * ESZ;
+            for (uint32_t b = part; b < nb; b += NP) tdst[b] = tsrc[b];
+            o += remaining;
+        }
+    }
+    if (part == 0 && p.meta) {
+        p.meta[c].status = status;
+        if (p.has_meta) {
+            p.meta[c].nbytes = (pos >> 3) - mis + remaining * ESZ;
+            p.meta[c].ngroups = ngroups;
+            p.meta[c].remaining = o;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ launch
+
+static int g_force_path = 0;       // 0 auto, 1 team kernels only, 2 lane kernels whenever the shape allows
+void set_force_path(int v) { g_force_path = v; }
+int get_force_path() { return g_force_path; }
+
+template <int W, bool FIRE, int D>
+static cudaError_t launch_lane(const DecParams& p, cudaStream_t stream)
+{
+    const uint64_t threads = p.nchunks * (uint64_t)(D / 8);
+    const uint64_t grid64 = (threads + kLaneThreads - 1) / kLaneThreads;
+    if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
+    spz_decode_lane_kernel<W, FIRE, D><<<(uint32_t)grid64, kLaneThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// Returns cudaErrorNotSupported when the shape is not covered (caller continues with the team kernels).
+cudaError_t launch_decode_lane(int elem_sz, int predictor, DecParams p, cudaStream_t stream)
+{
+    if (g_force_path == 1) return cudaErrorNotSupported;
+    if (p.ndims != 8 && p.ndims != 16) return cudaErrorNotSupported;
+    if (p.src_end == nullptr || p.src_end <= p.src) return cudaErrorNotSupported;
+    // a lane is a whole scalar decoder: only worth it when there are enough chunks to fill the machine
+    if (g_force_path != 2 && p.nchunks * (p.ndims / 8) < 16384) return cudaErrorNotSupported;
+    // vector stores: every chunk's output must start 16-byte aligned
+    if (((uintptr_t)p.dst & 15) != 0) return cudaErrorNotSupported;
+    if (p.nchunks > 1 && ((p.chunk_len * (uint64_t)elem_sz) & 15) != 0) return cudaErrorNotSupported;
+    if (p.chunk_len % p.ndims != 0 && p.nchunks > 1) return cudaErrorNotSupported;
+    // 32-bit bit cursors inside one chunk
+    if (p.chunk_len * (uint64_t)elem_sz > 0x0c000000ull) return cudaErrorNotSupported;
+#define SPZ_LANE(Wv, Dv) return predictor ? launch_lane<Wv, true, Dv>(p, stream) : launch_lane<Wv, false, Dv>(p, stream)
+    if (elem_sz == 1) { if (p.ndims == 8) SPZ_LANE(8, 8); else SPZ_LANE(8, 16); }
+    else              { if (p.ndims == 8) SPZ_LANE(16, 8); else SPZ_LANE(16, 16); }
+#undef SPZ_LANE
+}
+
+}  // namespace spz

@@ -1,7 +1,11 @@
-"""Per CUDA source line: share of executed warp instructions (ncu report captured with --import-source on)."""
+"""Per CUDA source line: share of executed warp instructions (ncu report captured with --import-source on).
+usage: ncu_lines.py report.ncu-rep [topn] [kernel-regex]"""
 import csv, io, subprocess, sys
 rep = sys.argv[1]; topn = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+kre = sys.argv[3] if len(sys.argv) > 3 else None
+cmd = ["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"]
+if kre: cmd += ["-k", "regex:" + kre, "-c", "1"]
+txt = subprocess.run(cmd, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
 cur_file = ""; ci = None
 lines = []
@@ -13,6 +17,11 @@ for r in rows:
         lines.append((int(r[ci]), cur_file, int(r[0]), r[1].strip()))
 tot = sum(l[0] for l in lines)
 print("total warp instr", tot)
-lines.sort(key=lambda l: -l[0])
-for n, f, ln, src in lines[:topn]:
-    print(f"{n / tot * 100:6.2f}%  {f}:{ln:<4d} {src[:110]}")
+if "--by-line" in sys.argv:
+    lines.sort(key=lambda l: (l[1], l[2]))
+    for n, f, ln, src in lines:
+        if n: print(f"{n / tot * 100:6.2f}%  {f}:{ln:<4d} {src[:110]}")
+else:
+    lines.sort(key=lambda l: -l[0])
+    for n, f, ln, src in lines[:topn]:
+        print(f"{n / tot * 100:6.2f}%  {f}:{ln:<4d} {src[:110]}")
