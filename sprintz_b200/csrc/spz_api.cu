@@ -134,9 +134,10 @@ extern "C" uint64_t spz_frame_nchunks(uint64_t len, uint16_t ndims, uint32_t chu
     return frame_layout(len, ndims, chunk_rows).nchunks;
 }
 
+static inline uint64_t align32(uint64_t x) { return (x + 31ull) & ~31ull; }
 static uint64_t slot_stride_of(int elem_sz, uint64_t chunk_len, uint16_t ndims)
 {
-    return spz_max_compressed_bytes(elem_sz, chunk_len, ndims);
+    return align32(spz_max_compressed_bytes(elem_sz, chunk_len, ndims));      // whole sectors: 256-bit stores
 }
 
 extern "C" uint64_t spz_frame_max_bytes(int elem_sz, uint64_t len, uint16_t ndims, uint32_t chunk_rows)
@@ -155,7 +156,7 @@ static WorkLayout work_layout(int elem_sz, uint64_t len, uint16_t ndims, uint32_
     w.off_state = 0;
     w.off_ticket = align16(8 * scan_tiles(f.nchunks));
     w.off_meta = w.off_ticket + 16;
-    w.off_slots = align16(w.off_meta + sizeof(ChunkMeta) * f.nchunks);
+    w.off_slots = align32(w.off_meta + sizeof(ChunkMeta) * f.nchunks);
     w.slot_stride = slot_stride_of(elem_sz, f.chunk_len < len || len == 0 ? f.chunk_len : len, ndims);
     w.total = w.off_slots + f.nchunks * w.slot_stride + 16;
     return w;
@@ -511,7 +512,7 @@ extern "C" int64_t spz_frame_compress_host(int predictor, int elem_sz, const voi
     const uint64_t off_ticket = align16(8 * tiles_per_slab * nslabs);
     const uint64_t off_tot = align16(off_ticket + 4 * nslabs);
     const uint64_t off_meta = align16(off_tot + 8 * (nslabs + 1));
-    const uint64_t off_slots = align16(off_meta + sizeof(ChunkMeta) * f.nchunks);
+    const uint64_t off_slots = align32(off_meta + sizeof(ChunkMeta) * f.nchunks);
     const uint64_t wtotal = off_slots + f.nchunks * w.slot_stride + 16;
     CK(g_pipe.init((int)nslabs));
     CK(g_cache.ensure(0, in_bytes + 16));

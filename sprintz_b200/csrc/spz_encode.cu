@@ -366,9 +366,14 @@ static void enc_layout(int elem_sz, bool low, EncParams& p)
 }
 
 cudaError_t launch_encode_hd(int elem_sz, int predictor, EncParams p, cudaStream_t stream);
+cudaError_t launch_encode_lane(int elem_sz, int predictor, EncParams p, cudaStream_t stream);
 
 cudaError_t launch_encode(int elem_sz, int predictor, EncParams p, cudaStream_t stream)
 {
+    {   // throughput path: frames with many chunks of 8 / 16 dims (spz_encode_lane.cu)
+        const cudaError_t e = launch_encode_lane(elem_sz, predictor, p, stream);
+        if (e != cudaErrorNotSupported) return e;
+    }
     {   // fast path for high-dim shapes; the generic kernel below covers everything else
         const cudaError_t e = launch_encode_hd(elem_sz, predictor, p, stream);
         if (e != cudaErrorNotSupported) return e;
