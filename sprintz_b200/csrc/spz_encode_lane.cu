@@ -28,6 +28,17 @@ namespace spz {
 
 constexpr int kEncLaneThreads = 128;
 
+// The output ring is addressed with absolute 32-bit shared-memory addresses and explicit st/ld.shared: with C++
+// pointers the compiler rebuilt the shared window base (S2R + MOV + LEA) under every predicated store.
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.b8 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ uint32_t lds32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+
 template <int W, bool FIRE, int D>
 __global__ void __launch_bounds__(kEncLaneThreads, 4) spz_encode_lane_kernel(const EncParams p)
 {
@@ -48,22 +59,23 @@ __global__ void __launch_bounds__(kEncLaneThreads, 4) spz_encode_lane_kernel(con
     static_assert((W == 8 && D == 8) || (W == 16 && (D == 8 || D == 16)), "shapes covered by the lane encoder");
     constexpr int NW = kEncLaneThreads / 32;
 
-    // [NW rings of 32 words x 32 lanes][NW staging areas of NVEC vectors x 32 lanes]
-    __shared__ __align__(16) uint8_t smem[NW * 4096 + NW * NVEC * 512];
+    // [pad to 4 KB][NW rings of 32 words x 32 lanes][NW staging areas of NVEC vectors x 32 lanes]
+    extern __shared__ __align__(16) uint8_t dsm[];
 
     const uint64_t c = (uint64_t)blockIdx.x * kEncLaneThreads + threadIdx.x;
     if (c >= p.nchunks) return;                            // lanes never cooperate: early exit is safe
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t ringoff = warp * 4096u + lane * 4u;     // word w of my output ring: ringoff | ((w & 31) << 7)
-    uint8_t* const stg = smem + NW * 4096 + warp * (NVEC * 512) + lane * 16;   // vector v of my block: stg + v * 512
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(dsm);
+    const uint32_t apad = (0u - sbase) & 4095u;            // the rings start 4 KB aligned: "row | lane" is an OR
+    const uint32_t ringabs = sbase + apad + warp * 4096u + lane * 4u;   // word w of my output ring: ringabs | ((w & 31) << 7)
+    uint8_t* const stg = dsm + apad + NW * 4096 + warp * (NVEC * 512) + lane * 16;   // vector v of my block: stg + v * 512
 
     // ---- this chunk
     const uint64_t first = c * p.chunk_len;
     const int32_t L = (int32_t)((first + p.chunk_len <= p.len) ? p.chunk_len : (p.len - first));
     const uint8_t* gin = p.src + first * ESZ;
     asm volatile("" : "+l"(gin));
-    uint8_t* gout = p.dst + c * p.slot_stride;
-    asm volatile("" : "+l"(gout));
+    uint8_t* const gout = p.dst + c * p.slot_stride;
     const uint32_t meta_bytes = p.write_size ? 8u : 0u;
 
     if (L < (int32_t)kMinDataSize) {                       // stored raw (sprintz_delta_rle.cpp:101-109)
@@ -76,52 +88,57 @@ __global__ void __launch_bounds__(kEncLaneThreads, 4) spz_encode_lane_kernel(con
         return;
     }
 
-    // ---- bit writer: 64-bit accumulator -> lane-private ring of words -> 256-bit stores
-    uint64_t acc = 0;
-    uint32_t pos = 0;                                      // bits held in acc (< 32 between puts)
+    // ---- bit writer: (lo, hi) accumulator -> lane-private ring of words -> 256-bit stores
+    // Invariant between puts: fewer than 32 bits are pending, all of them in `lo`.
+    uint32_t lo = 0, pos = 0;                              // pending bits, their count
     uint32_t wcount = 0;                                   // words written to the ring so far
     uint32_t flushed = 0;                                  // words already in HBM (multiple of 8)
-    auto ring_addr = [&](uint32_t w) -> uint32_t { return ((w << 7) & 0xF80u) | ringoff; };
+    // The address of a ring word is rebuilt from the counter for every store (a fresh register): updating an
+    // address register in place right after the STS that reads it stalls on the write-after-read scoreboard.
+    auto ring_at = [&](uint32_t w) -> uint32_t { return ((w << 7) & 0xF80u) | ringabs; };
     auto put = [&](uint32_t v, uint32_t nb) {              // v < 2^nb, nb <= 32
-        acc += (uint64_t)v * (uint64_t)(1u << pos);        // bits above pos are clear: add == or, one IMAD.WIDE
+        const uint32_t t = v << pos;
+        const uint32_t carry = __funnelshift_l(v, 0u, pos);                   // v >> (32 - pos), 0 when pos == 0
+        // the stored word gets its own register: the STS reads its operands late, and overwriting them right
+        // away (the compiler would fold `lo = full ? carry : w` into a predicated move onto w) stalls every put
+        uint32_t w;
+        asm volatile("or.b32 %0, %1, %2;" : "=r"(w) : "r"(lo), "r"(t));
         pos += nb;
-        if (pos >= 32u) {
-            *reinterpret_cast<uint32_t*>(smem + ring_addr(wcount)) = (uint32_t)acc;
-            wcount++; acc >>= 32; pos -= 32u;
-        }
+        const bool full = pos >= 32u;
+        if (full) { sts32(ring_at(wcount), w); wcount++; }
+        lo = full ? carry : (lo | t);
+        pos &= 31u;
     };
     auto row_end = [&]() {                                 // zero-pad to the next byte boundary
         pos = (pos + 7u) & ~7u;
-        if (pos >= 32u) {
-            *reinterpret_cast<uint32_t*>(smem + ring_addr(wcount)) = (uint32_t)acc;
-            wcount++; acc >>= 32; pos -= 32u;
-        }
+        if (pos >= 32u) { sts32(ring_at(wcount), lo); wcount++; lo = 0u; }
+        pos &= 31u;
     };
     auto maybe_flush = [&]() {                             // at most 32 new bytes between two calls
         if (wcount - flushed >= 8u) {
-            const uint32_t a = ((flushed << 7) & 0xC00u) | ringoff;
+            const uint32_t fa = ((flushed << 7) & 0xC00u) | ringabs;          // a multiple of 8 rows: no wrap
             uint32_t v[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) v[j] = *reinterpret_cast<const uint32_t*>(smem + a + j * 128);
+            for (int j = 0; j < 8; j++) v[j] = lds32(fa + j * 128);
             asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(gout + (size_t)flushed * 4),
                          "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
             flushed += 8u;
         }
     };
     auto cur_bytes = [&]() -> uint32_t { return wcount * 4u + (pos >> 3); };
-    // overwrite already-written bytes [off, off+nbytes) of the stream with the low bytes of (lo, hi)
-    auto patch = [&](uint32_t off, uint32_t lo, uint32_t hi, uint32_t nbytes) {
-        *reinterpret_cast<uint32_t*>(smem + ring_addr(wcount)) = (uint32_t)acc;      // the partial word joins the ring
+    // overwrite already-written bytes [off, off+nbytes) of the stream with the low bytes of (plo, phi)
+    auto patch = [&](uint32_t off, uint32_t plo, uint32_t phi, uint32_t nbytes) {
+        sts32(ring_at(wcount), lo);                                            // the partial word joins the ring
 #pragma unroll
         for (uint32_t b = 0; b < 8; b++) {
             if (b < nbytes) {
                 const uint32_t o = off + b;
-                const uint32_t val = ((b < 4 ? lo : hi) >> (8u * (b & 3u))) & 0xffu;
-                if ((o >> 2) >= flushed) smem[ring_addr(o >> 2) + (o & 3u)] = (uint8_t)val;
+                const uint32_t val = ((b < 4 ? plo : phi) >> (8u * (b & 3u))) & 0xffu;
+                if ((o >> 2) >= flushed) sts8(ring_at(o >> 2) + (o & 3u), val);
                 else gout[o] = (uint8_t)val;
             }
         }
-        acc = *reinterpret_cast<const uint32_t*>(smem + ring_addr(wcount));          // pos < 32: the high half is empty
+        lo = lds32(ring_at(wcount));
     };
 
     // ---- block input
@@ -186,9 +203,10 @@ __global__ void __launch_bounds__(kEncLaneThreads, 4) spz_encode_lane_kernel(con
                 if (FIRE) {
                     // prediction = (prev_delta * coef) >> W (sprintz_xff_rle.cpp:225): prev_delta is left-aligned
                     const int32_t pred = __mulhi(dprev[d], coef[e]);
-                    eh = dh - (int32_t)((uint32_t)pred << UP);                 // err, wraps to W bits
+                    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(eh) : "r"(pred), "n"(-(1 << UP)), "r"(dh));   // dh - (pred << UP): err, wraps to W bits
                     if (r & 1) {                                               // icopysign(err, prev_delta), odd rows
-                        if (eh > 0) gsh[e] += dprev[d]; else if (eh < 0) gsh[e] -= dprev[d];
+                        const int32_t sg = eh >> 31;
+                        if (eh != 0) gsh[e] += (dprev[d] ^ sg) - sg;
                     }
                     dprev[d] = dh;
                 }
@@ -196,11 +214,17 @@ __global__ void __launch_bounds__(kEncLaneThreads, 4) spz_encode_lane_kernel(con
             };
 
             if (W == 16) {
+                // rows are rolled in pairs (the odd/even gradient rule stays static): code size, not speed,
+                // limited the fully unrolled version (62 KB of SASS, instruction-cache stalls)
+                uint4 q = *reinterpret_cast<const uint4*>(stg + oc * 512);    // row 0; later rows are fetched one ahead
+#pragma unroll 1
+                for (int rp = 0; rp < 8; rp += 2)
 #pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    uint8_t* vp = stg + (r * NO + oc) * 512;
-                    const uint4 q = *reinterpret_cast<const uint4*>(vp);
+                for (int r1 = 0; r1 < 2; r1++) {
+                    const int r = r1;                                          // only the parity matters to elem()
+                    uint8_t* vp = stg + ((rp + r1) * NO + oc) * 512;
                     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+                    if (rp + r1 < 7) q = *reinterpret_cast<const uint4*>(vp + NO * 512);
                     uint32_t z[4];
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
@@ -308,12 +332,18 @@ __global__ void __launch_bounds__(kEncLaneThreads, 4) spz_encode_lane_kernel(con
             else patch(hdr_off + HSLOT, hlo, hhi, HSLOT);
             const bool have_next = (i + 2) * Bc <= L;
             const uint8_t* gnext = gin + (size_t)(have_next ? i + 1 : i) * BLKB;
-#pragma unroll
+            // the zigzagged words of a sector are fetched one sector ahead (registers), so the emit never waits on LDS
+            uint4 qa = *reinterpret_cast<const uint4*>(stg);
+            uint4 qb = *reinterpret_cast<const uint4*>(stg + 512);
+#pragma unroll(NSEC > 2 ? 2 : NSEC)
             for (int s = 0; s < NSEC; s++) {
                 uint32_t nx[8];
                 load_sector(gnext + s * 32, nx);                               // lands while this sector is emitted
-                const uint4 qa = *reinterpret_cast<const uint4*>(stg + (2 * s) * 512);
-                const uint4 qb = *reinterpret_cast<const uint4*>(stg + (2 * s + 1) * 512);
+                uint4 na = qa, nb4 = qb;
+                if (s + 1 < NSEC) {
+                    na = *reinterpret_cast<const uint4*>(stg + (2 * s + 2) * 512);
+                    nb4 = *reinterpret_cast<const uint4*>(stg + (2 * s + 3) * 512);
+                }
                 const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
                 constexpr int WPR = ROWB / 4;                                  // words per row: 2, 4 or 8
 #pragma unroll
@@ -334,6 +364,7 @@ __global__ void __launch_bounds__(kEncLaneThreads, 4) spz_encode_lane_kernel(con
                     if (ROWB == 32 || (rr & 1) || rr == RPS - 1) maybe_flush();
                 }
                 store_sector(s, nx);
+                qa = na; qb = nb4;
             }
             nslots++;
             i++;
@@ -348,9 +379,12 @@ __global__ void __launch_bounds__(kEncLaneThreads, 4) spz_encode_lane_kernel(con
 
     // ---- finish: remaining ring words, the partial word, the raw tail, the metadata
     uint32_t nbytes = cur_bytes();
-    for (uint32_t w = flushed; w < wcount; w++)
-        *reinterpret_cast<uint32_t*>(gout + (size_t)w * 4) = *reinterpret_cast<const uint32_t*>(smem + ring_addr(w));
-    for (uint32_t b = 0; b < (pos >> 3); b++) gout[(size_t)wcount * 4 + b] = (uint8_t)(acc >> (8u * b));
+    {
+        const uint32_t nw = wcount - flushed;
+        for (uint32_t w = 0; w < nw; w++)
+            *reinterpret_cast<uint32_t*>(gout + (size_t)(flushed + w) * 4) = lds32(ring_at(flushed + w));
+        for (uint32_t b = 0; b < (pos >> 3); b++) gout[(size_t)(flushed + nw) * 4 + b] = (uint8_t)(lo >> (8u * b));
+    }
     const uint32_t remaining = (uint32_t)(L - tail);
     {
         const uint8_t* tsrc = gin + (size_t)tail * ESZ;
@@ -373,7 +407,11 @@ static cudaError_t launch_enc_lane(const EncParams& p, cudaStream_t stream)
 {
     const uint64_t grid64 = (p.nchunks + kEncLaneThreads - 1) / kEncLaneThreads;
     if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
-    spz_encode_lane_kernel<W, FIRE, D><<<(uint32_t)grid64, kEncLaneThreads, 0, stream>>>(p);
+    constexpr int NW = kEncLaneThreads / 32, NVEC = 8 * D * (W / 8) / 16;
+    const size_t smem = 4096 + NW * 4096 + NW * NVEC * 512;            // alignment slack + rings + staging
+    cudaError_t e = cudaFuncSetAttribute(spz_encode_lane_kernel<W, FIRE, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    spz_encode_lane_kernel<W, FIRE, D><<<(uint32_t)grid64, kEncLaneThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
