@@ -50,12 +50,13 @@ def peaks():
 
 def ncu_traffic(cfg_name, kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full capture of this config (or None)."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    try:
-        with open(p) as f:
-            return json.load(f)["configs"][cfg_name][kernel]["traffic"]
-    except Exception:
-        return None
+    for name in ("r1b_traffic.json", "r1_traffic.json"):        # latest capture first
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return json.load(f)["configs"][cfg_name][kernel]["traffic"]
+        except Exception:
+            continue
+    return None
 
 
 class ClockSampler:
@@ -263,6 +264,9 @@ def run_ours(args, cfg, cfg_name):
     ncalls = C.c_int(0)
     L.spz_profile_collect(ms3, C.byref(ncalls))
     L.spz_profile_enable(0)
+    fam = ("spz_%s_kernel", "spz_%s_hd_kernel", "spz_%s_lane_kernel")      # which kernels the timed loop launched
+    k_enc = fam[L.spz_last_kernel_family(0)] % "encode"
+    k_dec = fam[L.spz_last_kernel_family(1)] % "decode"
     t_enc_kernel = ms3[0] / 1e3 / max(1, ncalls.value)     # per launch
     t_scan = ms3[1] / 1e3 / max(1, ncalls.value)
     t_gather = ms3[2] / 1e3 / max(1, ncalls.value)
@@ -326,9 +330,9 @@ def run_ours(args, cfg, cfg_name):
                    "l2": "inputs (>= 1 GiB) exceed the 126 MB L2; no explicit flush",
                    "parallelism": f"chunk-sharded x{world}, no data-path collective"},
         "encode_gbs": world * raw * steps / t_enc_m / 1e9, "decode_gbs": world * raw * steps / t_dec_m / 1e9,
-        "roofline": roof(dom_t, "spz_decode_hd_kernel" if dom_is_dec else "spz_encode_hd_kernel"),
-        "roofline_decode": roof(t_dec_kernel, "spz_decode_hd_kernel"),
-        "roofline_encode": roof(t_enc_kernel, "spz_encode_hd_kernel"),
+        "roofline": roof(dom_t, k_dec if dom_is_dec else k_enc),
+        "roofline_decode": roof(t_dec_kernel, k_dec),
+        "roofline_encode": roof(t_enc_kernel, k_enc),
         "encode_breakdown_ms": {"codec_kernel": 1e3 * t_enc_kernel, "directory_scan": 1e3 * t_scan,
                                 "compaction": 1e3 * t_gather},
         "e2e": {"value": world * raw * e2e_steps / t_e2e / 1e9, "unit": "GB/s",

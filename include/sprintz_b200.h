@@ -143,6 +143,9 @@ int spz_profile_collect(float* ms3, int* ncalls);
  * allows (testing: exercises them on small inputs). All families are CUDA and produce identical bytes.
  * Returns the previous setting. */
 int spz_set_kernel_path(int path);
+/* Kernel family used by the most recent encode (decode = 0) or decode (decode = 1) launch of this process:
+ * 0 = generic team kernel, 1 = fast team kernel (spz_*_hd_kernel), 2 = lane kernel (spz_*_lane_kernel). */
+int spz_last_kernel_family(int decode);
 
 /* releases the cached device workspaces of the host-buffer entry points */
 void spz_release_workspaces(void);

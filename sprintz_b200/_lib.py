@@ -63,6 +63,7 @@ SYMBOLS = {
     "spz_profile_enable": (_i, [_i]),
     "spz_profile_collect": (_i, [C.POINTER(C.c_float), C.POINTER(_i)]),
     "spz_set_kernel_path": (_i, [_i]),
+    "spz_last_kernel_family": (_i, [_i]),
     "spz_release_workspaces": (None, []),
 }
 

@@ -28,6 +28,8 @@ cudaError_t launch_gather(const uint8_t* slots, uint64_t slot_stride, uint64_t n
 uint64_t scan_tiles(uint64_t nchunks);
 void set_force_path(int v);
 int get_force_path();
+int last_encode_family();
+int last_decode_family();
 }  // namespace spz
 
 using namespace spz;
@@ -99,6 +101,8 @@ extern "C" int spz_set_kernel_path(int path)
     if (path >= 0 && path <= 2) set_force_path(path);
     return old;
 }
+
+extern "C" int spz_last_kernel_family(int decode) { return decode ? last_decode_family() : last_encode_family(); }
 
 extern "C" const char* spz_version(void) { return "sprintz_b200 0.1 (sm_100a)"; }
 extern "C" const char* spz_last_error(void) { return g_err; }

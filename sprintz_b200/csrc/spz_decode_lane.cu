@@ -112,7 +112,18 @@ __global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_k
     };
     // Every consumer takes at most 32 bytes between two calls, so one fill restores "48 bytes ahead"
     // (a unit of <= 32 bytes plus the 12-byte reach of a 3-word read from its last byte).
-    auto ensure = [&](uint32_t bit) { if (filled - (bit >> 3) < 48u) fill(); };
+    // Fills are made warp-coherent: when any lane of the warp has to fill, every lane with room for 32 more
+    // bytes fills too.  Lanes consume at similar rates, so this keeps their phases aligned: the warp executes the
+    // fill sequence once per ~32 consumed bytes instead of once per lane that runs dry, and -- because the
+    // scoreboard on the prefetch registers is per warp -- the one-fill-ahead load really has a whole fill
+    // interval to land (with per-lane fills every STS waited on a load issued moments earlier for another lane).
+    auto ensure = [&](uint32_t bit) {
+        const uint32_t avail = filled - (bit >> 3);
+        const bool need = avail < 48u;
+        if (__any_sync(__activemask(), need)) {
+            if (need || avail <= 88u) fill();
+        }
+    };
 
     load_next();
     fill(); fill(); fill();
@@ -262,7 +273,8 @@ __global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_k
                     if (W == 16 && j == 4) segment(rowbit + offB, lo, hi);
                     // zigzag^-1 (bitpack.h:303) in doubled form: m = u ^ -(u & 1) == 2 * err (bit 0 is always clear)
                     const uint32_t u = lo & fm[j];
-                    const uint32_t sgn = 0u - (u & 1u);
+                    uint32_t sgn;                                        // 0 - (u & 1) as one SGXT
+                    asm("bfe.s32 %0, %1, 0, 1;" : "=r"(sgn) : "r"(u));
                     const uint32_t m = u ^ sgn;
                     if (j != 7 && !(W == 16 && j == 3)) { lo = __funnelshift_r(lo, hi, nb[j]); hi >>= nb[j]; }
                     if (FIRE) {

@@ -368,16 +368,20 @@ static void enc_layout(int elem_sz, bool low, EncParams& p)
 cudaError_t launch_encode_hd(int elem_sz, int predictor, EncParams p, cudaStream_t stream);
 cudaError_t launch_encode_lane(int elem_sz, int predictor, EncParams p, cudaStream_t stream);
 
+static int g_last_encode_family = 0;     // 0 generic team kernel, 1 fast team kernel (hd), 2 lane kernel
+int last_encode_family() { return g_last_encode_family; }
+
 cudaError_t launch_encode(int elem_sz, int predictor, EncParams p, cudaStream_t stream)
 {
     {   // throughput path: frames with many chunks of 8 / 16 dims (spz_encode_lane.cu)
         const cudaError_t e = launch_encode_lane(elem_sz, predictor, p, stream);
-        if (e != cudaErrorNotSupported) return e;
+        if (e != cudaErrorNotSupported) { g_last_encode_family = 2; return e; }
     }
     {   // fast path for high-dim shapes; the generic kernel below covers everything else
         const cudaError_t e = launch_encode_hd(elem_sz, predictor, p, stream);
-        if (e != cudaErrorNotSupported) return e;
+        if (e != cudaErrorNotSupported) { g_last_encode_family = 1; return e; }
     }
+    g_last_encode_family = 0;
     const bool low = elem_sz == 1 ? (p.ndims <= 4) : (p.ndims <= 2);
     p.team = p.ndims >= 32 ? 32 : pow2_ceil(p.ndims);
     p.dpl = (p.ndims + p.team - 1) / p.team;
