@@ -271,26 +271,33 @@ __global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_k
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     if (W == 16 && j == 4) segment(rowbit + offB, lo, hi);
-                    // zigzag^-1 (bitpack.h:303) in doubled form: m = u ^ -(u & 1) == 2 * err (bit 0 is always clear)
+                    // zigzag^-1 (bitpack.h:303) in doubled form: m = u ^ -(u & 1) == 2 * err (bit 0 is always clear).
+                    // The kernel is bound by the half-rate INT32 ALU pipe (ncu: ALU 71 %, FMA 20 %), so the sign
+                    // handling is phrased as multiply-adds: with b = u & 1 and t = 1 - 2b, m = u * t - b, and the
+                    // same t is icopysign's factor in the gradient.
                     const uint32_t u = lo & fm[j];
-                    uint32_t sgn;                                        // 0 - (u & 1) as one SGXT
-                    asm("bfe.s32 %0, %1, 0, 1;" : "=r"(sgn) : "r"(u));
-                    const uint32_t m = u ^ sgn;
+                    const uint32_t b = lo & fm[j] & 1u;
                     if (j != 7 && !(W == 16 && j == 3)) { lo = __funnelshift_r(lo, hi, nb[j]); hi >>= nb[j]; }
+                    int32_t t, mi;
+                    asm("mad.lo.s32 %0, %1, -2, 1;" : "=r"(t) : "r"(b));
+                    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(mi) : "r"(u), "r"(t), "r"(0u - b));
+                    const uint32_t m = (uint32_t)mi;
                     if (FIRE) {
                         if (r & 1u) {
                             // icopysign(err, prev_delta) (util.h:63-68), accumulated left-aligned so the int_t wrap
                             // of grad_sum is the natural 32-bit wrap
-                            if (m != 0u) gsh[j] += (int32_t)(((uint32_t)pdh[j] ^ sgn) - sgn);
+                            if (m != 0u) gsh[j] += pdh[j] * t;
                         }
                         // prediction = (prev_delta * coef) >> W (sprintz_xff_rle.cpp:225): prev_delta is left-aligned
                         // by 32-W bits, so this is the high word of the product; delta = prediction + err, and
                         // (delta << UP) = (prediction << UP) + (m << (UP-1)) wraps to W bits by itself
                         const int32_t th = __mulhi(pdh[j], coef[j]);
-                        pdh[j] = (int32_t)(((uint32_t)th << UP) + (m << (UP - 1)));
+                        int32_t ths;
+                        asm("mad.lo.s32 %0, %1, %2, 0;" : "=r"(ths) : "r"(th), "n"(1 << UP));
+                        asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(pdh[j]) : "r"(mi), "n"(1 << (UP - 1)), "r"(ths));
                         pvh[j] += (uint32_t)pdh[j];
                     } else {
-                        pvh[j] += m << (UP - 1);
+                        asm("mad.lo.s32 %0, %1, %2, %0;" : "+r"(pvh[j]) : "r"(mi), "n"(1 << (UP - 1)));
                     }
                 }
                 store_row(r);

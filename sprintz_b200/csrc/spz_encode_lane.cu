@@ -97,8 +97,9 @@ __global__ void __launch_bounds__(kEncLaneThreads, 4) spz_encode_lane_kernel(con
     // address register in place right after the STS that reads it stalls on the write-after-read scoreboard.
     auto ring_at = [&](uint32_t w) -> uint32_t { return ((w << 7) & 0xF80u) | ringabs; };
     auto put = [&](uint32_t v, uint32_t nb) {              // v < 2^nb, nb <= 32
-        const uint32_t t = v << pos;
-        const uint32_t carry = __funnelshift_l(v, 0u, pos);                   // v >> (32 - pos), 0 when pos == 0
+        // (carry : t) = v << pos as ONE widening multiply on the FMA pipe (the two funnel shifts were ALU-pipe work)
+        uint32_t t, carry;
+        asm("{ .reg .b64 q; mul.wide.u32 q, %2, %3; mov.b64 {%0, %1}, q; }" : "=r"(t), "=r"(carry) : "r"(v), "r"(1u << pos));
         // the stored word gets its own register: the STS reads its operands late, and overwriting them right
         // away (the compiler would fold `lo = full ? carry : w` into a predicated move onto w) stalls every put
         uint32_t w;
@@ -194,7 +195,9 @@ __global__ void __launch_bounds__(kEncLaneThreads, 4) spz_encode_lane_kernel(con
 #pragma unroll
             for (int k = 0; k < (W == 16 ? 4 : 2); k++) mk[k] = 0;
 
-            // one element: left-aligned value in, zigzagged error out (low W bits valid)
+            // one element: left-aligned value in, zigzagged error out LEFT-ALIGNED (top W bits valid, the rest is
+            // sign fill that the PRMT packing drops).  The kernel is bound by the half-rate INT32 ALU pipe (ncu:
+            // ALU 77 %, FMA 24 %), so shifts-by-constant and the conditional negate are phrased as multiply-adds.
             auto elem = [&](uint32_t vh, int e, int r) -> uint32_t {
                 const int d = oc * 8 + e;
                 const int32_t dh = (int32_t)(vh - xprev[d]);                   // delta, wraps to W bits
@@ -204,13 +207,19 @@ __global__ void __launch_bounds__(kEncLaneThreads, 4) spz_encode_lane_kernel(con
                     // prediction = (prev_delta * coef) >> W (sprintz_xff_rle.cpp:225): prev_delta is left-aligned
                     const int32_t pred = __mulhi(dprev[d], coef[e]);
                     asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(eh) : "r"(pred), "n"(-(1 << UP)), "r"(dh));   // dh - (pred << UP): err, wraps to W bits
+                }
+                const int32_t sg = eh >> 31;
+                if (FIRE) {
                     if (r & 1) {                                               // icopysign(err, prev_delta), odd rows
-                        const int32_t sg = eh >> 31;
-                        if (eh != 0) gsh[e] += (dprev[d] ^ sg) - sg;
+                        int32_t cs;
+                        asm("mad.lo.s32 %0, %1, 2, 1;" : "=r"(cs) : "r"(sg));  // +1 / -1
+                        if (eh != 0) gsh[e] += dprev[d] * cs;
                     }
                     dprev[d] = dh;
                 }
-                return ((uint32_t)eh >> (UP - 1)) ^ (uint32_t)(eh >> 31);      // zigzag (bitpack.h:302)
+                int32_t e2;
+                asm("mad.lo.s32 %0, %1, 2, 0;" : "=r"(e2) : "r"(eh));          // eh << 1 on the FMA pipe
+                return (uint32_t)e2 ^ (uint32_t)sg;                            // zigzag (bitpack.h:302), left-aligned
             };
 
             if (W == 16) {
@@ -230,7 +239,7 @@ __global__ void __launch_bounds__(kEncLaneThreads, 4) spz_encode_lane_kernel(con
                     for (int k = 0; k < 4; k++) {
                         const uint32_t z0 = elem(w[k] << 16, 2 * k, r);
                         const uint32_t z1 = elem(w[k] & 0xffff0000u, 2 * k + 1, r);
-                        z[k] = __byte_perm(z0, z1, 0x5410);
+                        z[k] = __byte_perm(z0, z1, 0x7632);
                         mk[k] |= z[k];
                     }
                     *reinterpret_cast<uint4*>(vp) = make_uint4(z[0], z[1], z[2], z[3]);
@@ -252,7 +261,7 @@ __global__ void __launch_bounds__(kEncLaneThreads, 4) spz_encode_lane_kernel(con
                             const uint32_t z1 = elem(__byte_perm(x, 0, 0x1444), 4 * k + 1, r);
                             const uint32_t z2 = elem(__byte_perm(x, 0, 0x2444), 4 * k + 2, r);
                             const uint32_t z3 = elem(x & 0xff000000u, 4 * k + 3, r);
-                            const uint32_t a = __byte_perm(z0, z1, 0x0040), b = __byte_perm(z2, z3, 0x0040);
+                            const uint32_t a = __byte_perm(z0, z1, 0x0073), b = __byte_perm(z2, z3, 0x0073);
                             z[2 * h + k] = __byte_perm(a, b, 0x5410);
                             mk[k] |= z[2 * h + k];
                         }
