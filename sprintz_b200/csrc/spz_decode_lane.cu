@@ -266,18 +266,21 @@ __global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_k
             uint32_t rowbit = pos;
 #pragma unroll
             for (uint32_t r = 0; r < 8; r++) {
-                uint32_t lo, hi;
-                segment(rowbit + offA, lo, hi);
+                // int16: two 64-bit segments of 4 fields; int8: two 32-bit segments of 4 fields (one shift per field)
+                uint32_t lo, hi = 0;
+                if (W == 16) segment(rowbit + offA, lo, hi); else lo = window(rowbit + offA);
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    if (W == 16 && j == 4) segment(rowbit + offB, lo, hi);
+                    if (j == 4) { if (W == 16) segment(rowbit + offB, lo, hi); else lo = window(rowbit + offB); }
                     // zigzag^-1 (bitpack.h:303) in doubled form: m = u ^ -(u & 1) == 2 * err (bit 0 is always clear).
                     // The kernel is bound by the half-rate INT32 ALU pipe (ncu: ALU 71 %, FMA 20 %), so the sign
                     // handling is phrased as multiply-adds: with b = u & 1 and t = 1 - 2b, m = u * t - b, and the
                     // same t is icopysign's factor in the gradient.
                     const uint32_t u = lo & fm[j];
                     const uint32_t b = lo & fm[j] & 1u;
-                    if (j != 7 && !(W == 16 && j == 3)) { lo = __funnelshift_r(lo, hi, nb[j]); hi >>= nb[j]; }
+                    if (j != 7 && j != 3) {
+                        if (W == 16) { lo = __funnelshift_r(lo, hi, nb[j]); hi >>= nb[j]; } else { lo >>= nb[j]; }
+                    }
                     int32_t t, mi;
                     asm("mad.lo.s32 %0, %1, -2, 1;" : "=r"(t) : "r"(b));
                     asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(mi) : "r"(u), "r"(t), "r"(0u - b));
@@ -302,7 +305,9 @@ __global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_k
                 }
                 store_row(r);
                 rowbit += row_bits;
-                ensure(rowbit);
+                // a row is at most D*W/8 bytes: refill checks are only needed every 32 bytes of worst-case consumption
+                constexpr uint32_t CHK = (D * W / 8 >= 32) ? 1u : (32u / (D * W / 8));
+                if ((r + 1u) % CHK == 0u) ensure(rowbit);
             }
             pos = rowbit;
             if (FIRE) {
