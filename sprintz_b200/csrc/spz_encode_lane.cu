@@ -110,9 +110,18 @@ __global__ void __launch_bounds__(kEncLaneThreads, 4) spz_encode_lane_kernel(con
         lo = full ? carry : (lo | t);
         pos &= 31u;
     };
-    auto row_end = [&]() {                                 // zero-pad to the next byte boundary
-        pos = (pos + 7u) & ~7u;
-        if (pos >= 32u) { sts32(ring_at(wcount), lo); wcount++; lo = 0u; }
+    // last cluster of a row: append, then zero-pad to the next byte boundary (rows are byte padded).  Up to 7 pad
+    // bits on top of a 32-bit cluster can complete a second word; that (rare) case is the extra branch.
+    auto put_row_end = [&](uint32_t v, uint32_t nb) {
+        uint32_t t, carry;
+        asm("{ .reg .b64 q; mul.wide.u32 q, %2, %3; mov.b64 {%0, %1}, q; }" : "=r"(t), "=r"(carry) : "r"(v), "r"(1u << pos));
+        uint32_t w;
+        asm volatile("or.b32 %0, %1, %2;" : "=r"(w) : "r"(lo), "r"(t));
+        pos = (pos + nb + 7u) & ~7u;
+        const bool full = pos >= 32u;
+        if (full) { sts32(ring_at(wcount), w); wcount++; }
+        lo = full ? carry : (lo | t);
+        if (pos >= 64u) { sts32(ring_at(wcount), lo); wcount++; lo = 0u; }
         pos &= 31u;
     };
     auto maybe_flush = [&]() {                             // at most 32 new bytes between two calls
@@ -367,10 +376,10 @@ __global__ void __launch_bounds__(kEncLaneThreads, 4) spz_encode_lane_kernel(con
                             cl = pw + __byte_perm(pw, 0, 0x4441) * mulp[k * 3 + 0] + __byte_perm(pw, 0, 0x4442) * mulp[k * 3 + 1]
                                     + (pw >> 24) * mulp[k * 3 + 2];
                         }
-                        put(cl, cbits[k]);
+                        if (k == NCL - 1) put_row_end(cl, cbits[k]); else put(cl, cbits[k]);
                     }
-                    row_end();                                                 // rows are byte padded
-                    if (ROWB == 32 || (rr & 1) || rr == RPS - 1) maybe_flush();
+                    // flush checks every 32 bytes of worst-case output (a row is at most ROWB bytes)
+                    if (ROWB == 32 || (ROWB == 16 && (rr & 1)) || rr == RPS - 1) maybe_flush();
                 }
                 store_sector(s, nx);
                 qa = na; qb = nb4;
