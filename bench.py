@@ -277,6 +277,30 @@ def run_ours(args, cfg, cfg_name):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_total, t_enc_m, t_dec_m = (float(v) for v in tt.tolist())
 
+    # ---- optional exchange step: gather every rank's compressed payload + directory on rank 0 over
+    # NCCL / NVLink.  Not part of `value` (the codec path itself needs no collective); reported beside it.
+    gather_info = None
+    if world > 1:
+        from sprintz_b200.dist import gather_frames, shard_plan
+        plan = shard_plan(world * n, D, chunk_rows, world)
+        po = int(hdr.payload_off)
+        pay = fr.buf[po: po + payload]
+        nchunks = int(hdr.nchunks)
+        sizes = fr.buf[64 + 8 * (nchunks + 1): 64 + 8 * (nchunks + 1) + 4 * nchunks].view(torch.int32).to(torch.int64)
+        for it in range(5):                      # 2 warm-up + 3 timed
+            if it == 2:
+                barrier(); t_g0 = time.perf_counter()
+            got = gather_frames(pay, sizes, plan, dst=0)
+            torch.cuda.synchronize()
+        barrier()
+        t_g = torch.tensor([(time.perf_counter() - t_g0) / 3], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_g, op=dist.ReduceOp.MAX)
+        moved = (world - 1) * payload            # bytes that crossed NVLink into rank 0 (payloads are ~equal)
+        gather_info = {"ms": 1e3 * float(t_g.item()), "payload_bytes_total": world * payload,
+                       "gbs_into_rank0": moved / float(t_g.item()) / 1e9, "backend": "nccl send/recv",
+                       "note": "all-gather of chunk sizes -> exclusive scan -> variable-size send/recv to rank 0"}
+        del got, pay
+
     # ---- end to end through the host-buffer C ABI (pinned host memory), every step H2D + D2H
     e2e_steps = max(1, min(steps, args.e2e_steps))
     xh = torch.empty(n, dtype=x.dtype, pin_memory=True)
@@ -333,11 +357,17 @@ def run_ours(args, cfg, cfg_name):
         "roofline": roof(dom_t, k_dec if dom_is_dec else k_enc),
         "roofline_decode": roof(t_dec_kernel, k_dec),
         "roofline_encode": roof(t_enc_kernel, k_enc),
+        # the stricter read-only form the north star names: HBM bytes READ per launch / kernel time / peak
+        "hbm_read_roofline": {"decode_frac": raw / ratio / t_dec_kernel / 1e9 / peak,
+                              "encode_frac": raw / t_enc_kernel / 1e9 / peak,
+                              "decode_raw_gbs_kernel": raw / t_dec_kernel / 1e9,
+                              "encode_raw_gbs_kernel": raw / t_enc_kernel / 1e9},
         "encode_breakdown_ms": {"codec_kernel": 1e3 * t_enc_kernel, "directory_scan": 1e3 * t_scan,
                                 "compaction": 1e3 * t_gather},
         "e2e": {"value": world * raw * e2e_steps / t_e2e / 1e9, "unit": "GB/s",
                 "h2d_bytes_per_step": raw + int(fb), "d2h_bytes_per_step": int(fb) + raw, "steps": e2e_steps,
                 "api": "spz_frame_compress_host + spz_frame_decompress_host (pinned host buffers)"},
+        "gather": gather_info,
         "gpu_launches": steps * 4,     # encode, directory scan, compaction, decode per step
         "clocks": clocks,
     }
