@@ -37,6 +37,9 @@ CONFIGS = {
                nbytes=4 << 30, chunk_rows=1024),
     "c4": dict(desc="int8, 80-dim, delta+bitpack, 4 GB per GPU (32 GB over 8)", esz=1, D=80, pred=0,
                nbytes=4 << 30, chunk_rows=1024),
+    # the non-RLE sibling codec compress_rowmajor_delta_8b (frame codec id 2), generic kernels
+    "f1": dict(desc="int8, 8-dim rowmajor, delta+bitpack without RLE (compress_rowmajor_delta_8b), 1 GB synthetic AR(1)",
+               esz=1, D=8, pred=2, nbytes=1 << 30, chunk_rows=1024),
 }
 
 
@@ -175,7 +178,7 @@ def run_reference(args, cfg, cfg_name):
         "steps": steps, "warmup": warm, "ms_per_step": 1e3 * total / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8" if cfg["esz"] == 1 else "u16", "data": "synthetic",
         "config": {"workload": cfg_name + ": " + cfg["desc"], "elem_bits": 8 * cfg["esz"], "ndims": cfg["D"],
-                   "predictor": "xff" if cfg["pred"] else "delta", "bytes": raw, "chunk_rows": chunk_rows,
+                   "predictor": ("delta", "xff", "rowmajor_delta", "rowmajor_plain")[cfg["pred"]], "bytes": raw, "chunk_rows": chunk_rows,
                    "threads": ncores},
         "cpu_baseline": {"value": val, "unit": "GB/s", "cores": ncores, "kind": "reference",
                          "sample": f"whole {raw >> 20} MiB workload per step, {res['nchunks']} chunk slices, "
@@ -349,7 +352,7 @@ def run_ours(args, cfg, cfg_name):
         "warmup": warm, "ms_per_step": 1e3 * t_total / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8" if esz == 1 else "u16", "data": "synthetic",
         "config": {"workload": cfg_name + ": " + cfg["desc"], "elem_bits": 8 * esz, "ndims": D,
-                   "predictor": "xff" if pred else "delta", "bytes_per_gpu": raw, "chunk_rows": chunk_rows,
+                   "predictor": ("delta", "xff", "rowmajor_delta", "rowmajor_plain")[pred], "bytes_per_gpu": raw, "chunk_rows": chunk_rows,
                    "nchunks_per_gpu": int(hdr.nchunks), "ratio": ratio,
                    "l2": "inputs (>= 1 GiB) exceed the 126 MB L2; no explicit flush",
                    "parallelism": f"chunk-sharded x{world}, no data-path collective"},

@@ -26,6 +26,8 @@ extern "C" {
 
 #define SPZ_DELTA 0   /* sprintz_*_delta_*  */
 #define SPZ_XFF   1   /* sprintz_*_xff_*  (FIRE) */
+#define SPZ_RM_DELTA 2 /* frames only: compress_rowmajor_delta_* (non-RLE, sprintz_delta.h:36-44) */
+#define SPZ_RM_PLAIN 3 /* frames only: compress_rowmajor_*       (non-RLE, sprintz_delta.h:27-34) */
 
 #define SPZ_OK            0
 #define SPZ_E_ARG        -1   /* the reference's own error return (ndims == 0, sprintz.cpp:71) */
@@ -97,6 +99,22 @@ uint64_t spz_max_compressed_bytes(int elem_sz, uint64_t len, uint16_t ndims);
 /* walks a host stream's group headers: exact stream length in bytes and decoded element count */
 int spz_measure_stream(int elem_sz, const void* src, int has_meta, uint16_t ndims, uint32_t ngroups,
                        uint16_t remaining_len, uint64_t* stream_bytes, uint64_t* decoded_elems);
+
+/* Non-RLE sibling codecs of the same file family (sprintz_delta.h:27-44): delta + bit packing
+ * and plain bit packing with the 6-byte metadata [u32 len][u16 ndims] (format.h:65-85), fixed ngroups = len/(16*ndims),
+ * no run slots.  Same arguments / returns / bytes as compress_rowmajor_delta_{8b,16b}, compress_rowmajor_{8b,16b}
+ * and their decoders.  kind: 1 = delta, 2 = plain. */
+int64_t spz_compress_rowmajor_delta_8b (const uint8_t*  src, uint32_t len, int8_t*  dest, uint16_t ndims, int write_size);
+int64_t spz_decompress_rowmajor_delta_8b(const int8_t*  src, uint8_t*  dest);
+int64_t spz_compress_rowmajor_delta_16b(const uint16_t* src, uint32_t len, int16_t* dest, uint16_t ndims, int write_size);
+int64_t spz_decompress_rowmajor_delta_16b(const int16_t* src, uint16_t* dest);
+int64_t spz_compress_rowmajor_8b (const uint8_t*  src, uint32_t len, int8_t*  dest, uint16_t ndims, int write_size);
+int64_t spz_decompress_rowmajor_8b(const int8_t*  src, uint8_t*  dest);
+int64_t spz_compress_rowmajor_16b(const uint16_t* src, uint32_t len, int16_t* dest, uint16_t ndims, int write_size);
+int64_t spz_decompress_rowmajor_16b(const int16_t* src, uint16_t* dest);
+int64_t spz_compress_rowmajor_host(int kind, int elem_sz, const void* src, uint32_t len, void* dest, uint16_t ndims,
+                                   int write_size, uint64_t* true_nbytes);
+int64_t spz_decompress_rowmajor_host(int kind, int elem_sz, const void* src, void* dest);
 
 /* ---------------------------------------------------------------- 2. single stream, device buffers
  * d_dest must hold spz_max_compressed_bytes(); d_meta (1 record) receives sizes. Asynchronous on `stream`. */

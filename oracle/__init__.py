@@ -22,6 +22,7 @@ ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libsprintz_ref.so")
 
 DELTA, XFF = 0, 1
+RM_DELTA, RM_PLAIN = 1, 2     # non-RLE sibling codecs: compress_rowmajor_delta_*, compress_rowmajor_*
 SLACK = 4096  # the reference reads/writes past buffer ends; give every buffer slack
 
 
@@ -69,10 +70,33 @@ class Oracle(_Codec):
         L.oracle_decompress_raw.restype = C.c_int64
         L.oracle_decompress_raw.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                             C.c_uint16, C.c_uint32, C.c_uint16]
+        L.oracle_compress_rowmajor.restype = C.c_int64
+        L.oracle_compress_rowmajor.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p,
+                                               C.c_uint16, C.c_int, C.POINTER(C.c_uint64)]
+        L.oracle_decompress_rowmajor.restype = C.c_int64
+        L.oracle_decompress_rowmajor.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         self.L = L
+
+    def compress_rowmajor(self, kind, x, ndims, write_size=True):
+        esz = x.dtype.itemsize
+        src = _as_u8(x)
+        buf = np.zeros(self.max_bytes(esz, x.size, ndims) + SLACK, np.uint8)
+        nb = C.c_uint64(0)
+        ret = self.L.oracle_compress_rowmajor(kind, esz, src.ctypes.data, x.size, buf.ctypes.data, ndims,
+                                              int(write_size), C.byref(nb))
+        return buf[: nb.value].copy(), int(ret)
+
+    def decompress_rowmajor(self, kind, esz, stream, n_out):
+        src = np.concatenate([_as_u8(stream), np.zeros(SLACK, np.uint8)])
+        out = np.full((n_out + 64) * esz + SLACK, 0xAA, np.uint8)
+        ret = self.L.oracle_decompress_rowmajor(kind, esz, src.ctypes.data, out.ctypes.data)
+        dt = np.uint8 if esz == 1 else np.uint16
+        return out[: n_out * esz].view(dt).copy(), int(ret)
 
     def compress(self, predictor, x, ndims, write_size=True):
         """-> (stream bytes [exact true length], returned element count)"""
+        if predictor >= 2:                       # frame codec ids 2 / 3: the non-RLE sibling codecs
+            return self.compress_rowmajor(predictor - 1, x, ndims, write_size)
         esz = x.dtype.itemsize
         src = _as_u8(x)
         n = x.size
@@ -117,7 +141,28 @@ class Ref(_Codec):
         L.ref_decompress_chunks.restype = C.c_double
         L.ref_decompress_chunks.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64,
                                             C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]
+        if hasattr(L, "ref_compress_rowmajor"):
+            L.ref_compress_rowmajor.restype = C.c_int64
+            L.ref_compress_rowmajor.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint16, C.c_int]
+            L.ref_decompress_rowmajor.restype = C.c_int64
+            L.ref_decompress_rowmajor.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         self.L = L
+
+    def compress_rowmajor(self, kind, x, ndims, write_size=True):
+        esz = x.dtype.itemsize
+        src = np.concatenate([_as_u8(x), np.zeros(SLACK, np.uint8)])
+        buf = np.zeros(self.max_bytes(esz, x.size, ndims) + SLACK, np.uint8)
+        ret = int(self.L.ref_compress_rowmajor(kind, esz, src.ctypes.data, x.size, buf.ctypes.data, ndims, int(write_size)))
+        if ret < 0:
+            return buf[:0].copy(), ret
+        return buf[: ret * esz + (esz - 1)].copy(), ret
+
+    def decompress_rowmajor(self, kind, esz, stream, n_out):
+        src = np.concatenate([_as_u8(stream), np.zeros(SLACK, np.uint8)])
+        out = np.full((n_out + 64) * esz + SLACK, 0xAA, np.uint8)
+        ret = self.L.ref_decompress_rowmajor(kind, esz, src.ctypes.data, out.ctypes.data)
+        dt = np.uint8 if esz == 1 else np.uint16
+        return out[: n_out * esz].view(dt).copy(), int(ret)
 
     @staticmethod
     def available() -> bool:

@@ -20,14 +20,20 @@
 #include <chrono>
 
 #include "sprintz.h"   // from -I$(REF)/cpp/Compress
+#include "sprintz_delta.h"   // the non-RLE sibling codecs
 
 extern "C" {
 
 // codec ids shared with include/sprintz_b200.h: bit0 = predictor (0 delta,
 // 1 xff/FIRE), elem size passed separately.
+int64_t ref_compress_rowmajor(int kind, int elem_sz, const void* src, uint32_t len, void* dest, uint16_t ndims,
+                              int write_size);
+int64_t ref_decompress_rowmajor(int kind, int elem_sz, const void* src, void* dest);
+
 int64_t ref_compress(int predictor, int elem_sz, const void* src, uint32_t len,
                      void* dest, uint16_t ndims, int write_size)
 {
+    if (predictor >= 2) return ref_compress_rowmajor(predictor - 1, elem_sz, src, len, dest, ndims, write_size);
     if (elem_sz == 1) {
         return predictor
             ? sprintz_compress_xff_8b((const uint8_t*)src, len, (int8_t*)dest, ndims, write_size != 0)
@@ -40,6 +46,7 @@ int64_t ref_compress(int predictor, int elem_sz, const void* src, uint32_t len,
 
 int64_t ref_decompress(int predictor, int elem_sz, const void* src, void* dest)
 {
+    if (predictor >= 2) return ref_decompress_rowmajor(predictor - 1, elem_sz, src, dest);
     if (elem_sz == 1) {
         return predictor
             ? sprintz_decompress_xff_8b((const int8_t*)src, (uint8_t*)dest)
@@ -48,6 +55,30 @@ int64_t ref_decompress(int predictor, int elem_sz, const void* src, void* dest)
     return predictor
         ? sprintz_decompress_xff_16b((const int16_t*)src, (uint16_t*)dest)
         : sprintz_decompress_delta_16b((const int16_t*)src, (uint16_t*)dest);
+}
+
+// non-RLE sibling codecs: kind 1 = compress_rowmajor_delta_*, kind 2 = compress_rowmajor_* (sprintz_delta.h:27-44)
+int64_t ref_compress_rowmajor(int kind, int elem_sz, const void* src, uint32_t len, void* dest, uint16_t ndims,
+                              int write_size)
+{
+    if (elem_sz == 1) {
+        return kind == 1
+            ? compress_rowmajor_delta_8b((const uint8_t*)src, len, (int8_t*)dest, ndims, write_size != 0)
+            : compress_rowmajor_8b((const uint8_t*)src, len, (int8_t*)dest, ndims, write_size != 0);
+    }
+    return kind == 1
+        ? compress_rowmajor_delta_16b((const uint16_t*)src, len, (int16_t*)dest, ndims, write_size != 0)
+        : compress_rowmajor_16b((const uint16_t*)src, len, (int16_t*)dest, ndims, write_size != 0);
+}
+
+int64_t ref_decompress_rowmajor(int kind, int elem_sz, const void* src, void* dest)
+{
+    if (elem_sz == 1) {
+        return kind == 1 ? decompress_rowmajor_delta_8b((const int8_t*)src, (uint8_t*)dest)
+                         : decompress_rowmajor_8b((const int8_t*)src, (uint8_t*)dest);
+    }
+    return kind == 1 ? decompress_rowmajor_delta_16b((const int16_t*)src, (uint16_t*)dest)
+                     : decompress_rowmajor_16b((const int16_t*)src, (uint16_t*)dest);
 }
 
 // Compress `nchunks` consecutive slices of `src` (chunk c covers elements

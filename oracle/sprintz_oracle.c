@@ -406,6 +406,146 @@ int64_t oracle_decompress(int predictor, int elem_sz, const void* src_, void* de
     return oracle_decompress_raw(predictor, elem_sz, p + 8, dest, ndims, ngroups, rem);
 }
 
+
+/* ------------------------------------------------------------------ non-RLE sibling codecs
+ *
+ * compress_rowmajor_delta_{8b,16b} / compress_rowmajor_{8b,16b} and their decoders
+ * (sprintz_delta.h:27-44; sprintz_delta.cpp:64-392 plain, :776-1017 delta, decoders :394-770, :1021-1391).
+ * Same block / group / header / row-major payload layout as the RLE high-dim codecs for EVERY ndims (there is
+ * no low-dim dispatch here), but:
+ *   - 6-byte metadata [u32 len][u16 ndims] (format.h:65-85, kMetaDataLenBytesSimple)
+ *   - ngroups = len / (16*ndims) is implied; every block is a data slot, a block whose widths are all zero
+ *     simply has zero payload bytes; no run slots
+ *   - kind 1: zigzag(delta) with the delta carried across blocks; kind 2: the raw values, no zigzag
+ *   - the width rule is the high-dim one (7->8, 15->16) for all ndims
+ */
+#define KIND_DELTA 1
+#define KIND_PLAIN 2
+
+static uint32_t rowmajor_block(const cfg_t* c, int kind, uint32_t* prev_val, const uint8_t* src, uint64_t first_elem,
+                               uint32_t* zz, uint8_t* nbits)
+{
+    const int D = c->D, w = c->w;
+    const uint32_t wmask = (1u << w) - 1u;
+    uint32_t total = 0;
+    for (int d = 0; d < D; d++) {
+        uint32_t mask = 0, pv = prev_val[d];
+        for (int r = 0; r < BLOCK_SZ; r++) {
+            uint32_t v = load_elem(src, first_elem + (uint64_t)r * D + d, c->esz);
+            uint32_t z = v;
+            if (kind == KIND_DELTA) {
+                int32_t delta = (int32_t)sx((int64_t)v - (int64_t)pv, w);
+                z = (((uint32_t)delta << 1) ^ (uint32_t)(delta >> (w - 1))) & wmask;
+            }
+            zz[r * D + d] = z;
+            mask |= z;
+            pv = v;
+        }
+        prev_val[d] = pv;
+        nbits[d] = (uint8_t)nbits_rule(c, mask);
+        total += nbits[d];
+    }
+    return total;
+}
+
+int64_t oracle_compress_rowmajor(int kind, int elem_sz, const void* src_, uint32_t len, void* dest_,
+                                 uint16_t ndims, int write_size, uint64_t* true_nbytes)
+{
+    const uint8_t* src = (const uint8_t*)src_;
+    uint8_t* const orig = (uint8_t*)dest_;
+    uint8_t* dest = orig;
+    cfg_t c = make_cfg(0, elem_sz, ndims ? ndims : 1);
+    c.low = 0;                                            /* one layout / width rule for every ndims */
+    const int D = c.D;
+    if (write_size) {                                     /* format.h:65-73 */
+        dest[0] = (uint8_t)len; dest[1] = (uint8_t)(len >> 8); dest[2] = (uint8_t)(len >> 16); dest[3] = (uint8_t)(len >> 24);
+        dest[4] = (uint8_t)ndims; dest[5] = (uint8_t)(ndims >> 8);
+        dest += 6;
+    }
+    uint64_t tail = 0;
+    if (len >= MIN_DATA_SIZE && ndims != 0) {             /* sprintz_delta.cpp:817-821 */
+        const uint64_t B = (uint64_t)BLOCK_SZ * D, G = 2 * B;
+        const uint64_t ngroups = len / G;
+        uint32_t* prev = (uint32_t*)calloc(D, sizeof(uint32_t));
+        uint32_t* zz = (uint32_t*)malloc(sizeof(uint32_t) * BLOCK_SZ * D);
+        uint8_t* nbits = (uint8_t*)malloc(D);
+        for (uint64_t g = 0; g < ngroups; g++) {
+            uint8_t* hdr = dest;
+            memset(hdr, 0, c.H);
+            dest += c.H;
+            for (uint32_t b = 0; b < 2; b++) {
+                uint32_t total = rowmajor_block(&c, kind, prev, src, (g * 2 + b) * B, zz, nbits);
+                for (int d = 0; d < D; d++) {
+                    uint32_t field = nbits[d] - (nbits[d] == c.w);
+                    put_bits(hdr, (uint64_t)(b * (uint32_t)D + (uint32_t)d) * c.hb, field, c.hb);
+                }
+                uint32_t row_bytes = (total + 7) / 8;
+                memset(dest, 0, (size_t)row_bytes * BLOCK_SZ);
+                for (int r = 0; r < BLOCK_SZ; r++) {
+                    uint64_t bit = (uint64_t)r * row_bytes * 8;
+                    for (int d = 0; d < D; d++) { put_bits(dest, bit, zz[r * D + d], nbits[d]); bit += nbits[d]; }
+                }
+                dest += (size_t)row_bytes * BLOCK_SZ;
+            }
+        }
+        tail = ngroups * G;
+        free(prev); free(zz); free(nbits);
+    }
+    memcpy(dest, src + tail * c.esz, (size_t)(len - tail) * c.esz);
+    dest += (size_t)(len - tail) * c.esz;
+    if (true_nbytes) *true_nbytes = (uint64_t)(dest - orig);
+    return (int64_t)(dest - orig) / c.esz;
+}
+
+int64_t oracle_decompress_rowmajor(int kind, int elem_sz, const void* src_, void* dest_)
+{
+    const uint8_t* src = (const uint8_t*)src_;
+    uint8_t* out = (uint8_t*)dest_;
+    const uint32_t len = (uint32_t)src[0] | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16) | ((uint32_t)src[3] << 24);
+    const uint16_t ndims = (uint16_t)(src[4] | (src[5] << 8));
+    src += 6;
+    if (len < MIN_DATA_SIZE) { memcpy(out, src, (size_t)len * elem_sz); return len; }   /* sprintz_delta.cpp:1056-1060 */
+    if (ndims == 0) return 0;
+    cfg_t c = make_cfg(0, elem_sz, ndims);
+    c.low = 0;
+    const int D = c.D, w = c.w;
+    const uint32_t wmask = (1u << w) - 1u;
+    const uint64_t B = (uint64_t)BLOCK_SZ * D, G = 2 * B, ngroups = len / G;
+    uint32_t* prev = (uint32_t*)calloc(D, sizeof(uint32_t));
+    uint8_t* nbits = (uint8_t*)malloc(D);
+    uint64_t o = 0;
+    for (uint64_t g = 0; g < ngroups; g++) {
+        const uint8_t* hdr = src; src += c.H;
+        for (uint32_t b = 0; b < 2; b++) {
+            uint32_t total = 0;
+            for (int d = 0; d < D; d++) {
+                uint32_t f = get_bits(hdr, (uint64_t)(b * (uint32_t)D + (uint32_t)d) * c.hb, c.hb);
+                nbits[d] = (uint8_t)(f == (uint32_t)(w - 1) ? (uint32_t)w : f);
+                total += nbits[d];
+            }
+            uint32_t row_bytes = (total + 7) / 8;
+            for (int r = 0; r < BLOCK_SZ; r++) {
+                uint64_t bit = (uint64_t)r * row_bytes * 8;
+                for (int d = 0; d < D; d++) {
+                    uint32_t u = get_bits(src, bit, nbits[d]); bit += nbits[d];
+                    uint32_t v = u;
+                    if (kind == KIND_DELTA) {
+                        int32_t delta = (int32_t)sx((int64_t)((u >> 1) ^ (0u - (u & 1u))), w);
+                        v = (prev[d] + (uint32_t)delta) & wmask;
+                        prev[d] = v;
+                    }
+                    store_elem(out, o + (uint64_t)r * D + d, c.esz, v);
+                }
+            }
+            src += (size_t)row_bytes * BLOCK_SZ;
+            o += B;
+        }
+    }
+    memcpy(out + o * c.esz, src, (size_t)(len - o) * c.esz);
+    free(prev); free(nbits);
+    return (int64_t)len;
+}
+
 uint64_t oracle_max_compressed_bytes(int elem_sz, uint64_t len, uint16_t ndims)
 {
     uint64_t D = ndims ? ndims : 1;

@@ -34,6 +34,12 @@ int64_t oracle_decompress(int predictor, int elem_sz, const void* src, void* des
 int64_t oracle_decompress_raw(int predictor, int elem_sz, const void* src, void* dest,
                               uint16_t ndims, uint32_t ngroups, uint16_t remaining_len);
 
+/* Non-RLE sibling codecs: kind 1 = compress_rowmajor_delta_{8b,16b}, kind 2 =
+ * compress_rowmajor_{8b,16b} (sprintz_delta.h:27-44). 6-byte metadata [u32 len][u16 ndims]. */
+int64_t oracle_compress_rowmajor(int kind, int elem_sz, const void* src, uint32_t len, void* dest,
+                                 uint16_t ndims, int write_size, uint64_t* true_nbytes);
+int64_t oracle_decompress_rowmajor(int kind, int elem_sz, const void* src, void* dest);
+
 /* Worst-case stream size in bytes for `len` elements (our own bound, used by tests
  * to size buffers; the reference has no capacity arguments). */
 uint64_t oracle_max_compressed_bytes(int elem_sz, uint64_t len, uint16_t ndims);

@@ -45,6 +45,16 @@ SYMBOLS = {
     "spz_decompress_delta_16b": (_i64, [_vp, _vp]),
     "spz_compress_xff_16b": (_i64, [_vp, _u32, _vp, _u16, _i]),
     "spz_decompress_xff_16b": (_i64, [_vp, _vp]),
+    "spz_compress_rowmajor_delta_8b": (_i64, [_vp, _u32, _vp, _u16, _i]),
+    "spz_decompress_rowmajor_delta_8b": (_i64, [_vp, _vp]),
+    "spz_compress_rowmajor_delta_16b": (_i64, [_vp, _u32, _vp, _u16, _i]),
+    "spz_decompress_rowmajor_delta_16b": (_i64, [_vp, _vp]),
+    "spz_compress_rowmajor_8b": (_i64, [_vp, _u32, _vp, _u16, _i]),
+    "spz_decompress_rowmajor_8b": (_i64, [_vp, _vp]),
+    "spz_compress_rowmajor_16b": (_i64, [_vp, _u32, _vp, _u16, _i]),
+    "spz_decompress_rowmajor_16b": (_i64, [_vp, _vp]),
+    "spz_compress_rowmajor_host": (_i64, [_i, _i, _vp, _u32, _vp, _u16, _i, C.POINTER(_u64)]),
+    "spz_decompress_rowmajor_host": (_i64, [_i, _i, _vp, _vp]),
     "spz_compress_host": (_i64, [_i, _i, _vp, _u32, _vp, _u16, _i, C.POINTER(_u64)]),
     "spz_decompress_host": (_i64, [_i, _i, _vp, _vp]),
     "spz_decompress_raw_host": (_i64, [_i, _i, _vp, _vp, _u16, _u32, _u16]),

@@ -25,7 +25,10 @@ __all__ = [
     "sprintz_compress_xff_16b", "sprintz_decompress_xff_16b",
     "Frame", "frame_encode", "frame_decode", "frame_compress_host", "frame_decompress_host",
     "compress_dev", "decompress_dev", "set_kernel_path",
+    "RM_DELTA", "RM_PLAIN", "compress_rowmajor", "decompress_rowmajor",
 ]
+
+RM_DELTA, RM_PLAIN = 1, 2     # compress_rowmajor_delta_* / compress_rowmajor_* (sprintz_delta.h:27-44)
 
 _UDT = {1: np.uint8, 2: np.uint16}
 
@@ -57,6 +60,32 @@ def compress(predictor: int, x: np.ndarray, ndims: int, write_size: bool = True)
                                   C.byref(nb))
     check(ret, "spz_compress_host")
     return out[: nb.value].copy(), int(ret)
+
+
+def compress_rowmajor(kind: int, x: np.ndarray, ndims: int, write_size: bool = True):
+    """Non-RLE sibling codecs (sprintz_delta.h:27-44): kind RM_DELTA = compress_rowmajor_delta_{8b,16b},
+    RM_PLAIN = compress_rowmajor_{8b,16b}.  -> (stream, the reference's return value in elements)."""
+    x = np.ascontiguousarray(x)
+    esz = x.dtype.itemsize
+    out = np.empty(max_compressed_bytes(esz, x.size, max(1, ndims)), np.uint8)
+    nb = C.c_uint64(0)
+    ret = lib().spz_compress_rowmajor_host(kind, esz, x.ctypes.data, x.size, out.ctypes.data, ndims, int(write_size),
+                                           C.byref(nb))
+    if ret == -1 and ndims == 0:
+        return np.zeros(0, np.uint8), -1
+    check(ret, "spz_compress_rowmajor_host")
+    return out[: nb.value].copy(), int(ret)
+
+
+def decompress_rowmajor(kind: int, esz: int, stream: np.ndarray):
+    """-> (decoded elements, count); the length comes from the stream's 6-byte metadata."""
+    stream = np.ascontiguousarray(stream, dtype=np.uint8)
+    n = int(stream[:4].view(np.uint32)[0])
+    out = np.empty(n, _UDT[esz])
+    src = np.concatenate([stream, np.zeros(64, np.uint8)])
+    ret = lib().spz_decompress_rowmajor_host(kind, esz, src.ctypes.data, out.ctypes.data)
+    check(ret, "spz_decompress_rowmajor_host")
+    return out, int(ret)
 
 
 def measure(esz: int, stream: np.ndarray, has_meta=True, ndims=0, ngroups=0, remaining=0):

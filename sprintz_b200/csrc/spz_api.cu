@@ -48,6 +48,11 @@ static inline bool valid_codec(int predictor, int elem_sz)
 {
     return (predictor == 0 || predictor == 1) && (elem_sz == 1 || elem_sz == 2);
 }
+// frames also carry the non-RLE sibling codecs: SPZ_RM_DELTA (2), SPZ_RM_PLAIN (3)
+static inline bool valid_frame_codec(int predictor, int elem_sz)
+{
+    return predictor >= 0 && predictor <= 3 && (elem_sz == 1 || elem_sz == 2);
+}
 
 // ------------------------------------------------------------------ optional per-kernel timing of the frame encoder
 // bench.py needs the codec kernel's own duration (roofline), separate from scan + compaction. When enabled,
@@ -174,13 +179,23 @@ extern "C" uint64_t spz_frame_workspace_bytes(int elem_sz, uint64_t len, uint16_
 
 // ------------------------------------------------------------------ device entry points
 
+static int compress_dev_impl(uint32_t variant, int predictor, int elem_sz, const void* d_src, uint32_t len, uint16_t ndims,
+                             int write_size, void* d_dest, spz_chunk_meta* d_meta, spz_stream_t stream);
+
 extern "C" int spz_compress_dev(int predictor, int elem_sz, const void* d_src, uint32_t len, uint16_t ndims,
                                 int write_size, void* d_dest, spz_chunk_meta* d_meta, spz_stream_t stream)
+{
+    return compress_dev_impl(0, predictor, elem_sz, d_src, len, ndims, write_size, d_dest, d_meta, stream);
+}
+
+static int compress_dev_impl(uint32_t variant, int predictor, int elem_sz, const void* d_src, uint32_t len, uint16_t ndims,
+                             int write_size, void* d_dest, spz_chunk_meta* d_meta, spz_stream_t stream)
 {
     if (!valid_codec(predictor, elem_sz) || ndims == 0) return SPZ_E_ARG;
     if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
     EncParams p;
     memset(&p, 0, sizeof(p));
+    p.variant = variant;
     p.src = (const uint8_t*)d_src; p.dst = (uint8_t*)d_dest; p.meta = (ChunkMeta*)d_meta;
     p.len = len; p.chunk_len = len ? len : 1; p.nchunks = 1; p.slot_stride = 0;
     p.ndims = ndims; p.write_size = write_size ? 1 : 0;
@@ -188,15 +203,27 @@ extern "C" int spz_compress_dev(int predictor, int elem_sz, const void* d_src, u
     return SPZ_OK;
 }
 
+static int decompress_dev_impl(uint32_t variant, int predictor, int elem_sz, const void* d_src, uint64_t src_bytes, int has_meta,
+                               uint16_t ndims, void* d_dest, uint64_t dest_cap_elems, spz_chunk_meta* d_meta,
+                               spz_stream_t stream);
+
 extern "C" int spz_decompress_dev(int predictor, int elem_sz, const void* d_src, uint64_t src_bytes, int has_meta,
                                   uint16_t ndims, void* d_dest, uint64_t dest_cap_elems, spz_chunk_meta* d_meta,
                                   spz_stream_t stream)
+{
+    return decompress_dev_impl(0, predictor, elem_sz, d_src, src_bytes, has_meta, ndims, d_dest, dest_cap_elems, d_meta, stream);
+}
+
+static int decompress_dev_impl(uint32_t variant, int predictor, int elem_sz, const void* d_src, uint64_t src_bytes, int has_meta,
+                               uint16_t ndims, void* d_dest, uint64_t dest_cap_elems, spz_chunk_meta* d_meta,
+                               spz_stream_t stream)
 {
     if (!valid_codec(predictor, elem_sz) || ndims == 0) return SPZ_E_ARG;
     if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
     if (!has_meta && !d_meta) return SPZ_E_ARG;
     DecParams p;
     memset(&p, 0, sizeof(p));
+    p.variant = variant;
     p.src = (const uint8_t*)d_src; p.offsets = nullptr; p.dst = (uint8_t*)d_dest; p.meta = (ChunkMeta*)d_meta;
     p.len = dest_cap_elems; p.chunk_len = dest_cap_elems ? dest_cap_elems : 1; p.nchunks = 1; p.slot_stride = 0;
     p.dst_cap = dest_cap_elems; p.ndims = ndims; p.has_meta = has_meta ? 1 : 0;
@@ -209,7 +236,7 @@ extern "C" int spz_frame_encode_dev(int predictor, int elem_sz, const void* d_sr
                                     uint32_t chunk_rows, void* d_frame, uint64_t frame_cap,
                                     void* d_work, uint64_t work_bytes, uint64_t* d_frame_bytes, spz_stream_t stream_)
 {
-    if (!valid_codec(predictor, elem_sz) || ndims == 0 || chunk_rows == 0) return SPZ_E_ARG;
+    if (!valid_frame_codec(predictor, elem_sz) || ndims == 0 || chunk_rows == 0) return SPZ_E_ARG;
     if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
     cudaStream_t stream = (cudaStream_t)stream_;
     const FrameLayout f = frame_layout(len, ndims, chunk_rows);
@@ -252,7 +279,7 @@ extern "C" int spz_frame_decode_dev(int predictor, int elem_sz, const void* d_fr
                                     uint64_t len, uint16_t ndims, uint32_t chunk_rows, void* d_dest,
                                     uint64_t dest_cap_elems, spz_chunk_meta* d_status, spz_stream_t stream)
 {
-    if (!valid_codec(predictor, elem_sz) || ndims == 0 || chunk_rows == 0) return SPZ_E_ARG;
+    if (!valid_frame_codec(predictor, elem_sz) || ndims == 0 || chunk_rows == 0) return SPZ_E_ARG;
     if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
     if (dest_cap_elems < len) return SPZ_E_CAPACITY;
     const FrameLayout f = frame_layout(len, ndims, chunk_rows);
@@ -362,8 +389,17 @@ extern "C" int spz_measure_stream(int elem_sz, const void* src_, int has_meta, u
     return SPZ_OK;
 }
 
+static int64_t compress_host_impl(uint32_t variant, int predictor, int elem_sz, const void* src, uint32_t len, void* dest,
+                                  uint16_t ndims, int write_size, uint64_t* true_nbytes);
+
 extern "C" int64_t spz_compress_host(int predictor, int elem_sz, const void* src, uint32_t len, void* dest,
                                      uint16_t ndims, int write_size, uint64_t* true_nbytes)
+{
+    return compress_host_impl(0, predictor, elem_sz, src, len, dest, ndims, write_size, true_nbytes);
+}
+
+static int64_t compress_host_impl(uint32_t variant, int predictor, int elem_sz, const void* src, uint32_t len, void* dest,
+                                  uint16_t ndims, int write_size, uint64_t* true_nbytes)
 {
     if (ndims == 0) { printf("Received invalid ndims %d\n", (int)ndims); return -1; }   // sprintz.cpp:71
     if (!valid_codec(predictor, elem_sz)) return SPZ_E_ARG;
@@ -377,8 +413,8 @@ extern "C" int64_t spz_compress_host(int predictor, int elem_sz, const void* src
     CK(g_cache.ensure(1, out_cap + 16));
     CK(g_cache.ensure(2, 64));
     if (in_bytes) CK(cudaMemcpyAsync(g_cache.buf[0], src, in_bytes, cudaMemcpyHostToDevice, st));
-    int rc = spz_compress_dev(predictor, elem_sz, g_cache.buf[0], len, ndims, write_size, g_cache.buf[1],
-                              (spz_chunk_meta*)g_cache.buf[2], st);
+    int rc = compress_dev_impl(variant, predictor, elem_sz, g_cache.buf[0], len, ndims, write_size, g_cache.buf[1],
+                               (spz_chunk_meta*)g_cache.buf[2], st);
     if (rc != SPZ_OK) return rc;
     spz_chunk_meta m;
     CK(cudaMemcpyAsync(&m, g_cache.buf[2], sizeof(m), cudaMemcpyDeviceToHost, st));
@@ -447,6 +483,87 @@ extern "C" int64_t spz_decompress_delta_16b(const int16_t* s, uint16_t* d) { ret
 extern "C" int64_t spz_compress_xff_16b(const uint16_t* s, uint32_t n, int16_t* d, uint16_t nd, int ws) { return spz_compress_host(SPZ_XFF, 2, s, n, d, nd, ws, nullptr); }
 extern "C" int64_t spz_decompress_xff_16b(const int16_t* s, uint16_t* d) { return spz_decompress_host(SPZ_XFF, 2, s, d); }
 
+
+// ------------------------------------------------------------------ non-RLE sibling codecs
+// compress_rowmajor_delta_{8b,16b} / compress_rowmajor_{8b,16b} and their decoders (sprintz_delta.h:27-44).
+// kind 1 = delta, 2 = plain bit packing.  Same kernels as the RLE codecs (generic family, variant flag).
+
+static int measure_rowmajor(int elem_sz, const uint8_t* src, uint64_t* stream_bytes, uint64_t* decoded_elems, uint16_t* ndims_out)
+{
+    const uint32_t len = (uint32_t)src[0] | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16) | ((uint32_t)src[3] << 24);
+    const uint32_t D = (uint32_t)src[4] | ((uint32_t)src[5] << 8);
+    uint64_t pos = 6;
+    *ndims_out = (uint16_t)D;
+    uint64_t done = 0;
+    if (len >= kMinDataSize) {
+        if (D == 0) return SPZ_E_ARG;
+        const uint32_t w = 8u * elem_sz, hb = elem_sz == 1 ? 3 : 4;
+        const uint32_t H = (2 * D * hb + 7) / 8;
+        const uint64_t ngroups = len / (16ull * D);
+        for (uint64_t g = 0; g < ngroups; g++) {
+            const uint8_t* hdr = src + pos;
+            pos += H;
+            for (uint32_t s = 0; s < 2; s++) {
+                uint32_t total = 0;
+                for (uint32_t d = 0; d < D; d++) {
+                    const uint32_t bit = (s * D + d) * hb;
+                    uint32_t f = (((uint32_t)hdr[bit >> 3] | ((uint32_t)hdr[(bit >> 3) + 1] << 8)) >> (bit & 7)) & ((1u << hb) - 1);
+                    total += (f == w - 1) ? w : f;
+                }
+                pos += 8ull * ((total + 7) / 8);
+            }
+        }
+        done = ngroups * 16ull * D;
+    }
+    pos += (uint64_t)(len - done) * elem_sz;
+    *stream_bytes = pos;
+    *decoded_elems = len;
+    return SPZ_OK;
+}
+
+extern "C" int64_t spz_compress_rowmajor_host(int kind, int elem_sz, const void* src, uint32_t len, void* dest,
+                                              uint16_t ndims, int write_size, uint64_t* true_nbytes)
+{
+    if (kind != 1 && kind != 2) return SPZ_E_ARG;
+    return compress_host_impl((uint32_t)kind, SPZ_DELTA, elem_sz, src, len, dest, ndims, write_size, true_nbytes);
+}
+
+extern "C" int64_t spz_decompress_rowmajor_host(int kind, int elem_sz, const void* src, void* dest)
+{
+    if ((kind != 1 && kind != 2) || !valid_codec(SPZ_DELTA, elem_sz)) return SPZ_E_ARG;
+    uint64_t sbytes = 0, elems = 0;
+    uint16_t ndims = 0;
+    int rc = measure_rowmajor(elem_sz, (const uint8_t*)src, &sbytes, &elems, &ndims);
+    if (rc != SPZ_OK) return rc == SPZ_E_ARG ? 0 : rc;            // ndims == 0: the reference returns 0
+    if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    cudaStream_t st;
+    CK(g_cache.get_stream(&st));
+    CK(g_cache.ensure(0, sbytes + 32));
+    CK(g_cache.ensure(1, elems * elem_sz + 16));
+    CK(g_cache.ensure(2, 64));
+    CK(cudaMemcpyAsync(g_cache.buf[0], src, sbytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(g_cache.buf[2], 0, sizeof(spz_chunk_meta), st));
+    rc = decompress_dev_impl((uint32_t)kind, SPZ_DELTA, elem_sz, g_cache.buf[0], sbytes + 16, 1, ndims ? ndims : 1,
+                             g_cache.buf[1], elems, (spz_chunk_meta*)g_cache.buf[2], st);
+    if (rc != SPZ_OK) return rc;
+    spz_chunk_meta m;
+    CK(cudaMemcpyAsync(&m, g_cache.buf[2], sizeof(m), cudaMemcpyDeviceToHost, st));
+    if (elems) CK(cudaMemcpyAsync(dest, g_cache.buf[1], elems * elem_sz, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (m.status != 0) return SPZ_E_STREAM;
+    return (int64_t)elems;
+}
+
+extern "C" int64_t spz_compress_rowmajor_delta_8b(const uint8_t* s, uint32_t n, int8_t* d, uint16_t nd, int ws) { return spz_compress_rowmajor_host(1, 1, s, n, d, nd, ws, nullptr); }
+extern "C" int64_t spz_decompress_rowmajor_delta_8b(const int8_t* s, uint8_t* d) { return spz_decompress_rowmajor_host(1, 1, s, d); }
+extern "C" int64_t spz_compress_rowmajor_delta_16b(const uint16_t* s, uint32_t n, int16_t* d, uint16_t nd, int ws) { return spz_compress_rowmajor_host(1, 2, s, n, d, nd, ws, nullptr); }
+extern "C" int64_t spz_decompress_rowmajor_delta_16b(const int16_t* s, uint16_t* d) { return spz_decompress_rowmajor_host(1, 2, s, d); }
+extern "C" int64_t spz_compress_rowmajor_8b(const uint8_t* s, uint32_t n, int8_t* d, uint16_t nd, int ws) { return spz_compress_rowmajor_host(2, 1, s, n, d, nd, ws, nullptr); }
+extern "C" int64_t spz_decompress_rowmajor_8b(const int8_t* s, uint8_t* d) { return spz_decompress_rowmajor_host(2, 1, s, d); }
+extern "C" int64_t spz_compress_rowmajor_16b(const uint16_t* s, uint32_t n, int16_t* d, uint16_t nd, int ws) { return spz_compress_rowmajor_host(2, 2, s, n, d, nd, ws, nullptr); }
+extern "C" int64_t spz_decompress_rowmajor_16b(const int16_t* s, uint16_t* d) { return spz_decompress_rowmajor_host(2, 2, s, d); }
+
 // ------------------------------------------------------------------ frame, host buffers
 //
 // Both calls are software pipelines over SLABS of whole chunks on three streams (upload / kernels /
@@ -495,7 +612,7 @@ Pipe g_pipe;
 extern "C" int64_t spz_frame_compress_host(int predictor, int elem_sz, const void* src_, uint64_t len, uint16_t ndims,
                                            uint32_t chunk_rows, void* frame_, uint64_t frame_cap)
 {
-    if (!valid_codec(predictor, elem_sz) || ndims == 0 || chunk_rows == 0) return SPZ_E_ARG;
+    if (!valid_frame_codec(predictor, elem_sz) || ndims == 0 || chunk_rows == 0) return SPZ_E_ARG;
     if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
     std::lock_guard<std::mutex> lk(g_cache.mu);
     const uint8_t* src = (const uint8_t*)src_;
@@ -590,7 +707,7 @@ extern "C" int64_t spz_frame_decompress_host(const void* frame_, uint64_t frame_
     uint8_t* dest = (uint8_t*)dest_;
     spz_frame_header h;
     memcpy(&h, hframe, sizeof(h));
-    if (h.magic != SPZ_FRAME_MAGIC || h.frame_bytes > frame_bytes || !valid_codec(h.predictor, h.elem_sz) ||
+    if (h.magic != SPZ_FRAME_MAGIC || h.frame_bytes > frame_bytes || !valid_frame_codec(h.predictor, h.elem_sz) ||
         h.ndims == 0 || h.ndims > SPZ_MAX_NDIMS || h.chunk_rows == 0) return SPZ_E_STREAM;
     if (dest_cap_elems < h.len) return SPZ_E_CAPACITY;
     const FrameLayout f = frame_layout(h.len, (uint16_t)h.ndims, h.chunk_rows);

@@ -50,6 +50,7 @@ struct EncParams {
     uint32_t       nb_off, tile_off, tile_stride, out_off;   // layout inside team_smem
     uint32_t       out_cap;   // staging capacity (bytes)
     uint32_t       teams_per_cta;
+    uint32_t       variant;   // 0: RLE codecs (sprintz.h) | 1: compress_rowmajor_delta_* | 2: compress_rowmajor_* (no RLE, 6-byte metadata)
 };
 
 struct DecParams {
@@ -72,6 +73,7 @@ struct DecParams {
     uint32_t        ring_cap;  // fast path: bytes of the per-team input ring (power of two)
     uint32_t        out_cap;   // fast path: bytes of the per-team output staging
     uint32_t        ring_mask4;// fast path: (ring_cap - 1) & ~3, as a kernel constant so wrap+base is one LOP3
+    uint32_t        variant;   // as EncParams::variant
 };
 
 template <int W> struct Traits;

@@ -56,7 +56,18 @@ __global__ void __launch_bounds__(kThreads) spz_decode_kernel(const DecParams p)
 
     uint32_t ngroups, remaining, status = kStatusOk;
     uint64_t pos = 0;                   // byte cursor in the stream (team-uniform)
-    if (p.has_meta) {                   // format.h:47-62
+    const uint32_t variant = p.variant; // 1 / 2: non-RLE sibling codecs (see spz_encode.cu)
+    if (variant) {                      // format.h:75-85: [u32 len][u16 ndims]; ngroups is implied
+        const uint32_t len32 = (uint32_t)stream[0] | ((uint32_t)stream[1] << 8) | ((uint32_t)stream[2] << 16) | ((uint32_t)stream[3] << 24);
+        const uint32_t nd = (uint32_t)stream[4] | ((uint32_t)stream[5] << 8);
+        pos = 6;
+        if (len32 < kMinDataSize) { ngroups = 0; remaining = len32; }
+        else {
+            if (nd != (uint32_t)D) status = kStatusBadDims;
+            ngroups = len32 / (16u * (uint32_t)D);
+            remaining = len32 - ngroups * 16u * (uint32_t)D;
+        }
+    } else if (p.has_meta) {            // format.h:47-62
         ngroups = (uint32_t)stream[0] | ((uint32_t)stream[1] << 8) | ((uint32_t)stream[2] << 16) | ((uint32_t)stream[3] << 24);
         remaining = (uint32_t)stream[4] | ((uint32_t)stream[5] << 8);
         const uint32_t nd = (uint32_t)stream[6] | ((uint32_t)stream[7] << 8);
@@ -71,7 +82,7 @@ __global__ void __launch_bounds__(kThreads) spz_decode_kernel(const DecParams p)
     const uint32_t H = (2u * (uint32_t)D * HB + 7u) >> 3;
     const uint64_t B = (uint64_t)kBlockRows * D;
 
-    if (status == kStatusOk && !(ngroups == 0 && remaining < kMinDataSize)) {
+    if (status == kStatusOk && (variant ? ngroups != 0 : !(ngroups == 0 && remaining < kMinDataSize))) {
         for (uint32_t g = 0; g < ngroups && status == kStatusOk; g++) {
             const uint8_t* hdr = stream + pos;
             pos += H;
@@ -90,7 +101,7 @@ __global__ void __launch_bounds__(kThreads) spz_decode_kernel(const DecParams p)
                     total += team_last(incl, TEAM, tmask);
                 }
 
-                if (total == 0) {
+                if (total == 0 && variant == 0u) {
                     // ---- run slot (sprintz_delta_rle.cpp:640-667)
                     uint32_t nrun = stream[pos] & 0x7f;
                     if (stream[pos] & 0x80) { nrun |= (uint32_t)stream[pos + 1] << 7; pos += 2; } else { pos += 1; }
@@ -150,7 +161,7 @@ __global__ void __launch_bounds__(kThreads) spz_decode_kernel(const DecParams p)
                                 if (r & 1) gs += fire_grad<W>(err, pd);
                             }
                             pd = delta;
-                            pv = (pv + (uint32_t)delta) & WMASK;
+                            pv = (variant == 2u) ? u[r] : ((pv + (uint32_t)delta) & WMASK);
                             op[r * D] = (uint_t)pv;
                         }
                         s_pv[d] = (int32_t)pv;
@@ -180,7 +191,7 @@ __global__ void __launch_bounds__(kThreads) spz_decode_kernel(const DecParams p)
     }
     if (t == 0 && p.meta) {
         p.meta[c].status = status;
-        if (p.has_meta) { p.meta[c].nbytes = (uint32_t)(pos + (uint64_t)remaining * ESZ); p.meta[c].ngroups = ngroups; p.meta[c].remaining = (uint32_t)o; }
+        if (p.has_meta || variant) { p.meta[c].nbytes = (uint32_t)(pos + (uint64_t)remaining * ESZ); p.meta[c].ngroups = ngroups; p.meta[c].remaining = (uint32_t)o; }
     }
 }
 
@@ -206,16 +217,20 @@ int last_decode_family() { return g_last_decode_family; }
 
 cudaError_t launch_decode(int elem_sz, int predictor, DecParams p, cudaStream_t stream)
 {
+    if (predictor >= 2) { p.variant = (uint32_t)predictor - 1u; predictor = 0; }   // SPZ_RM_DELTA / SPZ_RM_PLAIN (frames)
+    if (p.variant == 0)
     {   // throughput path: frames with many chunks of 8 / 16 dims (spz_decode_lane.cu)
         const cudaError_t e = launch_decode_lane(elem_sz, predictor, p, stream);
         if (e != cudaErrorNotSupported) { g_last_decode_family = 2; return e; }
     }
+    if (p.variant == 0)
     {   // fast path for high-dim shapes; the generic kernel below covers everything else
         const cudaError_t e = launch_decode_hd(elem_sz, predictor, p, stream);
         if (e != cudaErrorNotSupported) { g_last_decode_family = 1; return e; }
     }
     g_last_decode_family = 0;
-    const bool low = elem_sz == 1 ? (p.ndims <= 4) : (p.ndims <= 2);
+    if (p.variant) predictor = 0;
+    const bool low = p.variant ? false : (elem_sz == 1 ? (p.ndims <= 4) : (p.ndims <= 2));
     p.team = p.ndims >= 32 ? 32 : pow2_ceil(p.ndims);
     p.dpl = (p.ndims + p.team - 1) / p.team;
     p.team_smem = (4u * 4u * p.team * p.dpl + 15u) & ~15u;

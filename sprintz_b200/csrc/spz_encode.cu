@@ -103,7 +103,11 @@ __global__ void __launch_bounds__(kThreads) spz_encode_kernel(const EncParams p)
     uint8_t* const gstream = p.dst + c * p.slot_stride;
     const int64_t B = (int64_t)kBlockRows * D, G = 2 * B;
     const uint32_t H = (2u * (uint32_t)D * HB + 7u) >> 3;
-    const uint32_t meta_bytes = p.write_size ? 8u : 0u;
+    // variant 1 / 2: the non-RLE sibling codecs compress_rowmajor_delta_* / compress_rowmajor_*
+    // (sprintz_delta.cpp:776-1017, :64-392): 6-byte metadata [u32 len][u16 ndims] (format.h:65-73), every block
+    // is a data slot (possibly of zero bytes), no zigzag/delta for variant 2
+    const uint32_t variant = p.variant;
+    const uint32_t meta_bytes = p.write_size ? (variant ? 6u : 8u) : 0u;
 
     OutStage o;
     o.init(s_out, gstream);
@@ -170,7 +174,7 @@ __global__ void __launch_bounds__(kThreads) spz_encode_kernel(const EncParams p)
                             err = sx<W>(delta - fire_predict<W>(pd, coef));
                             if (r & 1) gs += fire_grad<W>(err, pd);
                         }
-                        zz[r] = zigzag_enc<W>(err);
+                        zz[r] = (variant == 2u) ? x[r] : zigzag_enc<W>(err);
                         mask |= zz[r];
                         pv = x[r]; pd = delta;
                     }
@@ -213,7 +217,7 @@ __global__ void __launch_bounds__(kThreads) spz_encode_kernel(const EncParams p)
                 total += team_last(incl, TEAM, tmask);
             }
             __syncwarp(tmask);
-            const bool zero = (total == 0);
+            const bool zero = (total == 0) && variant == 0u;      // the non-RLE codecs have no run slots
 
             // ================= control: run-length / group state machine (team-uniform)
             bool emit_block = true;
@@ -314,7 +318,12 @@ stream_done:
         stage_flush(o, true, t, TEAM, tmask);
         __syncwarp(tmask);
         if (t == 0) {
-            if (p.write_size) {     // format.h:35-45, written last because ngroups is only known now
+            if (p.write_size && variant) {      // format.h:65-73
+                const uint32_t L32 = (uint32_t)L;
+                gstream[0] = (uint8_t)L32; gstream[1] = (uint8_t)(L32 >> 8);
+                gstream[2] = (uint8_t)(L32 >> 16); gstream[3] = (uint8_t)(L32 >> 24);
+                gstream[4] = (uint8_t)D; gstream[5] = (uint8_t)(D >> 8);
+            } else if (p.write_size) {     // format.h:35-45, written last because ngroups is only known now
                 const uint32_t rem16 = (uint32_t)rem_elems & 0xffffu;
                 gstream[0] = (uint8_t)ngroups; gstream[1] = (uint8_t)(ngroups >> 8);
                 gstream[2] = (uint8_t)(ngroups >> 16); gstream[3] = (uint8_t)(ngroups >> 24);
@@ -373,16 +382,20 @@ int last_encode_family() { return g_last_encode_family; }
 
 cudaError_t launch_encode(int elem_sz, int predictor, EncParams p, cudaStream_t stream)
 {
+    if (predictor >= 2) { p.variant = (uint32_t)predictor - 1u; predictor = 0; }   // SPZ_RM_DELTA / SPZ_RM_PLAIN (frames)
+    if (p.variant == 0)
     {   // throughput path: frames with many chunks of 8 / 16 dims (spz_encode_lane.cu)
         const cudaError_t e = launch_encode_lane(elem_sz, predictor, p, stream);
         if (e != cudaErrorNotSupported) { g_last_encode_family = 2; return e; }
     }
+    if (p.variant == 0)
     {   // fast path for high-dim shapes; the generic kernel below covers everything else
         const cudaError_t e = launch_encode_hd(elem_sz, predictor, p, stream);
         if (e != cudaErrorNotSupported) { g_last_encode_family = 1; return e; }
     }
     g_last_encode_family = 0;
-    const bool low = elem_sz == 1 ? (p.ndims <= 4) : (p.ndims <= 2);
+    if (p.variant) predictor = 0;
+    const bool low = p.variant ? false : (elem_sz == 1 ? (p.ndims <= 4) : (p.ndims <= 2));
     p.team = p.ndims >= 32 ? 32 : pow2_ceil(p.ndims);
     p.dpl = (p.ndims + p.team - 1) / p.team;
     enc_layout(elem_sz, low, p);
