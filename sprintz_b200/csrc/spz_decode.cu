@@ -218,7 +218,6 @@ int last_decode_family() { return g_last_decode_family; }
 cudaError_t launch_decode(int elem_sz, int predictor, DecParams p, cudaStream_t stream)
 {
     if (predictor >= 2) { p.variant = (uint32_t)predictor - 1u; predictor = 0; }   // SPZ_RM_DELTA / SPZ_RM_PLAIN (frames)
-    if (p.variant == 0)
     {   // throughput path: frames with many chunks of 8 / 16 dims (spz_decode_lane.cu)
         const cudaError_t e = launch_decode_lane(elem_sz, predictor, p, stream);
         if (e != cudaErrorNotSupported) { g_last_decode_family = 2; return e; }

@@ -165,7 +165,19 @@ __global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_k
 
     uint32_t pos = mis * 8u;                         // bit cursor relative to base32
     uint32_t ngroups = 0, remaining = 0, status = kStatusOk;
-    if (p.has_meta) {                                // format.h:47-62
+    const uint32_t variant = p.variant;              // 1 / 2: the non-RLE sibling codecs (6-byte metadata, no run slots)
+    if (variant) {                                   // format.h:75-85: [u32 len][u16 ndims]
+        const uint32_t len32 = window(pos);
+        const uint32_t nd = window(pos + 32u) & 0xffffu;
+        pos += 48u;
+        ensure(pos);
+        if (len32 < kMinDataSize) { remaining = len32; }
+        else {
+            if (nd != (uint32_t)D) status = kStatusBadDims;
+            ngroups = len32 / (16u * D);
+            remaining = len32 - ngroups * 16u * D;
+        }
+    } else if (p.has_meta) {                         // format.h:47-62
         ngroups = window(pos);
         const uint32_t w1 = window(pos + 32u);
         remaining = w1 & 0xffffu;
@@ -215,7 +227,7 @@ __global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_k
 #pragma unroll 1
         for (int s = 0; s < 2; s++) {
             const uint32_t tot = s ? total[1] : total[0];
-            if (tot == 0u) {
+            if (tot == 0u && variant == 0u) {
                 // ---- run slot (sprintz_delta_rle.cpp:640-667, sprintz_xff_rle.cpp:828-958)
                 const uint32_t rb = window(pos);
                 uint32_t nrun = rb & 0x7fu;
@@ -299,6 +311,8 @@ __global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_k
                         asm("mad.lo.s32 %0, %1, %2, 0;" : "=r"(ths) : "r"(th), "n"(1 << UP));
                         asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(pdh[j]) : "r"(mi), "n"(1 << (UP - 1)), "r"(ths));
                         pvh[j] += (uint32_t)pdh[j];
+                    } else if (variant == 2u) {
+                        pvh[j] = u << UP;                                    // plain bit packing: the field is the value
                     } else {
                         asm("mad.lo.s32 %0, %1, %2, %0;" : "+r"(pvh[j]) : "r"(mi), "n"(1 << (UP - 1)));
                     }
@@ -333,7 +347,7 @@ __global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_k
     }
     if (part == 0 && p.meta) {
         p.meta[c].status = status;
-        if (p.has_meta) {
+        if (p.has_meta || variant) {
             p.meta[c].nbytes = (pos >> 3) - mis + remaining * ESZ;
             p.meta[c].ngroups = ngroups;
             p.meta[c].remaining = o;
@@ -360,7 +374,7 @@ static cudaError_t launch_lane(const DecParams& p, cudaStream_t stream)
 // Returns cudaErrorNotSupported when the shape is not covered (caller continues with the team kernels).
 cudaError_t launch_decode_lane(int elem_sz, int predictor, DecParams p, cudaStream_t stream)
 {
-    if (g_force_path == 1) return cudaErrorNotSupported;
+    if (g_force_path == 1 || (p.variant && predictor)) return cudaErrorNotSupported;
     if (p.ndims != 8 && p.ndims != 16) return cudaErrorNotSupported;
     if (p.src_end == nullptr || p.src_end <= p.src) return cudaErrorNotSupported;
     // a lane is a whole scalar decoder: only worth it when there are enough chunks to fill the machine

@@ -383,7 +383,6 @@ int last_encode_family() { return g_last_encode_family; }
 cudaError_t launch_encode(int elem_sz, int predictor, EncParams p, cudaStream_t stream)
 {
     if (predictor >= 2) { p.variant = (uint32_t)predictor - 1u; predictor = 0; }   // SPZ_RM_DELTA / SPZ_RM_PLAIN (frames)
-    if (p.variant == 0)
     {   // throughput path: frames with many chunks of 8 / 16 dims (spz_encode_lane.cu)
         const cudaError_t e = launch_encode_lane(elem_sz, predictor, p, stream);
         if (e != cudaErrorNotSupported) { g_last_encode_family = 2; return e; }

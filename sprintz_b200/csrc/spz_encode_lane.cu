@@ -76,11 +76,16 @@ __global__ void __launch_bounds__(kEncLaneThreads, 4) spz_encode_lane_kernel(con
     const uint8_t* gin = p.src + first * ESZ;
     asm volatile("" : "+l"(gin));
     uint8_t* const gout = p.dst + c * p.slot_stride;
-    const uint32_t meta_bytes = p.write_size ? 8u : 0u;
+    // variant 1 / 2: the non-RLE sibling codecs (delta / plain bit packing, 6-byte metadata, no run slots)
+    const uint32_t variant = p.variant;
+    const uint32_t meta_bytes = p.write_size ? (variant ? 6u : 8u) : 0u;
 
     if (L < (int32_t)kMinDataSize) {                       // stored raw (sprintz_delta_rle.cpp:101-109)
-        if (meta_bytes) {
+        if (meta_bytes == 8u) {
             *reinterpret_cast<uint2*>(gout) = make_uint2(0u, (uint32_t)L | ((uint32_t)D << 16));
+        } else if (meta_bytes == 6u) {
+            *reinterpret_cast<uint32_t*>(gout) = (uint32_t)L;
+            *reinterpret_cast<uint16_t*>(gout + 4) = (uint16_t)D;
         }
         for (int32_t b = 0; b < L * ESZ; b++) gout[meta_bytes + b] = gin[b];
         p.meta[c].nbytes = meta_bytes + (uint32_t)L * ESZ; p.meta[c].ngroups = 0;
@@ -173,7 +178,7 @@ __global__ void __launch_bounds__(kEncLaneThreads, 4) spz_encode_lane_kernel(con
 #pragma unroll
     for (int d = 0; d < D; d++) { xprev[d] = 0; dprev[d] = 0; ct[d] = 0; }
 
-    if (meta_bytes) { put(0u, 32u); put(0u, 32u); }        // metadata placeholder (format.h:35-45, written last)
+    if (meta_bytes) { put(0u, 32u); put(0u, meta_bytes * 8u - 32u); }   // metadata placeholder (format.h:35-73, written last)
 
     int32_t i = 0;                                         // next block
     uint32_t run = 0, nslots = 0, ngroups = 0, hdr_off = 0;
@@ -209,6 +214,7 @@ __global__ void __launch_bounds__(kEncLaneThreads, 4) spz_encode_lane_kernel(con
             // ALU 77 %, FMA 24 %), so shifts-by-constant and the conditional negate are phrased as multiply-adds.
             auto elem = [&](uint32_t vh, int e, int r) -> uint32_t {
                 const int d = oc * 8 + e;
+                if (!FIRE && variant == 2u) return vh;                         // plain bit packing: the value itself
                 const int32_t dh = (int32_t)(vh - xprev[d]);                   // delta, wraps to W bits
                 xprev[d] = vh;
                 int32_t eh = dh;
@@ -312,7 +318,7 @@ __global__ void __launch_bounds__(kEncLaneThreads, 4) spz_encode_lane_kernel(con
                 }
             }
         }
-        const bool zero = total == 0u;
+        const bool zero = total == 0u && variant == 0u;   // the non-RLE codecs have no run slots
 
         // ================= control (sprintz_delta_rle.cpp:214-312 restated)
         auto begin_group = [&](uint32_t f_lo, uint32_t f_hi) {
@@ -411,8 +417,12 @@ __global__ void __launch_bounds__(kEncLaneThreads, 4) spz_encode_lane_kernel(con
         for (uint32_t b = 0; b < nb; b++) tdst[b] = tsrc[b];
         nbytes += nb;
     }
-    if (meta_bytes)                                                            // format.h:35-45
+    if (meta_bytes == 8u) {                                                    // format.h:35-45
         *reinterpret_cast<uint2*>(gout) = make_uint2(ngroups, (remaining & 0xffffu) | ((uint32_t)D << 16));
+    } else if (meta_bytes == 6u) {                                             // format.h:65-73
+        *reinterpret_cast<uint32_t*>(gout) = (uint32_t)L;
+        *reinterpret_cast<uint16_t*>(gout + 4) = (uint16_t)D;
+    }
     p.meta[c].nbytes = nbytes; p.meta[c].ngroups = ngroups; p.meta[c].remaining = remaining; p.meta[c].status = kStatusOk;
 }
 
@@ -437,7 +447,7 @@ static cudaError_t launch_enc_lane(const EncParams& p, cudaStream_t stream)
 cudaError_t launch_encode_lane(int elem_sz, int predictor, EncParams p, cudaStream_t stream)
 {
     const int force = get_force_path();
-    if (force == 1) return cudaErrorNotSupported;
+    if (force == 1 || (p.variant && predictor)) return cudaErrorNotSupported;
     if (!((elem_sz == 1 && p.ndims == 8) || (elem_sz == 2 && (p.ndims == 8 || p.ndims == 16)))) return cudaErrorNotSupported;
     if (p.meta == nullptr) return cudaErrorNotSupported;
     // a lane is a whole scalar encoder: only worth it when there are enough chunks to fill the machine

@@ -98,3 +98,39 @@ def test_gpu_rowmajor_frames(oracle, kind, esz, D):
     y = inputs.ar1(3000, D, esz, seed=1)
     fr = spz.frame_compress_host(kind + 1, y, D, 256)
     assert np.array_equal(spz.frame_decompress_host(fr), y)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,esz", KINDS, ids=KIDS)
+def test_gpu_rowmajor_lane_kernels(oracle, kind, esz):
+    """The lane kernels also carry the non-RLE variants (ndims 8 / 16); forced here on small inputs."""
+    import sprintz_b200 as spz
+    from test_gpu_frame import _frame_vs_oracle
+    spz.lib()
+    old = spz.set_kernel_path(2)
+    try:
+        bad = []
+        for D in (8, 16):
+            cases = []
+            for n in inputs.REF_SIZES:
+                cases += list(inputs.reference_families(n, esz).items())
+            for nrows in (24, 1000):
+                cases += [(f"{t}/r{nrows}", x) for t, x in inputs.adversarial_families(nrows, D, esz).items()]
+            cases.append(("zeros", np.zeros(40 * 16 * D + 5, np.uint8 if esz == 1 else np.uint16)))
+            for tag, x in cases:
+                ws, wr = oracle.compress_rowmajor(kind, x, D)
+                gs, gr = spz.compress_rowmajor(kind, x, D)
+                msg = parity.compare_stream(gs, gr, ws, wr, esz)
+                if msg is None and len(gs) != len(ws):
+                    msg = f"true byte length {len(gs)} != {len(ws)}"
+                if msg is None:
+                    dec, dr = spz.decompress_rowmajor(kind, esz, ws)
+                    msg = parity.compare_decoded(dec, dr, x)
+                if msg:
+                    bad.append((D, x.size, tag, msg))
+            for chunk_rows, nrows, ragged in ((16, 400, 0), (256, 5000, 3), (64, 64 * 300, 0)):
+                x = inputs.ar1(nrows, D, esz, seed=nrows)
+                _frame_vs_oracle(spz, oracle, kind + 1, esz, D, x[:-ragged] if ragged else x, chunk_rows)
+        assert not bad, (len(bad), bad[:5])
+    finally:
+        spz.set_kernel_path(old)
