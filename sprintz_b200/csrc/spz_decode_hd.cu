@@ -37,6 +37,11 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
     constexpr uint32_t FILL = TEAM * 16;            // bytes one ring fill brings in
     constexpr uint32_t FMASK = (1u << HB) - 1u;
     constexpr int TEAMS_PER_WARP = 32 / TEAM;
+    // Several dims per lane: give a lane CONSECUTIVE dims (d = t*DPL + k) instead of strided ones whenever the
+    // cover is exact and a lane's fields of one row fit a 64-bit segment.  Its header fields and its payload
+    // fields are then contiguous bit strings: one scan per group instead of DPL, three ring words + two funnel
+    // shifts per row instead of two LDS + a funnel shift per field (ncu on the 80-dim config: LSU pipe 67 % busy).
+    constexpr bool CONTIG = FULLD && DPL > 1 && DPL * W <= 64 && DPL * Traits<W>::HB <= 24;
 
     extern __shared__ __align__(16) uint8_t smem[];
 
@@ -204,6 +209,30 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
         const uint32_t hbit = ((pos + skew) & RMASK) * 8u;
         uint32_t nn[DPL], offs[DPL];
         uint32_t carry = 0;
+        if (CONTIG) {
+            const uint32_t fw0 = ring_bits(hbit + (uint32_t)(t * DPL) * HB);
+            const uint32_t fw1 = ring_bits(hbit + (uint32_t)(D + t * DPL) * HB);
+            uint32_t lanesum = 0;
+#pragma unroll
+            for (int k = 0; k < DPL; k++) {
+                const uint32_t f0 = (fw0 >> (k * HB)) & FMASK, f1 = (fw1 >> (k * HB)) & FMASK;
+                const uint32_t n0 = (f0 == (uint32_t)(W - 1)) ? (uint32_t)W : f0;
+                const uint32_t n1 = (f1 == (uint32_t)(W - 1)) ? (uint32_t)W : f1;
+                nn[k] = n0 | (n1 << 16);
+                offs[k] = lanesum;                  // exclusive prefix inside the lane
+                lanesum += nn[k];
+            }
+            uint32_t incl = lanesum;
+#pragma unroll
+            for (int s = 1; s < TEAM; s <<= 1) {
+                asm volatile("{ .reg .pred p; .reg .b32 r; shfl.sync.up.b32 r|p, %0, %1, %2, 0xffffffff; @p add.u32 %0, %0, r; }"
+                             : "+r"(incl) : "r"(s), "r"((32 - TEAM) << 8));
+            }
+            const uint32_t base = incl - lanesum;
+#pragma unroll
+            for (int k = 0; k < DPL; k++) offs[k] += base;
+            carry = __shfl_sync(kFull, incl, TEAM - 1, TEAM);
+        } else {
 #pragma unroll
         for (int k = 0; k < DPL; k++) {
             const int d = k * TEAM + t;
@@ -226,6 +255,7 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
             offs[k] = carry + incl - packed;
             carry += __shfl_sync(kFull, incl, TEAM - 1, TEAM);
         }
+        }
         if (act) pos += H;
 
         // One data slot: unpack + inverse predictor for my dims, rows staged at ob + ocur.
@@ -234,6 +264,51 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
             asm volatile("" : "+r"(row_bytes));      // keep it a register: byte += row_bytes stays an add (FMA-pipe IMAD.IADD)
             const uint32_t row_bits = row_bytes * 8u;
             const uint32_t pbit = ((pos + skew) & RMASK) * 8u;
+            if (CONTIG) {
+                // row-major over my DPL consecutive dims: one aligned 64-bit segment per row
+                uint8_t* op = ob + ocur + (uint32_t)(t * DPL) * ESZ;
+                uint32_t nk[DPL], fmk[DPL];
+                int32_t coef[DPL], gsh[DPL];
+#pragma unroll
+                for (int k = 0; k < DPL; k++) {
+                    nk[k] = (nn[k] >> sh16) & 0xffffu;
+                    fmk[k] = (1u << nk[k]) - 1u;
+                    coef[k] = FIRE ? fire_coef<W, false>(ct[k]) : 0;
+                    gsh[k] = 0;
+                }
+                uint32_t bit = pbit + ((offs[0] >> sh16) & 0xffffu);
+#pragma unroll
+                for (int r = 0; r < kBlockRows; r++) {
+                    const uint32_t bo = ((bit >> 3) & WMASK4) | ring_off;
+                    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(smem + bo);
+                    const uint32_t w1 = *reinterpret_cast<const uint32_t*>(smem + bo + 4);
+                    const uint32_t w2 = *reinterpret_cast<const uint32_t*>(smem + bo + 8);
+                    uint32_t lo = __funnelshift_r(w0, w1, bit), hi = __funnelshift_r(w1, w2, bit);
+                    bit += row_bits;
+#pragma unroll
+                    for (int k = 0; k < DPL; k++) {
+                        const uint32_t xk = lo;
+                        if (k != DPL - 1) {
+                            if (DPL * W <= 32) { lo >>= nk[k]; } else { lo = __funnelshift_r(lo, hi, nk[k]); hi >>= nk[k]; }
+                        }
+                        const uint32_t b = xk & fmk[k] & 1u;
+                        const int32_t err = (int32_t)((xk & fmk[k]) ^ (0u - b)) >> 1;
+                        int32_t delta = err;
+                        if (FIRE) {
+                            if (r & 1) { if (err != 0) gsh[k] += pdh[k] * (int32_t)(1u - 2u * b); }
+                            delta = __mulhi(pdh[k], coef[k]) + err;
+                            pdh[k] = (int32_t)((uint32_t)delta << UP);
+                        }
+                        pv[k] += (uint32_t)delta;
+                        *reinterpret_cast<uint_t*>(op + k * ESZ) = (uint_t)pv[k];
+                    }
+                    op += row_out;
+                }
+                if (FIRE) {
+#pragma unroll
+                    for (int k = 0; k < DPL; k++) ct[k] = sx<CB>(ct[k] + ((gsh[k] >> UP) >> 2));
+                }
+            } else {
             uint8_t* const obase = ob + ocur + (uint32_t)t * ESZ;
 #pragma unroll
             for (int k = 0; k < DPL; k++) {
@@ -275,6 +350,7 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
                     if (FIRE) ct[k] = sx<CB>(ct[k] + ((gsh >> UP) >> 2));     // sprintz_xff_rle.cpp:273-275
                 }
             }
+            }
             pos += row_bytes * kBlockRows;
             ocur += B * ESZ;
             o += B;
@@ -309,7 +385,7 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
                 if (go) {
 #pragma unroll
                     for (int k = 0; k < DPL; k++) {
-                        const int d = k * TEAM + t;
+                        const int d = CONTIG ? (t * DPL + k) : (k * TEAM + t);
                         if (FULLD || d < D) {
                             uint_t* op = out + o + d;
                             if (FIRE) {

@@ -187,3 +187,18 @@ def test_reference_named_entry_points(spz, oracle):
         assert r == wr and np.array_equal(s, ws)
         d, n = decomp(s)
         assert n == x.size and np.array_equal(d, x)
+
+
+@pytest.mark.parametrize("pred,esz", CODECS, ids=IDS)
+def test_exact_cover_team_shapes(spz, oracle, pred, esz):
+    """ndims that the team kernels cover exactly with several CONSECUTIVE dims per lane (24, 40, 48, 64, 80, 96, 128):
+    contiguous header fields / payload segments per lane (spz_decode_hd.cu CONTIG path)."""
+    bad = []
+    for D in (24, 40, 48, 64, 80, 96, 128):
+        for nrows in (40, 1000):
+            for tag, x in inputs.adversarial_families(nrows, D, esz).items():
+                _check_case(spz, oracle, pred, esz, D, x, bad, f"{tag}/r{nrows}")
+        x = inputs.random_walk_with_runs(3000, D, esz, seed=D)
+        _check_case(spz, oracle, pred, esz, D, x, bad, "walk+runs")
+        _check_case(spz, oracle, pred, esz, D, inputs.ar1(2048, D, esz, seed=D), bad, "ar1")
+    assert not bad, (len(bad), bad[:5])
