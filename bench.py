@@ -31,8 +31,9 @@ sys.path.insert(0, ROOT)
 # (name, elem_sz, ndims, predictor, bytes per GPU, default chunk_rows)
 CONFIGS = {
     "c1": dict(desc="int8, 1-dim, delta+bitpack, 64 KB", esz=1, D=1, pred=0, nbytes=64 << 10, chunk_rows=2048),
+    # 512-row chunks: 262144 lane tasks = 3.5 waves of resident lanes instead of 1.7 (+4 % decode), -0.8 % ratio
     "c2": dict(desc="int8, 8-dim rowmajor, FIRE+bitpack, 1 GB synthetic AR(1)", esz=1, D=8, pred=1,
-               nbytes=1 << 30, chunk_rows=1024),
+               nbytes=1 << 30, chunk_rows=512),
     "c3": dict(desc="int16, 16-dim rowmajor, FIRE+bitpack, 4 GB synthetic AR(1)", esz=2, D=16, pred=1,
                nbytes=4 << 30, chunk_rows=1024),
     "c4": dict(desc="int8, 80-dim, delta+bitpack, 4 GB per GPU (32 GB over 8)", esz=1, D=80, pred=0,

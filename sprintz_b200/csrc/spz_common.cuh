@@ -94,6 +94,8 @@ template <int W, bool LOW> __host__ __device__ __forceinline__ int32_t fire_coef
 {
     if (LOW) return counter >> 1;
     constexpr int SH = W - 4;
+    // 8-bit: the counter is an int16 (callers keep it sign-extended), so (counter >> 5) << 4 is already an int16
+    if (W == 8) return (int32_t)((uint32_t)(counter >> (1 + SH)) << SH);
     return sx<16>((int32_t)((uint32_t)(counter >> (1 + SH)) << SH));
 }
 
