@@ -28,6 +28,7 @@ extern "C" {
 #define SPZ_XFF   1   /* sprintz_*_xff_*  (FIRE) */
 #define SPZ_RM_DELTA 2 /* frames only: compress_rowmajor_delta_* (non-RLE, sprintz_delta.h:36-44) */
 #define SPZ_RM_PLAIN 3 /* frames only: compress_rowmajor_*       (non-RLE, sprintz_delta.h:27-34) */
+#define SPZ_RM_XFF   4 /* frames only: compress8b_rowmajor_xff   (non-RLE FIRE, 8-bit only, sprintz_xff.h:28-31) */
 
 #define SPZ_OK            0
 #define SPZ_E_ARG        -1   /* the reference's own error return (ndims == 0, sprintz.cpp:71) */
@@ -103,7 +104,7 @@ int spz_measure_stream(int elem_sz, const void* src, int has_meta, uint16_t ndim
 /* Non-RLE sibling codecs of the same file family (sprintz_delta.h:27-44): delta + bit packing
  * and plain bit packing with the 6-byte metadata [u32 len][u16 ndims] (format.h:65-85), fixed ngroups = len/(16*ndims),
  * no run slots.  Same arguments / returns / bytes as compress_rowmajor_delta_{8b,16b}, compress_rowmajor_{8b,16b}
- * and their decoders.  kind: 1 = delta, 2 = plain. */
+ * and their decoders.  kind: 1 = delta, 2 = plain, 3 = FIRE (8-bit only, see below). */
 int64_t spz_compress_rowmajor_delta_8b (const uint8_t*  src, uint32_t len, int8_t*  dest, uint16_t ndims, int write_size);
 int64_t spz_decompress_rowmajor_delta_8b(const int8_t*  src, uint8_t*  dest);
 int64_t spz_compress_rowmajor_delta_16b(const uint16_t* src, uint32_t len, int16_t* dest, uint16_t ndims, int write_size);
@@ -112,6 +113,10 @@ int64_t spz_compress_rowmajor_8b (const uint8_t*  src, uint32_t len, int8_t*  de
 int64_t spz_decompress_rowmajor_8b(const int8_t*  src, uint8_t*  dest);
 int64_t spz_compress_rowmajor_16b(const uint16_t* src, uint32_t len, int16_t* dest, uint16_t ndims, int write_size);
 int64_t spz_decompress_rowmajor_16b(const int16_t* src, uint16_t* dest);
+/* compress8b_rowmajor_xff / decompress8b_rowmajor_xff (sprintz_xff.h:28-31): FIRE without run slots, 8-bit only,
+ * 8-byte metadata [u48 len][u16 ndims]; kind 3 of the generic forms below. */
+int64_t spz_compress8b_rowmajor_xff(const uint8_t* src, uint64_t len, int8_t* dest, uint16_t ndims, int write_size);
+int64_t spz_decompress8b_rowmajor_xff(const int8_t* src, uint8_t* dest);
 int64_t spz_compress_rowmajor_host(int kind, int elem_sz, const void* src, uint32_t len, void* dest, uint16_t ndims,
                                    int write_size, uint64_t* true_nbytes);
 int64_t spz_decompress_rowmajor_host(int kind, int elem_sz, const void* src, void* dest);

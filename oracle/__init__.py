@@ -22,7 +22,8 @@ ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libsprintz_ref.so")
 
 DELTA, XFF = 0, 1
-RM_DELTA, RM_PLAIN = 1, 2     # non-RLE sibling codecs: compress_rowmajor_delta_*, compress_rowmajor_*
+RM_DELTA, RM_PLAIN, RM_XFF8 = 1, 2, 3   # non-RLE sibling codecs: compress_rowmajor_delta_*,
+                                        # compress_rowmajor_*, compress8b_rowmajor_xff (8-bit only)
 SLACK = 4096  # the reference reads/writes past buffer ends; give every buffer slack
 
 

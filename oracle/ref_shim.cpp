@@ -21,6 +21,7 @@
 
 #include "sprintz.h"   // from -I$(REF)/cpp/Compress
 #include "sprintz_delta.h"   // the non-RLE sibling codecs
+#include "sprintz_xff.h"     // compress8b_rowmajor_xff
 
 extern "C" {
 
@@ -61,6 +62,7 @@ int64_t ref_decompress(int predictor, int elem_sz, const void* src, void* dest)
 int64_t ref_compress_rowmajor(int kind, int elem_sz, const void* src, uint32_t len, void* dest, uint16_t ndims,
                               int write_size)
 {
+    if (kind == 3) return elem_sz == 1 ? compress8b_rowmajor_xff((const uint8_t*)src, len, (int8_t*)dest, ndims, write_size != 0) : -1;
     if (elem_sz == 1) {
         return kind == 1
             ? compress_rowmajor_delta_8b((const uint8_t*)src, len, (int8_t*)dest, ndims, write_size != 0)
@@ -73,6 +75,7 @@ int64_t ref_compress_rowmajor(int kind, int elem_sz, const void* src, uint32_t l
 
 int64_t ref_decompress_rowmajor(int kind, int elem_sz, const void* src, void* dest)
 {
+    if (kind == 3) return elem_sz == 1 ? decompress8b_rowmajor_xff((const int8_t*)src, (uint8_t*)dest) : -1;
     if (elem_sz == 1) {
         return kind == 1 ? decompress_rowmajor_delta_8b((const int8_t*)src, (uint8_t*)dest)
                          : decompress_rowmajor_8b((const int8_t*)src, (uint8_t*)dest);

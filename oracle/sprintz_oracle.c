@@ -421,27 +421,42 @@ int64_t oracle_decompress(int predictor, int elem_sz, const void* src_, void* de
  */
 #define KIND_DELTA 1
 #define KIND_PLAIN 2
+#define KIND_XFF8  3   /* compress8b_rowmajor_xff (sprintz_xff.cpp:35-303): FIRE exactly as the 8-bit RLE codec
+                        * (coef = (counter >> 5) << 4, odd-row gradients, counter += grad_sum >> 2), no run slots,
+                        * 8-byte metadata [u48 len][u16 ndims] (:64-69) */
 
-static uint32_t rowmajor_block(const cfg_t* c, int kind, uint32_t* prev_val, const uint8_t* src, uint64_t first_elem,
-                               uint32_t* zz, uint8_t* nbits)
+static uint32_t rowmajor_block(const cfg_t* c, int kind, uint32_t* prev_val, int32_t* prev_delta, int32_t* counter,
+                               const uint8_t* src, uint64_t first_elem, uint32_t* zz, uint8_t* nbits)
 {
     const int D = c->D, w = c->w;
     const uint32_t wmask = (1u << w) - 1u;
     uint32_t total = 0;
     for (int d = 0; d < D; d++) {
         uint32_t mask = 0, pv = prev_val[d];
+        int32_t pd = prev_delta[d], gs = 0;
+        const int32_t coef = (kind == KIND_XFF8) ? fire_coef(c, counter[d]) : 0;
         for (int r = 0; r < BLOCK_SZ; r++) {
             uint32_t v = load_elem(src, first_elem + (uint64_t)r * D + d, c->esz);
             uint32_t z = v;
-            if (kind == KIND_DELTA) {
+            if (kind != KIND_PLAIN) {
                 int32_t delta = (int32_t)sx((int64_t)v - (int64_t)pv, w);
-                z = (((uint32_t)delta << 1) ^ (uint32_t)(delta >> (w - 1))) & wmask;
+                int32_t err = delta;
+                if (kind == KIND_XFF8) {
+                    err = (int32_t)sx((int64_t)delta - fire_predict(c, pd, coef), w);
+                    if (r & 1) {
+                        int32_t g = (err == 0) ? 0 : (err < 0 ? (int32_t)sx(-(int64_t)pd, w) : pd);
+                        gs = (int32_t)sx((int64_t)gs + g, w);
+                    }
+                }
+                z = (((uint32_t)err << 1) ^ (uint32_t)(err >> (w - 1))) & wmask;
+                pd = delta;
             }
             zz[r * D + d] = z;
             mask |= z;
             pv = v;
         }
-        prev_val[d] = pv;
+        prev_val[d] = pv; prev_delta[d] = pd;
+        if (kind == KIND_XFF8) counter[d] = (int32_t)sx((int64_t)counter[d] + (gs >> 2), c->cb);
         nbits[d] = (uint8_t)nbits_rule(c, mask);
         total += nbits[d];
     }
@@ -454,11 +469,12 @@ int64_t oracle_compress_rowmajor(int kind, int elem_sz, const void* src_, uint32
     const uint8_t* src = (const uint8_t*)src_;
     uint8_t* const orig = (uint8_t*)dest_;
     uint8_t* dest = orig;
-    cfg_t c = make_cfg(0, elem_sz, ndims ? ndims : 1);
+    cfg_t c = make_cfg(kind == KIND_XFF8, elem_sz, ndims ? ndims : 1);
     c.low = 0;                                            /* one layout / width rule for every ndims */
     const int D = c.D;
-    if (write_size) {                                     /* format.h:65-73 */
+    if (write_size) {                                     /* format.h:65-73; sprintz_xff.cpp:64-69 for kind 3 */
         dest[0] = (uint8_t)len; dest[1] = (uint8_t)(len >> 8); dest[2] = (uint8_t)(len >> 16); dest[3] = (uint8_t)(len >> 24);
+        if (kind == KIND_XFF8) { dest[4] = 0; dest[5] = 0; dest += 2; }
         dest[4] = (uint8_t)ndims; dest[5] = (uint8_t)(ndims >> 8);
         dest += 6;
     }
@@ -467,6 +483,8 @@ int64_t oracle_compress_rowmajor(int kind, int elem_sz, const void* src_, uint32
         const uint64_t B = (uint64_t)BLOCK_SZ * D, G = 2 * B;
         const uint64_t ngroups = len / G;
         uint32_t* prev = (uint32_t*)calloc(D, sizeof(uint32_t));
+        int32_t* pdel = (int32_t*)calloc(D, sizeof(int32_t));
+        int32_t* cnt = (int32_t*)calloc(D, sizeof(int32_t));
         uint32_t* zz = (uint32_t*)malloc(sizeof(uint32_t) * BLOCK_SZ * D);
         uint8_t* nbits = (uint8_t*)malloc(D);
         for (uint64_t g = 0; g < ngroups; g++) {
@@ -474,7 +492,7 @@ int64_t oracle_compress_rowmajor(int kind, int elem_sz, const void* src_, uint32
             memset(hdr, 0, c.H);
             dest += c.H;
             for (uint32_t b = 0; b < 2; b++) {
-                uint32_t total = rowmajor_block(&c, kind, prev, src, (g * 2 + b) * B, zz, nbits);
+                uint32_t total = rowmajor_block(&c, kind, prev, pdel, cnt, src, (g * 2 + b) * B, zz, nbits);
                 for (int d = 0; d < D; d++) {
                     uint32_t field = nbits[d] - (nbits[d] == c.w);
                     put_bits(hdr, (uint64_t)(b * (uint32_t)D + (uint32_t)d) * c.hb, field, c.hb);
@@ -489,7 +507,7 @@ int64_t oracle_compress_rowmajor(int kind, int elem_sz, const void* src_, uint32
             }
         }
         tail = ngroups * G;
-        free(prev); free(zz); free(nbits);
+        free(prev); free(pdel); free(cnt); free(zz); free(nbits);
     }
     memcpy(dest, src + tail * c.esz, (size_t)(len - tail) * c.esz);
     dest += (size_t)(len - tail) * c.esz;
@@ -502,22 +520,28 @@ int64_t oracle_decompress_rowmajor(int kind, int elem_sz, const void* src_, void
     const uint8_t* src = (const uint8_t*)src_;
     uint8_t* out = (uint8_t*)dest_;
     const uint32_t len = (uint32_t)src[0] | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16) | ((uint32_t)src[3] << 24);
+    if (kind == KIND_XFF8) src += 2;                       /* u48 length (we only carry 32 bits of it) */
     const uint16_t ndims = (uint16_t)(src[4] | (src[5] << 8));
     src += 6;
     if (len < MIN_DATA_SIZE) { memcpy(out, src, (size_t)len * elem_sz); return len; }   /* sprintz_delta.cpp:1056-1060 */
     if (ndims == 0) return 0;
-    cfg_t c = make_cfg(0, elem_sz, ndims);
+    cfg_t c = make_cfg(kind == KIND_XFF8, elem_sz, ndims);
     c.low = 0;
     const int D = c.D, w = c.w;
     const uint32_t wmask = (1u << w) - 1u;
     const uint64_t B = (uint64_t)BLOCK_SZ * D, G = 2 * B, ngroups = len / G;
     uint32_t* prev = (uint32_t*)calloc(D, sizeof(uint32_t));
+    int32_t* pdel = (int32_t*)calloc(D, sizeof(int32_t));
+    int32_t* cnt = (int32_t*)calloc(D, sizeof(int32_t));
+    int32_t* gsum = (int32_t*)calloc(D, sizeof(int32_t));
+    int32_t* coefs = (int32_t*)calloc(D, sizeof(int32_t));
     uint8_t* nbits = (uint8_t*)malloc(D);
     uint64_t o = 0;
     for (uint64_t g = 0; g < ngroups; g++) {
         const uint8_t* hdr = src; src += c.H;
         for (uint32_t b = 0; b < 2; b++) {
             uint32_t total = 0;
+            for (int d = 0; d < D; d++) { gsum[d] = 0; coefs[d] = (kind == KIND_XFF8) ? fire_coef(&c, cnt[d]) : 0; }
             for (int d = 0; d < D; d++) {
                 uint32_t f = get_bits(hdr, (uint64_t)(b * (uint32_t)D + (uint32_t)d) * c.hb, c.hb);
                 nbits[d] = (uint8_t)(f == (uint32_t)(w - 1) ? (uint32_t)w : f);
@@ -529,20 +553,31 @@ int64_t oracle_decompress_rowmajor(int kind, int elem_sz, const void* src_, void
                 for (int d = 0; d < D; d++) {
                     uint32_t u = get_bits(src, bit, nbits[d]); bit += nbits[d];
                     uint32_t v = u;
-                    if (kind == KIND_DELTA) {
-                        int32_t delta = (int32_t)sx((int64_t)((u >> 1) ^ (0u - (u & 1u))), w);
+                    if (kind != KIND_PLAIN) {
+                        int32_t err = (int32_t)sx((int64_t)((u >> 1) ^ (0u - (u & 1u))), w);
+                        int32_t delta = err;
+                        if (kind == KIND_XFF8) {
+                            delta = (int32_t)sx((int64_t)err + fire_predict(&c, pdel[d], coefs[d]), w);
+                            if (r & 1) {
+                                int32_t gr = (err == 0) ? 0 : (err < 0 ? (int32_t)sx(-(int64_t)pdel[d], w) : pdel[d]);
+                                gsum[d] = (int32_t)sx((int64_t)gsum[d] + gr, w);
+                            }
+                            pdel[d] = delta;
+                        }
                         v = (prev[d] + (uint32_t)delta) & wmask;
                         prev[d] = v;
                     }
                     store_elem(out, o + (uint64_t)r * D + d, c.esz, v);
                 }
             }
+            if (kind == KIND_XFF8)
+                for (int d = 0; d < D; d++) cnt[d] = (int32_t)sx((int64_t)cnt[d] + (gsum[d] >> 2), c.cb);
             src += (size_t)row_bytes * BLOCK_SZ;
             o += B;
         }
     }
     memcpy(out + o * c.esz, src, (size_t)(len - o) * c.esz);
-    free(prev); free(nbits);
+    free(prev); free(pdel); free(cnt); free(gsum); free(coefs); free(nbits);
     return (int64_t)len;
 }
 

@@ -53,6 +53,8 @@ SYMBOLS = {
     "spz_decompress_rowmajor_8b": (_i64, [_vp, _vp]),
     "spz_compress_rowmajor_16b": (_i64, [_vp, _u32, _vp, _u16, _i]),
     "spz_decompress_rowmajor_16b": (_i64, [_vp, _vp]),
+    "spz_compress8b_rowmajor_xff": (_i64, [_vp, _u64, _vp, _u16, _i]),
+    "spz_decompress8b_rowmajor_xff": (_i64, [_vp, _vp]),
     "spz_compress_rowmajor_host": (_i64, [_i, _i, _vp, _u32, _vp, _u16, _i, C.POINTER(_u64)]),
     "spz_decompress_rowmajor_host": (_i64, [_i, _i, _vp, _vp]),
     "spz_compress_host": (_i64, [_i, _i, _vp, _u32, _vp, _u16, _i, C.POINTER(_u64)]),

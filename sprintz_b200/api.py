@@ -25,10 +25,10 @@ __all__ = [
     "sprintz_compress_xff_16b", "sprintz_decompress_xff_16b",
     "Frame", "frame_encode", "frame_decode", "frame_compress_host", "frame_decompress_host",
     "compress_dev", "decompress_dev", "set_kernel_path",
-    "RM_DELTA", "RM_PLAIN", "compress_rowmajor", "decompress_rowmajor",
+    "RM_DELTA", "RM_PLAIN", "RM_XFF8", "compress_rowmajor", "decompress_rowmajor",
 ]
 
-RM_DELTA, RM_PLAIN = 1, 2     # compress_rowmajor_delta_* / compress_rowmajor_* (sprintz_delta.h:27-44)
+RM_DELTA, RM_PLAIN, RM_XFF8 = 1, 2, 3   # compress_rowmajor_delta_* / compress_rowmajor_* / compress8b_rowmajor_xff
 
 _UDT = {1: np.uint8, 2: np.uint16}
 

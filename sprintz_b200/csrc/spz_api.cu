@@ -48,10 +48,10 @@ static inline bool valid_codec(int predictor, int elem_sz)
 {
     return (predictor == 0 || predictor == 1) && (elem_sz == 1 || elem_sz == 2);
 }
-// frames also carry the non-RLE sibling codecs: SPZ_RM_DELTA (2), SPZ_RM_PLAIN (3)
+// frames also carry the non-RLE sibling codecs: SPZ_RM_DELTA (2), SPZ_RM_PLAIN (3), SPZ_RM_XFF (4, 8-bit only)
 static inline bool valid_frame_codec(int predictor, int elem_sz)
 {
-    return predictor >= 0 && predictor <= 3 && (elem_sz == 1 || elem_sz == 2);
+    return predictor >= 0 && predictor <= 4 && (elem_sz == 1 || elem_sz == 2) && !(predictor == 4 && elem_sz != 1);
 }
 
 // ------------------------------------------------------------------ optional per-kernel timing of the frame encoder
@@ -488,11 +488,12 @@ extern "C" int64_t spz_decompress_xff_16b(const int16_t* s, uint16_t* d) { retur
 // compress_rowmajor_delta_{8b,16b} / compress_rowmajor_{8b,16b} and their decoders (sprintz_delta.h:27-44).
 // kind 1 = delta, 2 = plain bit packing.  Same kernels as the RLE codecs (generic family, variant flag).
 
-static int measure_rowmajor(int elem_sz, const uint8_t* src, uint64_t* stream_bytes, uint64_t* decoded_elems, uint16_t* ndims_out)
+static int measure_rowmajor(int kind, int elem_sz, const uint8_t* src, uint64_t* stream_bytes, uint64_t* decoded_elems, uint16_t* ndims_out)
 {
     const uint32_t len = (uint32_t)src[0] | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16) | ((uint32_t)src[3] << 24);
-    const uint32_t D = (uint32_t)src[4] | ((uint32_t)src[5] << 8);
-    uint64_t pos = 6;
+    const uint32_t at = kind == 3 ? 6u : 4u;                  // kind 3: [u48 len][u16 ndims]
+    const uint32_t D = (uint32_t)src[at] | ((uint32_t)src[at + 1] << 8);
+    uint64_t pos = at + 2;
     *ndims_out = (uint16_t)D;
     uint64_t done = 0;
     if (len >= kMinDataSize) {
@@ -524,16 +525,16 @@ static int measure_rowmajor(int elem_sz, const uint8_t* src, uint64_t* stream_by
 extern "C" int64_t spz_compress_rowmajor_host(int kind, int elem_sz, const void* src, uint32_t len, void* dest,
                                               uint16_t ndims, int write_size, uint64_t* true_nbytes)
 {
-    if (kind != 1 && kind != 2) return SPZ_E_ARG;
-    return compress_host_impl((uint32_t)kind, SPZ_DELTA, elem_sz, src, len, dest, ndims, write_size, true_nbytes);
+    if (kind < 1 || kind > 3 || (kind == 3 && elem_sz != 1)) return SPZ_E_ARG;
+    return compress_host_impl((uint32_t)kind, kind == 3 ? SPZ_XFF : SPZ_DELTA, elem_sz, src, len, dest, ndims, write_size, true_nbytes);
 }
 
 extern "C" int64_t spz_decompress_rowmajor_host(int kind, int elem_sz, const void* src, void* dest)
 {
-    if ((kind != 1 && kind != 2) || !valid_codec(SPZ_DELTA, elem_sz)) return SPZ_E_ARG;
+    if (kind < 1 || kind > 3 || (kind == 3 && elem_sz != 1) || !valid_codec(SPZ_DELTA, elem_sz)) return SPZ_E_ARG;
     uint64_t sbytes = 0, elems = 0;
     uint16_t ndims = 0;
-    int rc = measure_rowmajor(elem_sz, (const uint8_t*)src, &sbytes, &elems, &ndims);
+    int rc = measure_rowmajor(kind, elem_sz, (const uint8_t*)src, &sbytes, &elems, &ndims);
     if (rc != SPZ_OK) return rc == SPZ_E_ARG ? 0 : rc;            // ndims == 0: the reference returns 0
     if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
     std::lock_guard<std::mutex> lk(g_cache.mu);
@@ -544,7 +545,7 @@ extern "C" int64_t spz_decompress_rowmajor_host(int kind, int elem_sz, const voi
     CK(g_cache.ensure(2, 64));
     CK(cudaMemcpyAsync(g_cache.buf[0], src, sbytes, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(g_cache.buf[2], 0, sizeof(spz_chunk_meta), st));
-    rc = decompress_dev_impl((uint32_t)kind, SPZ_DELTA, elem_sz, g_cache.buf[0], sbytes + 16, 1, ndims ? ndims : 1,
+    rc = decompress_dev_impl((uint32_t)kind, kind == 3 ? SPZ_XFF : SPZ_DELTA, elem_sz, g_cache.buf[0], sbytes + 16, 1, ndims ? ndims : 1,
                              g_cache.buf[1], elems, (spz_chunk_meta*)g_cache.buf[2], st);
     if (rc != SPZ_OK) return rc;
     spz_chunk_meta m;
@@ -562,6 +563,8 @@ extern "C" int64_t spz_decompress_rowmajor_delta_16b(const int16_t* s, uint16_t*
 extern "C" int64_t spz_compress_rowmajor_8b(const uint8_t* s, uint32_t n, int8_t* d, uint16_t nd, int ws) { return spz_compress_rowmajor_host(2, 1, s, n, d, nd, ws, nullptr); }
 extern "C" int64_t spz_decompress_rowmajor_8b(const int8_t* s, uint8_t* d) { return spz_decompress_rowmajor_host(2, 1, s, d); }
 extern "C" int64_t spz_compress_rowmajor_16b(const uint16_t* s, uint32_t n, int16_t* d, uint16_t nd, int ws) { return spz_compress_rowmajor_host(2, 2, s, n, d, nd, ws, nullptr); }
+extern "C" int64_t spz_compress8b_rowmajor_xff(const uint8_t* s, uint64_t n, int8_t* d, uint16_t nd, int ws) { return n > 0xffffffffull ? SPZ_E_ARG : spz_compress_rowmajor_host(3, 1, s, (uint32_t)n, d, nd, ws, nullptr); }
+extern "C" int64_t spz_decompress8b_rowmajor_xff(const int8_t* s, uint8_t* d) { return spz_decompress_rowmajor_host(3, 1, s, d); }
 extern "C" int64_t spz_decompress_rowmajor_16b(const int16_t* s, uint16_t* d) { return spz_decompress_rowmajor_host(2, 2, s, d); }
 
 // ------------------------------------------------------------------ frame, host buffers

@@ -59,8 +59,9 @@ __global__ void __launch_bounds__(kThreads) spz_decode_kernel(const DecParams p)
     const uint32_t variant = p.variant; // 1 / 2: non-RLE sibling codecs (see spz_encode.cu)
     if (variant) {                      // format.h:75-85: [u32 len][u16 ndims]; ngroups is implied
         const uint32_t len32 = (uint32_t)stream[0] | ((uint32_t)stream[1] << 8) | ((uint32_t)stream[2] << 16) | ((uint32_t)stream[3] << 24);
-        const uint32_t nd = (uint32_t)stream[4] | ((uint32_t)stream[5] << 8);
-        pos = 6;
+        const uint32_t at = variant == 3u ? 6u : 4u;          // variant 3: [u48 len][u16 ndims] (sprintz_xff.cpp:64-69)
+        const uint32_t nd = (uint32_t)stream[at] | ((uint32_t)stream[at + 1] << 8);
+        pos = at + 2;
         if (len32 < kMinDataSize) { ngroups = 0; remaining = len32; }
         else {
             if (nd != (uint32_t)D) status = kStatusBadDims;
@@ -217,7 +218,8 @@ int last_decode_family() { return g_last_decode_family; }
 
 cudaError_t launch_decode(int elem_sz, int predictor, DecParams p, cudaStream_t stream)
 {
-    if (predictor >= 2) { p.variant = (uint32_t)predictor - 1u; predictor = 0; }   // SPZ_RM_DELTA / SPZ_RM_PLAIN (frames)
+    if (predictor >= 2) { p.variant = (uint32_t)predictor - 1u; }                  // SPZ_RM_DELTA / SPZ_RM_PLAIN / SPZ_RM_XFF (frames)
+    if (p.variant) predictor = (p.variant == 3u) ? 1 : 0;
     {   // throughput path: frames with many chunks of 8 / 16 dims (spz_decode_lane.cu)
         const cudaError_t e = launch_decode_lane(elem_sz, predictor, p, stream);
         if (e != cudaErrorNotSupported) { g_last_decode_family = 2; return e; }
@@ -228,7 +230,6 @@ cudaError_t launch_decode(int elem_sz, int predictor, DecParams p, cudaStream_t 
         if (e != cudaErrorNotSupported) { g_last_decode_family = 1; return e; }
     }
     g_last_decode_family = 0;
-    if (p.variant) predictor = 0;
     const bool low = p.variant ? false : (elem_sz == 1 ? (p.ndims <= 4) : (p.ndims <= 2));
     p.team = p.ndims >= 32 ? 32 : pow2_ceil(p.ndims);
     p.dpl = (p.ndims + p.team - 1) / p.team;

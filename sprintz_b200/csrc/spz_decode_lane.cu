@@ -168,8 +168,9 @@ __global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_k
     const uint32_t variant = p.variant;              // 1 / 2: the non-RLE sibling codecs (6-byte metadata, no run slots)
     if (variant) {                                   // format.h:75-85: [u32 len][u16 ndims]
         const uint32_t len32 = window(pos);
-        const uint32_t nd = window(pos + 32u) & 0xffffu;
-        pos += 48u;
+        const uint32_t w1 = window(pos + 32u);
+        const uint32_t nd = variant == 3u ? (w1 >> 16) : (w1 & 0xffffu);       // variant 3: [u48 len][u16 ndims]
+        pos += variant == 3u ? 64u : 48u;
         ensure(pos);
         if (len32 < kMinDataSize) { remaining = len32; }
         else {
@@ -374,7 +375,7 @@ static cudaError_t launch_lane(const DecParams& p, cudaStream_t stream)
 // Returns cudaErrorNotSupported when the shape is not covered (caller continues with the team kernels).
 cudaError_t launch_decode_lane(int elem_sz, int predictor, DecParams p, cudaStream_t stream)
 {
-    if (g_force_path == 1 || (p.variant && predictor)) return cudaErrorNotSupported;
+    if (g_force_path == 1) return cudaErrorNotSupported;
     if (p.ndims != 8 && p.ndims != 16) return cudaErrorNotSupported;
     if (p.src_end == nullptr || p.src_end <= p.src) return cudaErrorNotSupported;
     // a lane is a whole scalar decoder: only worth it when there are enough chunks to fill the machine

@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(kThreads) spz_encode_kernel(const EncParams p)
     // (sprintz_delta.cpp:776-1017, :64-392): 6-byte metadata [u32 len][u16 ndims] (format.h:65-73), every block
     // is a data slot (possibly of zero bytes), no zigzag/delta for variant 2
     const uint32_t variant = p.variant;
-    const uint32_t meta_bytes = p.write_size ? (variant ? 6u : 8u) : 0u;
+    // variant 3: compress8b_rowmajor_xff (sprintz_xff.cpp:35-303): FIRE without run slots, 8-byte metadata [u48 len][u16 ndims]
+    const uint32_t meta_bytes = p.write_size ? ((variant == 1u || variant == 2u) ? 6u : 8u) : 0u;
 
     OutStage o;
     o.init(s_out, gstream);
@@ -318,11 +319,13 @@ stream_done:
         stage_flush(o, true, t, TEAM, tmask);
         __syncwarp(tmask);
         if (t == 0) {
-            if (p.write_size && variant) {      // format.h:65-73
+            if (p.write_size && variant) {      // format.h:65-73; sprintz_xff.cpp:64-69 for variant 3
                 const uint32_t L32 = (uint32_t)L;
                 gstream[0] = (uint8_t)L32; gstream[1] = (uint8_t)(L32 >> 8);
                 gstream[2] = (uint8_t)(L32 >> 16); gstream[3] = (uint8_t)(L32 >> 24);
-                gstream[4] = (uint8_t)D; gstream[5] = (uint8_t)(D >> 8);
+                const uint32_t at = variant == 3u ? 6u : 4u;
+                if (variant == 3u) { gstream[4] = 0; gstream[5] = 0; }
+                gstream[at] = (uint8_t)D; gstream[at + 1] = (uint8_t)(D >> 8);
             } else if (p.write_size) {     // format.h:35-45, written last because ngroups is only known now
                 const uint32_t rem16 = (uint32_t)rem_elems & 0xffffu;
                 gstream[0] = (uint8_t)ngroups; gstream[1] = (uint8_t)(ngroups >> 8);
@@ -382,7 +385,8 @@ int last_encode_family() { return g_last_encode_family; }
 
 cudaError_t launch_encode(int elem_sz, int predictor, EncParams p, cudaStream_t stream)
 {
-    if (predictor >= 2) { p.variant = (uint32_t)predictor - 1u; predictor = 0; }   // SPZ_RM_DELTA / SPZ_RM_PLAIN (frames)
+    if (predictor >= 2) { p.variant = (uint32_t)predictor - 1u; }                  // SPZ_RM_DELTA / SPZ_RM_PLAIN / SPZ_RM_XFF (frames)
+    if (p.variant) predictor = (p.variant == 3u) ? 1 : 0;
     {   // throughput path: frames with many chunks of 8 / 16 dims (spz_encode_lane.cu)
         const cudaError_t e = launch_encode_lane(elem_sz, predictor, p, stream);
         if (e != cudaErrorNotSupported) { g_last_encode_family = 2; return e; }
@@ -393,7 +397,6 @@ cudaError_t launch_encode(int elem_sz, int predictor, EncParams p, cudaStream_t 
         if (e != cudaErrorNotSupported) { g_last_encode_family = 1; return e; }
     }
     g_last_encode_family = 0;
-    if (p.variant) predictor = 0;
     const bool low = p.variant ? false : (elem_sz == 1 ? (p.ndims <= 4) : (p.ndims <= 2));
     p.team = p.ndims >= 32 ? 32 : pow2_ceil(p.ndims);
     p.dpl = (p.ndims + p.team - 1) / p.team;

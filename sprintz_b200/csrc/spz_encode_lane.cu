@@ -78,11 +78,12 @@ __global__ void __launch_bounds__(kEncLaneThreads, 4) spz_encode_lane_kernel(con
     uint8_t* const gout = p.dst + c * p.slot_stride;
     // variant 1 / 2: the non-RLE sibling codecs (delta / plain bit packing, 6-byte metadata, no run slots)
     const uint32_t variant = p.variant;
-    const uint32_t meta_bytes = p.write_size ? (variant ? 6u : 8u) : 0u;
+    const uint32_t meta_bytes = p.write_size ? ((variant == 1u || variant == 2u) ? 6u : 8u) : 0u;   // variant 3: [u48 len][u16 ndims]
 
     if (L < (int32_t)kMinDataSize) {                       // stored raw (sprintz_delta_rle.cpp:101-109)
         if (meta_bytes == 8u) {
-            *reinterpret_cast<uint2*>(gout) = make_uint2(0u, (uint32_t)L | ((uint32_t)D << 16));
+            *reinterpret_cast<uint2*>(gout) = variant == 3u ? make_uint2((uint32_t)L, (uint32_t)D << 16)
+                                                            : make_uint2(0u, (uint32_t)L | ((uint32_t)D << 16));
         } else if (meta_bytes == 6u) {
             *reinterpret_cast<uint32_t*>(gout) = (uint32_t)L;
             *reinterpret_cast<uint16_t*>(gout + 4) = (uint16_t)D;
@@ -417,8 +418,9 @@ __global__ void __launch_bounds__(kEncLaneThreads, 4) spz_encode_lane_kernel(con
         for (uint32_t b = 0; b < nb; b++) tdst[b] = tsrc[b];
         nbytes += nb;
     }
-    if (meta_bytes == 8u) {                                                    // format.h:35-45
-        *reinterpret_cast<uint2*>(gout) = make_uint2(ngroups, (remaining & 0xffffu) | ((uint32_t)D << 16));
+    if (meta_bytes == 8u) {                                                    // format.h:35-45 | sprintz_xff.cpp:64-69
+        *reinterpret_cast<uint2*>(gout) = variant == 3u ? make_uint2((uint32_t)L, (uint32_t)D << 16)
+                                                        : make_uint2(ngroups, (remaining & 0xffffu) | ((uint32_t)D << 16));
     } else if (meta_bytes == 6u) {                                             // format.h:65-73
         *reinterpret_cast<uint32_t*>(gout) = (uint32_t)L;
         *reinterpret_cast<uint16_t*>(gout + 4) = (uint16_t)D;
@@ -447,7 +449,7 @@ static cudaError_t launch_enc_lane(const EncParams& p, cudaStream_t stream)
 cudaError_t launch_encode_lane(int elem_sz, int predictor, EncParams p, cudaStream_t stream)
 {
     const int force = get_force_path();
-    if (force == 1 || (p.variant && predictor)) return cudaErrorNotSupported;
+    if (force == 1) return cudaErrorNotSupported;
     if (!((elem_sz == 1 && p.ndims == 8) || (elem_sz == 2 && (p.ndims == 8 || p.ndims == 16)))) return cudaErrorNotSupported;
     if (p.meta == nullptr) return cudaErrorNotSupported;
     // a lane is a whole scalar encoder: only worth it when there are enough chunks to fill the machine

@@ -1,6 +1,6 @@
 """Generates tests/golden/golden_rowmajor_v1.npz from the UNMODIFIED reference (oracle/_ref/libsprintz_ref.so):
-the non-RLE sibling codecs compress_rowmajor_delta_{8b,16b} (kind 1) and compress_rowmajor_{8b,16b} (kind 2),
-sprintz_delta.h:27-44.  Run in the build container only:
+the non-RLE sibling codecs compress_rowmajor_delta_{8b,16b} (kind 1), compress_rowmajor_{8b,16b} (kind 2),
+sprintz_delta.h:27-44, and compress8b_rowmajor_xff (kind 3), sprintz_xff.h:28-31.  Run in the build container only:
 
     python tests/golden/make_golden_rowmajor.py
 
@@ -17,12 +17,12 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import inputs  # noqa: E402
-from oracle import RM_DELTA, RM_PLAIN, Ref  # noqa: E402
+from oracle import RM_DELTA, RM_PLAIN, RM_XFF8, Ref  # noqa: E402
 
 
 def cases():
     for esz in (1, 2):
-        for kind in (RM_DELTA, RM_PLAIN):
+        for kind in (RM_DELTA, RM_PLAIN) + ((RM_XFF8,) if esz == 1 else ()):
             for D in (1, 3, 5, 8, 16, 33):
                 for n in (1, 127, 128, 137, 1024 + 17):
                     fams = inputs.reference_families(n, esz)

@@ -8,10 +8,10 @@ import pytest
 
 import inputs
 import parity
-from oracle import RM_DELTA, RM_PLAIN
+from oracle import RM_DELTA, RM_PLAIN, RM_XFF8
 
-KINDS = [(RM_DELTA, 1), (RM_PLAIN, 1), (RM_DELTA, 2), (RM_PLAIN, 2)]
-KIDS = ["delta8", "plain8", "delta16", "plain16"]
+KINDS = [(RM_DELTA, 1), (RM_PLAIN, 1), (RM_DELTA, 2), (RM_PLAIN, 2), (RM_XFF8, 1)]
+KIDS = ["delta8", "plain8", "delta16", "plain16", "xff8"]
 DIMS = (1, 2, 3, 4, 5, 7, 8, 9, 16, 17, 33, 80)
 
 
@@ -70,21 +70,26 @@ def test_gpu_rowmajor_named_entry_points_vs_live_reference(ref):
     import sprintz_b200 as spz
     L = spz.lib()
     for name, kind, esz, D in (("rowmajor_delta_8b", RM_DELTA, 1, 8), ("rowmajor_delta_16b", RM_DELTA, 2, 16),
-                               ("rowmajor_8b", RM_PLAIN, 1, 5), ("rowmajor_16b", RM_PLAIN, 2, 3)):
+                               ("rowmajor_8b", RM_PLAIN, 1, 5), ("rowmajor_16b", RM_PLAIN, 2, 3),
+                               ("8b_rowmajor_xff", RM_XFF8, 1, 8)):
         x = inputs.random_walk_with_runs(900, D, esz, seed=3)
         rs, rr = ref.compress_rowmajor(kind, x, D)
         out = np.zeros(spz.max_compressed_bytes(esz, x.size, D), np.uint8)
-        ret = getattr(L, "spz_compress_" + name)(x.ctypes.data, x.size, out.ctypes.data, D, 1)
+        cname, dname = ("spz_compress" + name, "spz_decompress" + name) if kind == RM_XFF8 else \
+                       ("spz_compress_" + name, "spz_decompress_" + name)
+        ret = getattr(L, cname)(x.ctypes.data, x.size, out.ctypes.data, D, 1)
         assert ret == rr and np.array_equal(out[: rr * esz], rs[: rr * esz])
         dec = np.zeros(x.size, x.dtype)
-        n = getattr(L, "spz_decompress_" + name)(out.ctypes.data, dec.ctypes.data)
+        n = getattr(L, dname)(out.ctypes.data, dec.ctypes.data)
         assert n == x.size and np.array_equal(dec, x)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind", [RM_DELTA, RM_PLAIN], ids=["delta", "plain"])
+@pytest.mark.parametrize("kind", [RM_DELTA, RM_PLAIN, RM_XFF8], ids=["delta", "plain", "xff8"])
 @pytest.mark.parametrize("esz,D", [(1, 8), (2, 16), (1, 3), (1, 80)])
 def test_gpu_rowmajor_frames(oracle, kind, esz, D):
+    if kind == RM_XFF8 and esz != 1:
+        pytest.skip("compress8b_rowmajor_xff is 8-bit only")
     """Frames carry the non-RLE codecs as codec ids 2 / 3: every chunk is that codec's reference stream."""
     import sprintz_b200 as spz
     from test_gpu_frame import _frame_vs_oracle
