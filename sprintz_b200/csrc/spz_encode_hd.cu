@@ -195,13 +195,16 @@ __global__ void __launch_bounds__(kThreads) spz_encode_hd_kernel(const EncParams
 #pragma unroll 2
                 for (int q = 0; q < NCL; q++) {
                     uint32_t qv;
+                    // the cluster's zigzagged values come in as ONE aligned word (rows are 4-byte aligned, a cluster
+                    // is 4 bytes): the kernel is L1 / LSU bound (ncu: l1tex 94 %), byte loads were 1 LSU op per sample
+                    const uint32_t zw = reinterpret_cast<const uint32_t*>(zrow)[q];
                     if (CL == 4) {
                         const uint4 m = mul4[q];
-                        qv = (uint32_t)zrow[q * 4] * m.x + (uint32_t)zrow[q * 4 + 1] * m.y +
-                             (uint32_t)zrow[q * 4 + 2] * m.z + (uint32_t)zrow[q * 4 + 3] * m.w;
+                        qv = (zw & 0xffu) * m.x + __byte_perm(zw, 0, 0x4441) * m.y +
+                             __byte_perm(zw, 0, 0x4442) * m.z + (zw >> 24) * m.w;
                     } else {
                         const uint2 m = reinterpret_cast<const uint2*>(mul4)[q];
-                        qv = (uint32_t)zrow[q * 2] * m.x + (uint32_t)zrow[q * 2 + 1] * m.y;
+                        qv = (zw & 0xffffu) * m.x + (zw >> 16) * m.y;
                     }
                     const uint32_t p2 = 1u << pos;
                     asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(qv), "r"(p2));   // fields are disjoint: add == or
