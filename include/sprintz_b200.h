@@ -121,6 +121,27 @@ int64_t spz_compress_rowmajor_host(int kind, int elem_sz, const void* src, uint3
                                    int write_size, uint64_t* true_nbytes);
 int64_t spz_decompress_rowmajor_host(int kind, int elem_sz, const void* src, void* dest);
 
+/* Stand-alone forecaster transforms (delta.h:17-67, delta.cpp:34-744): same-size in/out,
+ * y[i] = x[i] - x[i-ndims] (delta) or its second difference (double delta), x[i<0] = 0, optional 6-byte metadata
+ * [u32 len][u16 ndims] in front of the output.  Same arguments and returns (len + metadata elements / len) as the
+ * reference functions of the same names; order: 1 = delta, 2 = double delta. */
+uint32_t spz_encode_delta_rowmajor_8b (const uint8_t*  src, uint32_t len, int8_t*  dest, uint16_t ndims, int write_size);
+uint32_t spz_decode_delta_rowmajor_8b (const int8_t*   src, uint32_t len, uint8_t*  dest, uint16_t ndims);
+uint32_t spz_encode_delta_rowmajor_16b(const uint16_t* src, uint32_t len, int16_t* dest, uint16_t ndims, int write_size);
+uint32_t spz_decode_delta_rowmajor_16b(const int16_t*  src, uint32_t len, uint16_t* dest, uint16_t ndims);
+uint32_t spz_encode_doubledelta_rowmajor_8b (const uint8_t*  src, uint32_t len, int8_t*  dest, uint16_t ndims, int write_size);
+uint32_t spz_decode_doubledelta_rowmajor_8b (const int8_t*   src, uint32_t len, uint8_t*  dest, uint16_t ndims);
+uint32_t spz_encode_doubledelta_rowmajor_16b(const uint16_t* src, uint32_t len, int16_t* dest, uint16_t ndims, int write_size);
+uint32_t spz_decode_doubledelta_rowmajor_16b(const int16_t*  src, uint32_t len, uint16_t* dest, uint16_t ndims);
+int64_t spz_encode_forecast_host(int order, int elem_sz, const void* src, uint32_t len, void* dest, uint16_t ndims, int write_size);
+int64_t spz_decode_forecast_host(int order, int elem_sz, const void* src, uint32_t len, void* dest, uint16_t ndims);
+/* device buffers (16-byte aligned, readable up to the next 16-byte boundary past len elements); decode needs
+ * spz_forecast_workspace_bytes() of scratch for its chained scan */
+uint64_t spz_forecast_workspace_bytes(uint64_t len, uint16_t ndims);
+int spz_forecast_encode_dev(int order, int elem_sz, const void* d_src, uint64_t len, uint16_t ndims, void* d_dest, spz_stream_t stream);
+int spz_forecast_decode_dev(int order, int elem_sz, const void* d_src, uint64_t len, uint16_t ndims, void* d_dest,
+                            void* d_work, uint64_t work_bytes, spz_stream_t stream);
+
 /* ---------------------------------------------------------------- 2. single stream, device buffers
  * d_dest must hold spz_max_compressed_bytes(); d_meta (1 record) receives sizes. Asynchronous on `stream`. */
 int spz_compress_dev(int predictor, int elem_sz, const void* d_src, uint32_t len, uint16_t ndims,

@@ -76,7 +76,28 @@ class Oracle(_Codec):
                                                C.c_uint16, C.c_int, C.POINTER(C.c_uint64)]
         L.oracle_decompress_rowmajor.restype = C.c_int64
         L.oracle_decompress_rowmajor.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.oracle_encode_forecast.restype = C.c_int64
+        L.oracle_encode_forecast.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint16, C.c_int]
+        L.oracle_decode_forecast.restype = C.c_int64
+        L.oracle_decode_forecast.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint16]
         self.L = L
+
+    def encode_forecast(self, order, x, ndims, write_size=True):
+        """Stand-alone forecaster transform (order 1 = delta, 2 = double delta). -> (bytes incl. metadata, ret)"""
+        esz = x.dtype.itemsize
+        src = _as_u8(x)
+        buf = np.zeros(x.size * esz + 6 + SLACK, np.uint8)
+        ret = int(self.L.oracle_encode_forecast(order, esz, src.ctypes.data, x.size, buf.ctypes.data, ndims, int(write_size)))
+        return buf[: ret * esz].copy(), ret
+
+    def decode_forecast(self, order, esz, y, ndims):
+        """y: transformed elements without metadata. -> (decoded elements, ret)"""
+        y = np.ascontiguousarray(y)
+        n = y.size
+        src = np.concatenate([_as_u8(y), np.zeros(SLACK, np.uint8)])
+        out = np.full(n * esz + SLACK, 0xAA, np.uint8)
+        ret = int(self.L.oracle_decode_forecast(order, esz, src.ctypes.data, n, out.ctypes.data, ndims))
+        return out[: n * esz].view(np.uint8 if esz == 1 else np.uint16).copy(), ret
 
     def compress_rowmajor(self, kind, x, ndims, write_size=True):
         esz = x.dtype.itemsize
@@ -147,7 +168,30 @@ class Ref(_Codec):
             L.ref_compress_rowmajor.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint16, C.c_int]
             L.ref_decompress_rowmajor.restype = C.c_int64
             L.ref_decompress_rowmajor.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        if hasattr(L, "ref_encode_forecast"):
+            L.ref_encode_forecast.restype = C.c_int64
+            L.ref_encode_forecast.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint16, C.c_int]
+            L.ref_decode_forecast.restype = C.c_int64
+            L.ref_decode_forecast.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint16]
         self.L = L
+
+    def encode_forecast(self, order, x, ndims, write_size=True):
+        esz = x.dtype.itemsize
+        # the reference reads up to ndims elements BEFORE the input (delta.cpp:112-115) and vector-width past it
+        pad = SLACK + 4 * max(1, ndims) * esz
+        src = np.concatenate([np.zeros(pad, np.uint8), _as_u8(x), np.zeros(SLACK, np.uint8)])
+        buf = np.zeros(x.size * esz + 6 + 2 * SLACK, np.uint8)
+        ret = int(self.L.ref_encode_forecast(order, esz, src.ctypes.data + pad, x.size, buf.ctypes.data, ndims, int(write_size)))
+        return buf[: ret * esz].copy(), ret
+
+    def decode_forecast(self, order, esz, y, ndims):
+        y = np.ascontiguousarray(y)
+        n = y.size
+        src = np.concatenate([_as_u8(y), np.zeros(SLACK, np.uint8)])
+        pad = SLACK + 4 * max(1, ndims) * esz
+        out = np.full(pad + n * esz + 2 * SLACK, 0, np.uint8)
+        ret = int(self.L.ref_decode_forecast(order, esz, src.ctypes.data, n, out.ctypes.data + pad, ndims))
+        return out[pad: pad + n * esz].view(np.uint8 if esz == 1 else np.uint16).copy(), ret
 
     def compress_rowmajor(self, kind, x, ndims, write_size=True):
         esz = x.dtype.itemsize

@@ -22,6 +22,7 @@
 #include "sprintz.h"   // from -I$(REF)/cpp/Compress
 #include "sprintz_delta.h"   // the non-RLE sibling codecs
 #include "sprintz_xff.h"     // compress8b_rowmajor_xff
+#include "delta.h"           // stand-alone forecaster transforms
 
 extern "C" {
 
@@ -82,6 +83,24 @@ int64_t ref_decompress_rowmajor(int kind, int elem_sz, const void* src, void* de
     }
     return kind == 1 ? decompress_rowmajor_delta_16b((const int16_t*)src, (uint16_t*)dest)
                      : decompress_rowmajor_16b((const int16_t*)src, (uint16_t*)dest);
+}
+
+// stand-alone forecaster transforms (delta.h:17-67): order 1 = delta, 2 = double delta
+int64_t ref_encode_forecast(int order, int elem_sz, const void* src, uint32_t len, void* dest, uint16_t ndims, int write_size)
+{
+    if (elem_sz == 1)
+        return order == 1 ? encode_delta_rowmajor_8b((const uint8_t*)src, len, (int8_t*)dest, ndims, write_size != 0)
+                          : encode_doubledelta_rowmajor_8b((const uint8_t*)src, len, (int8_t*)dest, ndims, write_size != 0);
+    return order == 1 ? encode_delta_rowmajor_16b((const uint16_t*)src, len, (int16_t*)dest, ndims, write_size != 0)
+                      : encode_doubledelta_rowmajor_16b((const uint16_t*)src, len, (int16_t*)dest, ndims, write_size != 0);
+}
+int64_t ref_decode_forecast(int order, int elem_sz, const void* src, uint32_t len, void* dest, uint16_t ndims)
+{
+    if (elem_sz == 1)
+        return order == 1 ? decode_delta_rowmajor_8b((const int8_t*)src, len, (uint8_t*)dest, ndims)
+                          : decode_doubledelta_rowmajor_8b((const int8_t*)src, len, (uint8_t*)dest, ndims);
+    return order == 1 ? decode_delta_rowmajor_16b((const int16_t*)src, len, (uint16_t*)dest, ndims)
+                      : decode_doubledelta_rowmajor_16b((const int16_t*)src, len, (uint16_t*)dest, ndims);
 }
 
 // Compress `nchunks` consecutive slices of `src` (chunk c covers elements

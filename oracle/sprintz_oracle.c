@@ -581,6 +581,57 @@ int64_t oracle_decompress_rowmajor(int kind, int elem_sz, const void* src_, void
     return (int64_t)len;
 }
 
+/* ------------------------------------------------------------------ stand-alone forecaster transforms
+ *
+ * encode/decode_{delta,doubledelta}_rowmajor_{8b,16b} (delta.h:17-67, delta.cpp:34-744): same-size in/out,
+ * optional 6-byte metadata [u32 len][u16 ndims] (format.h:65-85).  Behaviourally (whatever vector / serial path the
+ * reference takes) with x[i] = 0 for i < 0, all arithmetic mod 2^w:
+ *   delta       : y[i] = x[i] - x[i-D]
+ *   doubledelta : y[i] = (x[i] - x[i-D]) - (x[i-D] - x[i-2D])
+ * Returns len + the metadata length in ELEMENTS (6 for 8-bit, 3 for 16-bit), like the reference.  order: 1 | 2. */
+int64_t oracle_encode_forecast(int order, int elem_sz, const void* src_, uint32_t len, void* dest_, uint16_t ndims,
+                               int write_size)
+{
+    const uint8_t* src = (const uint8_t*)src_;
+    uint8_t* dest = (uint8_t*)dest_;
+    const int w = 8 * elem_sz;
+    const uint32_t wmask = (1u << w) - 1u;
+    uint32_t meta = 0;
+    if (write_size) {
+        dest[0] = (uint8_t)len; dest[1] = (uint8_t)(len >> 8); dest[2] = (uint8_t)(len >> 16); dest[3] = (uint8_t)(len >> 24);
+        dest[4] = (uint8_t)ndims; dest[5] = (uint8_t)(ndims >> 8);
+        dest += 6; meta = 6 / (uint32_t)elem_sz;
+    }
+    const uint64_t D = ndims;
+    for (uint64_t i = 0; i < len; i++) {
+        uint32_t x0 = load_elem(src, i, elem_sz);
+        uint32_t x1 = (D && i >= D) ? load_elem(src, i - D, elem_sz) : 0;
+        uint32_t x2 = (D && i >= 2 * D) ? load_elem(src, i - 2 * D, elem_sz) : 0;
+        uint32_t y = (order == 1) ? (x0 - x1) : (x0 - 2 * x1 + x2);
+        store_elem(dest, i, elem_sz, y & wmask);
+    }
+    return (int64_t)len + meta;
+}
+
+/* src points at the transformed elements (no metadata) */
+int64_t oracle_decode_forecast(int order, int elem_sz, const void* src_, uint32_t len, void* dest_, uint16_t ndims)
+{
+    const uint8_t* src = (const uint8_t*)src_;
+    uint8_t* out = (uint8_t*)dest_;
+    const int w = 8 * elem_sz;
+    const uint32_t wmask = (1u << w) - 1u;
+    const uint64_t D = ndims;
+    if (order == 2 && ndims == 0) return 0;                /* delta.cpp:631 */
+    for (uint64_t i = 0; i < len; i++) {
+        uint32_t y = load_elem(src, i, elem_sz);
+        uint32_t x1 = (D && i >= D) ? load_elem(out, i - D, elem_sz) : 0;
+        uint32_t x2 = (D && i >= 2 * D) ? load_elem(out, i - 2 * D, elem_sz) : 0;
+        uint32_t x = (order == 1) ? (y + x1) : (y + 2 * x1 - x2);
+        store_elem(out, i, elem_sz, x & wmask);
+    }
+    return (int64_t)len;
+}
+
 uint64_t oracle_max_compressed_bytes(int elem_sz, uint64_t len, uint16_t ndims)
 {
     uint64_t D = ndims ? ndims : 1;

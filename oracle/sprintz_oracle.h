@@ -40,6 +40,12 @@ int64_t oracle_compress_rowmajor(int kind, int elem_sz, const void* src, uint32_
                                  uint16_t ndims, int write_size, uint64_t* true_nbytes);
 int64_t oracle_decompress_rowmajor(int kind, int elem_sz, const void* src, void* dest);
 
+/* Stand-alone forecaster transforms (delta.h:17-67): order 1 = delta, 2 = double delta.
+ * encode returns len + metadata elements; decode takes the transformed elements WITHOUT metadata. */
+int64_t oracle_encode_forecast(int order, int elem_sz, const void* src, uint32_t len, void* dest, uint16_t ndims,
+                               int write_size);
+int64_t oracle_decode_forecast(int order, int elem_sz, const void* src, uint32_t len, void* dest, uint16_t ndims);
+
 /* Worst-case stream size in bytes for `len` elements (our own bound, used by tests
  * to size buffers; the reference has no capacity arguments). */
 uint64_t oracle_max_compressed_bytes(int elem_sz, uint64_t len, uint16_t ndims);

@@ -57,6 +57,19 @@ SYMBOLS = {
     "spz_decompress8b_rowmajor_xff": (_i64, [_vp, _vp]),
     "spz_compress_rowmajor_host": (_i64, [_i, _i, _vp, _u32, _vp, _u16, _i, C.POINTER(_u64)]),
     "spz_decompress_rowmajor_host": (_i64, [_i, _i, _vp, _vp]),
+    "spz_encode_delta_rowmajor_8b": (_u32, [_vp, _u32, _vp, _u16, _i]),
+    "spz_decode_delta_rowmajor_8b": (_u32, [_vp, _u32, _vp, _u16]),
+    "spz_encode_delta_rowmajor_16b": (_u32, [_vp, _u32, _vp, _u16, _i]),
+    "spz_decode_delta_rowmajor_16b": (_u32, [_vp, _u32, _vp, _u16]),
+    "spz_encode_doubledelta_rowmajor_8b": (_u32, [_vp, _u32, _vp, _u16, _i]),
+    "spz_decode_doubledelta_rowmajor_8b": (_u32, [_vp, _u32, _vp, _u16]),
+    "spz_encode_doubledelta_rowmajor_16b": (_u32, [_vp, _u32, _vp, _u16, _i]),
+    "spz_decode_doubledelta_rowmajor_16b": (_u32, [_vp, _u32, _vp, _u16]),
+    "spz_encode_forecast_host": (_i64, [_i, _i, _vp, _u32, _vp, _u16, _i]),
+    "spz_decode_forecast_host": (_i64, [_i, _i, _vp, _u32, _vp, _u16]),
+    "spz_forecast_workspace_bytes": (_u64, [_u64, _u16]),
+    "spz_forecast_encode_dev": (_i, [_i, _i, _vp, _u64, _u16, _vp, _vp]),
+    "spz_forecast_decode_dev": (_i, [_i, _i, _vp, _u64, _u16, _vp, _vp, _u64, _vp]),
     "spz_compress_host": (_i64, [_i, _i, _vp, _u32, _vp, _u16, _i, C.POINTER(_u64)]),
     "spz_decompress_host": (_i64, [_i, _i, _vp, _vp]),
     "spz_decompress_raw_host": (_i64, [_i, _i, _vp, _vp, _u16, _u32, _u16]),

@@ -26,6 +26,7 @@ __all__ = [
     "Frame", "frame_encode", "frame_decode", "frame_compress_host", "frame_decompress_host",
     "compress_dev", "decompress_dev", "set_kernel_path",
     "RM_DELTA", "RM_PLAIN", "RM_XFF8", "compress_rowmajor", "decompress_rowmajor",
+    "encode_forecast", "decode_forecast", "forecast_encode_dev", "forecast_decode_dev",
 ]
 
 RM_DELTA, RM_PLAIN, RM_XFF8 = 1, 2, 3   # compress_rowmajor_delta_* / compress_rowmajor_* / compress8b_rowmajor_xff
@@ -86,6 +87,49 @@ def decompress_rowmajor(kind: int, esz: int, stream: np.ndarray):
     ret = lib().spz_decompress_rowmajor_host(kind, esz, src.ctypes.data, out.ctypes.data)
     check(ret, "spz_decompress_rowmajor_host")
     return out, int(ret)
+
+
+def encode_forecast(order: int, x: np.ndarray, ndims: int, write_size: bool = True):
+    """Stand-alone forecaster transform (delta.h:17-67): order 1 = encode_delta_rowmajor_*, 2 =
+    encode_doubledelta_rowmajor_*.  -> (output bytes incl. the optional 6-byte metadata, the reference's return)."""
+    x = np.ascontiguousarray(x)
+    esz = x.dtype.itemsize
+    out = np.zeros(x.size * esz + 8, np.uint8)
+    ret = lib().spz_encode_forecast_host(order, esz, x.ctypes.data, x.size, out.ctypes.data, ndims, int(write_size))
+    check(ret, "spz_encode_forecast_host")
+    return out[: int(ret) * esz].copy(), int(ret)
+
+
+def decode_forecast(order: int, esz: int, y: np.ndarray, ndims: int):
+    """y: the transformed elements without metadata. -> (decoded elements, count)"""
+    y = np.ascontiguousarray(y)
+    out = np.zeros(y.size, _UDT[esz])
+    ret = lib().spz_decode_forecast_host(order, esz, y.ctypes.data, y.size, out.ctypes.data, ndims)
+    check(ret, "spz_decode_forecast_host")
+    return out, int(ret)
+
+
+def forecast_encode_dev(order: int, x, ndims: int):
+    """torch CUDA tensor in -> transformed tensor (same shape / dtype), on the current stream."""
+    torch = _torch()
+    n = x.numel()
+    pad = torch.empty(n * x.element_size() + 32, dtype=torch.uint8, device=x.device)
+    out = pad[: n * x.element_size()].view(x.dtype)
+    check(lib().spz_forecast_encode_dev(order, x.element_size(), x.data_ptr(), n, ndims, out.data_ptr(), _stream_ptr()),
+          "spz_forecast_encode_dev")
+    return out
+
+
+def forecast_decode_dev(order: int, y, ndims: int, work=None):
+    torch = _torch()
+    n = y.numel()
+    wb = int(lib().spz_forecast_workspace_bytes(n, ndims))
+    if work is None or work.numel() < wb:
+        work = torch.empty(wb, dtype=torch.uint8, device=y.device)
+    out = torch.empty_like(y)
+    check(lib().spz_forecast_decode_dev(order, y.element_size(), y.data_ptr(), n, ndims, out.data_ptr(), work.data_ptr(),
+                                        work.numel(), _stream_ptr()), "spz_forecast_decode_dev")
+    return out
 
 
 def measure(esz: int, stream: np.ndarray, has_meta=True, ndims=0, ngroups=0, remaining=0):

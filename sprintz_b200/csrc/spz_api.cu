@@ -30,6 +30,11 @@ void set_force_path(int v);
 int get_force_path();
 int last_encode_family();
 int last_decode_family();
+uint64_t forecast_workspace_bytes(uint64_t len, uint32_t D);
+cudaError_t launch_forecast_encode(int order, int elem_sz, const uint8_t* src, uint8_t* dst, uint64_t len, uint32_t D,
+                                   cudaStream_t stream);
+cudaError_t launch_forecast_decode(int order, int elem_sz, const uint8_t* src, uint8_t* dst, uint64_t len, uint32_t D,
+                                   unsigned long long* state, cudaStream_t stream);
 }  // namespace spz
 
 using namespace spz;
@@ -566,6 +571,92 @@ extern "C" int64_t spz_compress_rowmajor_16b(const uint16_t* s, uint32_t n, int1
 extern "C" int64_t spz_compress8b_rowmajor_xff(const uint8_t* s, uint64_t n, int8_t* d, uint16_t nd, int ws) { return n > 0xffffffffull ? SPZ_E_ARG : spz_compress_rowmajor_host(3, 1, s, (uint32_t)n, d, nd, ws, nullptr); }
 extern "C" int64_t spz_decompress8b_rowmajor_xff(const int8_t* s, uint8_t* d) { return spz_decompress_rowmajor_host(3, 1, s, d); }
 extern "C" int64_t spz_decompress_rowmajor_16b(const int16_t* s, uint16_t* d) { return spz_decompress_rowmajor_host(2, 2, s, d); }
+
+// ------------------------------------------------------------------ stand-alone forecaster transforms
+// encode/decode_{delta,doubledelta}_rowmajor_{8b,16b} (delta.h:17-67).  order 1 = delta, 2 = double delta.
+
+extern "C" uint64_t spz_forecast_workspace_bytes(uint64_t len, uint16_t ndims)
+{
+    return forecast_workspace_bytes(len, ndims) + 16;
+}
+
+extern "C" int spz_forecast_encode_dev(int order, int elem_sz, const void* d_src, uint64_t len, uint16_t ndims,
+                                       void* d_dest, spz_stream_t stream)
+{
+    if ((order != 1 && order != 2) || (elem_sz != 1 && elem_sz != 2) || ndims == 0) return SPZ_E_ARG;
+    if (((uintptr_t)d_src & 15) || ((uintptr_t)d_dest & 15)) return SPZ_E_ARG;
+    CK(launch_forecast_encode(order, elem_sz, (const uint8_t*)d_src, (uint8_t*)d_dest, len, ndims, (cudaStream_t)stream));
+    return SPZ_OK;
+}
+
+extern "C" int spz_forecast_decode_dev(int order, int elem_sz, const void* d_src, uint64_t len, uint16_t ndims,
+                                       void* d_dest, void* d_work, uint64_t work_bytes, spz_stream_t stream)
+{
+    if ((order != 1 && order != 2) || (elem_sz != 1 && elem_sz != 2) || ndims == 0) return SPZ_E_ARG;
+    if (((uintptr_t)d_src & (elem_sz - 1)) || ((uintptr_t)d_dest & (elem_sz - 1)) || ((uintptr_t)d_work & 7)) return SPZ_E_ARG;
+    if (work_bytes < forecast_workspace_bytes(len, ndims)) return SPZ_E_CAPACITY;
+    CK(launch_forecast_decode(order, elem_sz, (const uint8_t*)d_src, (uint8_t*)d_dest, len, ndims,
+                              (unsigned long long*)d_work, (cudaStream_t)stream));
+    return SPZ_OK;
+}
+
+// host buffers: returns len + metadata elements (encode) / len (decode), like the reference
+extern "C" int64_t spz_encode_forecast_host(int order, int elem_sz, const void* src, uint32_t len, void* dest,
+                                            uint16_t ndims, int write_size)
+{
+    if ((order != 1 && order != 2) || (elem_sz != 1 && elem_sz != 2) || ndims == 0) return SPZ_E_ARG;
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    cudaStream_t st;
+    CK(g_cache.get_stream(&st));
+    const uint64_t bytes = (uint64_t)len * elem_sz;
+    CK(g_cache.ensure(0, bytes + 32));
+    CK(g_cache.ensure(1, bytes + 32));
+    uint8_t* d8 = (uint8_t*)dest;
+    uint32_t meta = 0;
+    if (write_size) {                                   // format.h:65-73
+        d8[0] = (uint8_t)len; d8[1] = (uint8_t)(len >> 8); d8[2] = (uint8_t)(len >> 16); d8[3] = (uint8_t)(len >> 24);
+        d8[4] = (uint8_t)ndims; d8[5] = (uint8_t)(ndims >> 8);
+        d8 += 6; meta = 6u / (uint32_t)elem_sz;
+    }
+    if (bytes) {
+        CK(cudaMemcpyAsync(g_cache.buf[0], src, bytes, cudaMemcpyHostToDevice, st));
+        CK(launch_forecast_encode(order, elem_sz, (const uint8_t*)g_cache.buf[0], (uint8_t*)g_cache.buf[1], len, ndims, st));
+        CK(cudaMemcpyAsync(d8, g_cache.buf[1], bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return (int64_t)len + meta;
+}
+
+extern "C" int64_t spz_decode_forecast_host(int order, int elem_sz, const void* src, uint32_t len, void* dest,
+                                            uint16_t ndims)
+{
+    if ((order != 1 && order != 2) || (elem_sz != 1 && elem_sz != 2)) return SPZ_E_ARG;
+    if (ndims == 0) return order == 2 ? 0 : SPZ_E_ARG;  // delta.cpp:631
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    cudaStream_t st;
+    CK(g_cache.get_stream(&st));
+    const uint64_t bytes = (uint64_t)len * elem_sz;
+    CK(g_cache.ensure(0, bytes + 32));
+    CK(g_cache.ensure(1, bytes + 32));
+    CK(g_cache.ensure(2, forecast_workspace_bytes(len, ndims) + 64));
+    if (bytes) {
+        CK(cudaMemcpyAsync(g_cache.buf[0], src, bytes, cudaMemcpyHostToDevice, st));
+        CK(launch_forecast_decode(order, elem_sz, (const uint8_t*)g_cache.buf[0], (uint8_t*)g_cache.buf[1], len, ndims,
+                                  (unsigned long long*)g_cache.buf[2], st));
+        CK(cudaMemcpyAsync(dest, g_cache.buf[1], bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return (int64_t)len;
+}
+
+extern "C" uint32_t spz_encode_delta_rowmajor_8b(const uint8_t* s, uint32_t n, int8_t* d, uint16_t nd, int ws) { return (uint32_t)spz_encode_forecast_host(1, 1, s, n, d, nd, ws); }
+extern "C" uint32_t spz_decode_delta_rowmajor_8b(const int8_t* s, uint32_t n, uint8_t* d, uint16_t nd) { return (uint32_t)spz_decode_forecast_host(1, 1, s, n, d, nd); }
+extern "C" uint32_t spz_encode_delta_rowmajor_16b(const uint16_t* s, uint32_t n, int16_t* d, uint16_t nd, int ws) { return (uint32_t)spz_encode_forecast_host(1, 2, s, n, d, nd, ws); }
+extern "C" uint32_t spz_decode_delta_rowmajor_16b(const int16_t* s, uint32_t n, uint16_t* d, uint16_t nd) { return (uint32_t)spz_decode_forecast_host(1, 2, s, n, d, nd); }
+extern "C" uint32_t spz_encode_doubledelta_rowmajor_8b(const uint8_t* s, uint32_t n, int8_t* d, uint16_t nd, int ws) { return (uint32_t)spz_encode_forecast_host(2, 1, s, n, d, nd, ws); }
+extern "C" uint32_t spz_decode_doubledelta_rowmajor_8b(const int8_t* s, uint32_t n, uint8_t* d, uint16_t nd) { return (uint32_t)spz_decode_forecast_host(2, 1, s, n, d, nd); }
+extern "C" uint32_t spz_encode_doubledelta_rowmajor_16b(const uint16_t* s, uint32_t n, int16_t* d, uint16_t nd, int ws) { return (uint32_t)spz_encode_forecast_host(2, 2, s, n, d, nd, ws); }
+extern "C" uint32_t spz_decode_doubledelta_rowmajor_16b(const int16_t* s, uint32_t n, uint16_t* d, uint16_t nd) { return (uint32_t)spz_decode_forecast_host(2, 2, s, n, d, nd); }
 
 // ------------------------------------------------------------------ frame, host buffers
 //
