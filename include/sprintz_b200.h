@@ -142,6 +142,33 @@ int spz_forecast_encode_dev(int order, int elem_sz, const void* d_src, uint64_t 
 int spz_forecast_decode_dev(int order, int elem_sz, const void* d_src, uint64_t len, uint16_t ndims, void* d_dest,
                             void* d_work, uint64_t work_bytes, spz_stream_t stream);
 
+/* Query-on-compressed (query.hpp:22-29 QueryParams{op, materialize}, sprintz_delta.h:92-98,
+ * sprintz_xff.h:86-93).  The reference's functor state never reaches its caller (query.hpp:231); here `result`
+ * receives ndims u64: for every dim d the unsigned maximum (SPZ_Q_MAX) or the sum (SPZ_Q_SUM) of x[i], i % ndims == d,
+ * over all decoded elements.  materialize != 0 also writes the decoded elements to dest (exactly decompress);
+ * materialize == 0 leaves dest untouched (may be NULL).  Returns the decoded element count like the reference. */
+#define SPZ_Q_NOOP 0   /* QueryTypes::NOOP */
+#define SPZ_Q_MAX  1   /* QueryTypes::REDUCE_MAX */
+#define SPZ_Q_SUM  2   /* QueryTypes::REDUCE_SUM */
+int64_t spz_query_rowmajor_delta_rle_8b (const int8_t*  src, uint8_t*  dest, int op, int materialize, uint64_t* result);
+int64_t spz_query_rowmajor_delta_rle_16b(const int16_t* src, uint16_t* dest, int op, int materialize, uint64_t* result);
+int64_t spz_query_rowmajor_xff_rle_8b   (const int8_t*  src, uint8_t*  dest, int op, int materialize, uint64_t* result);
+int64_t spz_query_rowmajor_xff_rle_16b  (const int16_t* src, uint16_t* dest, int op, int materialize, uint64_t* result);
+int64_t spz_query_host(int predictor, int elem_sz, const void* src, void* dest, int op, int materialize, uint64_t* result);
+/* Frames on device buffers.  materialize == 0 on frames of many 8 / 16-dim chunks runs FUSED: the decoder lanes fold
+ * rows into registers and the launch reads the compressed bytes only (spz_last_query_fused() == 1).  Every other
+ * case decodes (into d_dest, or into d_work when materialize == 0: spz_frame_query_workspace_bytes) and reduces
+ * the decoded rows with a second kernel.  d_result: ndims u64 (device). */
+uint64_t spz_frame_query_workspace_bytes(int elem_sz, uint64_t len, int materialize);
+int spz_frame_query_dev(int predictor, int elem_sz, int op, int materialize, const void* d_frame, uint64_t frame_bytes,
+                        uint64_t len, uint16_t ndims, uint32_t chunk_rows, void* d_dest, uint64_t dest_cap_elems,
+                        spz_chunk_meta* d_status, uint64_t* d_result, void* d_work, uint64_t work_bytes,
+                        spz_stream_t stream);
+int spz_last_query_fused(void);
+/* per-dim max / sum of row-major device elements (d_src 16-byte aligned); d_result: ndims u64 */
+int spz_reduce_rows_dev(int op, int elem_sz, const void* d_src, uint64_t len, uint16_t ndims, uint64_t* d_result,
+                        spz_stream_t stream);
+
 /* ---------------------------------------------------------------- 2. single stream, device buffers
  * d_dest must hold spz_max_compressed_bytes(); d_meta (1 record) receives sizes. Asynchronous on `stream`. */
 int spz_compress_dev(int predictor, int elem_sz, const void* d_src, uint32_t len, uint16_t ndims,

@@ -135,6 +135,18 @@ class Oracle(_Codec):
         dt = np.uint8 if esz == 1 else np.uint16
         return out[: n_out * esz].view(dt).copy(), int(ret)
 
+    def query(self, predictor, esz, stream, n_out, op):
+        """-> (result uint64[ndims], decoded elements, returned count)"""
+        self.L.oracle_query.restype = C.c_int64
+        self.L.oracle_query.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        src = np.concatenate([_as_u8(stream), np.zeros(SLACK, np.uint8)])
+        ndims = int(src[6]) | (int(src[7]) << 8)
+        out = np.full((n_out + 64) * esz + SLACK, 0xAA, np.uint8)
+        res = np.zeros(max(ndims, 1), np.uint64)
+        ret = self.L.oracle_query(predictor, esz, src.ctypes.data, out.ctypes.data, op, res.ctypes.data)
+        dt = np.uint8 if esz == 1 else np.uint16
+        return res, out[: n_out * esz].view(dt).copy(), int(ret)
+
     def decompress_raw(self, predictor, esz, stream, n_out, ndims, ngroups, rem):
         src = np.concatenate([_as_u8(stream), np.zeros(SLACK, np.uint8)])
         out = np.full((n_out + 64) * esz + SLACK, 0xAA, np.uint8)

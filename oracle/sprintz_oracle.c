@@ -632,6 +632,29 @@ int64_t oracle_decode_forecast(int order, int elem_sz, const void* src_, uint32_
     return (int64_t)len;
 }
 
+/* ------------------------------------------------------------------ query-on-compressed
+ *
+ * query.hpp:22-29 QueryParams{op = REDUCE_MAX | REDUCE_SUM, materialize}; query_rowmajor_{delta,xff}_rle_{8b,16b}
+ * (sprintz_delta_rle_query.cpp:149-192, sprintz_xff_rle_query.cpp:106-137).  The reference's functors never hand
+ * their state back (query.hpp:231) and MaxQuery folds every stripe into state[0] (query.hpp:218, "TODO rm"), so
+ * there is no reference output to pin against: per SURVEY 8f the oracle is "the reduction of the decoded oracle
+ * output" -- decode with oracle_decompress, then for every dim d the unsigned max (op 1) or the 64-bit sum (op 2)
+ * of x[i], i % ndims == d.  Parity of the decoded elements themselves stays pinned as before. */
+int64_t oracle_query(int predictor, int elem_sz, const void* src, void* dest, int op, uint64_t* result)
+{
+    const uint8_t* s = (const uint8_t*)src;
+    const uint32_t D = (uint32_t)s[6] | ((uint32_t)s[7] << 8);
+    const int64_t n = oracle_decompress(predictor, elem_sz, src, dest);
+    if (n < 0 || D == 0) return n;
+    for (uint32_t d = 0; d < D; d++) result[d] = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const uint64_t v = load_elem((const uint8_t*)dest, (uint64_t)i, elem_sz);
+        uint64_t* r = &result[(uint64_t)i % D];
+        if (op == 1) { if (v > *r) *r = v; } else if (op == 2) *r += v;
+    }
+    return n;
+}
+
 uint64_t oracle_max_compressed_bytes(int elem_sz, uint64_t len, uint16_t ndims)
 {
     uint64_t D = ndims ? ndims : 1;

@@ -46,6 +46,10 @@ int64_t oracle_encode_forecast(int order, int elem_sz, const void* src, uint32_t
                                int write_size);
 int64_t oracle_decode_forecast(int order, int elem_sz, const void* src, uint32_t len, void* dest, uint16_t ndims);
 
+/* Query-on-compressed: decode, then per-dim unsigned max (op 1) / 64-bit sum (op 2) into
+ * result[ndims]; returns the decoded element count. */
+int64_t oracle_query(int predictor, int elem_sz, const void* src, void* dest, int op, uint64_t* result);
+
 /* Worst-case stream size in bytes for `len` elements (our own bound, used by tests
  * to size buffers; the reference has no capacity arguments). */
 uint64_t oracle_max_compressed_bytes(int elem_sz, uint64_t len, uint16_t ndims);

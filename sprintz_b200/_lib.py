@@ -70,6 +70,15 @@ SYMBOLS = {
     "spz_forecast_workspace_bytes": (_u64, [_u64, _u16]),
     "spz_forecast_encode_dev": (_i, [_i, _i, _vp, _u64, _u16, _vp, _vp]),
     "spz_forecast_decode_dev": (_i, [_i, _i, _vp, _u64, _u16, _vp, _vp, _u64, _vp]),
+    "spz_query_rowmajor_delta_rle_8b": (_i64, [_vp, _vp, _i, _i, _vp]),
+    "spz_query_rowmajor_delta_rle_16b": (_i64, [_vp, _vp, _i, _i, _vp]),
+    "spz_query_rowmajor_xff_rle_8b": (_i64, [_vp, _vp, _i, _i, _vp]),
+    "spz_query_rowmajor_xff_rle_16b": (_i64, [_vp, _vp, _i, _i, _vp]),
+    "spz_query_host": (_i64, [_i, _i, _vp, _vp, _i, _i, _vp]),
+    "spz_frame_query_workspace_bytes": (_u64, [_i, _u64, _i]),
+    "spz_frame_query_dev": (_i, [_i, _i, _i, _i, _vp, _u64, _u64, _u16, _u32, _vp, _u64, _vp, _vp, _vp, _u64, _vp]),
+    "spz_last_query_fused": (_i, []),
+    "spz_reduce_rows_dev": (_i, [_i, _i, _vp, _u64, _u16, _vp, _vp]),
     "spz_compress_host": (_i64, [_i, _i, _vp, _u32, _vp, _u16, _i, C.POINTER(_u64)]),
     "spz_decompress_host": (_i64, [_i, _i, _vp, _vp]),
     "spz_decompress_raw_host": (_i64, [_i, _i, _vp, _vp, _u16, _u32, _u16]),

@@ -27,7 +27,10 @@ __all__ = [
     "compress_dev", "decompress_dev", "set_kernel_path",
     "RM_DELTA", "RM_PLAIN", "RM_XFF8", "compress_rowmajor", "decompress_rowmajor",
     "encode_forecast", "decode_forecast", "forecast_encode_dev", "forecast_decode_dev",
+    "Q_NOOP", "Q_MAX", "Q_SUM", "query", "frame_query", "reduce_rows_dev", "last_query_fused",
 ]
+
+Q_NOOP, Q_MAX, Q_SUM = 0, 1, 2          # QueryTypes::Operation (query.hpp:22-24)
 
 RM_DELTA, RM_PLAIN, RM_XFF8 = 1, 2, 3   # compress_rowmajor_delta_* / compress_rowmajor_* / compress8b_rowmajor_xff
 
@@ -308,6 +311,58 @@ def frame_decode(frame: Frame):
     FrameCodec.decode(codec, frame, out)
     FrameCodec.check_status(codec)
     return out
+
+
+def frame_query(frame: Frame, op: int, materialize: bool = False, out=None, work=None):
+    """Query-on-compressed over a device frame (query.hpp:22-29). -> (result int64[ndims] CUDA tensor, decoded
+    tensor or None).  materialize=False on frames of many 8/16-dim chunks runs fused (last_query_fused() == 1)."""
+    torch = _torch()
+    L = lib()
+    dev = frame.buf.device
+    res = torch.empty(frame.ndims, dtype=torch.int64, device=dev)
+    status = torch.zeros(4 * frame.nchunks, dtype=torch.int32, device=dev)
+    if materialize and out is None:
+        out = torch.empty(frame.len, dtype=torch.uint8 if frame.elem_sz == 1 else torch.int16, device=dev)
+    wb = int(L.spz_frame_query_workspace_bytes(frame.elem_sz, frame.len, int(materialize)))
+    if wb and (work is None or work.numel() < wb):
+        work = torch.empty(wb, dtype=torch.uint8, device=dev)
+    check(L.spz_frame_query_dev(frame.predictor, frame.elem_sz, op, int(materialize), frame.buf.data_ptr(),
+                                frame.buf.numel(), frame.len, frame.ndims, frame.chunk_rows,
+                                out.data_ptr() if out is not None else None, out.numel() if out is not None else 0,
+                                status.data_ptr(), res.data_ptr(), work.data_ptr() if work is not None else None,
+                                work.numel() if work is not None else 0, _stream_ptr()), "spz_frame_query_dev")
+    bad = int((status.view(-1, 4)[:, 3] != 0).sum().item())
+    if bad:
+        raise SprintzError(f"{bad} chunk(s) failed to decode")
+    return res, (out if materialize else None)
+
+
+def last_query_fused() -> bool:
+    return bool(lib().spz_last_query_fused())
+
+
+def reduce_rows_dev(op: int, x, ndims: int):
+    """per-dim max / sum of a row-major CUDA tensor -> int64[ndims] CUDA tensor"""
+    torch = _torch()
+    res = torch.empty(ndims, dtype=torch.int64, device=x.device)
+    check(lib().spz_reduce_rows_dev(op, x.element_size(), x.data_ptr(), x.numel(), ndims, res.data_ptr(), _stream_ptr()),
+          "spz_reduce_rows_dev")
+    return res
+
+
+def query(predictor: int, esz: int, stream: np.ndarray, op: int, materialize: bool = True):
+    """query_rowmajor_{delta,xff}_rle_{8b,16b} on a host stream (sprintz_delta.h:95-98, sprintz_xff.h:90-93).
+    -> (result uint64[ndims], decoded elements or None, the reference's return value)"""
+    stream = np.ascontiguousarray(stream).view(np.uint8).reshape(-1)
+    padded = np.concatenate([stream, np.zeros(16, np.uint8)])
+    _, ne = measure(esz, padded)
+    ndims = int(padded[6]) | (int(padded[7]) << 8)
+    out = np.empty(ne, _UDT[esz])
+    res = np.zeros(max(ndims, 1), np.uint64)
+    ret = lib().spz_query_host(predictor, esz, padded.ctypes.data, out.ctypes.data if materialize else None, op,
+                               int(materialize), res.ctypes.data)
+    check(ret, "spz_query_host")
+    return res, (out[: max(ret, 0)] if materialize else None), int(ret)
 
 
 def frame_compress_host(predictor: int, x: np.ndarray, ndims: int, chunk_rows: int) -> np.ndarray:

@@ -30,6 +30,9 @@ void set_force_path(int v);
 int get_force_path();
 int last_encode_family();
 int last_decode_family();
+cudaError_t launch_query_fused(int elem_sz, int predictor, DecParams p, cudaStream_t stream);
+cudaError_t launch_reduce_rows(int op, int elem_sz, const uint8_t* src, uint64_t len, uint32_t D,
+                               unsigned long long* result, cudaStream_t stream);
 uint64_t forecast_workspace_bytes(uint64_t len, uint32_t D);
 cudaError_t launch_forecast_encode(int order, int elem_sz, const uint8_t* src, uint8_t* dst, uint64_t len, uint32_t D,
                                    cudaStream_t stream);
@@ -301,6 +304,75 @@ extern "C" int spz_frame_decode_dev(int predictor, int elem_sz, const void* d_fr
     return SPZ_OK;
 }
 
+// ------------------------------------------------------------------ query-on-compressed
+// query.hpp:22-29 QueryParams{op, materialize}; sprintz_delta.h:92-98, sprintz_xff.h:86-93.
+
+static int g_last_query_fused = 0;
+extern "C" int spz_last_query_fused(void) { return g_last_query_fused; }
+
+extern "C" uint64_t spz_frame_query_workspace_bytes(int elem_sz, uint64_t len, int materialize)
+{
+    return materialize ? 0 : align16(len * (uint64_t)elem_sz) + 64;
+}
+
+extern "C" int spz_frame_query_dev(int predictor, int elem_sz, int op, int materialize, const void* d_frame,
+                                   uint64_t frame_bytes, uint64_t len, uint16_t ndims, uint32_t chunk_rows,
+                                   void* d_dest, uint64_t dest_cap_elems, spz_chunk_meta* d_status,
+                                   uint64_t* d_result, void* d_work, uint64_t work_bytes, spz_stream_t stream)
+{
+    if (!valid_frame_codec(predictor, elem_sz) || ndims == 0 || chunk_rows == 0) return SPZ_E_ARG;
+    if (op < SPZ_Q_NOOP || op > SPZ_Q_SUM) return SPZ_E_ARG;
+    if (op != SPZ_Q_NOOP && !d_result) return SPZ_E_ARG;
+    if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    g_last_query_fused = 0;
+    if (op != SPZ_Q_NOOP) CK(cudaMemsetAsync(d_result, 0, 8ull * ndims, st));
+    if (!materialize && op != SPZ_Q_NOOP) {
+        const FrameLayout f = frame_layout(len, ndims, chunk_rows);
+        if (frame_bytes < f.payload_off + 16) return SPZ_E_STREAM;
+        const uint8_t* frame = (const uint8_t*)d_frame;
+        DecParams p;
+        memset(&p, 0, sizeof(p));
+        p.src = frame + f.payload_off; p.offsets = (const uint64_t*)(frame + f.off_dir);
+        p.dst = nullptr; p.meta = (ChunkMeta*)d_status;
+        p.len = len; p.chunk_len = f.chunk_len; p.nchunks = f.nchunks; p.dst_cap = len;
+        p.ndims = ndims; p.has_meta = 1;
+        p.src_end = frame + frame_bytes;
+        p.qop = (uint32_t)op; p.qresult = (unsigned long long*)d_result;
+        const cudaError_t e = launch_query_fused(elem_sz, predictor, p, st);
+        if (e == cudaSuccess) { g_last_query_fused = 1; return SPZ_OK; }
+        if (e != cudaErrorNotSupported) CK(e);
+        (void)cudaGetLastError();
+    }
+    // materialised: decode with the regular kernels (into d_dest, or the workspace when the caller does not want
+    // the elements), then reduce the decoded rows
+    void* out = d_dest;
+    uint64_t cap = dest_cap_elems;
+    if (!materialize) {
+        if (op == SPZ_Q_NOOP) return SPZ_OK;           // nothing to produce
+        if (!d_work || ((uintptr_t)d_work & 15) || work_bytes < align16(len * (uint64_t)elem_sz)) return SPZ_E_CAPACITY;
+        out = d_work; cap = len;
+    }
+    if (!out) return SPZ_E_ARG;
+    const int rc = spz_frame_decode_dev(predictor, elem_sz, d_frame, frame_bytes, len, ndims, chunk_rows, out, cap,
+                                        d_status, stream);
+    if (rc != SPZ_OK) return rc;
+    if (op != SPZ_Q_NOOP)
+        CK(launch_reduce_rows(op, elem_sz, (const uint8_t*)out, len, ndims, (unsigned long long*)d_result, st));
+    return SPZ_OK;
+}
+
+extern "C" int spz_reduce_rows_dev(int op, int elem_sz, const void* d_src, uint64_t len, uint16_t ndims,
+                                   uint64_t* d_result, spz_stream_t stream)
+{
+    if ((op != SPZ_Q_MAX && op != SPZ_Q_SUM) || (elem_sz != 1 && elem_sz != 2) || ndims == 0 || !d_result) return SPZ_E_ARG;
+    if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
+    if ((uintptr_t)d_src & 15) return SPZ_E_ARG;
+    CK(cudaMemsetAsync(d_result, 0, 8ull * ndims, (cudaStream_t)stream));
+    CK(launch_reduce_rows(op, elem_sz, (const uint8_t*)d_src, len, ndims, (unsigned long long*)d_result, (cudaStream_t)stream));
+    return SPZ_OK;
+}
+
 extern "C" int spz_frame_read_header(const void* d_frame, spz_frame_header* out, spz_stream_t stream)
 {
     CK(cudaMemcpyAsync(out, d_frame, sizeof(*out), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
@@ -432,9 +504,11 @@ static int64_t compress_host_impl(uint32_t variant, int predictor, int elem_sz, 
 }
 
 static int64_t decompress_host_impl(int predictor, int elem_sz, const void* src, void* dest, int has_meta,
-                                    uint16_t ndims, uint32_t ngroups, uint16_t remaining_len)
+                                    uint16_t ndims, uint32_t ngroups, uint16_t remaining_len,
+                                    int qop = 0, int materialize = 1, uint64_t* qresult = nullptr)
 {
     if (!valid_codec(predictor, elem_sz)) return SPZ_E_ARG;
+    if (qop < SPZ_Q_NOOP || qop > SPZ_Q_SUM || (qop != SPZ_Q_NOOP && !qresult)) return SPZ_E_ARG;
     uint64_t sbytes = 0, elems = 0;
     if (has_meta) {
         const uint8_t* s8 = (const uint8_t*)src;
@@ -452,7 +526,7 @@ static int64_t decompress_host_impl(int predictor, int elem_sz, const void* src,
     CK(g_cache.get_stream(&st));
     CK(g_cache.ensure(0, sbytes + 32));
     CK(g_cache.ensure(1, elems * elem_sz + 16));
-    CK(g_cache.ensure(2, 64));
+    CK(g_cache.ensure(2, 64 + 8ull * (ndims ? ndims : 1)));
     CK(cudaMemcpyAsync(g_cache.buf[0], src, sbytes, cudaMemcpyHostToDevice, st));
     spz_chunk_meta m;
     memset(&m, 0, sizeof(m));
@@ -462,11 +536,32 @@ static int64_t decompress_host_impl(int predictor, int elem_sz, const void* src,
                             g_cache.buf[1], elems, (spz_chunk_meta*)g_cache.buf[2], st);
     if (rc != SPZ_OK) return rc;
     CK(cudaMemcpyAsync(&m, g_cache.buf[2], sizeof(m), cudaMemcpyDeviceToHost, st));
-    if (elems) CK(cudaMemcpyAsync(dest, g_cache.buf[1], elems * elem_sz, cudaMemcpyDeviceToHost, st));
+    if (qop != SPZ_Q_NOOP) {
+        // a single stream is one serial decode: the query is the reduction of its decoded rows
+        const uint32_t D = ndims ? ndims : 1;
+        unsigned long long* d_res = (unsigned long long*)((uint8_t*)g_cache.buf[2] + 64);
+        CK(cudaMemsetAsync(d_res, 0, 8ull * D, st));
+        CK(launch_reduce_rows(qop, elem_sz, (const uint8_t*)g_cache.buf[1], elems, D, d_res, st));
+        CK(cudaMemcpyAsync(qresult, d_res, 8ull * D, cudaMemcpyDeviceToHost, st));
+    }
+    if (elems && materialize) CK(cudaMemcpyAsync(dest, g_cache.buf[1], elems * elem_sz, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (m.status != 0) return SPZ_E_STREAM;
     return (int64_t)elems;
 }
+
+// query_rowmajor_{delta,xff}_rle_{8b,16b}(src, dest, QueryParams) (sprintz_delta.h:95-98, sprintz_xff.h:90-93):
+// QueryParams is flattened to (op, materialize); `result` receives ndims u64 (unsigned max / sum per dim).
+extern "C" int64_t spz_query_host(int predictor, int elem_sz, const void* src, void* dest, int op, int materialize,
+                                  uint64_t* result)
+{
+    if (materialize && !dest) return SPZ_E_ARG;
+    return decompress_host_impl(predictor, elem_sz, src, dest, 1, 0, 0, 0, op, materialize, result);
+}
+extern "C" int64_t spz_query_rowmajor_delta_rle_8b(const int8_t* s, uint8_t* d, int op, int mat, uint64_t* r) { return spz_query_host(SPZ_DELTA, 1, s, d, op, mat, r); }
+extern "C" int64_t spz_query_rowmajor_delta_rle_16b(const int16_t* s, uint16_t* d, int op, int mat, uint64_t* r) { return spz_query_host(SPZ_DELTA, 2, s, d, op, mat, r); }
+extern "C" int64_t spz_query_rowmajor_xff_rle_8b(const int8_t* s, uint8_t* d, int op, int mat, uint64_t* r) { return spz_query_host(SPZ_XFF, 1, s, d, op, mat, r); }
+extern "C" int64_t spz_query_rowmajor_xff_rle_16b(const int16_t* s, uint16_t* d, int op, int mat, uint64_t* r) { return spz_query_host(SPZ_XFF, 2, s, d, op, mat, r); }
 
 extern "C" int64_t spz_decompress_host(int predictor, int elem_sz, const void* src, void* dest)
 {

@@ -74,6 +74,8 @@ struct DecParams {
     uint32_t        out_cap;   // fast path: bytes of the per-team output staging
     uint32_t        ring_mask4;// fast path: (ring_cap - 1) & ~3, as a kernel constant so wrap+base is one LOP3
     uint32_t        variant;   // as EncParams::variant
+    uint32_t        qop;       // query-on-compressed (lane kernels only): 0 decode | 1 per-dim max | 2 per-dim sum; dst unused
+    unsigned long long* qresult;   // [ndims] u64, zero-initialised by the caller
 };
 
 template <int W> struct Traits;

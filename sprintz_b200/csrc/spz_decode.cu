@@ -253,4 +253,14 @@ cudaError_t launch_decode(int elem_sz, int predictor, DecParams p, cudaStream_t 
 #undef SPZ_GO
 }
 
+// query-on-compressed without materialisation (p.qop != 0): only the lane kernels fold rows in registers.
+// cudaErrorNotSupported: the caller decodes into a workspace and reduces that (spz_query.cu).
+cudaError_t launch_query_fused(int elem_sz, int predictor, DecParams p, cudaStream_t stream)
+{
+    if (predictor >= 2) { p.variant = (uint32_t)predictor - 1u; }
+    if (p.variant) predictor = (p.variant == 3u) ? 1 : 0;
+    if (p.qop != 1u && p.qop != 2u) return cudaErrorInvalidValue;
+    return launch_decode_lane(elem_sz, predictor, p, stream);
+}
+
 }  // namespace spz

@@ -37,7 +37,11 @@ constexpr int kLaneThreads = 128;
 #endif
 constexpr uint32_t kLaneWarpSmem = 8192;      // 33 rows x 128 B used; the stride keeps "row | lane" an OR
 
-template <int W, bool FIRE, int D>
+// Q = 0: decode.  Q = 1 / 2: query-on-compressed (query.hpp:22-29 REDUCE_MAX / REDUCE_SUM with
+// materialize == false): the same decoder, but a row is folded into per-dim running maxima / sums instead of being
+// stored, so the launch reads the compressed bytes only.  Lanes reduce across the warp, warps across the CTA, and
+// one atomic per dim and CTA lands in p.qresult[ndims] (u64, zeroed by the caller).
+template <int W, bool FIRE, int D, int Q>
 __global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_kernel(const DecParams p)
 {
     typedef typename Traits<W>::uint_t uint_t;
@@ -56,9 +60,13 @@ __global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_k
     __shared__ __align__(16) uint8_t smem[(kLaneThreads / 32) * kLaneWarpSmem];
 
     const uint64_t gtid = (uint64_t)blockIdx.x * kLaneThreads + threadIdx.x;
-    const uint64_t c = gtid / NP;
+    uint64_t c = gtid / NP;
     const uint32_t part = (uint32_t)(gtid % NP);
-    if (c >= p.nchunks) return;                     // lanes never cooperate: early exit is safe
+    bool live = true;
+    if (c >= p.nchunks) {
+        if (!Q) return;                             // decoding lanes never cooperate: early exit is safe
+        live = false; c = p.nchunks - 1;            // query lanes meet in the final reduction: shadow the last chunk
+    }
     const uint32_t rboff = (threadIdx.x >> 5) * kLaneWarpSmem + (threadIdx.x & 31) * 4u;
 
     // ---- input ring
@@ -143,7 +151,9 @@ __global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_k
 
     // my 8 values of one row -> HBM
     auto store_row = [&](uint32_t r) {
-        if (W == 16) {
+        if (Q) {
+            // rows are folded (qfold below): nothing is materialised
+        } else if (W == 16) {
             uint4 v;
             v.x = __byte_perm(pvh[0], pvh[1], 0x7632); v.y = __byte_perm(pvh[2], pvh[3], 0x7632);
             v.z = __byte_perm(pvh[4], pvh[5], 0x7632); v.w = __byte_perm(pvh[6], pvh[7], 0x7632);
@@ -161,6 +171,49 @@ __global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_k
                 orow += ROWB;
             }
         }
+    };
+
+    // ---- query accumulators (Q != 0): running maximum (left-aligned, order preserving) | 32-bit partial sums,
+    // drained into lane-private 64-bit totals (rows 34..49 of the warp's shared region) every 4096 blocks
+    uint32_t qa[8];
+    uint32_t qblocks = 0;
+    if (Q) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) qa[j] = 0;
+        if (Q == 2) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) *reinterpret_cast<uint32_t*>(smem + rboff + (34 + j) * 128) = 0u;
+        }
+    }
+    auto qdrain = [&]() {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            uint32_t* lo = reinterpret_cast<uint32_t*>(smem + rboff + (34 + 2 * j) * 128);
+            uint32_t* hi = reinterpret_cast<uint32_t*>(smem + rboff + (35 + 2 * j) * 128);
+            const uint32_t t = *lo + qa[j];
+            *hi += (t < qa[j]) ? 1u : 0u;
+            *lo = t;
+            qa[j] = 0;
+        }
+    };
+    // fold `reps` identical rows (the current running values) into the accumulators
+    auto qfold = [&](uint32_t reps) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (Q == 1) qa[j] = pvh[j] > qa[j] ? pvh[j] : qa[j];
+            else if (reps == 1u) asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(qa[j]) : "r"(pvh[j]), "n"(1u << W));
+            else {                                   // rare: a delta run; add the 64-bit product to the totals
+                uint32_t* lo = reinterpret_cast<uint32_t*>(smem + rboff + (34 + 2 * j) * 128);
+                uint32_t* hi = reinterpret_cast<uint32_t*>(smem + rboff + (35 + 2 * j) * 128);
+                const unsigned long long t = (((unsigned long long)*hi << 32) | *lo) + qa[j]
+                                             + (unsigned long long)(pvh[j] >> UP) * reps;
+                *lo = (uint32_t)t; *hi = (uint32_t)(t >> 32);
+                qa[j] = 0;
+            }
+        }
+    };
+    auto qblock_done = [&]() {
+        if (Q == 2) { if ((++qblocks & 4095u) == 0u) qdrain(); }
     };
 
     uint32_t pos = mis * 8u;                         // bit cursor relative to base32
@@ -238,8 +291,14 @@ __global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_k
                 int32_t coef[8];
 #pragma unroll
                 for (int j = 0; j < 8; j++) coef[j] = FIRE ? fire_coef<W, false>(ct[j]) : 0;
+                if (Q && !FIRE) {                    // a delta run repeats the previous row: fold it in one step
+                    if (nrun) qfold(nrun * 8u);
+                    o += nrun * B;
+                    continue;
+                }
 #pragma unroll 1
                 for (uint32_t b = 0; b < nrun; b++) {
+                    if (Q) qblock_done();
 #pragma unroll
                     for (uint32_t r = 0; r < 8; r++) {
                         if (FIRE) {
@@ -251,7 +310,7 @@ __global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_k
                                 pvh[j] += (uint32_t)pdh[j];
                             }
                         }
-                        store_row(r);
+                        if (Q) qfold(1u); else store_row(r);
                     }
                 }
                 o += nrun * B;
@@ -318,7 +377,7 @@ __global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_k
                         asm("mad.lo.s32 %0, %1, %2, %0;" : "+r"(pvh[j]) : "r"(mi), "n"(1 << (UP - 1)));
                     }
                 }
-                store_row(r);
+                if (Q) qfold(1u); else store_row(r);
                 rowbit += row_bits;
                 // a row is at most D*W/8 bytes: refill checks are only needed every 32 bytes of worst-case consumption
                 constexpr uint32_t CHK = (D * W / 8 >= 32) ? 1u : (32u / (D * W / 8));
@@ -330,6 +389,7 @@ __global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_k
                 for (int j = 0; j < 8; j++) ct[j] = sx<CB>(ct[j] + ((gsh[j] >> UP) >> 2));   // sprintz_xff_rle.cpp:273-275
             }
             o += B;
+            if (Q) qblock_done();
         }
         if (status != kStatusOk) break;
     }
@@ -340,11 +400,58 @@ __global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_k
             status = kStatusOverflow;
         } else {
             const uint8_t* tsrc = base32 + (pos >> 3);
-            uint8_t* tdst = reinterpret_cast<uint8_t*>(out + o);
-            const uint32_t nb = remaining * ESZ;
-            for (uint32_t b = part; b < nb; b += NP) tdst[b] = tsrc[b];
+            if (Q) {
+                // raw tail elements go straight to the result (short, rare): element e belongs to dim e % D
+                if (live && part == 0) {
+                    for (uint32_t e = 0; e < remaining; e++) {
+                        const unsigned long long v = (W == 16) ? (unsigned long long)(tsrc[2 * e] | (tsrc[2 * e + 1] << 8))
+                                                               : (unsigned long long)tsrc[e];
+                        if (Q == 1) atomicMax(p.qresult + (o + e) % D, v); else atomicAdd(p.qresult + (o + e) % D, v);
+                    }
+                }
+            } else {
+                uint8_t* tdst = reinterpret_cast<uint8_t*>(out + o);
+                const uint32_t nb = remaining * ESZ;
+                for (uint32_t b = part; b < nb; b += NP) tdst[b] = tsrc[b];
+            }
             o += remaining;
         }
+    }
+    if (Q) {
+        // ---- lanes -> warp -> CTA -> one atomic per dim
+        unsigned long long v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (Q == 1) v[j] = qa[j] >> UP;
+            else {
+                const uint32_t lo = *reinterpret_cast<uint32_t*>(smem + rboff + (34 + 2 * j) * 128);
+                const uint32_t hi = *reinterpret_cast<uint32_t*>(smem + rboff + (35 + 2 * j) * 128);
+                v[j] = (((unsigned long long)hi << 32) | lo) + qa[j];
+            }
+            if (!live || status != kStatusOk) v[j] = 0;
+#pragma unroll
+            for (int off = NP; off < 32; off <<= 1) {
+                const unsigned long long w = __shfl_xor_sync(0xffffffffu, v[j], off);
+                v[j] = (Q == 1) ? (w > v[j] ? w : v[j]) : (v[j] + w);
+            }
+        }
+        __syncthreads();                             // everyone is done with the rings: reuse the first bytes
+        unsigned long long* cta = reinterpret_cast<unsigned long long*>(smem);
+        if ((threadIdx.x & 31) < NP) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) cta[(threadIdx.x >> 5) * D + part * 8 + j] = v[j];
+        }
+        __syncthreads();
+        if (threadIdx.x < D) {
+            unsigned long long r = cta[threadIdx.x];
+#pragma unroll
+            for (int w = 1; w < kLaneThreads / 32; w++) {
+                const unsigned long long x = cta[w * D + threadIdx.x];
+                r = (Q == 1) ? (x > r ? x : r) : (r + x);
+            }
+            if (Q == 1) { if (r) atomicMax(p.qresult + threadIdx.x, r); } else atomicAdd(p.qresult + threadIdx.x, r);
+        }
+        if (!live) return;
     }
     if (part == 0 && p.meta) {
         p.meta[c].status = status;
@@ -362,13 +469,25 @@ static int g_force_path = 0;       // 0 auto, 1 team kernels only, 2 lane kernel
 void set_force_path(int v) { g_force_path = v; }
 int get_force_path() { return g_force_path; }
 
-template <int W, bool FIRE, int D>
-static cudaError_t launch_lane(const DecParams& p, cudaStream_t stream)
+template <int W, bool FIRE, int D, int Q>
+static cudaError_t launch_lane_q(const DecParams& p, cudaStream_t stream)
 {
     const uint64_t threads = p.nchunks * (uint64_t)(D / 8);
     const uint64_t grid64 = (threads + kLaneThreads - 1) / kLaneThreads;
     if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
-    spz_decode_lane_kernel<W, FIRE, D><<<(uint32_t)grid64, kLaneThreads, 0, stream>>>(p);
+    spz_decode_lane_kernel<W, FIRE, D, Q><<<(uint32_t)grid64, kLaneThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <int W, bool FIRE, int D>
+static cudaError_t launch_lane(const DecParams& p, cudaStream_t stream)
+{
+    if (p.qop == 1) return launch_lane_q<W, FIRE, D, 1>(p, stream);
+    if (p.qop == 2) return launch_lane_q<W, FIRE, D, 2>(p, stream);
+    const uint64_t threads = p.nchunks * (uint64_t)(D / 8);
+    const uint64_t grid64 = (threads + kLaneThreads - 1) / kLaneThreads;
+    if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
+    spz_decode_lane_kernel<W, FIRE, D, 0><<<(uint32_t)grid64, kLaneThreads, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -381,8 +500,8 @@ cudaError_t launch_decode_lane(int elem_sz, int predictor, DecParams p, cudaStre
     // a lane is a whole scalar decoder: only worth it when there are enough chunks to fill the machine
     if (g_force_path != 2 && p.nchunks * (p.ndims / 8) < 16384) return cudaErrorNotSupported;
     // vector stores: every chunk's output must start 16-byte aligned
-    if (((uintptr_t)p.dst & 15) != 0) return cudaErrorNotSupported;
-    if (p.nchunks > 1 && ((p.chunk_len * (uint64_t)elem_sz) & 15) != 0) return cudaErrorNotSupported;
+    if (!p.qop && ((uintptr_t)p.dst & 15) != 0) return cudaErrorNotSupported;
+    if (!p.qop && p.nchunks > 1 && ((p.chunk_len * (uint64_t)elem_sz) & 15) != 0) return cudaErrorNotSupported;
     if (p.chunk_len % p.ndims != 0 && p.nchunks > 1) return cudaErrorNotSupported;
     // 32-bit bit cursors inside one chunk
     if (p.chunk_len * (uint64_t)elem_sz > 0x0c000000ull) return cudaErrorNotSupported;
