@@ -281,6 +281,42 @@ def run_ours(args, cfg, cfg_name):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_total, t_enc_m, t_dec_m = (float(v) for v in tt.tolist())
 
+    # ---- query-on-compressed, outside the timed region: per-dim REDUCE_SUM / REDUCE_MAX over the
+    # frame without materialising it (fused into the lane decoder where the shape allows); reads N/r bytes only
+    query_info = None
+    try:
+        qres = torch.empty(D, dtype=torch.int64, device=dev)
+        wb = int(L.spz_frame_query_workspace_bytes(esz, n, 0))
+        qwork = out.view(torch.uint8)               # decode+reduce shapes decode into this (>= n * esz bytes)
+        xu = x.view(-1, D)[: (n // D)].to(torch.int32) & ((1 << (8 * esz)) - 1) if n % D == 0 else None
+        query_info = {}
+        for opname, op in (("REDUCE_SUM", 2), ("REDUCE_MAX", 1)):
+            def q():
+                spz._lib.check(L.spz_frame_query_dev(pred, esz, op, 0, fr.buf.data_ptr(), fr.buf.numel(), n, D, chunk_rows,
+                                                     None, 0, codec.status.data_ptr(), qres.data_ptr(), qwork.data_ptr(),
+                                                     qwork.numel(), spz.api._stream_ptr()), "spz_frame_query_dev")
+            for _ in range(2):
+                q()
+            torch.cuda.synchronize()
+            qe = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            qe[0].record()
+            for _ in range(5):
+                q()
+            qe[1].record()
+            torch.cuda.synchronize()
+            tq = qe[0].elapsed_time(qe[1]) / 5e3
+            ok = None
+            if xu is not None:
+                want = xu.sum(0, dtype=torch.int64) if op == 2 else xu.max(0).values.to(torch.int64)
+                ok = bool(torch.equal(qres, want))
+            fused = bool(L.spz_last_query_fused())
+            query_info[opname] = {"ms": 1e3 * tq, "fused": fused, "raw_gbs": raw / tq / 1e9,
+                                  "hbm_bytes_read": payload, "hbm_read_frac": payload / tq / 1e9 / peaks()[0],
+                                  "matches_reduction_of_input": ok}
+        del xu
+    except Exception as e:  # noqa: BLE001
+        query_info = {"error": f"{type(e).__name__}: {e}"}
+
     # ---- optional exchange step: gather every rank's compressed payload + directory on rank 0 over
     # NCCL / NVLink.  Not part of `value` (the codec path itself needs no collective); reported beside it.
     gather_info = None
@@ -371,6 +407,7 @@ def run_ours(args, cfg, cfg_name):
         "e2e": {"value": world * raw * e2e_steps / t_e2e / 1e9, "unit": "GB/s",
                 "h2d_bytes_per_step": raw + int(fb), "d2h_bytes_per_step": int(fb) + raw, "steps": e2e_steps,
                 "api": "spz_frame_compress_host + spz_frame_decompress_host (pinned host buffers)"},
+        "query": query_info,
         "gather": gather_info,
         "gpu_launches": steps * 4,     # encode, directory scan, compaction, decode per step
         "clocks": clocks,
