@@ -479,7 +479,10 @@ cudaError_t launch_decode_hd(int elem_sz, int predictor, DecParams p, cudaStream
     p.ring_cap = pow2_ceil(max_group + 8 + team * 16);
     p.ring_mask4 = (p.ring_cap - 1u) & ~3u;
     p.out_cap = (16 + 2 * 8 * p.ndims * elem_sz + 16 + 15) & ~15u;
-    p.team_smem = ((p.ring_cap + 16 + 2 * p.out_cap + 128 + p.ring_cap - 1) / p.ring_cap) * p.ring_cap;
+    // the two output tiles start at ring_cap + 16 + (team index within the warp) * 32 (bank skew, see the kernel):
+    // up to 224 bytes for 4-lane teams
+    const uint32_t skew_max = (32u / team - 1u) * 32u;
+    p.team_smem = ((p.ring_cap + 16 + 2 * p.out_cap + (skew_max > 128u ? skew_max : 128u) + p.ring_cap - 1) / p.ring_cap) * p.ring_cap;
     const uint32_t teams_per_cta = kThreads / team;
     p.teams_per_cta = teams_per_cta;
     const size_t smem = (size_t)teams_per_cta * p.team_smem;

@@ -27,7 +27,6 @@ __global__ void __launch_bounds__(kRedThreads) spz_reduce_rows_kernel(const uint
 {
     constexpr int ESZ = W / 8;
     constexpr int EPV = 16 / ESZ;
-    constexpr uint32_t EM = (1u << W) - 1u;
     extern __shared__ unsigned long long sh[];      // [D]
     for (uint32_t d = threadIdx.x; d < D; d += kRedThreads) sh[d] = 0ull;
     __syncthreads();
@@ -35,10 +34,29 @@ __global__ void __launch_bounds__(kRedThreads) spz_reduce_rows_kernel(const uint
     const uint64_t g = (uint64_t)blockIdx.x * kRedThreads + threadIdx.x;
     const uint64_t units = (len + EPV - 1) / EPV;
     if (g < S) {
-        uint32_t acc[EPV];
-        unsigned long long tot[EPV];
+        // Packed accumulators: a 16-byte unit is 4 words; 8-bit elements are split into two words of 16-bit lanes
+        // (even / odd bytes), so max is one VIMNMX.U16x2 and sum one IADD per two elements.  Lane sums are drained
+        // into 32-bit (8-bit data, every 256 sweeps) / 64-bit totals before they can overflow.
+        constexpr int NA = (W == 8) ? 8 : (OP == 1 ? 4 : 8);
+        uint32_t acc[NA];
+        uint32_t tot32[(W == 8 && OP == 2) ? 16 : 1];
+        unsigned long long tot64[(W == 16 && OP == 2) ? 8 : 1];
 #pragma unroll
-        for (int k = 0; k < EPV; k++) { acc[k] = 0; tot[k] = 0; }
+        for (int k = 0; k < NA; k++) acc[k] = 0;
+#pragma unroll
+        for (int k = 0; k < (int)(sizeof(tot32) / 4); k++) tot32[k] = 0;
+#pragma unroll
+        for (int k = 0; k < (int)(sizeof(tot64) / 8); k++) tot64[k] = 0;
+        auto drain = [&]() {
+            if (W == 8 && OP == 2) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) { tot32[2 * k] += acc[k] & 0xffffu; tot32[2 * k + 1] += acc[k] >> 16; acc[k] = 0; }
+            }
+            if (W == 16 && OP == 2) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) { tot64[k] += acc[k]; acc[k] = 0; }
+            }
+        };
         uint32_t sweeps = 0;
         for (uint64_t u = g; u < units; u += S) {
             uint32_t w[4];
@@ -46,23 +64,42 @@ __global__ void __launch_bounds__(kRedThreads) spz_reduce_rows_kernel(const uint
                 const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + u);
                 w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
             } else {                                // ragged last unit: missing elements read as 0 (identity of both ops)
-                w[0] = w[1] = w[2] = w[3] = 0;
-                for (uint64_t b = u * 16; b < len * ESZ; b++) w[(b >> 2) & 3] |= (uint32_t)src[b] << (8 * (b & 3));
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    w[j] = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const uint64_t at = u * 16 + 4 * j + b;
+                        if (at < len * ESZ) w[j] |= (uint32_t)src[at] << (8 * b);
+                    }
+                }
             }
 #pragma unroll
-            for (int k = 0; k < EPV; k++) {
-                const uint32_t x = (w[k * ESZ / 4] >> (8 * ((k * ESZ) & 3))) & EM;
-                if (OP == 1) acc[k] = x > acc[k] ? x : acc[k]; else acc[k] += x;
+            for (int j = 0; j < 4; j++) {
+                if (W == 8) {
+                    const uint32_t ev = w[j] & 0x00ff00ffu, od = (w[j] >> 8) & 0x00ff00ffu;
+                    if (OP == 1) { acc[2 * j] = __vmaxu2(acc[2 * j], ev); acc[2 * j + 1] = __vmaxu2(acc[2 * j + 1], od); }
+                    else         { acc[2 * j] += ev; acc[2 * j + 1] += od; }
+                } else {
+                    if (OP == 1) acc[j] = __vmaxu2(acc[j], w[j]);
+                    else         { acc[2 * j] += w[j] & 0xffffu; acc[2 * j + 1] += w[j] >> 16; }
+                }
             }
-            if (OP == 2 && (++sweeps & 0x7fffu) == 0u) {            // 32768 x 65535 < 2^32
-#pragma unroll
-                for (int k = 0; k < EPV; k++) { tot[k] += acc[k]; acc[k] = 0; }
-            }
+            ++sweeps;
+            if (OP == 2 && (sweeps & (W == 8 ? 0xffu : 0x7fffu)) == 0u) drain();     // 256 x 255 < 2^16; 32768 x 65535 < 2^32
         }
+        drain();
         uint32_t d = (uint32_t)((g * EPV) % D);
 #pragma unroll
         for (int k = 0; k < EPV; k++) {
-            const unsigned long long v = tot[k] + acc[k];
+            unsigned long long v;
+            if (W == 8) {
+                // element k: word k / 4, byte k % 4 -> even / odd split word, low / high lane
+                const int a = 2 * (k / 4) + (k & 1), hi = (k >> 1) & 1;
+                v = (OP == 1) ? ((acc[a] >> (16 * hi)) & 0xffffu) : tot32[2 * a + hi];
+            } else {
+                v = (OP == 1) ? ((acc[k / 2] >> (16 * (k & 1))) & 0xffffu) : tot64[k];
+            }
             if (OP == 1) { if (v) atomicMax(&sh[d], v); } else { if (v) atomicAdd(&sh[d], v); }
             if (++d == D) d = 0;
         }

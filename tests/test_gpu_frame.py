@@ -111,3 +111,32 @@ def test_full_size_properties(spz, ref, cfg):
     torch.cuda.synchronize()
     sums2 = fr2.buf[po: po + payload_bytes].view(torch.int64)[: payload_bytes // 8].sum().item()
     assert sums1 == sums2
+
+
+SWEEP_DIMS = (1, 2, 3, 4, 5, 6, 7, 8, 9, 12, 16, 17, 24, 31, 32, 33, 40, 48, 64, 65, 80, 96, 128, 129, 200, 256)
+
+
+@pytest.mark.parametrize("pred", [DELTA, XFF], ids=["delta", "xff"])
+@pytest.mark.parametrize("esz", [1, 2])
+def test_frame_many_chunks_every_team_shape(spz, oracle, pred, esz):
+    """BASELINE config 5's dims axis (1..256) at the reference's block size: frames with hundreds of chunks, so every
+    team shape fills whole CTAs (the last team of a CTA sits at the end of its shared-memory window).  Round trip
+    over the whole frame + a sample of chunks byte-for-byte against the oracle."""
+    import torch
+    rng = np.random.default_rng(7)
+    for D in SWEEP_DIMS:
+        chunk_rows = 64
+        nrows = chunk_rows * 300 + 16
+        x = inputs.ar1(nrows, D, esz, seed=D)
+        xt = torch.from_numpy(x.view(np.uint8 if esz == 1 else np.int16)).cuda()
+        fr = spz.frame_encode(pred, xt, D, chunk_rows)
+        out = spz.frame_decode(fr)
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy().view(x.dtype), x), f"round trip, ndims {D}"
+        off, nb, po = fr.directory()
+        buf = fr.buf[: fr.nbytes()].cpu().numpy()
+        clen = chunk_rows * D
+        for c in sorted(set([0, 1, 31, 32, 127, 128, 299, 300] + list(rng.integers(0, 301, size=6)))):
+            ws, wr = oracle.compress(pred, x[c * clen: (c + 1) * clen], D)
+            gs = buf[po + off[c]: po + off[c] + nb[c]]
+            assert len(gs) == len(ws) and np.array_equal(gs, ws), f"ndims {D} chunk {c}"
