@@ -460,7 +460,7 @@ static inline uint32_t pow2_ceil(uint32_t x) { uint32_t v = 1; while (v < x) v <
 cudaError_t launch_decode_hd(int elem_sz, int predictor, DecParams p, cudaStream_t stream)
 {
     const bool low = elem_sz == 1 ? (p.ndims <= 4) : (p.ndims <= 2);
-    if (low || p.ndims > 128 || p.src_end == nullptr) return cudaErrorNotSupported;
+    if (low || p.ndims > 256 || p.src_end == nullptr) return cudaErrorNotSupported;
     // 32-bit stream / output offsets inside one chunk
     if (p.chunk_len * (uint64_t)elem_sz > 0x70000000ull) return cudaErrorNotSupported;
     // team shape: a power-of-two slice of the warp with DPL dims per lane. Prefer an exact cover of ndims
@@ -505,6 +505,10 @@ cudaError_t launch_decode_hd(int elem_sz, int predictor, DecParams p, cudaStream
         if (dpl == 2) SPZ_HD(8, 32, 2);
         if (dpl == 3) SPZ_HD(8, 32, 3);
         if (dpl == 4) SPZ_HD(8, 32, 4);
+        if (dpl == 5) SPZ_HD(8, 32, 5);
+        if (dpl == 6) SPZ_HD(8, 32, 6);
+        if (dpl == 7) SPZ_HD(8, 32, 7);
+        if (dpl == 8) SPZ_HD(8, 32, 8);
     } else {
         if (team == 4) SPZ_HD(16, 4, 1);
         if (team == 8 && dpl == 1) SPZ_HD(16, 8, 1);
@@ -517,6 +521,10 @@ cudaError_t launch_decode_hd(int elem_sz, int predictor, DecParams p, cudaStream
         if (dpl == 2) SPZ_HD(16, 32, 2);
         if (dpl == 3) SPZ_HD(16, 32, 3);
         if (dpl == 4) SPZ_HD(16, 32, 4);
+        if (dpl == 5) SPZ_HD(16, 32, 5);
+        if (dpl == 6) SPZ_HD(16, 32, 6);
+        if (dpl == 7) SPZ_HD(16, 32, 7);
+        if (dpl == 8) SPZ_HD(16, 32, 8);
     }
 #undef SPZ_HD
 #undef SPZ_HD2

@@ -497,8 +497,10 @@ cudaError_t launch_decode_lane(int elem_sz, int predictor, DecParams p, cudaStre
     if (g_force_path == 1) return cudaErrorNotSupported;
     if (p.ndims != 8 && p.ndims != 16) return cudaErrorNotSupported;
     if (p.src_end == nullptr || p.src_end <= p.src) return cudaErrorNotSupported;
-    // a lane is a whole scalar decoder: only worth it when there are enough chunks to fill the machine
-    if (g_force_path != 2 && p.nchunks * (p.ndims / 8) < 16384) return cudaErrorNotSupported;
+    // a lane is a whole scalar decoder: only worth it when there are enough lane tasks to fill the machine (one wave
+    // is 148 SMs x 4 CTAs x 128 lanes = 75 776).  Measured crossover against the team kernels at 1024-row chunks
+    // (gpurun s43, 64..512 MiB frames): ~20-28 Ki lane tasks for int8, ~50 Ki for int16.
+    if (g_force_path != 2 && p.nchunks * (p.ndims / 8) < (elem_sz == 1 ? 24576u : 49152u)) return cudaErrorNotSupported;
     // vector stores: every chunk's output must start 16-byte aligned
     if (!p.qop && ((uintptr_t)p.dst & 15) != 0) return cudaErrorNotSupported;
     if (!p.qop && p.nchunks > 1 && ((p.chunk_len * (uint64_t)elem_sz) & 15) != 0) return cudaErrorNotSupported;

@@ -478,7 +478,7 @@ static inline uint32_t up16(uint32_t x) { return (x + 15u) & ~15u; }
 cudaError_t launch_encode_hd(int elem_sz, int predictor, EncParams p, cudaStream_t stream)
 {
     const bool low = elem_sz == 1 ? (p.ndims <= 4) : (p.ndims <= 2);
-    if (low || p.ndims > 128) return cudaErrorNotSupported;
+    if (low || p.ndims > 256) return cudaErrorNotSupported;
     if (p.chunk_len * (uint64_t)elem_sz > 0x70000000ull) return cudaErrorNotSupported;     // 32-bit offsets
     // 128-bit input loads: every chunk must start 16-byte aligned
     if (((uintptr_t)p.src & 15) || (p.nchunks > 1 && ((p.chunk_len * elem_sz) & 15))) return cudaErrorNotSupported;
@@ -533,6 +533,10 @@ cudaError_t launch_encode_hd(int elem_sz, int predictor, EncParams p, cudaStream
         if (dpl == 2) SPZ_HD(8, 32, 2);
         if (dpl == 3) SPZ_HD(8, 32, 3);
         if (dpl == 4) SPZ_HD(8, 32, 4);
+        if (dpl == 5) SPZ_HD(8, 32, 5);
+        if (dpl == 6) SPZ_HD(8, 32, 6);
+        if (dpl == 7) SPZ_HD(8, 32, 7);
+        if (dpl == 8) SPZ_HD(8, 32, 8);
     } else {
         if (team == 4) SPZ_HD(16, 4, 1);
         if (team == 8 && dpl == 1) SPZ_HD(16, 8, 1);
@@ -545,6 +549,10 @@ cudaError_t launch_encode_hd(int elem_sz, int predictor, EncParams p, cudaStream
         if (dpl == 2) SPZ_HD(16, 32, 2);
         if (dpl == 3) SPZ_HD(16, 32, 3);
         if (dpl == 4) SPZ_HD(16, 32, 4);
+        if (dpl == 5) SPZ_HD(16, 32, 5);
+        if (dpl == 6) SPZ_HD(16, 32, 6);
+        if (dpl == 7) SPZ_HD(16, 32, 7);
+        if (dpl == 8) SPZ_HD(16, 32, 8);
     }
 #undef SPZ_HD
 #undef SPZ_HD2

@@ -453,7 +453,8 @@ cudaError_t launch_encode_lane(int elem_sz, int predictor, EncParams p, cudaStre
     if (!((elem_sz == 1 && p.ndims == 8) || (elem_sz == 2 && (p.ndims == 8 || p.ndims == 16)))) return cudaErrorNotSupported;
     if (p.meta == nullptr) return cudaErrorNotSupported;
     // a lane is a whole scalar encoder: only worth it when there are enough chunks to fill the machine
-    if (force != 2 && p.nchunks < 16384) return cudaErrorNotSupported;
+    // measured crossover against the team kernels (gpurun s43): 16 Ki chunks for 8 dims, ~24 Ki for int16 x 16
+    if (force != 2 && p.nchunks < (p.ndims == 16 ? 24576u : 16384u)) return cudaErrorNotSupported;
     // 256-bit loads / stores: every chunk's input and output slot must start 32-byte aligned
     if (((uintptr_t)p.src & 31) != 0 || ((uintptr_t)p.dst & 31) != 0) return cudaErrorNotSupported;
     if (p.nchunks > 1 && (((p.chunk_len * (uint64_t)elem_sz) & 31) != 0 || (p.slot_stride & 31) != 0)) return cudaErrorNotSupported;
