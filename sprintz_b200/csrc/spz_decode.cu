@@ -212,6 +212,7 @@ static inline uint32_t pow2_ceil(uint32_t x) { uint32_t p = 1; while (p < x) p <
 
 cudaError_t launch_decode_hd(int elem_sz, int predictor, DecParams p, cudaStream_t stream);
 cudaError_t launch_decode_lane(int elem_sz, int predictor, DecParams p, cudaStream_t stream);
+cudaError_t launch_decode_lowlane(int elem_sz, int predictor, DecParams p, cudaStream_t stream);
 
 static int g_last_decode_family = 0;     // 0 generic team kernel, 1 fast team kernel (hd), 2 lane kernel
 int last_decode_family() { return g_last_decode_family; }
@@ -229,8 +230,13 @@ cudaError_t launch_decode(int elem_sz, int predictor, DecParams p, cudaStream_t 
         const cudaError_t e = launch_decode_hd(elem_sz, predictor, p, stream);
         if (e != cudaErrorNotSupported) { g_last_decode_family = 1; return e; }
     }
-    g_last_decode_family = 0;
     const bool low = p.variant ? false : (elem_sz == 1 ? (p.ndims <= 4) : (p.ndims <= 2));
+    if (low)
+    {   // throughput path of the low-dim codecs: frames with many chunks (spz_decode_lowlane.cu)
+        const cudaError_t e = launch_decode_lowlane(elem_sz, predictor, p, stream);
+        if (e != cudaErrorNotSupported) { g_last_decode_family = 2; return e; }
+    }
+    g_last_decode_family = 0;
     p.team = p.ndims >= 32 ? 32 : pow2_ceil(p.ndims);
     p.dpl = (p.ndims + p.team - 1) / p.team;
     p.team_smem = (4u * 4u * p.team * p.dpl + 15u) & ~15u;
