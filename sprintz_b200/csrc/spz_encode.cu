@@ -379,6 +379,7 @@ static void enc_layout(int elem_sz, bool low, EncParams& p)
 
 cudaError_t launch_encode_hd(int elem_sz, int predictor, EncParams p, cudaStream_t stream);
 cudaError_t launch_encode_lane(int elem_sz, int predictor, EncParams p, cudaStream_t stream);
+cudaError_t launch_encode_lowlane(int elem_sz, int predictor, EncParams p, cudaStream_t stream);
 
 static int g_last_encode_family = 0;     // 0 generic team kernel, 1 fast team kernel (hd), 2 lane kernel
 int last_encode_family() { return g_last_encode_family; }
@@ -396,8 +397,13 @@ cudaError_t launch_encode(int elem_sz, int predictor, EncParams p, cudaStream_t 
         const cudaError_t e = launch_encode_hd(elem_sz, predictor, p, stream);
         if (e != cudaErrorNotSupported) { g_last_encode_family = 1; return e; }
     }
-    g_last_encode_family = 0;
     const bool low = p.variant ? false : (elem_sz == 1 ? (p.ndims <= 4) : (p.ndims <= 2));
+    if (low)
+    {   // throughput path of the low-dim codecs: frames with many chunks (spz_encode_lowlane.cu)
+        const cudaError_t e = launch_encode_lowlane(elem_sz, predictor, p, stream);
+        if (e != cudaErrorNotSupported) { g_last_encode_family = 2; return e; }
+    }
+    g_last_encode_family = 0;
     p.team = p.ndims >= 32 ? 32 : pow2_ceil(p.ndims);
     p.dpl = (p.ndims + p.team - 1) / p.team;
     enc_layout(elem_sz, low, p);

@@ -111,6 +111,7 @@ def test_lowlane_reference_matrix_and_runs(spz, oracle, pred, esz):
             for tag, x in inputs.reference_families(n, esz).items():
                 _check_case(spz, oracle, pred, esz, D, x, bad, tag)
         assert spz.lib().spz_last_kernel_family(1) == 2, "low-dim lane decoder did not run"
+        assert spz.lib().spz_last_kernel_family(0) == 2, "low-dim lane encoder did not run"
         for nrows in (24, 100, 1000):
             for tag, x in inputs.adversarial_families(nrows, D, esz).items():
                 _check_case(spz, oracle, pred, esz, D, x, bad, f"{tag}/r{nrows}")
@@ -146,6 +147,7 @@ def test_lowlane_frames_match_oracle(spz, oracle, pred, esz, D):
             x = x[:-ragged]
         _frame_vs_oracle(spz, oracle, pred, esz, D, x, chunk_rows)
     assert spz.lib().spz_last_kernel_family(1) == 2, "low-dim lane decoder did not run"
+    assert spz.lib().spz_last_kernel_family(0) == 2, "low-dim lane encoder did not run"
     _frame_vs_oracle(spz, oracle, pred, esz, D, inputs.random_walk_with_runs(3000, D, esz, seed=5), 512)
     _frame_vs_oracle(spz, oracle, pred, esz, D, np.zeros(4096 * D, x.dtype), 1024)
     _frame_vs_oracle(spz, oracle, pred, esz, D, inputs.linear_ramp(70000, D, esz, slope=997), 35008)
@@ -156,8 +158,11 @@ def test_lowlane_golden_vectors(spz, golden):
     for c in golden.cases:
         if c["D"] not in LOW_DIMS[c["esz"]]:
             continue
-        dec, dr = spz.decompress(c["pred"], c["esz"], c["stream"])
-        msg = parity.compare_decoded(dec, dr, c["x"])
+        gs, gr = spz.compress(c["pred"], c["x"], c["D"])
+        msg = parity.compare_stream(gs, gr, c["stream"], c["ret"], c["esz"])
+        if msg is None:
+            dec, dr = spz.decompress(c["pred"], c["esz"], c["stream"])
+            msg = parity.compare_decoded(dec, dr, c["x"])
         if msg:
             bad.append((c["pred"], c["esz"], c["D"], c["tag"], msg))
     assert not bad, (len(bad), bad[:5])
