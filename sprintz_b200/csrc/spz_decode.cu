@@ -266,6 +266,8 @@ cudaError_t launch_query_fused(int elem_sz, int predictor, DecParams p, cudaStre
     if (predictor >= 2) { p.variant = (uint32_t)predictor - 1u; }
     if (p.variant) predictor = (p.variant == 3u) ? 1 : 0;
     if (p.qop != 1u && p.qop != 2u) return cudaErrorInvalidValue;
+    const bool low = p.variant ? false : (elem_sz == 1 ? (p.ndims <= 4) : (p.ndims <= 2));
+    if (low) return launch_decode_lowlane(elem_sz, predictor, p, stream);
     return launch_decode_lane(elem_sz, predictor, p, stream);
 }
 

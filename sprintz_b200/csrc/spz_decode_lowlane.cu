@@ -20,8 +20,10 @@ constexpr uint32_t kLowLaneWarpSmem = 8192;   // 33 rows x 128 B used; the strid
 #define kLaneThreads kLowLaneThreads
 #define kLaneWarpSmem kLowLaneWarpSmem
 
-template <int W, bool FIRE, int D>
-__global__ void __launch_bounds__(kLowLaneThreads, 4) spz_decode_lowlane_kernel(const DecParams p)
+// Q = 0: decode.  Q = 1 / 2: query-on-compressed (REDUCE_MAX / REDUCE_SUM without materialising, see
+// spz_decode_lane.cu): rows are folded into per-dim registers instead of being packed and stored.
+template <int W, bool FIRE, int D, int Q>
+__global__ void __launch_bounds__(kLowLaneThreads, (D * W <= 16) ? 7 : 5) spz_decode_lowlane_kernel(const DecParams p)
 {
     typedef typename Traits<W>::uint_t uint_t;
     constexpr int ESZ = W / 8;
@@ -36,8 +38,12 @@ __global__ void __launch_bounds__(kLowLaneThreads, 4) spz_decode_lowlane_kernel(
 
     __shared__ __align__(16) uint8_t smem[(kLowLaneThreads / 32) * kLowLaneWarpSmem];
 
-    const uint64_t c = (uint64_t)blockIdx.x * kLowLaneThreads + threadIdx.x;
-    if (c >= p.nchunks) return;                     // lanes never cooperate: early exit is safe
+    uint64_t c = (uint64_t)blockIdx.x * kLowLaneThreads + threadIdx.x;
+    bool live = true;
+    if (c >= p.nchunks) {
+        if (!Q) return;                             // decoding lanes never cooperate: early exit is safe
+        live = false; c = p.nchunks - 1;            // query lanes meet in the final reduction: shadow the last chunk
+    }
     const uint32_t rboff = (threadIdx.x >> 5) * kLowLaneWarpSmem + (threadIdx.x & 31) * 4u;
 
     // ---- input ring
@@ -123,22 +129,74 @@ __global__ void __launch_bounds__(kLowLaneThreads, 4) spz_decode_lowlane_kernel(
 #pragma unroll
     for (int k = 0; k < NWORD; k++) wd[k] = 0;
     // element (row r, dim d) of the block <- the current running value of dim d
+    // ---- query accumulators (Q != 0): running maximum (left-aligned) | 32-bit partial sums drained into lane-private
+    // 64-bit totals (rows 34.. of the warp's shared region; the store staging is unused when nothing is stored)
+    uint32_t qa[D];
+    uint32_t qblocks = 0;
+    if (Q) {
+#pragma unroll
+        for (int d = 0; d < D; d++) qa[d] = 0;
+        if (Q == 2) {
+#pragma unroll
+            for (int j = 0; j < 2 * D; j++) *reinterpret_cast<uint32_t*>(smem + rboff + (34 + j) * 128) = 0u;
+        }
+    }
+    auto qtot_add = [&](int d, unsigned long long v) {
+        uint32_t* lo = reinterpret_cast<uint32_t*>(smem + rboff + (34 + 2 * d) * 128);
+        uint32_t* hi = reinterpret_cast<uint32_t*>(smem + rboff + (35 + 2 * d) * 128);
+        const unsigned long long t = (((unsigned long long)*hi << 32) | *lo) + v;
+        *lo = (uint32_t)t; *hi = (uint32_t)(t >> 32);
+    };
+    auto qfold1 = [&](int d) {                      // the current running value of dim d, once
+        if (Q == 1) qa[d] = pvh[d] > qa[d] ? pvh[d] : qa[d];
+        else asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(qa[d]) : "r"(pvh[d]), "n"(1u << W));
+    };
+    auto qblock_done = [&]() {
+        if (Q == 2 && (++qblocks & 4095u) == 0u) {
+#pragma unroll
+            for (int d = 0; d < D; d++) { qtot_add(d, qa[d]); qa[d] = 0; }
+        }
+    };
     auto put = [&](int r, int d) {
+        if (Q) { qfold1(d); return; }
         const int at = (r * D + d) * ESZ;           // byte offset inside the block
         const int w = at >> 2;
         if (W == 16) wd[w] = __byte_perm(wd[w], pvh[d], (at & 2) ? 0x7610 : 0x3276);
         else wd[w] = __byte_perm(wd[w], pvh[d], (at & 3) == 0 ? 0x3217 : (at & 3) == 1 ? 0x3270 : (at & 3) == 2 ? 0x3710 : 0x7210);
     };
+    // Blocks smaller than a 32-byte sector (8 / 16 / 24 bytes) are collected in a lane-private 16-word ring (rows
+    // 34..49 of the warp's shared region, bank-private like the input ring) and leave as whole aligned sectors:
+    // 8-byte stores per lane cost a partial-sector write each (measured: 1 dim decoded at half the speed of 4 dims).
+    uint32_t swi = 0, sri = 0;                      // staged words written / flushed
+    auto stage_at = [&](uint32_t w) -> uint32_t { return rboff + (34u + (w & 15u)) * 128u; };
     auto store_block = [&]() {
-        if (NWORD % 4 == 0) {
-#pragma unroll
-            for (int k = 0; k < NWORD / 4; k++)
-                reinterpret_cast<uint4*>(oblk)[k] = make_uint4(wd[4 * k], wd[4 * k + 1], wd[4 * k + 2], wd[4 * k + 3]);
+        if (Q) {
+            qblock_done();
+        } else if (NWORD == 8) {
+            reinterpret_cast<uint4*>(oblk)[0] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+            reinterpret_cast<uint4*>(oblk)[1] = make_uint4(wd[4], wd[5], wd[6], wd[7]);
+            oblk += 32;
         } else {
 #pragma unroll
-            for (int k = 0; k < NWORD / 2; k++) reinterpret_cast<uint2*>(oblk)[k] = make_uint2(wd[2 * k], wd[2 * k + 1]);
+            for (int k = 0; k < NWORD; k++) *reinterpret_cast<uint32_t*>(smem + stage_at(swi + k)) = wd[k];
+            swi += NWORD;
+            if (swi - sri >= 8u) {
+                uint32_t v[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[k] = *reinterpret_cast<const uint32_t*>(smem + stage_at(sri + k));
+                reinterpret_cast<uint4*>(oblk)[0] = make_uint4(v[0], v[1], v[2], v[3]);
+                reinterpret_cast<uint4*>(oblk)[1] = make_uint4(v[4], v[5], v[6], v[7]);
+                oblk += 32;
+                sri += 8u;
+            }
         }
-        oblk += B * ESZ;
+    };
+    auto store_finish = [&]() {                      // the staged remainder (a multiple of 8 bytes)
+        for (; sri != swi; sri += 2u) {
+            *reinterpret_cast<uint2*>(oblk) = make_uint2(*reinterpret_cast<const uint32_t*>(smem + stage_at(sri)),
+                                                         *reinterpret_cast<const uint32_t*>(smem + stage_at(sri + 1u)));
+            oblk += 8;
+        }
     };
     // FIRE prediction on the left-aligned previous delta (sprintz_xff_lowdim.cpp:170-173: coef = counter >> 1).
     // 8-bit: |coef| < 2^14, the product cannot wrap: the high word of (prev_delta << 24) * coef is (prev_delta * coef) >> 8.
@@ -188,7 +246,13 @@ __global__ void __launch_bounds__(kLowLaneThreads, 4) spz_decode_lowlane_kernel(
                 if (rb & 0x80u) { nrun |= ((rb >> 8) & 0xffu) << 7; pos += 16u; } else { pos += 8u; }
                 ensure(pos);
                 if ((uint64_t)o + (uint64_t)nrun * B > cap) { status = kStatusOverflow; break; }
-                if (!FIRE) {                         // the previous row, repeated
+                if (Q && !FIRE) {                    // a delta run repeats the previous row: fold it in one step
+#pragma unroll
+                    for (int d = 0; d < D; d++) {
+                        if (Q == 1) qfold1(d);
+                        else if (nrun) qtot_add(d, (unsigned long long)(pvh[d] >> UP) * (nrun * 8u));
+                    }
+                } else if (!FIRE) {                  // the previous row, repeated
 #pragma unroll
                     for (int k = 0; k < NWORD; k++) wd[k] = 0;
 #pragma unroll
@@ -260,17 +324,64 @@ __global__ void __launch_bounds__(kLowLaneThreads, 4) spz_decode_lowlane_kernel(
         if (status != kStatusOk) break;
     }
 
+    if (!Q) store_finish();
     // ---- trailing raw elements (also the whole stream when it was stored raw)
     if (status == kStatusOk) {
         if ((uint64_t)o + remaining > cap) {
             status = kStatusOverflow;
         } else {
             const uint8_t* tsrc = base32 + (pos >> 3);
-            uint8_t* tdst = reinterpret_cast<uint8_t*>(out + o);
-            const uint32_t nbytes = remaining * ESZ;
-            for (uint32_t b = 0; b < nbytes; b++) tdst[b] = tsrc[b];
+            if (Q) {                                 // raw tail elements go straight to the result (short, rare)
+                if (live) {
+                    for (uint32_t e = 0; e < remaining; e++) {
+                        const unsigned long long v = (W == 16) ? (unsigned long long)(tsrc[2 * e] | (tsrc[2 * e + 1] << 8))
+                                                               : (unsigned long long)tsrc[e];
+                        if (Q == 1) atomicMax(p.qresult + (o + e) % D, v); else atomicAdd(p.qresult + (o + e) % D, v);
+                    }
+                }
+            } else {
+                uint8_t* tdst = reinterpret_cast<uint8_t*>(out + o);
+                const uint32_t nbytes = remaining * ESZ;
+                for (uint32_t b = 0; b < nbytes; b++) tdst[b] = tsrc[b];
+            }
             o += remaining;
         }
+    }
+    if (Q) {
+        // ---- lanes -> warp -> CTA -> one atomic per dim (every lane holds the same dims)
+        unsigned long long v[D];
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            if (Q == 1) v[d] = qa[d] >> UP;
+            else {
+                const uint32_t lo = *reinterpret_cast<uint32_t*>(smem + rboff + (34 + 2 * d) * 128);
+                const uint32_t hi = *reinterpret_cast<uint32_t*>(smem + rboff + (35 + 2 * d) * 128);
+                v[d] = (((unsigned long long)hi << 32) | lo) + qa[d];
+            }
+            if (!live || status != kStatusOk) v[d] = 0;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned long long w = __shfl_xor_sync(0xffffffffu, v[d], off);
+                v[d] = (Q == 1) ? (w > v[d] ? w : v[d]) : (v[d] + w);
+            }
+        }
+        __syncthreads();                             // everyone is done with the rings: reuse the first bytes
+        unsigned long long* cta = reinterpret_cast<unsigned long long*>(smem);
+        if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+            for (int d = 0; d < D; d++) cta[(threadIdx.x >> 5) * D + d] = v[d];
+        }
+        __syncthreads();
+        if (threadIdx.x < D) {
+            unsigned long long r = cta[threadIdx.x];
+#pragma unroll
+            for (int w = 1; w < kLowLaneThreads / 32; w++) {
+                const unsigned long long x = cta[w * D + threadIdx.x];
+                r = (Q == 1) ? (x > r ? x : r) : (r + x);
+            }
+            if (Q == 1) { if (r) atomicMax(p.qresult + threadIdx.x, r); } else atomicAdd(p.qresult + threadIdx.x, r);
+        }
+        if (!live) return;
     }
     if (p.meta) {
         p.meta[c].status = status;
@@ -292,7 +403,9 @@ static cudaError_t launch_lowlane(const DecParams& p, cudaStream_t stream)
 {
     const uint64_t grid64 = (p.nchunks + kLowLaneThreads - 1) / kLowLaneThreads;
     if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
-    spz_decode_lowlane_kernel<W, FIRE, D><<<(uint32_t)grid64, kLowLaneThreads, 0, stream>>>(p);
+    if (p.qop == 1) spz_decode_lowlane_kernel<W, FIRE, D, 1><<<(uint32_t)grid64, kLowLaneThreads, 0, stream>>>(p);
+    else if (p.qop == 2) spz_decode_lowlane_kernel<W, FIRE, D, 2><<<(uint32_t)grid64, kLowLaneThreads, 0, stream>>>(p);
+    else spz_decode_lowlane_kernel<W, FIRE, D, 0><<<(uint32_t)grid64, kLowLaneThreads, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -306,8 +419,8 @@ cudaError_t launch_decode_lowlane(int elem_sz, int predictor, DecParams p, cudaS
     // a lane is a whole scalar decoder: only worth it when there are enough chunks to fill the machine
     if (force != 2 && p.nchunks < 16384) return cudaErrorNotSupported;
     // vector stores: every chunk's output must start 16-byte aligned
-    if (((uintptr_t)p.dst & 15) != 0) return cudaErrorNotSupported;
-    if (p.nchunks > 1 && ((p.chunk_len * (uint64_t)elem_sz) & 15) != 0) return cudaErrorNotSupported;
+    if (!p.qop && ((uintptr_t)p.dst & 15) != 0) return cudaErrorNotSupported;
+    if (!p.qop && p.nchunks > 1 && ((p.chunk_len * (uint64_t)elem_sz) & 15) != 0) return cudaErrorNotSupported;
     if (p.chunk_len % p.ndims != 0 && p.nchunks > 1) return cudaErrorNotSupported;
     if (p.chunk_len * (uint64_t)elem_sz > 0x0c000000ull) return cudaErrorNotSupported;   // 32-bit bit cursors
 #define SPZ_LL(Wv, Dv) return predictor ? launch_lowlane<Wv, true, Dv>(p, stream) : launch_lowlane<Wv, false, Dv>(p, stream)

@@ -30,7 +30,7 @@ __device__ __forceinline__ uint32_t llds32(uint32_t a)
 #define lds32 llds32
 
 template <int W, bool FIRE, int D>
-__global__ void __launch_bounds__(kEncLowThreads, 4) spz_encode_lowlane_kernel(const EncParams p)
+__global__ void __launch_bounds__(kEncLowThreads, (D * W == 8) ? 8 : (D * W == 16) ? 7 : 5) spz_encode_lowlane_kernel(const EncParams p)
 {
     constexpr int ESZ = W / 8;
     constexpr int HB = Traits<W>::HB;

@@ -176,3 +176,31 @@ def test_gpu_frame_query_full_size(pred, esz, D, rows):
         assert spz.last_query_fused() == (D in (8, 16))
         want = xu.max(0).values if op == Q_MAX else xu.sum(0)
         assert torch.equal(res, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pred", [DELTA, XFF], ids=["delta", "xff"])
+@pytest.mark.parametrize("esz,D", [(1, 1), (1, 2), (1, 3), (1, 4), (2, 1), (2, 2)])
+def test_gpu_frame_query_fused_lowdim_lane_path(pred, esz, D):
+    """the low-dim lane decoder (univariate / few-variable frames) folds rows the same way"""
+    import sprintz_b200 as spz
+    spz.lib()
+    old = spz.set_kernel_path(2)
+    try:
+        udt = np.uint8 if esz == 1 else np.uint16
+        for chunk_rows, nrows, ragged in ((16, 400, 0), (256, 5000, 3 if D > 1 else 1), (4096, 20000, 0), (256, 100, 0),
+                                          (64, 64 * 300, 0)):
+            x = inputs.ar1(nrows, D, esz, seed=nrows)
+            if ragged:
+                x = x[:-ragged]
+            _frame_query_case(spz, pred, esz, D, x, chunk_rows, True)
+        _frame_query_case(spz, pred, esz, D, inputs.random_walk_with_runs(3000, D, esz, seed=5), 512, True)
+        _frame_query_case(spz, pred, esz, D, np.zeros(4096 * D, udt), 1024, True)
+        x = np.full(70000 * D, (1 << (8 * esz)) - 2, udt)
+        x[-500 * D:] = inputs.fuzz(500 * D, esz)["fuzz256"]
+        _frame_query_case(spz, pred, esz, D, x, 35008, True)
+        x = ((1 << (8 * esz)) - 1 - inputs.fuzz(40000 * D, esz)["fuzz16"]).astype(udt)
+        _frame_query_case(spz, pred, esz, D, x, 40000, True)
+        _frame_query_case(spz, pred, esz, D, inputs.linear_ramp(6000, D, esz), 2048, True)
+    finally:
+        spz.set_kernel_path(old)
