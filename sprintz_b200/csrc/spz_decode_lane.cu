@@ -142,12 +142,17 @@ __global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_k
     const uint64_t cap64 = first >= p.dst_cap ? 0 : ((p.dst_cap - first < p.chunk_len) ? (p.dst_cap - first) : p.chunk_len);
     const uint32_t cap = cap64 > 0xffffffffull ? 0xffffffffu : (uint32_t)cap64;
     uint8_t* orow = reinterpret_cast<uint8_t*>(out) + part * LB;        // my bytes of the next row to write
+    const bool al32 = ((uintptr_t)out & 31) == 0;                       // whole-sector stores may be 256-bit
 
     uint32_t pvh[8];                                // running values, left-aligned (value << (32-W))
     int32_t pdh[8], ct[8];                          // previous deltas (left-aligned), FIRE counters
 #pragma unroll
     for (int j = 0; j < 8; j++) { pvh[j] = 0; pdh[j] = 0; ct[j] = 0; }
-    uint32_t held0 = 0, held1 = 0;                  // even row of a pair when a row is only 8 bytes (NP == 1, W == 8)
+    // int8 rows are 8 bytes per lane: rows are held back so that a lane always completes a whole 32-byte sector with
+    // back-to-back stores (partial-sector writes cost a read-modify-write in L2: measured on the low-dim decoder,
+    // 16-byte stores -> whole sectors = +38 %).  NP == 1: rows r..r+3 leave as two 128-bit stores; NP == 2: the two
+    // lanes of a chunk write rows r, r+1 (2 x 16 bytes, one sector) in consecutive instructions.
+    uint32_t held[6] = {0, 0, 0, 0, 0, 0};
 
     // my 8 values of one row -> HBM
     auto store_row = [&](uint32_t r) {
@@ -163,12 +168,25 @@ __global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_k
             const uint32_t a = __byte_perm(pvh[0], pvh[1], 0x0073), b = __byte_perm(pvh[2], pvh[3], 0x0073);
             const uint32_t e = __byte_perm(pvh[4], pvh[5], 0x0073), f = __byte_perm(pvh[6], pvh[7], 0x0073);
             const uint32_t w0 = __byte_perm(a, b, 0x5410), w1 = __byte_perm(e, f, 0x5410);
-            if (NP == 1) {                           // rows are 8 bytes: rows r, r+1 form one 16-byte store
-                if ((r & 1u) == 0u) { held0 = w0; held1 = w1; }
-                else { *reinterpret_cast<uint4*>(orow) = make_uint4(held0, held1, w0, w1); orow += 2 * ROWB; }
-            } else {
-                *reinterpret_cast<uint2*>(orow) = make_uint2(w0, w1);
-                orow += ROWB;
+            if (NP == 1) {                           // rows are 8 bytes: rows r..r+3 form one sector
+                if ((r & 3u) != 3u) { held[2 * (r & 3u)] = w0; held[2 * (r & 3u) + 1] = w1; }
+                else {
+                    if (al32) {                      // one 256-bit store == one whole sector (sm_100: STG.E.256)
+                        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(orow), "r"(held[0]), "r"(held[1]),
+                                     "r"(held[2]), "r"(held[3]), "r"(held[4]), "r"(held[5]), "r"(w0), "r"(w1) : "memory");
+                    } else {
+                        reinterpret_cast<uint4*>(orow)[0] = make_uint4(held[0], held[1], held[2], held[3]);
+                        reinterpret_cast<uint4*>(orow)[1] = make_uint4(held[4], held[5], w0, w1);
+                    }
+                    orow += 4 * ROWB;
+                }
+            } else {                                 // 16-byte rows, 8 bytes per lane: rows r, r+1 form one sector
+                if ((r & 1u) == 0u) { held[0] = w0; held[1] = w1; }
+                else {
+                    *reinterpret_cast<uint2*>(orow) = make_uint2(held[0], held[1]);
+                    *reinterpret_cast<uint2*>(orow + ROWB) = make_uint2(w0, w1);
+                    orow += 2 * ROWB;
+                }
             }
         }
     };

@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(kLowLaneThreads, (D * W <= 16) ? 7 : 5) spz_de
     const uint64_t cap64 = first >= p.dst_cap ? 0 : ((p.dst_cap - first < p.chunk_len) ? (p.dst_cap - first) : p.chunk_len);
     const uint32_t cap = cap64 > 0xffffffffull ? 0xffffffffu : (uint32_t)cap64;
     uint8_t* oblk = reinterpret_cast<uint8_t*>(out);                    // where the next block goes
+    const bool al32 = ((uintptr_t)out & 31) == 0;                       // whole-sector stores may be 256-bit
 
     uint32_t pvh[D];                                // running values, left-aligned (value << (32-W))
     int32_t pdh[D], ct[D];                          // previous deltas (left-aligned), FIRE counters
@@ -173,8 +174,13 @@ __global__ void __launch_bounds__(kLowLaneThreads, (D * W <= 16) ? 7 : 5) spz_de
         if (Q) {
             qblock_done();
         } else if (NWORD == 8) {
-            reinterpret_cast<uint4*>(oblk)[0] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
-            reinterpret_cast<uint4*>(oblk)[1] = make_uint4(wd[4], wd[5], wd[6], wd[7]);
+            if (al32) {                              // one 256-bit store == one whole sector (sm_100: STG.E.256)
+                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(oblk), "r"(wd[0]), "r"(wd[1]), "r"(wd[2]),
+                             "r"(wd[3]), "r"(wd[4]), "r"(wd[5]), "r"(wd[6]), "r"(wd[7]) : "memory");
+            } else {
+                reinterpret_cast<uint4*>(oblk)[0] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+                reinterpret_cast<uint4*>(oblk)[1] = make_uint4(wd[4], wd[5], wd[6], wd[7]);
+            }
             oblk += 32;
         } else {
 #pragma unroll
@@ -184,8 +190,13 @@ __global__ void __launch_bounds__(kLowLaneThreads, (D * W <= 16) ? 7 : 5) spz_de
                 uint32_t v[8];
 #pragma unroll
                 for (int k = 0; k < 8; k++) v[k] = *reinterpret_cast<const uint32_t*>(smem + stage_at(sri + k));
-                reinterpret_cast<uint4*>(oblk)[0] = make_uint4(v[0], v[1], v[2], v[3]);
-                reinterpret_cast<uint4*>(oblk)[1] = make_uint4(v[4], v[5], v[6], v[7]);
+                if (al32) {
+                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(oblk), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+                } else {
+                    reinterpret_cast<uint4*>(oblk)[0] = make_uint4(v[0], v[1], v[2], v[3]);
+                    reinterpret_cast<uint4*>(oblk)[1] = make_uint4(v[4], v[5], v[6], v[7]);
+                }
                 oblk += 32;
                 sri += 8u;
             }
