@@ -146,12 +146,45 @@ __global__ void __launch_bounds__(kEncLowThreads, (D * W == 8) ? 8 : (D * W == 1
     int32_t tail = 0;
     uint2 cur[NW2], nxt[NW2];
     load_block(0, cur);
+    // Blocks smaller than a sector: a per-block 64-bit load per lane costs one L1 wavefront per lane for part of a
+    // sector (ncu: L1 85 % busy, 32 sectors per request).  For int16 x 1 whole sectors are fetched with ONE 256-bit
+    // load, parked in a lane-private shared column (bank-private, like the ring) and the blocks are read from there
+    // (+13 %).  Measured slower for the int8 shapes (8-byte blocks: 790 -> 736 GB/s, the extra shared traffic and
+    // branches cost more than the wavefronts they save), so those keep the plain loads.
+    constexpr int BPS = (W == 16 && D == 1) ? 2 : 1;                          // blocks per sector when staging applies
+    const bool stage = BPS > 1 && (((uintptr_t)gin & 31) == 0);
+    const uint32_t stgabs = sbase + apad + NW * 4096u + warp * 1024u + lane * 4u;   // word k of my sector: stgabs + k * 128
+    bool staged_ok = false;
+    auto ldg256 = [&](const uint8_t* g, uint32_t (&v)[8]) {
+        asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(g));
+    };
+    if (stage) {                                           // sector 0 (L >= 128 elements: always inside the chunk)
+        uint32_t v[8];
+        ldg256(gin, v);
+#pragma unroll
+        for (int k = 0; k < 8; k++) sts32(stgabs + k * 128, v[k]);
+        staged_ok = true;
+    }
 
 #pragma unroll 1
     for (;;) {
         if (outer && i * Bc > L - G) { tail = i * Bc; break; }
         const bool have_next = (i + 2) * Bc <= L;
-        load_block(have_next ? i + 1 : i, nxt);
+        uint32_t sv[8];
+        bool newsec = false;
+        if (stage) {
+            if (have_next) {
+                const int32_t nb_ = i + 1;
+                if ((nb_ & (BPS - 1)) == 0) {              // first block of a sector: fetch it if it lies inside the chunk
+                    if ((nb_ + BPS) * Bc <= L) { ldg256(gin + (size_t)nb_ * BLKB, sv); newsec = true; }
+                    else staged_ok = false;                // ragged end: plain per-block loads from here on
+                }
+                if (!newsec && !staged_ok) load_block(nb_, nxt);
+            }
+        } else {
+            load_block(have_next ? i + 1 : i, nxt);
+        }
 
         // ================= pass 1: forecast -> zigzag -> masks (registers)
         uint32_t zz[D][8], nb[D];
@@ -252,6 +285,18 @@ __global__ void __launch_bounds__(kEncLowThreads, (D * W == 8) ? 8 : (D * W == 1
         if (stop) break;
 #pragma unroll
         for (int k = 0; k < NW2; k++) cur[k] = nxt[k];
+        if (stage && have_next) {
+            if (newsec) {                                  // every block of the previous sector has been consumed
+#pragma unroll
+                for (int k = 0; k < 8; k++) sts32(stgabs + k * 128, sv[k]);
+                staged_ok = true;
+            }
+            if (staged_ok) {                               // block i (already incremented) from the parked sector
+                const uint32_t a = stgabs + (uint32_t)(i & (BPS - 1)) * (uint32_t)(BLKB / 4) * 128u;
+#pragma unroll
+                for (int k = 0; k < NW2; k++) { cur[k].x = lds32(a + (2 * k) * 128); cur[k].y = lds32(a + (2 * k + 1) * 128); }
+            }
+        }
     }
 
     // ---- finish: remaining ring words, the partial word, the raw tail, the metadata
@@ -292,7 +337,7 @@ static cudaError_t launch_enc_lowlane(const EncParams& p, cudaStream_t stream)
 {
     const uint64_t grid64 = (p.nchunks + kEncLowThreads - 1) / kEncLowThreads;
     if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
-    const size_t smem = 4096 + (kEncLowThreads / 32) * 4096;                   // alignment slack + rings
+    const size_t smem = 4096 + (kEncLowThreads / 32) * (4096 + 1024);          // alignment slack + rings + sector columns
     spz_encode_lowlane_kernel<W, FIRE, D><<<(uint32_t)grid64, kEncLowThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }
