@@ -40,7 +40,8 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a)
 }
 
 template <int W, bool FIRE, int D>
-__global__ void __launch_bounds__(kEncLaneThreads, 4) spz_encode_lane_kernel(const EncParams p)
+// int8 x 8 fits 5 CTAs per SM without spills (96 registers); the int16 shapes spill there and stay at 4
+__global__ void __launch_bounds__(kEncLaneThreads, (W == 8) ? 5 : 4) spz_encode_lane_kernel(const EncParams p)
 {
     constexpr int ESZ = W / 8;
     constexpr int HB = Traits<W>::HB;
