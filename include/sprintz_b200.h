@@ -209,6 +209,14 @@ int64_t spz_frame_decompress_host(const void* frame, uint64_t frame_bytes, void*
 int spz_profile_enable(int on);
 int spz_profile_collect(float* ms3, int* ncalls);
 
+/* EXPERIMENTAL, off by default: with on != 0, frame encode behind the lane encoders overlaps the directory scan +
+ * compaction with the encoding (a small resident kernel on a second stream chases the encoder chunk by chunk).
+ * Verified bit-exact on frames of up to 148 tiles of 128 chunks only; larger frames run into the kernel's wait bounds
+ * (the frame header is then written with magic 0, so spz_frame_read_header fails).  Returns the previous setting;
+ * spz_last_encode_overlapped() reports what the last spz_frame_encode_dev call did. */
+int spz_set_encode_overlap(int on);
+int spz_last_encode_overlapped(void);
+
 /* Kernel family used by the codec launches: 0 = automatic (lane-per-octet kernels for frames with many chunks of
  * 8 / 16 dims, team-per-chunk kernels otherwise), 1 = team kernels only, 2 = lane kernels whenever the shape
  * allows (testing: exercises them on small inputs). All families are CUDA and produce identical bytes.

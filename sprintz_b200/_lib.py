@@ -79,6 +79,8 @@ SYMBOLS = {
     "spz_frame_query_dev": (_i, [_i, _i, _i, _i, _vp, _u64, _u64, _u16, _u32, _vp, _u64, _vp, _vp, _vp, _u64, _vp]),
     "spz_last_query_fused": (_i, []),
     "spz_reduce_rows_dev": (_i, [_i, _i, _vp, _u64, _u16, _vp, _vp]),
+    "spz_set_encode_overlap": (_i, [_i]),
+    "spz_last_encode_overlapped": (_i, []),
     "spz_compress_host": (_i64, [_i, _i, _vp, _u32, _vp, _u16, _i, C.POINTER(_u64)]),
     "spz_decompress_host": (_i64, [_i, _i, _vp, _vp]),
     "spz_decompress_raw_host": (_i64, [_i, _i, _vp, _vp, _u16, _u32, _u16]),

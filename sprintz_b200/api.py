@@ -27,7 +27,7 @@ __all__ = [
     "compress_dev", "decompress_dev", "set_kernel_path",
     "RM_DELTA", "RM_PLAIN", "RM_XFF8", "compress_rowmajor", "decompress_rowmajor",
     "encode_forecast", "decode_forecast", "forecast_encode_dev", "forecast_decode_dev",
-    "Q_NOOP", "Q_MAX", "Q_SUM", "query", "frame_query", "reduce_rows_dev", "last_query_fused",
+    "set_encode_overlap", "last_encode_overlapped", "Q_NOOP", "Q_MAX", "Q_SUM", "query", "frame_query", "reduce_rows_dev", "last_query_fused",
 ]
 
 Q_NOOP, Q_MAX, Q_SUM = 0, 1, 2          # QueryTypes::Operation (query.hpp:22-24)
@@ -335,6 +335,16 @@ def frame_query(frame: Frame, op: int, materialize: bool = False, out=None, work
     if bad:
         raise SprintzError(f"{bad} chunk(s) failed to decode")
     return res, (out if materialize else None)
+
+
+def set_encode_overlap(mode: int) -> int:
+    """0 (default): directory scan + compaction after the encoder; 1: EXPERIMENTAL overlapped scan + copy behind the lane
+    encoders (verified on frames of up to 148 tiles of 128 chunks only).  -> previous mode"""
+    return int(lib().spz_set_encode_overlap(mode))
+
+
+def last_encode_overlapped() -> bool:
+    return bool(lib().spz_last_encode_overlapped())
 
 
 def last_query_fused() -> bool:

@@ -26,6 +26,12 @@ cudaError_t launch_scan_sizes(const ChunkMeta* meta, uint64_t nchunks, uint64_t*
 cudaError_t launch_gather(const uint8_t* slots, uint64_t slot_stride, uint64_t nchunks, const uint64_t* chunk_off,
                           const uint32_t* chunk_nbytes, uint8_t* payload, cudaStream_t stream);
 uint64_t scan_tiles(uint64_t nchunks);
+uint64_t chase_tiles(uint64_t nchunks);
+cudaError_t launch_chase(const ChunkMeta* meta, uint64_t nchunks, const uint8_t* slots, uint64_t slot_stride,
+                         uint64_t* chunk_off, uint32_t* chunk_nbytes, uint8_t* payload, unsigned long long* tile_state,
+                         spz_frame_header* hdr, const spz_frame_header& hdr_in, uint64_t* d_frame_bytes, unsigned int* err,
+                         cudaStream_t stream);
+bool encode_uses_lane(int elem_sz, int predictor, EncParams p);
 void set_force_path(int v);
 int get_force_path();
 int last_encode_family();
@@ -171,7 +177,7 @@ static WorkLayout work_layout(int elem_sz, uint64_t len, uint16_t ndims, uint32_
     const FrameLayout f = frame_layout(len, ndims, chunk_rows);
     WorkLayout w;
     w.off_state = 0;
-    w.off_ticket = align16(8 * scan_tiles(f.nchunks));
+    w.off_ticket = align16(8 * chase_tiles(f.nchunks));           // >= scan_tiles: either directory kernel fits; ticket at +0, error flag at +4
     w.off_meta = w.off_ticket + 16;
     w.off_slots = align32(w.off_meta + sizeof(ChunkMeta) * f.nchunks);
     w.slot_stride = slot_stride_of(elem_sz, f.chunk_len < len || len == 0 ? f.chunk_len : len, ndims);
@@ -240,6 +246,36 @@ static int decompress_dev_impl(uint32_t variant, int predictor, int elem_sz, con
     return SPZ_OK;
 }
 
+// second stream + events of the overlapped frame encode; one per process (one process per GPU)
+namespace {
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_done = nullptr;
+    cudaError_t init()
+    {
+        if (stream) return cudaSuccess;
+        int lo = 0, hi = 0;
+        cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, hi);     // highest priority: its few CTAs get SM slots first
+        if (e != cudaSuccess) return e;
+        e = cudaEventCreateWithFlags(&ev_begin, cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+        return cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming);
+    }
+} g_side;
+int g_overlap_mode = 0;             // 1: overlap directory + compaction with the lane encoders (experimental); 0: run them afterwards
+int g_last_encode_overlapped = 0;
+}  // namespace
+
+extern "C" int spz_set_encode_overlap(int on)
+{
+    const int old = g_overlap_mode;
+    g_overlap_mode = on ? 1 : 0;
+    return old;
+}
+extern "C" int spz_last_encode_overlapped(void) { return g_last_encode_overlapped; }
+
 extern "C" int spz_frame_encode_dev(int predictor, int elem_sz, const void* d_src, uint64_t len, uint16_t ndims,
                                     uint32_t chunk_rows, void* d_frame, uint64_t frame_cap,
                                     void* d_work, uint64_t work_bytes, uint64_t* d_frame_bytes, spz_stream_t stream_)
@@ -255,16 +291,12 @@ extern "C" int spz_frame_encode_dev(int predictor, int elem_sz, const void* d_sr
 
     uint8_t* work = (uint8_t*)d_work;
     uint8_t* frame = (uint8_t*)d_frame;
-    CK(cudaMemsetAsync(work, 0, w.off_meta, stream));             // scan tile states + ticket
 
     EncParams p;
     memset(&p, 0, sizeof(p));
     p.src = (const uint8_t*)d_src; p.dst = work + w.off_slots; p.meta = (ChunkMeta*)(work + w.off_meta);
     p.len = len; p.chunk_len = f.chunk_len; p.nchunks = f.nchunks; p.slot_stride = w.slot_stride;
     p.ndims = ndims; p.write_size = 1;
-    PROF_MARK(0);
-    CK(launch_encode(elem_sz, predictor, p, stream));
-    PROF_MARK(1);
 
     spz_frame_header h;
     memset(&h, 0, sizeof(h));
@@ -272,6 +304,36 @@ extern "C" int spz_frame_encode_dev(int predictor, int elem_sz, const void* d_sr
     h.ndims = ndims; h.chunk_rows = chunk_rows; h.len = len; h.nchunks = f.nchunks; h.payload_off = f.payload_off;
     uint64_t* chunk_off = (uint64_t*)(frame + f.off_dir);
     uint32_t* chunk_nbytes = (uint32_t*)(frame + f.off_sizes);
+
+    // EXPERIMENTAL, off by default (spz_set_encode_overlap): overlapped directory + compaction (spz_chase_kernel), only
+    // behind the lane encoders (they publish every chunk record with a release).  Bit-exact on frames of up to 148
+    // tiles of 128 chunks (tests/test_gpu_lane.py); on BASELINE-sized frames (2048 tiles) the waits run into their
+    // bounds and the frame is flagged invalid -- see DESIGN.md section 7.
+    g_last_encode_overlapped = 0;
+    if (g_overlap_mode != 0 && encode_uses_lane(elem_sz, predictor, p)) {
+        CK(g_side.init());
+        CK(cudaMemsetAsync(work, 0, w.off_slots, stream));        // tile states, error flag AND the chunk records (nbytes == 0: not ready)
+        CK(cudaEventRecord(g_side.ev_begin, stream));
+        CK(cudaStreamWaitEvent(g_side.stream, g_side.ev_begin, 0));
+        CK(launch_chase(p.meta, f.nchunks, work + w.off_slots, w.slot_stride, chunk_off, chunk_nbytes, frame + f.payload_off,
+                        (unsigned long long*)(work + w.off_state), (spz_frame_header*)frame, h, d_frame_bytes,
+                        (unsigned int*)(work + w.off_ticket + 4), g_side.stream));
+        CK(cudaEventRecord(g_side.ev_done, g_side.stream));
+        PROF_MARK(0);
+        CK(launch_encode(elem_sz, predictor, p, stream));
+        PROF_MARK(1);
+        PROF_MARK(2);
+        CK(cudaStreamWaitEvent(stream, g_side.ev_done, 0));       // the exposed remainder of the copy (last wave of chunks)
+        PROF_MARK(3);
+        PROF_NEXT();
+        g_last_encode_overlapped = 1;
+        return SPZ_OK;
+    }
+
+    CK(cudaMemsetAsync(work, 0, w.off_meta, stream));             // scan tile states + ticket
+    PROF_MARK(0);
+    CK(launch_encode(elem_sz, predictor, p, stream));
+    PROF_MARK(1);
     CK(launch_scan_sizes(p.meta, f.nchunks, chunk_off, chunk_nbytes,
                          (unsigned long long*)(work + w.off_state), (unsigned int*)(work + w.off_ticket),
                          nullptr, nullptr, 1, (spz_frame_header*)frame, h, d_frame_bytes, stream));

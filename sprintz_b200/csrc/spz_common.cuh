@@ -134,6 +134,14 @@ template <int W, bool LOW> __device__ __forceinline__ uint32_t nbits_rule(uint32
     return n;
 }
 
+// A lane encoder hands its chunk to the chase kernel (spz_frame.cu) by writing the record's nbytes LAST, after a
+// device-scope fence: a non-zero nbytes means every stream byte of the chunk is visible in L2.
+__device__ __forceinline__ void publish_nbytes(uint32_t* p, uint32_t nbytes)
+{
+    __threadfence();
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(nbytes) : "memory");
+}
+
 // ------------------------------------------------------------------ team (sub-warp) primitives
 
 __device__ __forceinline__ uint32_t team_mask_of(int lane, int team)

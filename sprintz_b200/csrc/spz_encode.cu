@@ -381,8 +381,23 @@ cudaError_t launch_encode_hd(int elem_sz, int predictor, EncParams p, cudaStream
 cudaError_t launch_encode_lane(int elem_sz, int predictor, EncParams p, cudaStream_t stream);
 cudaError_t launch_encode_lowlane(int elem_sz, int predictor, EncParams p, cudaStream_t stream);
 
+extern bool g_encode_dry_run;
 static int g_last_encode_family = 0;     // 0 generic team kernel, 1 fast team kernel (hd), 2 lane kernel
 int last_encode_family() { return g_last_encode_family; }
+
+// Will launch_encode() run a LANE encoder for this call?  (Those publish each chunk record with a release after the
+// chunk's last byte, which is what the overlapped scan-and-copy kernel of spz_frame.cu waits on.)
+bool encode_uses_lane(int elem_sz, int predictor, EncParams p)
+{
+    if (predictor >= 2) { p.variant = (uint32_t)predictor - 1u; }
+    if (p.variant) predictor = (p.variant == 3u) ? 1 : 0;
+    g_encode_dry_run = true;
+    cudaError_t e = launch_encode_lane(elem_sz, predictor, p, nullptr);
+    const bool low = p.variant ? false : (elem_sz == 1 ? (p.ndims <= 4) : (p.ndims <= 2));
+    if (e == cudaErrorNotSupported && low) e = launch_encode_lowlane(elem_sz, predictor, p, nullptr);
+    g_encode_dry_run = false;
+    return e == cudaSuccess;
+}
 
 cudaError_t launch_encode(int elem_sz, int predictor, EncParams p, cudaStream_t stream)
 {

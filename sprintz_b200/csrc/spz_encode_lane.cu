@@ -27,6 +27,7 @@
 namespace spz {
 
 constexpr int kEncLaneThreads = 128;
+bool g_encode_dry_run = false;                             // launchers return without launching (single-threaded use under the API's call)
 
 // The output ring is addressed with absolute 32-bit shared-memory addresses and explicit st/ld.shared: with C++
 // pointers the compiler rebuilt the shared window base (S2R + MOV + LEA) under every predicated store.
@@ -90,8 +91,8 @@ __global__ void __launch_bounds__(kEncLaneThreads, (W == 8) ? 5 : 4) spz_encode_
             *reinterpret_cast<uint16_t*>(gout + 4) = (uint16_t)D;
         }
         for (int32_t b = 0; b < L * ESZ; b++) gout[meta_bytes + b] = gin[b];
-        p.meta[c].nbytes = meta_bytes + (uint32_t)L * ESZ; p.meta[c].ngroups = 0;
-        p.meta[c].remaining = (uint32_t)L; p.meta[c].status = kStatusOk;
+        p.meta[c].ngroups = 0; p.meta[c].remaining = (uint32_t)L; p.meta[c].status = kStatusOk;
+        publish_nbytes(&p.meta[c].nbytes, meta_bytes + (uint32_t)L * ESZ);
         return;
     }
 
@@ -426,7 +427,8 @@ __global__ void __launch_bounds__(kEncLaneThreads, (W == 8) ? 5 : 4) spz_encode_
         *reinterpret_cast<uint32_t*>(gout) = (uint32_t)L;
         *reinterpret_cast<uint16_t*>(gout + 4) = (uint16_t)D;
     }
-    p.meta[c].nbytes = nbytes; p.meta[c].ngroups = ngroups; p.meta[c].remaining = remaining; p.meta[c].status = kStatusOk;
+    p.meta[c].ngroups = ngroups; p.meta[c].remaining = remaining; p.meta[c].status = kStatusOk;
+    publish_nbytes(&p.meta[c].nbytes, nbytes);
 }
 
 // ------------------------------------------------------------------ launch
@@ -440,10 +442,17 @@ static cudaError_t launch_enc_lane(const EncParams& p, cudaStream_t stream)
     if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
     constexpr int NW = kEncLaneThreads / 32, NVEC = 8 * D * (W / 8) / 16;
     const size_t smem = 4096 + NW * 4096 + NW * NVEC * 512;            // alignment slack + rings + staging
+    // Eligibility probe of the overlapped frame encode: only once this instantiation has been launched before.  Its
+    // first launch loads the kernel lazily (and may synchronise the device), which must not happen while the chase
+    // kernel is already spinning on this encoder's output.
+    static bool warmed = false;
+    if (g_encode_dry_run) return warmed ? cudaSuccess : cudaErrorNotReady;
     cudaError_t e = cudaFuncSetAttribute(spz_encode_lane_kernel<W, FIRE, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     spz_encode_lane_kernel<W, FIRE, D><<<(uint32_t)grid64, kEncLaneThreads, smem, stream>>>(p);
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    if (e == cudaSuccess) warmed = true;
+    return e;
 }
 
 // Returns cudaErrorNotSupported when the shape is not covered (caller continues with the team kernels).

@@ -14,6 +14,7 @@
 namespace spz {
 
 int get_force_path();
+extern bool g_encode_dry_run;
 
 constexpr int kEncLowThreads = 128;
 
@@ -64,8 +65,8 @@ __global__ void __launch_bounds__(kEncLowThreads, (D * W == 8) ? 8 : (D * W == 1
     if (L < (int32_t)kMinDataSize) {                       // stored raw (sprintz_delta_lowdim.cpp:72-80)
         if (meta_bytes) *reinterpret_cast<uint2*>(gout) = make_uint2(0u, (uint32_t)L | ((uint32_t)D << 16));
         for (int32_t b = 0; b < L * ESZ; b++) gout[meta_bytes + b] = gin[b];
-        p.meta[c].nbytes = meta_bytes + (uint32_t)L * ESZ; p.meta[c].ngroups = 0;
-        p.meta[c].remaining = (uint32_t)L; p.meta[c].status = kStatusOk;
+        p.meta[c].ngroups = 0; p.meta[c].remaining = (uint32_t)L; p.meta[c].status = kStatusOk;
+        publish_nbytes(&p.meta[c].nbytes, meta_bytes + (uint32_t)L * ESZ);
         return;
     }
 
@@ -322,7 +323,8 @@ __global__ void __launch_bounds__(kEncLowThreads, (D * W == 8) ? 8 : (D * W == 1
         *reinterpret_cast<uint32_t*>(gout) = (uint32_t)L;
         *reinterpret_cast<uint16_t*>(gout + 4) = (uint16_t)D;
     }
-    p.meta[c].nbytes = nbytes; p.meta[c].ngroups = ngroups; p.meta[c].remaining = remaining; p.meta[c].status = kStatusOk;
+    p.meta[c].ngroups = ngroups; p.meta[c].remaining = remaining; p.meta[c].status = kStatusOk;
+    publish_nbytes(&p.meta[c].nbytes, nbytes);
 }
 
 
@@ -338,8 +340,12 @@ static cudaError_t launch_enc_lowlane(const EncParams& p, cudaStream_t stream)
     const uint64_t grid64 = (p.nchunks + kEncLowThreads - 1) / kEncLowThreads;
     if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
     const size_t smem = 4096 + (kEncLowThreads / 32) * (4096 + 1024);          // alignment slack + rings + sector columns
+    static bool warmed = false;                                                // see launch_enc_lane (spz_encode_lane.cu)
+    if (g_encode_dry_run) return warmed ? cudaSuccess : cudaErrorNotReady;
     spz_encode_lowlane_kernel<W, FIRE, D><<<(uint32_t)grid64, kEncLowThreads, smem, stream>>>(p);
-    return cudaGetLastError();
+    const cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) warmed = true;
+    return e;
 }
 
 // Returns cudaErrorNotSupported when the shape is not covered (caller continues with the generic kernel).
