@@ -80,7 +80,27 @@ class Oracle(_Codec):
         L.oracle_encode_forecast.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint16, C.c_int]
         L.oracle_decode_forecast.restype = C.c_int64
         L.oracle_decode_forecast.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint16]
+        L.oracle_encode_xff_forecast.restype = C.c_int64
+        L.oracle_encode_xff_forecast.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint16, C.c_int]
+        L.oracle_decode_xff_forecast.restype = C.c_int64
+        L.oracle_decode_xff_forecast.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint16]
         self.L = L
+
+    def encode_xff_forecast(self, x, ndims, write_size=True):
+        """Stand-alone FIRE transform (predict.h). -> (bytes incl. metadata, ret)"""
+        esz = x.dtype.itemsize
+        src = _as_u8(x)
+        buf = np.zeros(x.size * esz + 6 + SLACK, np.uint8)
+        ret = int(self.L.oracle_encode_xff_forecast(esz, src.ctypes.data, x.size, buf.ctypes.data, ndims, int(write_size)))
+        return buf[: ret * esz].copy(), ret
+
+    def decode_xff_forecast(self, esz, y, ndims):
+        y = np.ascontiguousarray(y)
+        n = y.size
+        src = np.concatenate([_as_u8(y), np.zeros(SLACK, np.uint8)])
+        out = np.full(n * esz + SLACK, 0xAA, np.uint8)
+        ret = int(self.L.oracle_decode_xff_forecast(esz, src.ctypes.data, n, out.ctypes.data, ndims))
+        return out[: n * esz].view(np.uint8 if esz == 1 else np.uint16).copy(), ret
 
     def encode_forecast(self, order, x, ndims, write_size=True):
         """Stand-alone forecaster transform (order 1 = delta, 2 = double delta). -> (bytes incl. metadata, ret)"""
@@ -186,6 +206,28 @@ class Ref(_Codec):
             L.ref_decode_forecast.restype = C.c_int64
             L.ref_decode_forecast.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint16]
         self.L = L
+
+    def encode_xff_forecast(self, x, ndims, write_size=True):
+        esz = x.dtype.itemsize
+        self.L.ref_encode_xff_forecast.restype = C.c_int64
+        self.L.ref_encode_xff_forecast.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint16, C.c_int]
+        # the reference's vector loads / stores run up to 32 bytes past a row and it reads ndims elements before the input
+        pad = SLACK + 4 * max(1, ndims) * esz
+        src = np.concatenate([np.zeros(pad, np.uint8), _as_u8(x), np.zeros(2 * SLACK, np.uint8)])
+        buf = np.zeros(x.size * esz + 6 + 4 * SLACK, np.uint8)
+        ret = int(self.L.ref_encode_xff_forecast(esz, src.ctypes.data + pad, x.size, buf.ctypes.data, ndims, int(write_size)))
+        return buf[: ret * esz].copy(), ret
+
+    def decode_xff_forecast(self, esz, y, ndims):
+        self.L.ref_decode_xff_forecast.restype = C.c_int64
+        self.L.ref_decode_xff_forecast.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint16]
+        y = np.ascontiguousarray(y)
+        n = y.size
+        src = np.concatenate([_as_u8(y), np.zeros(2 * SLACK, np.uint8)])
+        pad = SLACK + 4 * max(1, ndims) * esz
+        out = np.full(pad + n * esz + 4 * SLACK, 0, np.uint8)
+        ret = int(self.L.ref_decode_xff_forecast(esz, src.ctypes.data, n, out.ctypes.data + pad, ndims))
+        return out[pad: pad + n * esz].view(np.uint8 if esz == 1 else np.uint16).copy(), ret
 
     def encode_forecast(self, order, x, ndims, write_size=True):
         esz = x.dtype.itemsize

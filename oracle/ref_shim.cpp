@@ -23,6 +23,7 @@
 #include "sprintz_delta.h"   // the non-RLE sibling codecs
 #include "sprintz_xff.h"     // compress8b_rowmajor_xff
 #include "delta.h"           // stand-alone forecaster transforms
+#include "predict.h"         // stand-alone FIRE transform
 
 extern "C" {
 
@@ -101,6 +102,18 @@ int64_t ref_decode_forecast(int order, int elem_sz, const void* src, uint32_t le
                           : decode_doubledelta_rowmajor_8b((const int8_t*)src, len, (uint8_t*)dest, ndims);
     return order == 1 ? decode_delta_rowmajor_16b((const int16_t*)src, len, (uint16_t*)dest, ndims)
                       : decode_doubledelta_rowmajor_16b((const int16_t*)src, len, (uint16_t*)dest, ndims);
+}
+
+// stand-alone FIRE transform (predict.h:15-30)
+int64_t ref_encode_xff_forecast(int elem_sz, const void* src, uint32_t len, void* dest, uint16_t ndims, int write_size)
+{
+    return elem_sz == 1 ? encode_xff_rowmajor_8b((const uint8_t*)src, len, (int8_t*)dest, ndims, write_size != 0)
+                        : encode_xff_rowmajor_16b((const uint16_t*)src, len, (int16_t*)dest, ndims, write_size != 0);
+}
+int64_t ref_decode_xff_forecast(int elem_sz, const void* src, uint32_t len, void* dest, uint16_t ndims)
+{
+    return elem_sz == 1 ? decode_xff_rowmajor_8b((const int8_t*)src, len, (uint8_t*)dest, ndims)
+                        : decode_xff_rowmajor_16b((const int16_t*)src, len, (uint16_t*)dest, ndims);
 }
 
 // Compress `nchunks` consecutive slices of `src` (chunk c covers elements

@@ -632,6 +632,139 @@ int64_t oracle_decode_forecast(int order, int elem_sz, const void* src_, uint32_
     return (int64_t)len;
 }
 
+/* ------------------------------------------------------------------ stand-alone FIRE transform
+ *
+ * encode/decode_xff_rowmajor_{8b,16b} (predict.h:15-30, predict.cpp:56-527): same-size in/out like the delta
+ * transforms, but the forecaster is an older prototype of FIRE whose arithmetic differs from the codec's
+ * (sprintz_xff_rle.cpp) in several observable ways.  Restated per dim d (the AVX2 lanes beyond ndims only touch bytes
+ * that are rewritten later):
+ *   blocks    nblocks = (len / ndims) / 8, reduced so that the vector stores of the last block stay inside the
+ *             buffer (predict.cpp:99-106); every element after the block part -- whole rows included -- is plain DELTA
+ *             coded with lag ndims (:268-279), and when there is no block at all the first ndims elements are copied.
+ *   8-bit     counter int16, coef = (counter >> 5) << 4 (learning_shift 1); the prediction of an EVEN dim multiplies the
+ *             previous delta as an UNSIGNED byte (and_si256 with 0x00ff, :163-164), of an odd dim as a signed one;
+ *             both keep bits 8..15 of the 16-bit product; the gradient sum wraps at 8 bits ("faster, but can
+ *             overflow", :189); counter += (int8)gsum >> 2.
+ *   16-bit    counter int32, coef = low16((counter >> 15)) << 12 as int16 (learning_shift 3); prediction =
+ *             (mulhi(prev_delta, coef) << 2) wrapped to 16 bits; gradient sum wraps at 16 bits; counter += (int16)gsum >> 2.
+ * TEST INFRASTRUCTURE ONLY.  No product kernel exists for this transform yet. */
+static int32_t xffp_nblocks(uint32_t len, uint32_t ndims, int elem_sz)
+{
+    const uint32_t vector_sz = 32u / (uint32_t)elem_sz;
+    const uint32_t bse = 8u * ndims;
+    int32_t nblocks = (int32_t)((len / ndims) / 8u);
+    const uint32_t overrun = vector_sz - (ndims % vector_sz);
+    const uint32_t trailing = len % bse;
+    if (overrun > trailing) {
+        nblocks -= (int32_t)((overrun + bse - 1) / bse);
+        if (nblocks < 0) nblocks = 0;
+    }
+    return nblocks;
+}
+
+static int32_t xffp_predict(int elem_sz, uint32_t d, int32_t pd, int32_t counter)
+{
+    if (elem_sz == 1) {
+        const int32_t coef = (int32_t)(int16_t)(((int16_t)counter >> 5) << 4);
+        const uint32_t a = (d & 1u) ? (uint32_t)(int32_t)(int8_t)pd : (uint32_t)(uint8_t)pd;
+        const uint32_t prod = (a * (uint32_t)coef) & 0xffffu;
+        return (int32_t)(int8_t)(prod >> 8);
+    }
+    const int32_t coef = (int32_t)(int16_t)((((uint32_t)(counter >> 15)) << 12) & 0xffffu);
+    const int32_t hi = ((int32_t)(int16_t)pd * coef) >> 16;
+    return (int32_t)(int16_t)((uint32_t)hi << 2);
+}
+
+static int32_t xffp_sign(int elem_sz, int32_t pd, int32_t err)   /* psignb / psignw(prev_delta, err) */
+{
+    int32_t g = err == 0 ? 0 : (err < 0 ? -pd : pd);
+    return elem_sz == 1 ? (int32_t)(int8_t)g : (int32_t)(int16_t)g;
+}
+
+int64_t oracle_encode_xff_forecast(int elem_sz, const void* src_, uint32_t len, void* dest_, uint16_t ndims, int write_size)
+{
+    const uint8_t* src = (const uint8_t*)src_;
+    uint8_t* dest = (uint8_t*)dest_;
+    const int w = 8 * elem_sz;
+    const uint32_t wmask = (1u << w) - 1u;
+    uint32_t meta = 0;
+    if (ndims == 0) return -1;
+    if (write_size) {
+        dest[0] = (uint8_t)len; dest[1] = (uint8_t)(len >> 8); dest[2] = (uint8_t)(len >> 16); dest[3] = (uint8_t)(len >> 24);
+        dest[4] = (uint8_t)ndims; dest[5] = (uint8_t)(ndims >> 8);
+        dest += 6; meta = 6 / (uint32_t)elem_sz;
+    }
+    const uint32_t D = ndims;
+    const int32_t nblocks = xffp_nblocks(len, D, elem_sz);
+    for (uint32_t d = 0; d < D; d++) {
+        uint32_t pv = 0; int32_t pd = 0, counter = 0;
+        for (int32_t b = 0; b < nblocks; b++) {
+            int32_t gsum = 0;
+            for (uint32_t i = 0; i < 8; i++) {
+                const uint64_t at = ((uint64_t)b * 8 + i) * D + d;
+                const uint32_t x = load_elem(src, at, elem_sz);
+                const int32_t delta = (int32_t)sx((int32_t)((x - pv) & wmask), w);
+                const int32_t pred = xffp_predict(elem_sz, d, pd, counter);
+                const int32_t err = (int32_t)sx((int32_t)(((uint32_t)delta - (uint32_t)pred) & wmask), w);
+                if (i & 1u) gsum = (int32_t)sx((int32_t)(((uint32_t)gsum + (uint32_t)xffp_sign(elem_sz, pd, err)) & wmask), w);
+                store_elem(dest, at, elem_sz, (uint32_t)err & wmask);
+                pd = delta; pv = x;
+            }
+            if (elem_sz == 1) counter = (int32_t)(int16_t)(counter + (gsum >> 2));
+            else counter = (int32_t)((uint32_t)counter + (uint32_t)(gsum >> 2));
+        }
+    }
+    /* everything after the block part: delta with lag ndims (predict.cpp:268-279) */
+    uint64_t i0 = (uint64_t)nblocks * 8 * D;
+    if (nblocks == 0) {
+        const uint64_t cpy = D < len ? D : len;
+        for (uint64_t i = 0; i < cpy; i++) store_elem(dest, i, elem_sz, load_elem(src, i, elem_sz));
+        i0 = D;
+    }
+    for (uint64_t i = i0; i < len; i++)
+        store_elem(dest, i, elem_sz, (load_elem(src, i, elem_sz) - load_elem(src, i - D, elem_sz)) & wmask);
+    return (int64_t)len + meta;
+}
+
+/* src points at the transformed elements (no metadata) */
+int64_t oracle_decode_xff_forecast(int elem_sz, const void* src_, uint32_t len, void* dest_, uint16_t ndims)
+{
+    const uint8_t* src = (const uint8_t*)src_;
+    uint8_t* out = (uint8_t*)dest_;
+    const int w = 8 * elem_sz;
+    const uint32_t wmask = (1u << w) - 1u;
+    if (ndims == 0) return 0;                              /* predict.cpp:318 */
+    const uint32_t D = ndims;
+    const int32_t nblocks = xffp_nblocks(len, D, elem_sz);
+    for (uint32_t d = 0; d < D; d++) {
+        uint32_t pv = 0; int32_t pd = 0, counter = 0;
+        for (int32_t b = 0; b < nblocks; b++) {
+            int32_t gsum = 0;
+            for (uint32_t i = 0; i < 8; i++) {
+                const uint64_t at = ((uint64_t)b * 8 + i) * D + d;
+                const int32_t err = (int32_t)sx((int32_t)load_elem(src, at, elem_sz), w);
+                const int32_t pred = xffp_predict(elem_sz, d, pd, counter);
+                if (i & 1u) gsum = (int32_t)sx((int32_t)(((uint32_t)gsum + (uint32_t)xffp_sign(elem_sz, pd, err)) & wmask), w);
+                const int32_t delta = (int32_t)sx((int32_t)(((uint32_t)err + (uint32_t)pred) & wmask), w);
+                pv = (pv + (uint32_t)delta) & wmask;
+                store_elem(out, at, elem_sz, pv);
+                pd = delta;
+            }
+            if (elem_sz == 1) counter = (int32_t)(int16_t)(counter + (gsum >> 2));
+            else counter = (int32_t)((uint32_t)counter + (uint32_t)(gsum >> 2));
+        }
+    }
+    uint64_t i0 = (uint64_t)nblocks * 8 * D;
+    if (nblocks == 0) {
+        const uint64_t cpy = D < len ? D : len;
+        for (uint64_t i = 0; i < cpy; i++) store_elem(out, i, elem_sz, load_elem(src, i, elem_sz));
+        i0 = D;
+    }
+    for (uint64_t i = i0; i < len; i++)
+        store_elem(out, i, elem_sz, (load_elem(src, i, elem_sz) + load_elem(out, i - D, elem_sz)) & wmask);
+    return (int64_t)len;
+}
+
 /* ------------------------------------------------------------------ query-on-compressed
  *
  * query.hpp:22-29 QueryParams{op = REDUCE_MAX | REDUCE_SUM, materialize}; query_rowmajor_{delta,xff}_rle_{8b,16b}

@@ -46,6 +46,11 @@ int64_t oracle_encode_forecast(int order, int elem_sz, const void* src, uint32_t
                                int write_size);
 int64_t oracle_decode_forecast(int order, int elem_sz, const void* src, uint32_t len, void* dest, uint16_t ndims);
 
+/* Stand-alone FIRE transform (predict.h:15-30): encode returns len + metadata elements; decode takes the transformed
+ * elements WITHOUT metadata.  Restatement only -- there is no product kernel for it yet. */
+int64_t oracle_encode_xff_forecast(int elem_sz, const void* src, uint32_t len, void* dest, uint16_t ndims, int write_size);
+int64_t oracle_decode_xff_forecast(int elem_sz, const void* src, uint32_t len, void* dest, uint16_t ndims);
+
 /* Query-on-compressed: decode, then per-dim unsigned max (op 1) / 64-bit sum (op 2) into
  * result[ndims]; returns the decoded element count. */
 int64_t oracle_query(int predictor, int elem_sz, const void* src, void* dest, int op, uint64_t* result);

@@ -44,6 +44,33 @@ def test_oracle_forecast_vs_reference(oracle, ref, order, esz):
     assert not bad, (len(bad), bad[:5])
 
 
+@pytest.mark.parametrize("esz", [1, 2], ids=["xff8", "xff16"])
+def test_oracle_xff_forecast_vs_reference(oracle, ref, esz):
+    """encode/decode_xff_rowmajor_{8b,16b} (predict.h:15-30): the restatement of the prototype FIRE transform -- block
+    count rule, delta-coded remainder, unsigned even-dim multiply (8-bit), wrapping gradient sums -- against the
+    compiled reference: bytes incl. metadata, return values, and both decoders invert both encoders' output.
+    Groundwork: there is no product kernel for this transform yet."""
+    bad = []
+    for D in DIMS:
+        for tag, x in _cases(esz):
+            ws, wr = oracle.encode_xff_forecast(x, D)
+            rs, rr = ref.encode_xff_forecast(x, D)
+            msg = None
+            if wr != rr:
+                msg = f"return {wr} != {rr}"
+            elif not np.array_equal(ws, rs):
+                msg = "transformed bytes differ"
+            else:
+                y = ws[6:].view(x.dtype)
+                d, dn = oracle.decode_xff_forecast(esz, y, D)
+                rd, rn = ref.decode_xff_forecast(esz, y, D)
+                if dn != rn or not np.array_equal(d, x) or not np.array_equal(rd, x):
+                    msg = "decode differs"
+            if msg:
+                bad.append((D, tag, msg))
+    assert not bad, (len(bad), bad[:5])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("order,esz", ORDERS, ids=OIDS)
 def test_gpu_forecast_matches_oracle(oracle, order, esz):
