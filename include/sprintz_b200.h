@@ -135,6 +135,15 @@ uint32_t spz_encode_doubledelta_rowmajor_16b(const uint16_t* src, uint32_t len, 
 uint32_t spz_decode_doubledelta_rowmajor_16b(const int16_t*  src, uint32_t len, uint16_t* dest, uint16_t ndims);
 int64_t spz_encode_forecast_host(int order, int elem_sz, const void* src, uint32_t len, void* dest, uint16_t ndims, int write_size);
 int64_t spz_decode_forecast_host(int order, int elem_sz, const void* src, uint32_t len, void* dest, uint16_t ndims);
+/* Stand-alone FIRE transform, encode/decode_xff_rowmajor_{8b,16b} (predict.h:15-30, predict.cpp:56-527): same
+ * arguments and returns.  The predictor state of a dim runs through the whole stream, so a single stream is decoded by
+ * one thread per dim -- a correctness path (long streams belong in the frame codec). */
+uint32_t spz_encode_xff_rowmajor_8b (const uint8_t*  src, uint32_t len, int8_t*  dest, uint16_t ndims, int write_size);
+uint32_t spz_decode_xff_rowmajor_8b (const int8_t*   src, uint32_t len, uint8_t*  dest, uint16_t ndims);
+uint32_t spz_encode_xff_rowmajor_16b(const uint16_t* src, uint32_t len, int16_t* dest, uint16_t ndims, int write_size);
+uint32_t spz_decode_xff_rowmajor_16b(const int16_t*  src, uint32_t len, uint16_t* dest, uint16_t ndims);
+int64_t spz_xff_forecast_host(int enc, int elem_sz, const void* src, uint32_t len, void* dest, uint16_t ndims, int write_size);
+int spz_xff_forecast_dev(int enc, int elem_sz, const void* d_src, uint64_t len, uint16_t ndims, void* d_dest, spz_stream_t stream);
 /* device buffers (16-byte aligned, readable up to the next 16-byte boundary past len elements); decode needs
  * spz_forecast_workspace_bytes() of scratch for its chained scan */
 uint64_t spz_forecast_workspace_bytes(uint64_t len, uint16_t ndims);

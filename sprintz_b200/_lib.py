@@ -65,6 +65,12 @@ SYMBOLS = {
     "spz_decode_doubledelta_rowmajor_8b": (_u32, [_vp, _u32, _vp, _u16]),
     "spz_encode_doubledelta_rowmajor_16b": (_u32, [_vp, _u32, _vp, _u16, _i]),
     "spz_decode_doubledelta_rowmajor_16b": (_u32, [_vp, _u32, _vp, _u16]),
+    "spz_encode_xff_rowmajor_8b": (_u32, [_vp, _u32, _vp, _u16, _i]),
+    "spz_decode_xff_rowmajor_8b": (_u32, [_vp, _u32, _vp, _u16]),
+    "spz_encode_xff_rowmajor_16b": (_u32, [_vp, _u32, _vp, _u16, _i]),
+    "spz_decode_xff_rowmajor_16b": (_u32, [_vp, _u32, _vp, _u16]),
+    "spz_xff_forecast_host": (_i64, [_i, _i, _vp, _u32, _vp, _u16, _i]),
+    "spz_xff_forecast_dev": (_i, [_i, _i, _vp, _u64, _u16, _vp, _vp]),
     "spz_encode_forecast_host": (_i64, [_i, _i, _vp, _u32, _vp, _u16, _i]),
     "spz_decode_forecast_host": (_i64, [_i, _i, _vp, _u32, _vp, _u16]),
     "spz_forecast_workspace_bytes": (_u64, [_u64, _u16]),

@@ -27,6 +27,7 @@ __all__ = [
     "compress_dev", "decompress_dev", "set_kernel_path",
     "RM_DELTA", "RM_PLAIN", "RM_XFF8", "compress_rowmajor", "decompress_rowmajor",
     "encode_forecast", "decode_forecast", "forecast_encode_dev", "forecast_decode_dev",
+    "encode_xff_forecast", "decode_xff_forecast",
     "set_encode_overlap", "last_encode_overlapped", "Q_NOOP", "Q_MAX", "Q_SUM", "query", "frame_query", "reduce_rows_dev", "last_query_fused",
 ]
 
@@ -109,6 +110,26 @@ def decode_forecast(order: int, esz: int, y: np.ndarray, ndims: int):
     out = np.zeros(y.size, _UDT[esz])
     ret = lib().spz_decode_forecast_host(order, esz, y.ctypes.data, y.size, out.ctypes.data, ndims)
     check(ret, "spz_decode_forecast_host")
+    return out, int(ret)
+
+
+def encode_xff_forecast(x: np.ndarray, ndims: int, write_size: bool = True):
+    """Stand-alone FIRE transform (predict.h:15-30): encode_xff_rowmajor_*.  -> (output bytes incl. the optional
+    6-byte metadata, the reference's return)."""
+    x = np.ascontiguousarray(x)
+    esz = x.dtype.itemsize
+    out = np.zeros(x.size * esz + 8, np.uint8)
+    ret = lib().spz_xff_forecast_host(1, esz, x.ctypes.data, x.size, out.ctypes.data, ndims, int(write_size))
+    check(ret, "spz_xff_forecast_host")
+    return out[: int(ret) * esz].copy(), int(ret)
+
+
+def decode_xff_forecast(esz: int, y: np.ndarray, ndims: int):
+    """y: the transformed elements without metadata. -> (decoded elements, count)"""
+    y = np.ascontiguousarray(y)
+    out = np.zeros(y.size, _UDT[esz])
+    ret = lib().spz_xff_forecast_host(0, esz, y.ctypes.data, y.size, out.ctypes.data, ndims, 0)
+    check(ret, "spz_xff_forecast_host")
     return out, int(ret)
 
 

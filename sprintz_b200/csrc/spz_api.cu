@@ -39,6 +39,8 @@ int last_decode_family();
 cudaError_t launch_query_fused(int elem_sz, int predictor, DecParams p, cudaStream_t stream);
 cudaError_t launch_reduce_rows(int op, int elem_sz, const uint8_t* src, uint64_t len, uint32_t D,
                                unsigned long long* result, cudaStream_t stream);
+cudaError_t launch_xff_forecast(int enc, int elem_sz, const uint8_t* src, uint8_t* dst, uint64_t len, uint32_t D,
+                                cudaStream_t stream);
 uint64_t forecast_workspace_bytes(uint64_t len, uint32_t D);
 cudaError_t launch_forecast_encode(int order, int elem_sz, const uint8_t* src, uint8_t* dst, uint64_t len, uint32_t D,
                                    cudaStream_t stream);
@@ -805,6 +807,48 @@ extern "C" int64_t spz_decode_forecast_host(int order, int elem_sz, const void* 
     }
     return (int64_t)len;
 }
+
+// stand-alone FIRE transform (predict.h:15-30): one thread per dim (see spz_forecast.cu)
+extern "C" int spz_xff_forecast_dev(int enc, int elem_sz, const void* d_src, uint64_t len, uint16_t ndims, void* d_dest,
+                                    spz_stream_t stream)
+{
+    if ((elem_sz != 1 && elem_sz != 2) || ndims == 0) return SPZ_E_ARG;
+    if (((uintptr_t)d_src & (elem_sz - 1)) || ((uintptr_t)d_dest & (elem_sz - 1))) return SPZ_E_ARG;
+    CK(launch_xff_forecast(enc, elem_sz, (const uint8_t*)d_src, (uint8_t*)d_dest, len, ndims, (cudaStream_t)stream));
+    return SPZ_OK;
+}
+
+// host buffers: encode returns len + metadata elements, decode returns len, like the reference
+extern "C" int64_t spz_xff_forecast_host(int enc, int elem_sz, const void* src, uint32_t len, void* dest, uint16_t ndims,
+                                         int write_size)
+{
+    if (elem_sz != 1 && elem_sz != 2) return SPZ_E_ARG;
+    if (ndims == 0) return enc ? SPZ_E_ARG : 0;         // predict.cpp:318
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    cudaStream_t st;
+    CK(g_cache.get_stream(&st));
+    const uint64_t bytes = (uint64_t)len * elem_sz;
+    CK(g_cache.ensure(0, bytes + 32));
+    CK(g_cache.ensure(1, bytes + 32));
+    uint8_t* d8 = (uint8_t*)dest;
+    uint32_t meta = 0;
+    if (enc && write_size) {                            // format.h:65-73
+        d8[0] = (uint8_t)len; d8[1] = (uint8_t)(len >> 8); d8[2] = (uint8_t)(len >> 16); d8[3] = (uint8_t)(len >> 24);
+        d8[4] = (uint8_t)ndims; d8[5] = (uint8_t)(ndims >> 8);
+        d8 += 6; meta = 6u / (uint32_t)elem_sz;
+    }
+    if (bytes) {
+        CK(cudaMemcpyAsync(g_cache.buf[0], src, bytes, cudaMemcpyHostToDevice, st));
+        CK(launch_xff_forecast(enc, elem_sz, (const uint8_t*)g_cache.buf[0], (uint8_t*)g_cache.buf[1], len, ndims, st));
+        CK(cudaMemcpyAsync(d8, g_cache.buf[1], bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return (int64_t)len + meta;
+}
+extern "C" uint32_t spz_encode_xff_rowmajor_8b(const uint8_t* s, uint32_t n, int8_t* d, uint16_t nd, int ws) { return (uint32_t)spz_xff_forecast_host(1, 1, s, n, d, nd, ws); }
+extern "C" uint32_t spz_decode_xff_rowmajor_8b(const int8_t* s, uint32_t n, uint8_t* d, uint16_t nd) { return (uint32_t)spz_xff_forecast_host(0, 1, s, n, d, nd, 0); }
+extern "C" uint32_t spz_encode_xff_rowmajor_16b(const uint16_t* s, uint32_t n, int16_t* d, uint16_t nd, int ws) { return (uint32_t)spz_xff_forecast_host(1, 2, s, n, d, nd, ws); }
+extern "C" uint32_t spz_decode_xff_rowmajor_16b(const int16_t* s, uint32_t n, uint16_t* d, uint16_t nd) { return (uint32_t)spz_xff_forecast_host(0, 2, s, n, d, nd, 0); }
 
 extern "C" uint32_t spz_encode_delta_rowmajor_8b(const uint8_t* s, uint32_t n, int8_t* d, uint16_t nd, int ws) { return (uint32_t)spz_encode_forecast_host(1, 1, s, n, d, nd, ws); }
 extern "C" uint32_t spz_decode_delta_rowmajor_8b(const int8_t* s, uint32_t n, uint8_t* d, uint16_t nd) { return (uint32_t)spz_decode_forecast_host(1, 1, s, n, d, nd); }

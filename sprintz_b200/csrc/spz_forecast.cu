@@ -13,6 +13,7 @@
 //        the double-delta recurrence is the pair (delta, value); a tile of n rows maps (d0, x0) to
 //        (d0 + S1, x0 + n*d0 + S2) with S1 = sum y_k, S2 = sum (n-k)*y_k, which composes associatively.
 #include "spz_common.cuh"
+#include "spz_xff_forecast.cuh"
 #include "../../include/sprintz_b200.h"
 
 namespace spz {
@@ -144,6 +145,34 @@ __global__ void __launch_bounds__(kFcThreads) spz_forecast_decode_kernel(const u
 }
 
 }  // namespace
+
+// Stand-alone FIRE transform (predict.h:15-30): the predictor state of a dim runs through the WHOLE stream and is not
+// associative, so one stream offers ndims-way parallelism only -- one thread per dim, the per-dim code of
+// spz_xff_forecast.cuh (pinned on the CPU by tests/test_xff_forecast_host.py).  A correctness path: long streams belong
+// in the chunked frame codec, which is this transform plus bit packing at full parallelism.
+template <int W, bool ENC>
+__global__ void __launch_bounds__(128) spz_xff_forecast_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                               uint64_t len, uint32_t D, int32_t nblocks)
+{
+    const uint32_t d = blockIdx.x * 128u + threadIdx.x;
+    if (d < D) xffp_dim<W, ENC>(src, dst, len, D, d, nblocks);
+}
+
+cudaError_t launch_xff_forecast(int enc, int elem_sz, const uint8_t* src, uint8_t* dst, uint64_t len, uint32_t D,
+                                cudaStream_t stream)
+{
+    if (len == 0 || D == 0) return cudaSuccess;
+    const int32_t nb = xffp_nblocks(len, D, elem_sz);
+    const unsigned grid = (D + 127u) / 128u;
+    if (elem_sz == 1) {
+        if (enc) spz_xff_forecast_kernel<8, true><<<grid, 128, 0, stream>>>(src, dst, len, D, nb);
+        else     spz_xff_forecast_kernel<8, false><<<grid, 128, 0, stream>>>(src, dst, len, D, nb);
+    } else {
+        if (enc) spz_xff_forecast_kernel<16, true><<<grid, 128, 0, stream>>>(src, dst, len, D, nb);
+        else     spz_xff_forecast_kernel<16, false><<<grid, 128, 0, stream>>>(src, dst, len, D, nb);
+    }
+    return cudaGetLastError();
+}
 
 static uint32_t forecast_tile_rows(uint64_t len, uint32_t D)
 {
