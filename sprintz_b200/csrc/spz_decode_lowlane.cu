@@ -17,8 +17,6 @@ int get_force_path();
 
 constexpr int kLowLaneThreads = 128;
 constexpr uint32_t kLowLaneWarpSmem = 8192;   // 33 rows x 128 B used; the stride keeps "row | lane" an OR
-#define kLaneThreads kLowLaneThreads
-#define kLaneWarpSmem kLowLaneWarpSmem
 
 // Q = 0: decode.  Q = 1 / 2: query-on-compressed (REDUCE_MAX / REDUCE_SUM without materialising, see
 // spz_decode_lane.cu): rows are folded into per-dim registers instead of being packed and stored.
@@ -404,8 +402,6 @@ __global__ void __launch_bounds__(kLowLaneThreads, (D * W <= 16) ? 7 : 5) spz_de
     }
 }
 
-#undef kLaneThreads
-#undef kLaneWarpSmem
 
 // ------------------------------------------------------------------ launch
 
