@@ -360,7 +360,7 @@ def frame_query(frame: Frame, op: int, materialize: bool = False, out=None, work
 
 def set_encode_overlap(mode: int) -> int:
     """0 (default): directory scan + compaction after the encoder; 1: EXPERIMENTAL overlapped scan + copy behind the lane
-    encoders (verified on frames of up to 148 tiles of 128 chunks only).  -> previous mode"""
+    encoders, applied to frames of up to 148 x 128 chunks only (the verified configuration).  -> previous mode"""
     return int(lib().spz_set_encode_overlap(mode))
 
 
