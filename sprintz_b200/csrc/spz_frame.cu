@@ -283,6 +283,17 @@ cudaError_t launch_chase(const ChunkMeta* meta, uint64_t nchunks, const uint8_t*
 {
     const uint64_t tiles = chase_tiles(nchunks);
     const unsigned grid = (unsigned)(tiles < 148 ? tiles : 148);       // one small CTA per SM: stays resident beside the encoder
+    // Ask for the largest shared-memory carveout: this kernel needs 1.5 KB, but an SM keeps the carveout of the CTAs
+    // resident on it, and the lane encoder needs 29 KB per CTA -- with a small carveout pinned on every SM by the
+    // spinning chase CTAs the encoder could not be placed anywhere.  (The prime suspect for the stall seen when the
+    // grid covered all 148 SMs; not yet re-measured, so spz_frame_encode_dev still limits this path to <= 148 tiles.)
+    static bool carveout_set = false;
+    if (!carveout_set) {
+        const cudaError_t ce = cudaFuncSetAttribute(spz_chase_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                    (int)cudaSharedmemCarveoutMaxShared);
+        if (ce != cudaSuccess) return ce;
+        carveout_set = true;
+    }
     spz_chase_kernel<<<grid, kChaseThreads, 0, stream>>>(meta, nchunks, slots, slot_stride, chunk_off, chunk_nbytes, payload,
                                                         tile_state, hdr, hdr_in, d_frame_bytes, err);
     return cudaGetLastError();
