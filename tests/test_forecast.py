@@ -71,6 +71,42 @@ def test_oracle_xff_forecast_vs_reference(oracle, ref, esz):
     assert not bad, (len(bad), bad[:5])
 
 
+def _golden_forecast():
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_forecast_v1.npz"))
+    for k, line in enumerate(z["index"]):
+        tr, esz, D, ret, tag = str(line).split("|", 4)
+        yield int(tr), int(esz), int(D), int(ret), tag, z[f"x{k}"], z[f"y{k}"]
+
+
+def test_oracle_matches_golden_forecast_vectors(oracle):
+    """committed fixtures generated from the compiled reference (tests/golden/make_golden_forecast.py): they travel to
+    hosts without the reference tree"""
+    n = 0
+    for tr, esz, D, ret, tag, x, y in _golden_forecast():
+        got, r = oracle.encode_xff_forecast(x, D) if tr == 3 else oracle.encode_forecast(tr, x, D)
+        assert r == ret and np.array_equal(got, y), (tr, esz, D, tag)
+        dec, _ = (oracle.decode_xff_forecast(esz, y[6:].view(x.dtype), D) if tr == 3
+                  else oracle.decode_forecast(tr, esz, y[6:].view(x.dtype), D))
+        assert np.array_equal(dec, x), (tr, esz, D, tag)
+        n += 1
+    assert n > 1000
+
+
+@pytest.mark.gpu
+def test_gpu_forecast_matches_golden_vectors():
+    """the delta / double-delta kernels against the reference's own output bytes"""
+    import sprintz_b200 as spz
+    spz.lib()
+    for tr, esz, D, ret, tag, x, y in _golden_forecast():
+        if tr == 3:
+            continue                                   # the FIRE transform: tests/test_zz_xff_forecast_gpu.py
+        got, r = spz.encode_forecast(tr, x, D)
+        assert r == ret and np.array_equal(got, y), (tr, esz, D, tag)
+        dec, _ = spz.decode_forecast(tr, esz, y[6:].view(x.dtype), D)
+        assert np.array_equal(dec, x), (tr, esz, D, tag)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("order,esz", ORDERS, ids=OIDS)
 def test_gpu_forecast_matches_oracle(oracle, order, esz):

@@ -74,3 +74,20 @@ def test_gpu_xff_forecast_device_api_roundtrip():
         assert L.spz_xff_forecast_dev(0, esz, y.data_ptr(), x.numel(), D, z.data_ptr(), sp) == 0
         torch.cuda.synchronize()
         assert torch.equal(z, x) and not torch.equal(y, x)
+
+
+def test_gpu_xff_forecast_matches_golden_vectors():
+    """against the reference's own output bytes (tests/golden/golden_forecast_v1.npz, transform 3)"""
+    import sprintz_b200 as spz
+    from test_forecast import _golden_forecast
+    spz.lib()
+    n = 0
+    for tr, esz, D, ret, tag, x, y in _golden_forecast():
+        if tr != 3:
+            continue
+        got, r = spz.encode_xff_forecast(x, D)
+        assert r == ret and np.array_equal(got, y), (esz, D, tag)
+        dec, _ = spz.decode_xff_forecast(esz, y[6:].view(x.dtype), D)
+        assert np.array_equal(dec, x), (esz, D, tag)
+        n += 1
+    assert n > 300
