@@ -221,8 +221,8 @@ int spz_profile_collect(float* ms3, int* ncalls);
 /* EXPERIMENTAL, off by default: with on != 0, frame encode behind the lane encoders overlaps the directory scan +
  * compaction with the encoding (a small resident kernel on a second stream chases the encoder chunk by chunk) for
  * frames of up to 148 x 128 chunks -- the verified configuration; larger frames keep the classic path.  Same frame
- * bytes either way.  Returns the previous setting; spz_last_encode_overlapped() reports what the last
- * spz_frame_encode_dev call did. */
+ * bytes either way.  (on == 2 lifts the size cap: unverified, for tools/overlap_probe.py only.)  Returns the previous
+ * setting; spz_last_encode_overlapped() reports what the last spz_frame_encode_dev call did. */
 int spz_set_encode_overlap(int on);
 int spz_last_encode_overlapped(void);
 

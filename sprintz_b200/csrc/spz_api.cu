@@ -273,7 +273,7 @@ int g_last_encode_overlapped = 0;
 extern "C" int spz_set_encode_overlap(int on)
 {
     const int old = g_overlap_mode;
-    g_overlap_mode = on ? 1 : 0;
+    g_overlap_mode = on == 2 ? 2 : (on ? 1 : 0);      // 2: no tile cap (UNVERIFIED above 148 tiles; tools/overlap_probe.py)
     return old;
 }
 extern "C" int spz_last_encode_overlapped(void) { return g_last_encode_overlapped; }
@@ -313,7 +313,7 @@ extern "C" int spz_frame_encode_dev(int predictor, int elem_sz, const void* d_sr
     // (tests/test_gpu_lane.py).  Larger frames take the classic path: with several tiles per CTA the waits ran into
     // their bounds on BASELINE-sized frames and the cause is not isolated yet.
     g_last_encode_overlapped = 0;
-    if (g_overlap_mode != 0 && chase_tiles(f.nchunks) <= 148 && encode_uses_lane(elem_sz, predictor, p)) {
+    if (g_overlap_mode != 0 && (chase_tiles(f.nchunks) <= 148 || g_overlap_mode == 2) && encode_uses_lane(elem_sz, predictor, p)) {
         CK(g_side.init());
         CK(cudaMemsetAsync(work, 0, w.off_slots, stream));        // tile states, error flag AND the chunk records (nbytes == 0: not ready)
         CK(cudaEventRecord(g_side.ev_begin, stream));
