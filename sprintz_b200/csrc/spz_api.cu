@@ -30,7 +30,7 @@ uint64_t chase_tiles(uint64_t nchunks);
 cudaError_t launch_chase(const ChunkMeta* meta, uint64_t nchunks, const uint8_t* slots, uint64_t slot_stride,
                          uint64_t* chunk_off, uint32_t* chunk_nbytes, uint8_t* payload, unsigned long long* tile_state,
                          spz_frame_header* hdr, const spz_frame_header& hdr_in, uint64_t* d_frame_bytes, unsigned int* err,
-                         cudaStream_t stream);
+                         bool fast, cudaStream_t stream);
 bool encode_uses_lane(int elem_sz, int predictor, EncParams p);
 void set_force_path(int v);
 int get_force_path();
@@ -320,7 +320,7 @@ extern "C" int spz_frame_encode_dev(int predictor, int elem_sz, const void* d_sr
         CK(cudaStreamWaitEvent(g_side.stream, g_side.ev_begin, 0));
         CK(launch_chase(p.meta, f.nchunks, work + w.off_slots, w.slot_stride, chunk_off, chunk_nbytes, frame + f.payload_off,
                         (unsigned long long*)(work + w.off_state), (spz_frame_header*)frame, h, d_frame_bytes,
-                        (unsigned int*)(work + w.off_ticket + 4), g_side.stream));
+                        (unsigned int*)(work + w.off_ticket + 4), g_overlap_mode == 2, g_side.stream));
         CK(cudaEventRecord(g_side.ev_done, g_side.stream));
         PROF_MARK(0);
         CK(launch_encode(elem_sz, predictor, p, stream));

@@ -164,6 +164,8 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p)
     return v;
 }
 
+// FAST (uncapped probe mode only, unverified): the copy keeps four 128-bit loads in flight per lane.
+template <bool FAST>
 __global__ void __launch_bounds__(kChaseThreads)
 spz_chase_kernel(const ChunkMeta* meta, uint64_t nchunks, const uint8_t* __restrict__ slots, uint64_t slot_stride,
                  uint64_t* __restrict__ chunk_off, uint32_t* __restrict__ chunk_nbytes, uint8_t* __restrict__ payload,
@@ -253,7 +255,15 @@ spz_chase_kernel(const ChunkMeta* meta, uint64_t nchunks, const uint8_t* __restr
             const uint32_t units = (cnb + 15u) >> 4;
             const uint4* s4 = reinterpret_cast<const uint4*>(slots + c * slot_stride);
             uint4* d4 = reinterpret_cast<uint4*>(payload + s_off[k]);
-            for (uint32_t u = lane; u < units; u += 32) {
+            uint32_t u = lane;
+            if (FAST && units > 128u) {
+                // whole groups of 4 x 32 units that do not contain the chunk's last (possibly partial) unit
+                for (; u + 96u + (31u - lane) < units - 1u; u += 128u) {
+                    const uint4 x0 = __ldcg(s4 + u), x1 = __ldcg(s4 + u + 32), x2 = __ldcg(s4 + u + 64), x3 = __ldcg(s4 + u + 96);
+                    d4[u] = x0; d4[u + 32] = x1; d4[u + 64] = x2; d4[u + 96] = x3;
+                }
+            }
+            for (; u < units; u += 32) {
                 uint4 x = __ldcg(s4 + u);
                 if (u == units - 1 && (cnb & 15u)) {
                     uint32_t w[4] = {x.x, x.y, x.z, x.w};
@@ -279,7 +289,7 @@ uint64_t chase_tiles(uint64_t nchunks) { return (nchunks + kChaseThreads - 1) / 
 cudaError_t launch_chase(const ChunkMeta* meta, uint64_t nchunks, const uint8_t* slots, uint64_t slot_stride,
                          uint64_t* chunk_off, uint32_t* chunk_nbytes, uint8_t* payload, unsigned long long* tile_state,
                          spz_frame_header* hdr, const spz_frame_header& hdr_in, uint64_t* d_frame_bytes, unsigned int* err,
-                         cudaStream_t stream)
+                         bool fast, cudaStream_t stream)
 {
     const uint64_t tiles = chase_tiles(nchunks);
     const unsigned grid = (unsigned)(tiles < 148 ? tiles : 148);       // one small CTA per SM: stays resident beside the encoder
@@ -289,13 +299,20 @@ cudaError_t launch_chase(const ChunkMeta* meta, uint64_t nchunks, const uint8_t*
     // grid covered all 148 SMs; not yet re-measured, so spz_frame_encode_dev still limits this path to <= 148 tiles.)
     static bool carveout_set = false;
     if (!carveout_set) {
-        const cudaError_t ce = cudaFuncSetAttribute(spz_chase_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                    (int)cudaSharedmemCarveoutMaxShared);
+        cudaError_t ce = cudaFuncSetAttribute(spz_chase_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                              (int)cudaSharedmemCarveoutMaxShared);
+        if (ce != cudaSuccess) return ce;
+        ce = cudaFuncSetAttribute(spz_chase_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  (int)cudaSharedmemCarveoutMaxShared);
         if (ce != cudaSuccess) return ce;
         carveout_set = true;
     }
-    spz_chase_kernel<<<grid, kChaseThreads, 0, stream>>>(meta, nchunks, slots, slot_stride, chunk_off, chunk_nbytes, payload,
-                                                        tile_state, hdr, hdr_in, d_frame_bytes, err);
+    if (fast)
+        spz_chase_kernel<true><<<grid, kChaseThreads, 0, stream>>>(meta, nchunks, slots, slot_stride, chunk_off, chunk_nbytes,
+                                                                  payload, tile_state, hdr, hdr_in, d_frame_bytes, err);
+    else
+        spz_chase_kernel<false><<<grid, kChaseThreads, 0, stream>>>(meta, nchunks, slots, slot_stride, chunk_off, chunk_nbytes,
+                                                                   payload, tile_state, hdr, hdr_in, d_frame_bytes, err);
     return cudaGetLastError();
 }
 
