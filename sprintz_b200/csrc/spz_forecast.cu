@@ -13,19 +13,13 @@
 //        the double-delta recurrence is the pair (delta, value); a tile of n rows maps (d0, x0) to
 //        (d0 + S1, x0 + n*d0 + S2) with S1 = sum y_k, S2 = sum (n-k)*y_k, which composes associatively.
 #include "spz_common.cuh"
+#include "spz_swar.cuh"
 #include "spz_xff_forecast.cuh"
 #include "../../include/sprintz_b200.h"
 
 namespace spz {
 
 namespace {
-
-// per-byte / per-halfword a - b on packed words
-template <int W> __device__ __forceinline__ uint32_t psub(uint32_t a, uint32_t b)
-{
-    constexpr uint32_t H = (W == 8) ? 0x80808080u : 0x80008000u;
-    return ((a | H) - (b & ~H)) ^ ((a ^ ~b) & H);
-}
 
 // word at byte offset `off` (any alignment) of `base` (4-byte aligned), zero before the buffer
 __device__ __forceinline__ uint32_t word_at(const uint8_t* base, int64_t off)

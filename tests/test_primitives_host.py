@@ -27,6 +27,8 @@ def prim(tmp_path_factory):
                        ("h_fire_grad", [C.c_int, C.c_int32, C.c_int32]), ("h_sx", [C.c_int, C.c_int32])):
         getattr(L, name).argtypes = args
         getattr(L, name).restype = C.c_uint32 if name == "h_zigzag_enc" else C.c_int32
+    L.h_swar.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.h_swar.restype = None
     return L
 
 
@@ -77,3 +79,39 @@ def test_fire_coefficient_prediction_gradient(prim, w):
         for err in (0, 1, -1, 77, -77):
             want = 0 if err == 0 else (-pd if err < 0 else pd)       # util.h:63-68
             assert prim.h_fire_grad(w, err, pd) == want
+
+
+@pytest.mark.parametrize("w", [8, 16])
+def test_packed_lane_arithmetic(prim, w):
+    """spz_swar.cuh (the packed subtract of the delta forecaster kernels, and the per-lane zigzag planned for the packed
+    delta encoder): every lane behaves like the scalar W-bit operation, with no borrow / carry / shift leaking between
+    lanes -- all values of one lane against extreme neighbours, plus random words."""
+    udt = np.uint8 if w == 8 else np.uint16
+    nl = 32 // w
+    rng = np.random.default_rng(w)
+    words = [rng.integers(0, 1 << 32, 200000, dtype=np.uint64).astype(np.uint32) for _ in range(2)]
+    vals = np.arange(1 << w, dtype=np.uint32)
+    for lane in range(nl):
+        for fill in (0, (1 << w) - 1, 1 << (w - 1)):
+            base = np.uint32(sum(fill << (w * k) for k in range(nl) if k != lane))
+            a = (vals << np.uint32(w * lane)) | base
+            if w == 8:                                            # all 65536 pairs of one lane
+                aa = np.repeat(a, 256); bb = np.tile(a, 256)
+            else:
+                aa = a; bb = np.roll(a, 12345)
+            words.append(aa.astype(np.uint32)); words.append(bb.astype(np.uint32))
+    a = np.ascontiguousarray(np.concatenate(words[0::2])); b = np.ascontiguousarray(np.concatenate(words[1::2]))
+    n = min(a.size, b.size); a, b = a[:n].copy(), b[:n].copy()
+    al, bl = a.view(udt).astype(np.int64), b.view(udt).astype(np.int64)
+    out = np.zeros(n, np.uint32)
+    mask = (1 << w) - 1
+    want = {0: (al - bl) & mask, 1: (al + bl) & mask,
+            2: ((al << 1) ^ np.where(al >> (w - 1), mask, 0)) & mask, 3: ((al >> 1) ^ np.where(al & 1, mask, 0)) & mask}
+    for op in (0, 1, 2, 3):
+        prim.h_swar(w, op, a.ctypes.data, b.ctypes.data, out.ctypes.data, n)
+        assert np.array_equal(out.view(udt).astype(np.int64), want[op]), (w, op)
+    # zigzag round trip per lane
+    z = np.zeros(n, np.uint32)
+    prim.h_swar(w, 2, a.ctypes.data, b.ctypes.data, z.ctypes.data, n)
+    prim.h_swar(w, 3, z.ctypes.data, b.ctypes.data, out.ctypes.data, n)
+    assert np.array_equal(out, a)
