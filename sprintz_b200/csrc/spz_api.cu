@@ -310,7 +310,7 @@ extern "C" int spz_frame_encode_dev(int predictor, int elem_sz, const void* d_sr
     // EXPERIMENTAL, off by default (spz_set_encode_overlap): overlapped directory + compaction (spz_chase_kernel), only
     // behind the lane encoders (they publish every chunk record with a release) and only for frames of up to 148
     // tiles of 128 chunks, where every chase CTA owns one tile -- the configuration that is verified bit-exact
-    // (tests/test_gpu_lane.py).  Larger frames take the classic path: with several tiles per CTA the waits ran into
+    // (tests/test_zy_overlap_gpu.py).  Larger frames take the classic path: with several tiles per CTA the waits ran into
     // their bounds on BASELINE-sized frames and the cause is not isolated yet.
     g_last_encode_overlapped = 0;
     if (g_overlap_mode != 0 && (chase_tiles(f.nchunks) <= 148 || g_overlap_mode == 2) && encode_uses_lane(elem_sz, predictor, p)) {
