@@ -142,6 +142,17 @@ __device__ __forceinline__ void publish_nbytes(uint32_t* p, uint32_t nbytes)
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(nbytes) : "memory");
 }
 
+// The output rings of the lane encoders are addressed with absolute 32-bit shared-memory addresses and explicit st/ld.shared:
+// with C++ pointers the compiler rebuilt the shared window base (S2R + MOV + LEA) under every predicated store.
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.b8 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ uint32_t lds32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+
 // ------------------------------------------------------------------ team (sub-warp) primitives
 
 __device__ __forceinline__ uint32_t team_mask_of(int lane, int team)

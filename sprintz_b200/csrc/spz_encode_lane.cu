@@ -29,17 +29,6 @@ namespace spz {
 constexpr int kEncLaneThreads = 128;
 bool g_encode_dry_run = false;                             // launchers return without launching (single-threaded use under the API's call)
 
-// The output ring is addressed with absolute 32-bit shared-memory addresses and explicit st/ld.shared: with C++
-// pointers the compiler rebuilt the shared window base (S2R + MOV + LEA) under every predicated store.
-__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v)); }
-__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.b8 [%0], %1;" ::"r"(a), "r"(v)); }
-__device__ __forceinline__ uint32_t lds32(uint32_t a)
-{
-    uint32_t v;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-
 template <int W, bool FIRE, int D>
 // int8 x 8 fits 5 CTAs per SM without spills (96 registers); the int16 shapes spill there and stay at 4
 __global__ void __launch_bounds__(kEncLaneThreads, (W == 8) ? 5 : 4) spz_encode_lane_kernel(const EncParams p)

@@ -18,18 +18,6 @@ extern bool g_encode_dry_run;
 
 constexpr int kEncLowThreads = 128;
 
-__device__ __forceinline__ void lsts32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v)); }
-__device__ __forceinline__ void lsts8(uint32_t a, uint32_t v) { asm volatile("st.shared.b8 [%0], %1;" ::"r"(a), "r"(v)); }
-__device__ __forceinline__ uint32_t llds32(uint32_t a)
-{
-    uint32_t v;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-#define sts32 lsts32
-#define sts8 lsts8
-#define lds32 llds32
-
 template <int W, bool FIRE, int D>
 __global__ void __launch_bounds__(kEncLowThreads, (D * W == 8) ? 8 : (D * W == 16) ? 7 : 5) spz_encode_lowlane_kernel(const EncParams p)
 {
@@ -327,10 +315,6 @@ __global__ void __launch_bounds__(kEncLowThreads, (D * W == 8) ? 8 : (D * W == 1
     publish_nbytes(&p.meta[c].nbytes, nbytes);
 }
 
-
-#undef sts32
-#undef sts8
-#undef lds32
 
 // ------------------------------------------------------------------ launch
 
