@@ -179,7 +179,8 @@ int spz_reduce_rows_dev(int op, int elem_sz, const void* d_src, uint64_t len, ui
                         spz_stream_t stream);
 
 /* ---------------------------------------------------------------- 2. single stream, device buffers
- * d_dest must hold spz_max_compressed_bytes(); d_meta (1 record) receives sizes. Asynchronous on `stream`. */
+ * The same codecs as layer 1 (sprintz.cpp:92-251) without the host copies; no reference equivalent -- the reference is
+ * host-only.  d_dest must hold spz_max_compressed_bytes(); d_meta (1 record) receives sizes. Asynchronous on `stream`. */
 int spz_compress_dev(int predictor, int elem_sz, const void* d_src, uint32_t len, uint16_t ndims,
                      int write_size, void* d_dest, spz_chunk_meta* d_meta, spz_stream_t stream);
 /* has_meta == 0: d_meta->ngroups / ->remaining are inputs.  src_bytes = readable bytes at d_src; it must
@@ -189,6 +190,8 @@ int spz_decompress_dev(int predictor, int elem_sz, const void* d_src, uint64_t s
                        spz_stream_t stream);
 
 /* ---------------------------------------------------------------- 3. chunked frame
+ * No reference equivalent: one reference call is one serial stream with a uint32_t length (sprintz.cpp:92-109,
+ * sprintz_delta_rle.cpp:54-72); the frame is how the path is made parallel -- every chunk IS one reference stream.
  * chunk c covers elements [c*chunk_rows*ndims, (c+1)*chunk_rows*ndims) and is encoded exactly as the
  * reference encodes that slice. chunk_rows should be a multiple of 16 (whole groups). */
 uint64_t spz_frame_nchunks(uint64_t len, uint16_t ndims, uint32_t chunk_rows);
