@@ -1,18 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- encode+decode throughput of the Sprintz frame path on B200 (see DESIGN.md "Measurement").
 
-    python bench.py --gpus N --steps K --warmup W [--config c2] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--config c3] [--impl reference]
 
 A *step* is one pass of the hot path over one batch: frame-encode the rank's stream, then frame-decode it.
+The default workload is BASELINE.json's north-star configuration c3 (int16, 16-dim row-major, FIRE+bitpack,
+4 GiB per GPU -- also the largest single-GPU configuration); c2 and c4 ride along as sub-records in the same line.
+
 metric  = raw bytes / (t_encode + t_decode), whole job over N GPUs (weak scaling: every rank owns a full
           copy of the per-GPU workload, sharded by chunks with no data-path collective).
 value   : inputs and outputs resident in HBM, CUDA events around exactly K steps, max over ranks.
 e2e     : same metric through the host-buffer C ABI (spz_frame_compress_host / spz_frame_decompress_host):
           pinned host input -> H2D -> kernels -> D2H, every step.
 roofline: dominant codec kernel, algorithmic bytes N*(1+1/ratio) / its CUDA-event time, against the measured
-          HBM copy bandwidth in MEASURED_PEAKS.json.
+          HBM copy bandwidth in MEASURED_PEAKS.json (SURVEY 8d's form; the stricter read-only form the north star
+          names is reported beside it as hbm_read_roofline).
+parity  : EVERY chunk stream of the timed frame is compared with the bytes the unmodified reference
+          (oracle/_ref) produces for the same slice (N = 1: the whole stream; N > 1: a bounded sample on rank 0).
 cpu_baseline / --impl reference: the UNMODIFIED reference compiled from its own sources (oracle/_ref) on
-          the box's host cores, all threads, over the same chunk slices.
+          the box's host cores, all threads, over the same chunk slices; plus one thread on one whole stream
+          (the paper's setting).
+N > 1   : sub-record c4 shards the 32 GB int8 x 80 stream (4 GiB per GPU) and gathers the compressed frames on
+          rank 0 over NCCL (ncclSend/ncclRecv inside libsprintz_b200.so): `value_with_gather` has the collective
+          inside the timed region.
 """
 from __future__ import annotations
 
@@ -28,20 +38,23 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+PRED_NAMES = ("delta", "xff", "rowmajor_delta", "rowmajor_plain", "rowmajor_xff")
+
 # (name, elem_sz, ndims, predictor, bytes per GPU, default chunk_rows)
 CONFIGS = {
     "c1": dict(desc="int8, 1-dim, delta+bitpack, 64 KB", esz=1, D=1, pred=0, nbytes=64 << 10, chunk_rows=2048),
-    # 512-row chunks: 262144 lane tasks = 3.5 waves of resident lanes instead of 1.7 (+4 % decode), -0.8 % ratio
     "c2": dict(desc="int8, 8-dim rowmajor, FIRE+bitpack, 1 GB synthetic AR(1)", esz=1, D=8, pred=1,
                nbytes=1 << 30, chunk_rows=512),
     "c3": dict(desc="int16, 16-dim rowmajor, FIRE+bitpack, 4 GB synthetic AR(1)", esz=2, D=16, pred=1,
                nbytes=4 << 30, chunk_rows=1024),
     "c4": dict(desc="int8, 80-dim, delta+bitpack, 4 GB per GPU (32 GB over 8)", esz=1, D=80, pred=0,
                nbytes=4 << 30, chunk_rows=1024),
-    # the non-RLE sibling codec compress_rowmajor_delta_8b (frame codec id 2), generic kernels
+    # the non-RLE sibling codec compress_rowmajor_delta_8b (frame codec id 2)
     "f1": dict(desc="int8, 8-dim rowmajor, delta+bitpack without RLE (compress_rowmajor_delta_8b), 1 GB synthetic AR(1)",
                esz=1, D=8, pred=2, nbytes=1 << 30, chunk_rows=1024),
 }
+MAIN_CONFIG = "c3"
+SUB_CONFIGS = ("c2", "c4")
 
 
 def peaks():
@@ -52,15 +65,17 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(cfg_name, kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture of this config (or None)."""
-    for name in ("r1b_traffic.json", "r1_traffic.json"):        # latest capture first
-        try:
-            with open(os.path.join(ROOT, "profiles", name)) as f:
-                return json.load(f)["configs"][cfg_name][kernel]["traffic"]
-        except Exception:
-            continue
-    return None
+def ncu_traffic(cfg_name, kernel, chunk_rows):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture of this config AND chunk_rows
+    (profiles/r2_traffic.json); None when no capture of exactly this launch shape exists."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+            rec = json.load(f)["configs"][cfg_name]
+        if int(rec.get("chunk_rows", -1)) != int(chunk_rows):
+            return None
+        return rec[kernel]["traffic"]
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -120,10 +135,21 @@ def make_stream(cfg, device, seed):
     return ar1_stream(rows, cfg["D"], cfg["esz"], seed=seed, device=device), rows
 
 
-# ------------------------------------------------------------------ CPU reference timing (oracle/_ref)
+def config_record(cfg_name, cfg, raw, chunk_rows, world):
+    """The `config` object of the JSON line: identical for both arms of the same workload."""
+    clen = chunk_rows * cfg["D"]
+    return {"workload": cfg_name + ": " + cfg["desc"], "elem_bits": 8 * cfg["esz"], "ndims": cfg["D"],
+            "predictor": PRED_NAMES[cfg["pred"]], "bytes_per_gpu": raw, "chunk_rows": chunk_rows,
+            "nchunks_per_gpu": (raw // cfg["esz"] + clen - 1) // clen,
+            "l2": "inputs (>= 1 GiB) exceed the 126 MB L2; no explicit flush",
+            "parallelism": f"chunk-sharded x{world}, no data-path collective"}
 
-def time_reference(cfg, x_host, chunk_rows, nthreads, repeats=3):
-    """Times the unmodified reference on host cores over the same chunk slices. -> dict"""
+
+# ------------------------------------------------------------------ CPU reference (oracle/_ref): timing + parity source
+
+def reference_chunks(cfg, x_host, chunk_rows, nthreads, repeats=1, keep=False):
+    """Runs the unmodified reference on host cores over the chunk slices of x_host (numpy). -> dict
+    keep=True also returns the compressed bytes (comp, stride, rets) for the parity check."""
     import numpy as np
     from oracle import Ref
     R = Ref()
@@ -147,8 +173,61 @@ def time_reference(cfg, x_host, chunk_rows, nthreads, repeats=3):
     ok = bool(np.array_equal(dec[: n * esz], src[: n * esz]))
     raw = n * esz
     comp_bytes = int(rets.sum()) * esz
-    return dict(t_enc=min(te), t_dec=min(td), t_enc_all=te, t_dec_all=td, raw=raw, ratio=raw / max(1, comp_bytes),
-                roundtrip_ok=ok, nchunks=int(nchunks))
+    out = dict(t_enc=min(te), t_dec=min(td), t_enc_all=te, t_dec_all=td, raw=raw, comp_bytes=comp_bytes,
+               ratio=raw / max(1, comp_bytes), roundtrip_ok=ok, nchunks=int(nchunks))
+    if keep:
+        out.update(comp=comp, stride=stride, rets=rets)
+    return out
+
+
+def reference_single_stream(cfg, x_host, max_mb=512):
+    """ONE thread, ONE reference call on one whole stream (the paper's setting): the first
+    `max_mb` MiB of the workload as a single sprintz_compress_* / sprintz_decompress_* call."""
+    import numpy as np
+    from oracle import Ref
+    R = Ref()
+    esz, D, pred = cfg["esz"], cfg["D"], cfg["pred"]
+    n = min(x_host.size, (max_mb << 20) // esz // (16 * D) * (16 * D), 0xffffff00 // (16 * D) * (16 * D))
+    src = np.concatenate([x_host[:n].view(np.uint8).reshape(-1), np.zeros(4096, np.uint8)])
+    comp = np.zeros(R.max_bytes(esz, n, D) + 4096, np.uint8)
+    dec = np.zeros(n * esz + 4096, np.uint8)
+    best_e, best_d, ret = 1e30, 1e30, 0
+    for _ in range(2):
+        t0 = time.perf_counter()
+        ret = int(R.L.ref_compress(pred, esz, src.ctypes.data, n, comp.ctypes.data, D, 1))
+        t1 = time.perf_counter()
+        R.L.ref_decompress(pred, esz, comp.ctypes.data, dec.ctypes.data)
+        t2 = time.perf_counter()
+        best_e, best_d = min(best_e, t1 - t0), min(best_d, t2 - t1)
+    raw = n * esz
+    return {"threads": 1, "sample": f"first {raw >> 20} MiB of the stream as ONE reference call (no chunking), best of 2",
+            "encode_gbs": raw / best_e / 1e9, "decode_gbs": raw / best_d / 1e9,
+            "value": raw / (best_e + best_d) / 1e9, "ratio": raw / max(1, ret * esz),
+            "roundtrip_ok": bool(np.array_equal(dec[: raw], src[: raw]))}
+
+
+def parity_vs_reference(esz, refrun, payload, off, nb, first_chunk=0):
+    """Compares chunk streams [first_chunk, first_chunk + refrun.nchunks) of the GPU frame (payload bytes + directory
+    off/nb, numpy) with the reference's bytes for the same slices.  The reference returns floor(bytes/2) elements
+    for 16-bit streams, so a GPU stream may be one byte longer than ret*esz; everything the reference
+    counts must be identical."""
+    import numpy as np
+    comp, stride, rets = refrun["comp"], refrun["stride"], refrun["rets"]
+    nchunks = refrun["nchunks"]
+    equal, first_bad, gpu_bytes = 0, None, 0
+    for c in range(nchunks):
+        want_n = int(rets[c]) * esz
+        a = int(off[first_chunk + c]); n = int(nb[first_chunk + c])
+        gpu_bytes += n
+        ok = (n == want_n or (esz == 2 and n == want_n + 1)) and \
+            np.array_equal(payload[a: a + want_n], comp[c * stride: c * stride + want_n])
+        if ok:
+            equal += 1
+        elif first_bad is None:
+            first_bad = first_chunk + c
+    return {"chunks_compared": nchunks, "chunks_equal": equal, "all_equal": equal == nchunks,
+            "first_differing_chunk": first_bad, "gpu_stream_bytes": gpu_bytes, "reference_stream_bytes": refrun["comp_bytes"],
+            "against": "oracle/_ref (unmodified reference) on the same chunk slices"}
 
 
 def run_reference(args, cfg, cfg_name):
@@ -168,7 +247,7 @@ def run_reference(args, cfg, cfg_name):
     ts = []
     res = None
     for i in range(warm + steps):
-        res = time_reference(cfg, xh, chunk_rows, ncores, repeats=1)
+        res = reference_chunks(cfg, xh, chunk_rows, ncores, repeats=1)
         if i >= warm:
             ts.append(res["t_enc"] + res["t_dec"])
     raw = res["raw"]
@@ -178,13 +257,12 @@ def run_reference(args, cfg, cfg_name):
         "impl": "reference", "metric": "encode+decode GB/s", "value": val, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": 1e3 * total / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8" if cfg["esz"] == 1 else "u16", "data": "synthetic",
-        "config": {"workload": cfg_name + ": " + cfg["desc"], "elem_bits": 8 * cfg["esz"], "ndims": cfg["D"],
-                   "predictor": ("delta", "xff", "rowmajor_delta", "rowmajor_plain")[cfg["pred"]], "bytes": raw, "chunk_rows": chunk_rows,
-                   "threads": ncores},
+        "config": config_record(cfg_name, cfg, raw, chunk_rows, max(1, args.gpus)),
+        "ratio": res["ratio"],
         "cpu_baseline": {"value": val, "unit": "GB/s", "cores": ncores, "kind": "reference",
                          "sample": f"whole {raw >> 20} MiB workload per step, {res['nchunks']} chunk slices, "
                                    f"std::thread pool over oracle/_ref (unmodified reference, g++ -O3 -mavx2 -mbmi2)",
-                         "encode_gbs": raw / min(t for t in [res["t_enc"]]) / 1e9,
+                         "encode_gbs": raw / res["t_enc"] / 1e9,
                          "decode_gbs": raw / res["t_dec"] / 1e9, "ratio": res["ratio"],
                          "roundtrip_ok": res["roundtrip_ok"]},
         "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -195,72 +273,63 @@ def run_reference(args, cfg, cfg_name):
 
 # ------------------------------------------------------------------ the GPU arm
 
-def run_ours(args, cfg, cfg_name):
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    import sprintz_b200 as spz
+class Env:
+    """Process-wide state of the GPU arm (one process per GPU)."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the Sprintz B200 path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    def __init__(self):
+        import torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the Sprintz B200 path has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.comm = None
 
-    L = spz.lib()
-    esz, D, pred = cfg["esz"], cfg["D"], cfg["pred"]
-    chunk_rows = args.chunk_rows or cfg["chunk_rows"]
-    x, rows = make_stream(cfg, dev, seed=12345 + rank)
-    n = x.numel()
-    raw = n * esz
-    codec = spz.FrameCodec(pred, esz, n, D, chunk_rows, device=dev)
-    out = torch.empty_like(x)
-    steps, warm = args.steps, args.warmup
-
-    def barrier():
-        if world > 1:
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        if self.world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- correctness of exactly what is timed (round trip; per-chunk byte parity is tests/'s job)
-    fr = codec.encode(x)
-    codec.decode(fr, out)
-    torch.cuda.synchronize()
-    codec.check_status()
-    if not torch.equal(out, x):
-        raise SystemExit("bench.py: decode(encode(x)) != x")
-    hdr = fr.header()
-    payload = int(hdr.payload_bytes)
-    frame_bytes = int(hdr.frame_bytes)
-    ratio = raw / payload
+    def max_over_ranks(self, vals):
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor(list(vals), dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
 
-    # clocks are sampled from the start of warm-up to the end of the timed region (the timed region alone can
-    # be shorter than one nvidia-smi period); warm-up is extended until a few samples under load exist
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    for _ in range(warm):
-        codec.decode(codec.encode(x), out)
-    t_w = time.time()
-    while len(sampler.lines) < 3 and time.time() - t_w < 4.0:
-        codec.decode(codec.encode(x), out)
-        torch.cuda.synchronize()
-    barrier()
 
+def roof_record(alg_bytes, t, kern, cfg_name, chunk_rows, full_size):
+    peak, peak_src = peaks()
+    return {"bound": "hbm", "achieved": alg_bytes / t / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": alg_bytes / t / 1e9 / peak,
+            "traffic": ncu_traffic(cfg_name, kern, chunk_rows) if full_size else None,
+            "alg_bytes_per_launch": alg_bytes, "ms_per_launch": 1e3 * t, "peak_source": peak_src,
+            "formula": "N*(1+1/ratio) / kernel time / measured HBM copy bandwidth (SURVEY 8d)", "kernel": kern}
+
+
+def timed_codec_loop(env, codec, x, out, steps):
+    """K steps of encode + decode, CUDA events on the launching stream. -> per-rank times (s) and kernel splits."""
+    import torch
+    import sprintz_b200 as spz
+    L = spz.lib()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps + 1)]
     L.spz_profile_enable(1)
-    barrier()
+    launches0 = int(L.spz_kernel_launches())
+    env.barrier()
     ev[0].record()
+    fr = None
     for i in range(steps):
         fr = codec.encode(x)
         ev[2 * i + 1].record()
         codec.decode(fr, out)
         ev[2 * i + 2].record()
-    barrier()
-    clocks = sampler.stop()
+    env.barrier()
+    launches = int(L.spz_kernel_launches()) - launches0
     t_total = ev[0].elapsed_time(ev[2 * steps]) / 1e3
     t_enc = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(steps)) / 1e3
     t_dec = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(steps)) / 1e3
@@ -268,28 +337,201 @@ def run_ours(args, cfg, cfg_name):
     ncalls = C.c_int(0)
     L.spz_profile_collect(ms3, C.byref(ncalls))
     L.spz_profile_enable(0)
-    fam = ("spz_%s_kernel", "spz_%s_hd_kernel", "spz_%s_lane_kernel")      # which kernels the timed loop launched
-    k_enc = fam[L.spz_last_kernel_family(0)] % "encode"
-    k_dec = fam[L.spz_last_kernel_family(1)] % "decode"
-    t_enc_kernel = ms3[0] / 1e3 / max(1, ncalls.value)     # per launch
-    t_scan = ms3[1] / 1e3 / max(1, ncalls.value)
-    t_gather = ms3[2] / 1e3 / max(1, ncalls.value)
-    t_dec_kernel = t_dec / steps
+    k = max(1, ncalls.value)
+    return dict(fr=fr, t_total=t_total, t_enc=t_enc, t_dec=t_dec, launches=launches,
+                t_enc_kernel=ms3[0] / 1e3 / k, t_scan=ms3[1] / 1e3 / k, t_gather=ms3[2] / 1e3 / k,
+                t_dec_kernel=t_dec / steps)
 
-    tt = torch.tensor([t_total, t_enc, t_dec], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_total, t_enc_m, t_dec_m = (float(v) for v in tt.tolist())
 
-    # ---- query-on-compressed, outside the timed region: per-dim REDUCE_SUM / REDUCE_MAX over the
-    # frame without materialising it (fused into the lane decoder where the shape allows); reads N/r bytes only
-    query_info = None
+def kernel_names():
+    import sprintz_b200 as spz
+    L = spz.lib()
+    fam = ("spz_%s_kernel", "spz_%s_hd_kernel", "spz_%s_lane_kernel", "spz_%s_wide_kernel")
+    return fam[L.spz_last_kernel_family(0)] % "encode", fam[L.spz_last_kernel_family(1)] % "decode"
+
+
+def frame_to_host(fr, hdr):
+    """-> (payload bytes, chunk_off, chunk_nbytes) as numpy, for the parity check."""
+    off, nb, po = fr.directory()
+    payload = fr.buf[po: po + int(hdr.payload_bytes)].cpu().numpy()
+    return payload, off, nb
+
+
+def measure_config(env, args, cfg_name, cfg, steps, warm, main):
+    """Device-timed encode+decode of one configuration on this rank's shard. `main` adds clocks, query, e2e."""
+    import numpy as np
+    import torch
+    import sprintz_b200 as spz
+    L = spz.lib()
+    esz, D, pred = cfg["esz"], cfg["D"], cfg["pred"]
+    chunk_rows = (args.chunk_rows if main and args.chunk_rows else 0) or cfg["chunk_rows"]
+    world, rank, dev = env.world, env.rank, env.dev
+    x, rows = make_stream(cfg, dev, seed=12345 + rank)
+    n = x.numel()
+    raw = n * esz
+    codec = spz.FrameCodec(pred, esz, n, D, chunk_rows, device=dev)
+    out = torch.empty_like(x)
+    full_size = not args.bytes_mb
+
+    # ---- correctness of exactly what is timed: the round trip here, byte parity with the reference below
+    fr = codec.encode(x)
+    codec.decode(fr, out)
+    torch.cuda.synchronize()
+    codec.check_status()
+    if not torch.equal(out, x):
+        raise SystemExit(f"bench.py: {cfg_name}: decode(encode(x)) != x")
+    hdr = fr.header()
+    payload = int(hdr.payload_bytes)
+
+    # clocks are sampled from the start of warm-up to the end of the timed region (the timed region alone can
+    # be shorter than one nvidia-smi period); warm-up is extended until a few samples under load exist
+    sampler = None
+    if main:
+        sampler = ClockSampler(env.local_rank)
+        sampler.start()
+    for _ in range(warm):
+        codec.decode(codec.encode(x), out)
+    if main:
+        t_w = time.time()
+        while len(sampler.lines) < 3 and time.time() - t_w < 4.0:
+            codec.decode(codec.encode(x), out)
+            torch.cuda.synchronize()
+    r = timed_codec_loop(env, codec, x, out, steps)
+    clocks = sampler.stop() if sampler else None
+    fr = r["fr"]
+    k_enc, k_dec = kernel_names()
+    t_total, t_enc_m, t_dec_m = env.max_over_ranks([r["t_total"], r["t_enc"], r["t_dec"]])
+
+    # exact sizes from the frame's own directory: ratio_exact = raw / sum(chunk_nbytes) is the reference's ratio
+    # (payload_bytes also counts the 16-byte alignment padding between chunk streams)
+    sizes = fr.buf[64 + 8 * (codec.nchunks + 1): 64 + 8 * (codec.nchunks + 1) + 4 * codec.nchunks].view(torch.int32)
+    stream_bytes = int(sizes.to(torch.int64).sum().item())
+    ratio = raw / payload
+    alg_bytes = raw * (1.0 + 1.0 / ratio)               # SURVEY 8d: N*(1 + 1/r), both directions
+    peak, _ = peaks()
+    rec = {
+        "config": config_record(cfg_name, cfg, raw, chunk_rows, world),
+        "value": world * raw * steps / t_total / 1e9, "unit": "GB/s", "ms_per_step": 1e3 * t_total / steps,
+        "encode_gbs": world * raw * steps / t_enc_m / 1e9, "decode_gbs": world * raw * steps / t_dec_m / 1e9,
+        "ratio": ratio, "ratio_exact": raw / stream_bytes, "stream_bytes": stream_bytes, "payload_bytes": payload,
+        "roofline_decode": roof_record(alg_bytes, r["t_dec_kernel"], k_dec, cfg_name, chunk_rows, full_size),
+        "roofline_encode": roof_record(alg_bytes, r["t_enc_kernel"], k_enc, cfg_name, chunk_rows, full_size),
+        # the whole frame encode (codec kernel + directory scan + compaction) against the same algorithmic bytes
+        "roofline_encode_whole": {"frac": alg_bytes / (r["t_enc"] / steps) / 1e9 / peak, "ms": 1e3 * r["t_enc"] / steps},
+        # the stricter read-only form the north star names: HBM bytes READ per launch / kernel time / peak
+        "hbm_read_roofline": {"decode_frac": raw / ratio / r["t_dec_kernel"] / 1e9 / peak,
+                              "encode_frac": raw / r["t_enc_kernel"] / 1e9 / peak,
+                              "decode_raw_gbs_kernel": raw / r["t_dec_kernel"] / 1e9,
+                              "encode_raw_gbs_kernel": raw / r["t_enc_kernel"] / 1e9},
+        "encode_breakdown_ms": {"codec_kernel": 1e3 * r["t_enc_kernel"], "directory_scan": 1e3 * r["t_scan"],
+                                "compaction": 1e3 * r["t_gather"], "pipelined": bool(L.spz_last_encode_overlapped())},
+        "gpu_launches": r["launches"],
+    }
+    dom_is_dec = r["t_dec_kernel"] >= r["t_enc_kernel"]
+    rec["roofline"] = rec["roofline_decode"] if dom_is_dec else rec["roofline_encode"]
+    if clocks is not None:
+        rec["clocks"] = clocks
+
+    # ---- the frame on the host, for the parity check (before the buffers go away)
+    want_parity = rank == 0 and not args.no_cpu_baseline
+    host_frame = frame_to_host(fr, hdr) if want_parity else None
+
+    # ---- query-on-compressed (SURVEY 8f row 2), outside the timed region
+    if main:
+        rec["query"] = measure_query(env, codec, fr, x, out, cfg, chunk_rows, payload)
+
+    # ---- exchange step (SURVEY 8e): gather every rank's frame on rank 0 over NCCL, inside the timed region
+    if world > 1 and env.comm is not None:
+        rec.update(measure_gather(env, args, codec, fr, x, out, cfg, chunk_rows, raw, payload, r, steps))
+
+    # ---- end to end through the host-buffer C ABI (pinned host memory), every step H2D + D2H
+    xh = None
+    if main:
+        e2e_steps = max(1, min(steps, args.e2e_steps))
+        xh = torch.empty(n, dtype=x.dtype, pin_memory=True)
+        xh.copy_(x)
+        fcap = int(L.spz_frame_max_bytes(esz, n, D, chunk_rows))
+        fh = torch.empty(fcap, dtype=torch.uint8, pin_memory=True)
+        oh = torch.empty(n, dtype=x.dtype, pin_memory=True)
+        del codec, out, fr
+        torch.cuda.empty_cache()
+
+        def e2e_step():
+            fb = L.spz_frame_compress_host(pred, esz, xh.data_ptr(), n, D, chunk_rows, fh.data_ptr(), fcap)
+            spz._lib.check(fb, "spz_frame_compress_host")
+            ne = L.spz_frame_decompress_host(fh.data_ptr(), fb, oh.data_ptr(), n)
+            spz._lib.check(ne, "spz_frame_decompress_host")
+            return fb
+
+        fb = e2e_step()
+        if not torch.equal(oh, xh):
+            raise SystemExit("bench.py: host-buffer round trip mismatch")
+        env.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            fb = e2e_step()
+        torch.cuda.synchronize()
+        t_e2e = env.max_over_ranks([time.perf_counter() - t0])[0]
+        L.spz_release_workspaces()
+        rec["e2e"] = {"value": world * raw * e2e_steps / t_e2e / 1e9, "unit": "GB/s",
+                      "h2d_bytes_per_step": raw + int(fb), "d2h_bytes_per_step": int(fb) + raw, "steps": e2e_steps,
+                      "api": "spz_frame_compress_host + spz_frame_decompress_host (pinned host buffers)"}
+        del fh, oh
+    else:
+        del codec, out, fr
+
+    # ---- the reference on the host cores beside it + byte parity of the whole frame (rank 0)
+    if want_parity:
+        try:
+            ncores = os.cpu_count() or 1
+            xs = (xh.numpy() if xh is not None else x.cpu().numpy()).view(np.uint8 if esz == 1 else np.uint16)
+            clen = chunk_rows * D
+            # N = 1, main config: the WHOLE stream; otherwise a bounded sample of leading chunks
+            if main and world == 1 and not args.cpu_sample_mb:
+                sample_elems = n
+            else:
+                mb = args.cpu_sample_mb or 256
+                if not (main and world == 1):
+                    mb = min(mb, 256)
+                sample_elems = min(n, max(clen, (mb << 20) // esz // clen * clen))
+            rr = reference_chunks(cfg, xs[:sample_elems], chunk_rows, ncores, repeats=1, keep=True)
+            pay_h, off_h, nb_h = host_frame
+            rec["parity"] = parity_vs_reference(esz, rr, pay_h, off_h, nb_h)
+            rec["parity"]["whole_stream"] = sample_elems == n
+            if sample_elems == n:
+                rec["parity"]["ratio_reference"] = rr["ratio"]
+                rec["parity"]["ratio_equal"] = rec["parity"]["gpu_stream_bytes"] == rr["comp_bytes"]
+            cb = {"value": rr["raw"] / (rr["t_enc"] + rr["t_dec"]) / 1e9, "unit": "GB/s", "cores": ncores,
+                  "kind": "reference",
+                  "sample": f"first {rr['raw'] >> 20} MiB of the same stream, same {chunk_rows}-row chunk slices, "
+                            f"oracle/_ref (unmodified reference) on {ncores} threads",
+                  "encode_gbs": rr["raw"] / rr["t_enc"] / 1e9, "decode_gbs": rr["raw"] / rr["t_dec"] / 1e9,
+                  "ratio": rr["ratio"], "roundtrip_ok": rr["roundtrip_ok"]}
+            del rr
+            if main:
+                cb["single_thread_whole_stream"] = reference_single_stream(cfg, xs)
+            rec["cpu_baseline"] = cb
+        except Exception as e:  # noqa: BLE001
+            rec["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference",
+                                   "sample": f"unavailable: {type(e).__name__}: {e}"}
+    del x, xh, host_frame
+    torch.cuda.empty_cache()
+    return rec
+
+
+def measure_query(env, codec, fr, x, out, cfg, chunk_rows, payload):
+    """per-dim REDUCE_SUM / REDUCE_MAX over the frame without materialising it (fused into the lane decoder where
+    the shape allows); reads N/r bytes only"""
+    import torch
+    import sprintz_b200 as spz
+    L = spz.lib()
+    esz, D, pred = cfg["esz"], cfg["D"], cfg["pred"]
+    n = x.numel()
+    raw = n * esz
     try:
-        qres = torch.empty(D, dtype=torch.int64, device=dev)
-        wb = int(L.spz_frame_query_workspace_bytes(esz, n, 0))
+        qres = torch.empty(D, dtype=torch.int64, device=env.dev)
         qwork = out.view(torch.uint8)               # decode+reduce shapes decode into this (>= n * esz bytes)
-        xu = x.view(-1, D)[: (n // D)].to(torch.int32) & ((1 << (8 * esz)) - 1) if n % D == 0 else None
-        query_info = {}
+        info = {}
         for opname, op in (("REDUCE_SUM", 2), ("REDUCE_MAX", 1)):
             def q():
                 spz._lib.check(L.spz_frame_query_dev(pred, esz, op, 0, fr.buf.data_ptr(), fr.buf.numel(), n, D, chunk_rows,
@@ -305,137 +547,141 @@ def run_ours(args, cfg, cfg_name):
             qe[1].record()
             torch.cuda.synchronize()
             tq = qe[0].elapsed_time(qe[1]) / 5e3
-            ok = None
-            if xu is not None:
-                want = xu.sum(0, dtype=torch.int64) if op == 2 else xu.max(0).values.to(torch.int64)
-                ok = bool(torch.equal(qres, want))
             fused = bool(L.spz_last_query_fused())
-            query_info[opname] = {"ms": 1e3 * tq, "fused": fused, "raw_gbs": raw / tq / 1e9,
-                                  "hbm_bytes_read": payload, "hbm_read_frac": payload / tq / 1e9 / peaks()[0],
-                                  "matches_reduction_of_input": ok}
-        del xu
+            ok = None
+            if n % D == 0:
+                want = torch.zeros(D, dtype=torch.int64, device=env.dev)
+                rows_per = max(1, (1 << 26) // D)
+                xv = x.view(-1, D)
+                for a in range(0, xv.shape[0], rows_per):       # slab by slab: no 4x-sized temporaries
+                    s = xv[a: a + rows_per].to(torch.int32) & ((1 << (8 * esz)) - 1)
+                    if op == 2:
+                        want += s.sum(0, dtype=torch.int64)
+                    else:
+                        want = torch.maximum(want, s.max(0).values.to(torch.int64))
+                ok = bool(torch.equal(qres, want))
+            info[opname] = {"ms": 1e3 * tq, "fused": fused, "raw_gbs": raw / tq / 1e9,
+                            "hbm_bytes_read": payload, "hbm_read_frac": payload / tq / 1e9 / peaks()[0],
+                            "matches_reduction_of_input": ok}
+        return info
     except Exception as e:  # noqa: BLE001
-        query_info = {"error": f"{type(e).__name__}: {e}"}
+        return {"error": f"{type(e).__name__}: {e}"}
 
-    # ---- optional exchange step: gather every rank's compressed payload + directory on rank 0 over
-    # NCCL / NVLink.  Not part of `value` (the codec path itself needs no collective); reported beside it.
-    gather_info = None
-    if world > 1:
-        from sprintz_b200.dist import gather_frames, shard_plan
-        plan = shard_plan(world * n, D, chunk_rows, world)
-        po = int(hdr.payload_off)
-        pay = fr.buf[po: po + payload]
-        nchunks = int(hdr.nchunks)
-        sizes = fr.buf[64 + 8 * (nchunks + 1): 64 + 8 * (nchunks + 1) + 4 * nchunks].view(torch.int32).to(torch.int64)
-        for it in range(5):                      # 2 warm-up + 3 timed
-            if it == 2:
-                barrier(); t_g0 = time.perf_counter()
-            got = gather_frames(pay, sizes, plan, dst=0)
-            torch.cuda.synchronize()
-        barrier()
-        t_g = torch.tensor([(time.perf_counter() - t_g0) / 3], dtype=torch.float64, device=dev)
-        dist.all_reduce(t_g, op=dist.ReduceOp.MAX)
-        moved = (world - 1) * payload            # bytes that crossed NVLink into rank 0 (payloads are ~equal)
-        gather_info = {"ms": 1e3 * float(t_g.item()), "payload_bytes_total": world * payload,
-                       "gbs_into_rank0": moved / float(t_g.item()) / 1e9, "backend": "nccl send/recv",
-                       "note": "all-gather of chunk sizes -> exclusive scan -> variable-size send/recv to rank 0"}
-        del got, pay
 
-    # ---- end to end through the host-buffer C ABI (pinned host memory), every step H2D + D2H
-    e2e_steps = max(1, min(steps, args.e2e_steps))
-    xh = torch.empty(n, dtype=x.dtype, pin_memory=True)
-    xh.copy_(x)
-    fcap = int(L.spz_frame_max_bytes(esz, n, D, chunk_rows))
-    fh = torch.empty(fcap, dtype=torch.uint8, pin_memory=True)
-    oh = torch.empty(n, dtype=x.dtype, pin_memory=True)
-    del codec, out
-    torch.cuda.empty_cache()
+def measure_gather(env, args, codec, fr, x, out, cfg, chunk_rows, raw, payload, r, steps):
+    """Encode + NCCL gather of every rank's frame into ONE decodable frame on rank 0 (spz_frame_gather_dev), with the
+    collective inside the timed region; rank 0 decodes the gathered frame and checks it against the inputs."""
+    import torch
+    import torch.distributed as dist
+    import sprintz_b200 as spz
+    world, rank, dev = env.world, env.rank, env.dev
+    try:
+        g = spz.FrameGather(env.comm, codec, dst=0)
+        gf = g.gather(fr)                                   # warm-up + correctness
+        torch.cuda.synchronize()
+        ok = None
+        if rank == 0:
+            ok = g.verify_against_shards(gf, x)             # decodes the gathered frame; shard 0 == x on rank 0
+        env.barrier()
+        reps = max(3, min(steps, 10))
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        for _ in range(reps):
+            g.gather(fr)
+        ev[1].record()
+        for _ in range(reps):                               # encode + gather, streamed (send of range i overlaps encode of i+1)
+            g.encode_and_gather(x)
+        ev[2].record()
+        env.barrier()
+        t_g = ev[0].elapsed_time(ev[1]) / reps / 1e3
+        t_eg = ev[1].elapsed_time(ev[2]) / reps / 1e3
+        t_g, t_eg = env.max_over_ranks([t_g, t_eg])
+        ok2 = None
+        if rank == 0:
+            ok2 = g.verify_against_shards(g.last_frame, x)
+        moved = (world - 1) * payload                       # bytes that crossed NVLink into rank 0 (payloads are ~equal)
+        t_enc_step = r["t_enc"] / steps
+        t_dec_step = r["t_dec"] / steps
+        return {"gather": {"ms": 1e3 * t_g, "payload_bytes_total": world * payload, "gbs_into_rank0": moved / t_g / 1e9,
+                           "backend": "ncclSend/ncclRecv grouped, libsprintz_b200.so (spz_frame_gather_dev)",
+                           "encode_plus_gather_ms": 1e3 * t_eg, "encode_ms": 1e3 * t_enc_step,
+                           "overlap_efficiency": max(t_enc_step, t_g) / t_eg,
+                           "gathered_frame_decodes_to_input": ok, "streamed_frame_decodes_to_input": ok2},
+                "value_with_gather": world * raw / (t_eg + t_dec_step) / 1e9,
+                "encode_with_gather_gbs": world * raw / t_eg / 1e9}
+    except Exception as e:  # noqa: BLE001
+        return {"gather": {"error": f"{type(e).__name__}: {e}"}}
 
-    def e2e_step():
-        fb = L.spz_frame_compress_host(pred, esz, xh.data_ptr(), n, D, chunk_rows, fh.data_ptr(), fcap)
-        spz._lib.check(fb, "spz_frame_compress_host")
-        ne = L.spz_frame_decompress_host(fh.data_ptr(), fb, oh.data_ptr(), n)
-        spz._lib.check(ne, "spz_frame_decompress_host")
-        return fb
 
-    fb = e2e_step()
-    if not torch.equal(oh, xh):
-        raise SystemExit("bench.py: host-buffer round trip mismatch")
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        fb = e2e_step()
-    torch.cuda.synchronize()
-    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    t_e2e = float(t_e2e.item())
-    L.spz_release_workspaces()
+def run_ours(args, cfg, cfg_name):
+    import torch
+    import torch.distributed as dist
+    import sprintz_b200 as spz
 
-    peak, peak_src = peaks()
-    alg_bytes = raw * (1.0 + 1.0 / ratio)               # N*(1 + 1/r), both directions
-    dom_is_dec = t_dec_kernel >= t_enc_kernel
-    dom_t = t_dec_kernel if dom_is_dec else t_enc_kernel
-    full_size = not args.bytes_mb
-    roof = lambda t, kern: {"bound": "hbm", "achieved": alg_bytes / t / 1e9, "peak": peak, "unit": "GB/s",  # noqa: E731
-                            "frac": alg_bytes / t / 1e9 / peak,
-                            "traffic": ncu_traffic(cfg_name, kern) if full_size else None,
-                            "alg_bytes_per_launch": alg_bytes, "ms_per_launch": 1e3 * t, "peak_source": peak_src,
-                            "kernel": kern}
-
-    value = world * raw * steps / t_total / 1e9
-    line = {
-        "metric": "encode+decode GB/s", "value": value, "unit": "GB/s", "n_gpus": world, "steps": steps,
-        "warmup": warm, "ms_per_step": 1e3 * t_total / steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8" if esz == 1 else "u16", "data": "synthetic",
-        "config": {"workload": cfg_name + ": " + cfg["desc"], "elem_bits": 8 * esz, "ndims": D,
-                   "predictor": ("delta", "xff", "rowmajor_delta", "rowmajor_plain")[pred], "bytes_per_gpu": raw, "chunk_rows": chunk_rows,
-                   "nchunks_per_gpu": int(hdr.nchunks), "ratio": ratio,
-                   "l2": "inputs (>= 1 GiB) exceed the 126 MB L2; no explicit flush",
-                   "parallelism": f"chunk-sharded x{world}, no data-path collective"},
-        "encode_gbs": world * raw * steps / t_enc_m / 1e9, "decode_gbs": world * raw * steps / t_dec_m / 1e9,
-        "roofline": roof(dom_t, k_dec if dom_is_dec else k_enc),
-        "roofline_decode": roof(t_dec_kernel, k_dec),
-        "roofline_encode": roof(t_enc_kernel, k_enc),
-        # the stricter read-only form the north star names: HBM bytes READ per launch / kernel time / peak
-        "hbm_read_roofline": {"decode_frac": raw / ratio / t_dec_kernel / 1e9 / peak,
-                              "encode_frac": raw / t_enc_kernel / 1e9 / peak,
-                              "decode_raw_gbs_kernel": raw / t_dec_kernel / 1e9,
-                              "encode_raw_gbs_kernel": raw / t_enc_kernel / 1e9},
-        # overlapped: the directory scan + compaction run on a second stream WHILE the lane encoder runs; then
-        # "compaction" is only the part left exposed after the encoder's last wave and "directory_scan" is ~0
-        "encode_breakdown_ms": {"codec_kernel": 1e3 * t_enc_kernel, "directory_scan": 1e3 * t_scan,
-                                "compaction": 1e3 * t_gather, "overlapped": bool(L.spz_last_encode_overlapped())},
-        "e2e": {"value": world * raw * e2e_steps / t_e2e / 1e9, "unit": "GB/s",
-                "h2d_bytes_per_step": raw + int(fb), "d2h_bytes_per_step": int(fb) + raw, "steps": e2e_steps,
-                "api": "spz_frame_compress_host + spz_frame_decompress_host (pinned host buffers)"},
-        "query": query_info,
-        "gather": gather_info,
-        "gpu_launches": steps * 4,     # encode, directory scan, compaction, decode per step
-        "clocks": clocks,
-    }
-
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    env = Env()
+    pin_to_gpu_numa_node(env.local_rank)
+    if env.world > 1:
+        dist.init_process_group("nccl", device_id=env.dev)
         try:
-            ncores = os.cpu_count() or 1
-            xs = xh.numpy().view(np.uint8 if esz == 1 else np.uint16)
-            sample_elems = min(n, (args.cpu_sample_mb << 20) // esz // (chunk_rows * D) * (chunk_rows * D))
-            r = time_reference(cfg, xs[:sample_elems], chunk_rows, ncores, repeats=3)
-            line["cpu_baseline"] = {
-                "value": r["raw"] / (r["t_enc"] + r["t_dec"]) / 1e9, "unit": "GB/s", "cores": ncores,
-                "kind": "reference",
-                "sample": f"first {r['raw'] >> 20} MiB of the same stream, same {chunk_rows}-row chunk slices, "
-                          f"best of 3, oracle/_ref (unmodified reference) on {ncores} threads",
-                "encode_gbs": r["raw"] / r["t_enc"] / 1e9, "decode_gbs": r["raw"] / r["t_dec"] / 1e9,
-                "ratio": r["ratio"], "roundtrip_ok": r["roundtrip_ok"]}
+            env.comm = spz.Communicator.from_torch(env.rank, env.world)
         except Exception as e:  # noqa: BLE001
-            line["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference",
-                                    "sample": f"unavailable: {type(e).__name__}: {e}"}
-    if rank == 0:
+            print(f"bench.py: NCCL communicator unavailable: {e}", file=sys.stderr)
+    steps, warm = args.steps, args.warmup
+    rec = measure_config(env, args, cfg_name, cfg, steps, warm, main=True)
+    dtype = "u8" if cfg["esz"] == 1 else "u16"
+    line = {"metric": "encode+decode GB/s", "value": rec.pop("value"), "unit": rec.pop("unit"), "n_gpus": env.world,
+            "steps": steps, "warmup": warm, "ms_per_step": rec.pop("ms_per_step"), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic"}
+    line.update(rec)
+    # ---- the other BASELINE configs as sub-records (shorter runs, same measurements)
+    if not args.no_sub and not args.bytes_mb:
+        subs = {}
+        for name in SUB_CONFIGS:
+            if name == cfg_name:
+                continue
+            try:
+                subs[name] = measure_config(env, args, name, dict(CONFIGS[name]), max(3, min(steps, 10)), 3, main=False)
+            except SystemExit:
+                raise
+            except Exception as e:  # noqa: BLE001
+                subs[name] = {"error": f"{type(e).__name__}: {e}"}
+        line["sub_records"] = subs
+    if env.rank == 0:
         emit(line, args.real_stdout)
-    if world > 1:
+    if env.comm is not None:
+        env.comm.close()
+    if env.world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def pin_to_gpu_numa_node(local_rank):
+    """Host buffers of the e2e path are first-touched by this process: keep it on the CPUs of its GPU's NUMA node."""
+    try:
+        import torch
+        pci = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+        if pci is None:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                                 capture_output=True, text=True, timeout=10).stdout.strip()
+            pci = out.lower()[-12:] if out else None
+        if not pci:
+            return
+        node_f = f"/sys/bus/pci/devices/{pci.lower() if len(pci) == 12 else '0000:' + pci.lower()[-7:]}/numa_node"
+        if not os.path.exists(node_f):
+            return
+        node = int(open(node_f).read().strip())
+        if node < 0:
+            return
+        cpus_f = f"/sys/devices/system/node/node{node}/cpulist"
+        cpus = set()
+        for part in open(cpus_f).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
 
 
 def main():
@@ -461,11 +707,13 @@ def _main(real_stdout):
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--config", default=MAIN_CONFIG, choices=sorted(CONFIGS))
     ap.add_argument("--chunk-rows", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-sample-mb", type=int, default=1024)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-mb", type=int, default=0,
+                    help="bound the reference / parity run to the first N MiB (0 = the whole stream at N = 1)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="also skips the byte-parity check (it needs the reference bytes)")
+    ap.add_argument("--no-sub", action="store_true", help="skip the c2 / c4 sub-records")
     ap.add_argument("--bytes-mb", type=int, default=0, help="override the per-GPU stream size (testing only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

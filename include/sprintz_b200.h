@@ -68,7 +68,7 @@ typedef struct spz_frame_header {
 } spz_frame_header;
 
 const char* spz_version(void);
-const char* spz_last_error(void);    /* thread-local description of the last SPZ_E_CUDA */
+const char* spz_last_error(void);    /* thread-local description of the calling thread's last failure; reading clears it */
 
 /* ---------------------------------------------------------------- 1. reference drop-ins (host buffers)
  * Same arguments, return values and stream bytes as sprintz.h:16-32 (the C++ default `write_size=true`
@@ -217,17 +217,22 @@ int64_t spz_frame_compress_host(int predictor, int elem_sz, const void* src, uin
 int64_t spz_frame_decompress_host(const void* frame, uint64_t frame_bytes, void* dest, uint64_t dest_cap_elems);
 
 /* Optional timing of spz_frame_encode_dev's launches with CUDA events on the call's stream (up to 64 calls
- * between enable and collect). ms3 = summed milliseconds of {codec kernel, directory scan, compaction}. */
+ * between enable and collect). ms3 = summed milliseconds of {codec kernel, directory scan, compaction}; for a
+ * pipelined encode: {all codec kernels with the overlapped scan + compaction, 0, the exposed remainder}.
+ * Process-wide measurement switch: not meant to be toggled while other threads encode. */
 int spz_profile_enable(int on);
 int spz_profile_collect(float* ms3, int* ncalls);
 
-/* EXPERIMENTAL, off by default: with on != 0, frame encode behind the lane encoders overlaps the directory scan +
- * compaction with the encoding (a small resident kernel on a second stream chases the encoder chunk by chunk) for
- * frames of up to 148 x 128 chunks -- the verified configuration; larger frames keep the classic path.  Same frame
- * bytes either way.  (on == 2 lifts the size cap: unverified, for tools/overlap_probe.py only.)  Returns the previous
- * setting; spz_last_encode_overlapped() reports what the last spz_frame_encode_dev call did. */
-int spz_set_encode_overlap(int on);
-int spz_last_encode_overlapped(void);
+/* spz_frame_encode_dev cuts long frames into SLABS of whole chunks and runs slab k's directory scan + compaction
+ * on a second stream while slab k+1 is being encoded (the codec kernels are instruction-bound, the compaction is
+ * HBM-bound).  The frame bytes do not depend on the slab count.  slabs: 0 = automatic (whole machine rounds, a
+ * single slab for frames of only a few rounds), 1 = no pipelining (codec kernel, scan, compaction back to back),
+ * n > 1 = n slabs.  Returns the previous setting; spz_last_encode_slabs() = slabs of this thread's last frame encode. */
+int spz_set_encode_pipeline(int slabs);
+int spz_last_encode_slabs(void);
+
+/* number of CUDA kernels this library has launched in this process so far */
+uint64_t spz_kernel_launches(void);
 
 /* Kernel family used by the codec launches: 0 = automatic (lane-per-octet kernels for frames with many chunks of
  * 8 / 16 dims, team-per-chunk kernels otherwise), 1 = team kernels only, 2 = lane kernels whenever the shape
@@ -235,8 +240,50 @@ int spz_last_encode_overlapped(void);
  * Returns the previous setting. */
 int spz_set_kernel_path(int path);
 /* Kernel family used by the most recent encode (decode = 0) or decode (decode = 1) launch of this process:
- * 0 = generic team kernel, 1 = fast team kernel (spz_*_hd_kernel), 2 = lane kernel (spz_*_lane_kernel). */
+ * 0 = generic team kernel, 1 = fast team kernel (spz_*_hd_kernel), 2 = lane kernel (spz_*_lane_kernel),
+ * 3 = wide-row octet kernel (spz_*_wide_kernel).  Per calling thread. */
 int spz_last_kernel_family(int decode);
+
+/* ---------------------------------------------------------------- 4. multi-GPU: one process per GPU
+ * No reference equivalent (the reference is single-threaded host code).  The path shards at chunk granularity with no
+ * data-path collective; the one exchange step is gathering the ranks' compressed frames into ONE decodable frame on
+ * a destination rank, over NCCL (ncclSend / ncclRecv grouped, NVLink / NVSwitch).
+ *
+ * Partition of a global stream of total_len elements over nranks (spz_shard_*): the stream is cut into STRIPES of
+ * stripe_chunks chunks dealt round-robin -- rank r owns global stripes r, r + nranks, ... and holds them back to back in
+ * its local buffer; stripe_chunks == 0 means one contiguous, balanced range of whole chunks per rank.  Only the last
+ * global stripe can be short. */
+typedef void* spz_comm_t;
+#define SPZ_COMM_ID_BYTES 256
+int spz_comm_unique_id(void* id);                                   /* rank 0; broadcast the bytes to every rank (host harness) */
+int spz_comm_init(spz_comm_t* comm, int nranks, int rank, const void* id);      /* on the current CUDA device */
+int spz_comm_destroy(spz_comm_t comm);
+/* elements of the global stream that rank `rank` owns */
+uint64_t spz_shard_len(uint64_t total_len, uint16_t ndims, uint32_t chunk_rows, uint32_t stripe_chunks, int nranks, int rank);
+/* gathers the ranks' local frames (each encoded from that rank's shard with identical codec parameters) into one frame
+ * of the global stream on rank dst.  d_gathered: spz_frame_gather_bytes() on dst (ignored elsewhere).  Asynchronous on
+ * `stream` after a short host-side size exchange. */
+uint64_t spz_frame_gather_max_bytes(int elem_sz, uint64_t total_len, uint16_t ndims, uint32_t chunk_rows);
+int spz_frame_gather_dev(spz_comm_t comm, int dst, uint64_t total_len, uint32_t stripe_chunks, const void* d_frame,
+                         void* d_gathered, uint64_t gathered_cap, spz_stream_t stream);
+/* encode + gather, streamed stripe by stripe: stripe k travels while stripe k+1 is being encoded (stripe_chunks > 0).
+ * The local frame (d_frame) is complete and valid as after spz_frame_encode_dev. */
+int spz_frame_encode_gather_dev(spz_comm_t comm, int dst, int predictor, int elem_sz, const void* d_src, uint64_t total_len,
+                                uint16_t ndims, uint32_t chunk_rows, uint32_t stripe_chunks, void* d_frame, uint64_t frame_cap,
+                                void* d_work, uint64_t work_bytes, void* d_gathered, uint64_t gathered_cap, spz_stream_t stream);
+
+/* ---------------------------------------------------------------- 5. float -> integer quantiser
+ * python/datasets/compress_bench.py:45-60 (_quantize, axis = 0): the step that turns a float dataset (rows x ndims,
+ * row-major) into the integer stream the codecs eat.  Per dim d, exactly the reference's arithmetic:
+ *     y = x - min_d            (in the input precision: float32 or float64)
+ *     y = float32(y) / max(1, float32(max_d - min_d))          (float32 division)
+ *     q = trunc(y * (2^w - 1))                                 (float32 product, w = 8 | 16)
+ * src_f64 != 0: the input is float64.  d_work: spz_quantize_workspace_bytes(ndims) of device scratch (per-dim
+ * min / max).  NaN inputs are not supported (numpy propagates them into an undefined integer cast). */
+uint64_t spz_quantize_workspace_bytes(uint16_t ndims);
+int spz_quantize_dev(int elem_sz, int src_f64, const void* d_src, uint64_t len, uint16_t ndims, void* d_dest,
+                     void* d_work, uint64_t work_bytes, spz_stream_t stream);
+int64_t spz_quantize_host(int elem_sz, int src_f64, const void* src, uint64_t len, uint16_t ndims, void* dest);
 
 /* releases the cached device workspaces of the host-buffer entry points */
 void spz_release_workspaces(void);

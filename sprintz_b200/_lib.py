@@ -85,8 +85,19 @@ SYMBOLS = {
     "spz_frame_query_dev": (_i, [_i, _i, _i, _i, _vp, _u64, _u64, _u16, _u32, _vp, _u64, _vp, _vp, _vp, _u64, _vp]),
     "spz_last_query_fused": (_i, []),
     "spz_reduce_rows_dev": (_i, [_i, _i, _vp, _u64, _u16, _vp, _vp]),
-    "spz_set_encode_overlap": (_i, [_i]),
-    "spz_last_encode_overlapped": (_i, []),
+    "spz_set_encode_pipeline": (_i, [_i]),
+    "spz_last_encode_slabs": (_i, []),
+    "spz_kernel_launches": (_u64, []),
+    "spz_comm_unique_id": (_i, [_vp]),
+    "spz_comm_init": (_i, [C.POINTER(_vp), _i, _i, _vp]),
+    "spz_comm_destroy": (_i, [_vp]),
+    "spz_shard_len": (_u64, [_u64, _u16, _u32, _u32, _i, _i]),
+    "spz_frame_gather_max_bytes": (_u64, [_i, _u64, _u16, _u32]),
+    "spz_frame_gather_dev": (_i, [_vp, _i, _u64, _u32, _vp, _vp, _u64, _vp]),
+    "spz_frame_encode_gather_dev": (_i, [_vp, _i, _i, _i, _vp, _u64, _u16, _u32, _u32, _vp, _u64, _vp, _u64, _vp, _u64, _vp]),
+    "spz_quantize_workspace_bytes": (_u64, [_u16]),
+    "spz_quantize_dev": (_i, [_i, _i, _vp, _u64, _u16, _vp, _vp, _u64, _vp]),
+    "spz_quantize_host": (_i64, [_i, _i, _vp, _u64, _u16, _vp]),
     "spz_compress_host": (_i64, [_i, _i, _vp, _u32, _vp, _u16, _i, C.POINTER(_u64)]),
     "spz_decompress_host": (_i64, [_i, _i, _vp, _vp]),
     "spz_decompress_raw_host": (_i64, [_i, _i, _vp, _vp, _u16, _u32, _u16]),
@@ -141,6 +152,6 @@ def lib() -> C.CDLL:
 def check(rc: int, what: str) -> int:
     if rc < 0:
         msg = ERRORS.get(int(rc), str(rc))
-        detail = lib().spz_last_error().decode() if rc == -2 else ""
+        detail = lib().spz_last_error().decode()
         raise SprintzError(f"{what}: {msg} {detail}")
     return rc

@@ -28,7 +28,8 @@ __all__ = [
     "RM_DELTA", "RM_PLAIN", "RM_XFF8", "compress_rowmajor", "decompress_rowmajor",
     "encode_forecast", "decode_forecast", "forecast_encode_dev", "forecast_decode_dev",
     "encode_xff_forecast", "decode_xff_forecast",
-    "set_encode_overlap", "last_encode_overlapped", "Q_NOOP", "Q_MAX", "Q_SUM", "query", "frame_query", "reduce_rows_dev", "last_query_fused",
+    "set_encode_pipeline", "last_encode_slabs", "kernel_launches", "Communicator", "FrameGather", "shard_len",
+    "quantize", "quantize_dev", "Q_NOOP", "Q_MAX", "Q_SUM", "query", "frame_query", "reduce_rows_dev", "last_query_fused",
 ]
 
 Q_NOOP, Q_MAX, Q_SUM = 0, 1, 2          # QueryTypes::Operation (query.hpp:22-24)
@@ -57,6 +58,9 @@ def compress(predictor: int, x: np.ndarray, ndims: int, write_size: bool = True)
     if esz not in (1, 2):
         raise SprintzError("only 8- and 16-bit elements are supported (sprintz.h:16-32)")
     n = x.size
+    if n >= 1 << 32:
+        raise SprintzError("a single reference stream holds fewer than 2**32 elements (uint32_t len, sprintz.h:16-32); "
+                           "use the frame API")
     if ndims == 0:
         return np.zeros(0, np.uint8), int(lib().spz_compress_host(predictor, esz, None, n, None, 0, 1, None))
     out = np.empty(max_compressed_bytes(esz, n, ndims), np.uint8)
@@ -72,6 +76,8 @@ def compress_rowmajor(kind: int, x: np.ndarray, ndims: int, write_size: bool = T
     RM_PLAIN = compress_rowmajor_{8b,16b}.  -> (stream, the reference's return value in elements)."""
     x = np.ascontiguousarray(x)
     esz = x.dtype.itemsize
+    if x.size >= 1 << 32:
+        raise SprintzError("a single reference stream holds fewer than 2**32 elements (uint32_t len)")
     out = np.empty(max_compressed_bytes(esz, x.size, max(1, ndims)), np.uint8)
     nb = C.c_uint64(0)
     ret = lib().spz_compress_rowmajor_host(kind, esz, x.ctypes.data, x.size, out.ctypes.data, ndims, int(write_size),
@@ -358,14 +364,19 @@ def frame_query(frame: Frame, op: int, materialize: bool = False, out=None, work
     return res, (out if materialize else None)
 
 
-def set_encode_overlap(mode: int) -> int:
-    """0 (default): directory scan + compaction after the encoder; 1: EXPERIMENTAL overlapped scan + copy behind the lane
-    encoders, applied to frames of up to 148 x 128 chunks only (the verified configuration).  -> previous mode"""
-    return int(lib().spz_set_encode_overlap(mode))
+def set_encode_pipeline(slabs: int) -> int:
+    """Slabs of a frame encode (include/sprintz_b200.h: spz_set_encode_pipeline): 0 = automatic, 1 = codec kernel, directory
+    scan and compaction back to back, n > 1 = n slabs whose scan + compaction overlap the next slab's encoding.
+    -> previous setting"""
+    return int(lib().spz_set_encode_pipeline(int(slabs)))
 
 
-def last_encode_overlapped() -> bool:
-    return bool(lib().spz_last_encode_overlapped())
+def last_encode_slabs() -> int:
+    return int(lib().spz_last_encode_slabs())
+
+
+def kernel_launches() -> int:
+    return int(lib().spz_kernel_launches())
 
 
 def last_query_fused() -> bool:
@@ -413,3 +424,141 @@ def frame_decompress_host(frame: np.ndarray) -> np.ndarray:
     ret = lib().spz_frame_decompress_host(frame.ctypes.data, frame.size, out.ctypes.data, out.size)
     check(ret, "spz_frame_decompress_host")
     return out
+
+
+# ------------------------------------------------------------------ float -> integer quantiser
+
+def quantize(x: np.ndarray, ndims: int, dtype=np.uint8) -> np.ndarray:
+    """_quantize(mat, dtype, axis=0) of python/datasets/compress_bench.py:45-60 on a row-major (rows x ndims) float32 /
+    float64 array -> flat uint8 / uint16 array, computed on the GPU."""
+    x = np.ascontiguousarray(x)
+    if x.dtype not in (np.float32, np.float64):
+        raise SprintzError("quantize expects float32 or float64 input")
+    esz = np.dtype(dtype).itemsize
+    out = np.empty(x.size, _UDT[esz])
+    check(lib().spz_quantize_host(esz, int(x.dtype == np.float64), x.ctypes.data, x.size, ndims, out.ctypes.data),
+          "spz_quantize_host")
+    return out
+
+
+def quantize_dev(x, ndims: int, elem_sz: int):
+    """torch CUDA float32 / float64 tensor -> uint8 / int16 (uint16 bit pattern) tensor, on the current stream."""
+    torch = _torch()
+    out = torch.empty(x.numel(), dtype=torch.uint8 if elem_sz == 1 else torch.int16, device=x.device)
+    wb = int(lib().spz_quantize_workspace_bytes(ndims))
+    work = torch.empty(wb, dtype=torch.uint8, device=x.device)
+    check(lib().spz_quantize_dev(elem_sz, int(x.dtype == torch.float64), x.data_ptr(), x.numel(), ndims, out.data_ptr(),
+                                 work.data_ptr(), wb, _stream_ptr()), "spz_quantize_dev")
+    return out
+
+
+# ------------------------------------------------------------------ multi-GPU: one process per GPU (include/sprintz_b200.h section 4)
+
+def shard_len(total_len: int, ndims: int, chunk_rows: int, stripe_chunks: int, nranks: int, rank: int) -> int:
+    """Elements of a global stream that `rank` owns (stripes of stripe_chunks chunks dealt round-robin; 0 = one
+    contiguous balanced range of whole chunks per rank)."""
+    return int(lib().spz_shard_len(total_len, ndims, chunk_rows, stripe_chunks, nranks, rank))
+
+
+class Communicator:
+    """The library's NCCL communicators of this process (one process per GPU)."""
+
+    def __init__(self, handle, rank, world):
+        self.handle, self.rank, self.world = handle, rank, world
+
+    @classmethod
+    def from_torch(cls, rank: int, world: int):
+        """Bootstraps through torch.distributed (already initialised by the harness): rank 0 draws the NCCL unique ids,
+        everyone receives them, spz_comm_init joins."""
+        import torch.distributed as dist
+        torch = _torch()
+        ident = C.create_string_buffer(256)
+        if rank == 0:
+            check(lib().spz_comm_unique_id(ident), "spz_comm_unique_id")
+        backend = dist.get_backend()
+        t = torch.frombuffer(bytearray(ident.raw), dtype=torch.uint8).clone()
+        if backend == "nccl":
+            t = t.cuda()
+        dist.broadcast(t, src=0)
+        blob = bytes(t.cpu().numpy().tobytes())
+        h = C.c_void_p(None)
+        check(lib().spz_comm_init(C.byref(h), world, rank, blob), "spz_comm_init")
+        return cls(h, rank, world)
+
+    def close(self):
+        if self.handle:
+            lib().spz_comm_destroy(self.handle)
+            self.handle = None
+
+
+class FrameGather:
+    """Gathers every rank's frame of one codec shape into ONE decodable frame of the global stream on rank `dst`
+    (spz_frame_gather_dev / spz_frame_encode_gather_dev).  All ranks hold shards of equal length here."""
+
+    def __init__(self, comm: Communicator, codec: FrameCodec, dst: int = 0, stripe_chunks: int = 0):
+        torch = _torch()
+        L = lib()
+        self.comm, self.codec, self.dst, self.stripe_chunks = comm, codec, dst, stripe_chunks
+        self.total_len = codec.len * comm.world
+        for s in (0, stripe_chunks):
+            if shard_len(self.total_len, codec.ndims, codec.chunk_rows, s, comm.world, comm.rank) != codec.len:
+                raise SprintzError("FrameGather: shards must be whole stripes of equal length on every rank")
+        self.cap = 0
+        self.buf = None
+        if comm.rank == dst:
+            self.cap = int(L.spz_frame_gather_max_bytes(codec.elem_sz, self.total_len, codec.ndims, codec.chunk_rows))
+            self.buf = torch.empty(self.cap, dtype=torch.uint8, device=codec.frame.device)
+        self.last_frame = None
+        self.last_stripes = 0
+
+    def _frame(self, stripes):
+        if self.comm.rank != self.dst:
+            return None
+        nb = torch_scalar = None  # noqa: F841
+        torch = _torch()
+        nbytes = torch.zeros(1, dtype=torch.int64, device=self.buf.device)
+        self.last_stripes = stripes
+        self.last_frame = Frame(self.buf, self.codec.predictor, self.codec.elem_sz, self.total_len, self.codec.ndims,
+                                self.codec.chunk_rows, nbytes)
+        return self.last_frame
+
+    def gather(self, frame: Frame):
+        """contiguous shards (rank-major): the global stream is the concatenation of the ranks' shards"""
+        check(lib().spz_frame_gather_dev(self.comm.handle, self.dst, self.total_len, 0, frame.buf.data_ptr(),
+                                         self.buf.data_ptr() if self.buf is not None else None, self.cap, _stream_ptr()),
+              "spz_frame_gather_dev")
+        return self._frame(0)
+
+    def encode_and_gather(self, x):
+        """streamed: stripes of stripe_chunks chunks dealt round-robin; stripe k travels while stripe k+1 is encoded"""
+        c = self.codec
+        check(lib().spz_frame_encode_gather_dev(self.comm.handle, self.dst, c.predictor, c.elem_sz, x.data_ptr(), self.total_len,
+                                                c.ndims, c.chunk_rows, self.stripe_chunks, c.frame.data_ptr(), c.frame_cap,
+                                                c.work.data_ptr(), c.work_bytes,
+                                                self.buf.data_ptr() if self.buf is not None else None, self.cap, _stream_ptr()),
+              "spz_frame_encode_gather_dev")
+        return self._frame(self.stripe_chunks)
+
+    def shard_positions(self, rank: int, stripes: int):
+        """[(global element lo, local element lo, count)] of `rank`'s pieces inside the global stream"""
+        c = self.codec
+        clen = c.chunk_rows * c.ndims
+        if stripes == 0:
+            return [(rank * c.len, 0, c.len)]
+        S = stripes * clen
+        out, k = [], 0
+        while k * S < c.len:
+            n = min(S, c.len - k * S)
+            out.append(((k * self.comm.world + rank) * S, k * S, n))
+            k += 1
+        return out
+
+    def verify_against_shards(self, gframe: Frame, x) -> bool:
+        """dst: decodes the gathered frame and compares this rank's pieces with x (the other ranks' pieces are checked
+        through per-piece checksums by the harness: tests/mgpu_worker.py)."""
+        out = frame_decode(gframe)
+        ok = True
+        for glo, llo, n in self.shard_positions(self.comm.rank, self.last_stripes):
+            ok = ok and bool(_torch().equal(out[glo: glo + n], x[llo: llo + n]))
+        self.decoded = out
+        return ok

@@ -9,66 +9,33 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <atomic>
 #include <mutex>
 #include <vector>
 
-#include "spz_common.cuh"
-#include "../../include/sprintz_b200.h"
-
-namespace spz {
-cudaError_t launch_encode(int elem_sz, int predictor, EncParams p, cudaStream_t stream);
-cudaError_t launch_decode(int elem_sz, int predictor, DecParams p, cudaStream_t stream);
-cudaError_t launch_scan_sizes(const ChunkMeta* meta, uint64_t nchunks, uint64_t* chunk_off, uint32_t* chunk_nbytes,
-                              unsigned long long* tile_state, unsigned int* ticket,
-                              const unsigned long long* base_in, unsigned long long* total_out, int is_last,
-                              spz_frame_header* hdr, const spz_frame_header& hdr_in, uint64_t* d_frame_bytes,
-                              cudaStream_t stream);
-cudaError_t launch_gather(const uint8_t* slots, uint64_t slot_stride, uint64_t nchunks, const uint64_t* chunk_off,
-                          const uint32_t* chunk_nbytes, uint8_t* payload, cudaStream_t stream);
-uint64_t scan_tiles(uint64_t nchunks);
-uint64_t chase_tiles(uint64_t nchunks);
-cudaError_t launch_chase(const ChunkMeta* meta, uint64_t nchunks, const uint8_t* slots, uint64_t slot_stride,
-                         uint64_t* chunk_off, uint32_t* chunk_nbytes, uint8_t* payload, unsigned long long* tile_state,
-                         spz_frame_header* hdr, const spz_frame_header& hdr_in, uint64_t* d_frame_bytes, unsigned int* err,
-                         bool fast, cudaStream_t stream);
-bool encode_uses_lane(int elem_sz, int predictor, EncParams p);
-void set_force_path(int v);
-int get_force_path();
-int last_encode_family();
-int last_decode_family();
-cudaError_t launch_query_fused(int elem_sz, int predictor, DecParams p, cudaStream_t stream);
-cudaError_t launch_reduce_rows(int op, int elem_sz, const uint8_t* src, uint64_t len, uint32_t D,
-                               unsigned long long* result, cudaStream_t stream);
-cudaError_t launch_xff_forecast(int enc, int elem_sz, const uint8_t* src, uint8_t* dst, uint64_t len, uint32_t D,
-                                cudaStream_t stream);
-uint64_t forecast_workspace_bytes(uint64_t len, uint32_t D);
-cudaError_t launch_forecast_encode(int order, int elem_sz, const uint8_t* src, uint8_t* dst, uint64_t len, uint32_t D,
-                                   cudaStream_t stream);
-cudaError_t launch_forecast_decode(int order, int elem_sz, const uint8_t* src, uint8_t* dst, uint64_t len, uint32_t D,
-                                   unsigned long long* state, cudaStream_t stream);
-}  // namespace spz
+#include "spz_host.h"
 
 using namespace spz;
 
 static thread_local char g_err[256] = "";
+static std::atomic<unsigned long long> g_launches{0};
 
-static int cuda_fail(cudaError_t e, const char* where)
+namespace spz {
+int cuda_fail(cudaError_t e, const char* where)
 {
     snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
     return SPZ_E_CUDA;
 }
-#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(e__, #call); } while (0)
+int fail_msg(int code, const char* msg)
+{
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return code;
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace spz
 
-static inline uint64_t align16(uint64_t x) { return (x + 15ull) & ~15ull; }
-static inline bool valid_codec(int predictor, int elem_sz)
-{
-    return (predictor == 0 || predictor == 1) && (elem_sz == 1 || elem_sz == 2);
-}
-// frames also carry the non-RLE sibling codecs: SPZ_RM_DELTA (2), SPZ_RM_PLAIN (3), SPZ_RM_XFF (4, 8-bit only)
-static inline bool valid_frame_codec(int predictor, int elem_sz)
-{
-    return predictor >= 0 && predictor <= 4 && (elem_sz == 1 || elem_sz == 2) && !(predictor == 4 && elem_sz != 1);
-}
+// number of CUDA kernels this library has launched in this process (bench.py's gpu_launches)
+extern "C" uint64_t spz_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // ------------------------------------------------------------------ optional per-kernel timing of the frame encoder
 // bench.py needs the codec kernel's own duration (roofline), separate from scan + compaction. When enabled,
@@ -126,7 +93,14 @@ extern "C" int spz_set_kernel_path(int path)
 extern "C" int spz_last_kernel_family(int decode) { return decode ? last_decode_family() : last_encode_family(); }
 
 extern "C" const char* spz_version(void) { return "sprintz_b200 0.1 (sm_100a)"; }
-extern "C" const char* spz_last_error(void) { return g_err; }
+// description of this thread's most recent failure; reading it clears it
+extern "C" const char* spz_last_error(void)
+{
+    static thread_local char out[256];
+    memcpy(out, g_err, sizeof(out));
+    g_err[0] = 0;
+    return out;
+}
 
 extern "C" uint64_t spz_max_compressed_bytes(int elem_sz, uint64_t len, uint16_t ndims)
 {
@@ -139,10 +113,8 @@ extern "C" uint64_t spz_max_compressed_bytes(int elem_sz, uint64_t len, uint16_t
 
 // ------------------------------------------------------------------ layout of a frame
 
-struct FrameLayout {
-    uint64_t nchunks, chunk_len, off_dir, off_sizes, payload_off;
-};
-static FrameLayout frame_layout(uint64_t len, uint16_t ndims, uint32_t chunk_rows)
+namespace spz {
+FrameLayout frame_layout(uint64_t len, uint16_t ndims, uint32_t chunk_rows)
 {
     FrameLayout f;
     f.chunk_len = (uint64_t)chunk_rows * ndims;
@@ -152,6 +124,7 @@ static FrameLayout frame_layout(uint64_t len, uint16_t ndims, uint32_t chunk_row
     f.payload_off = align16(f.off_sizes + 4 * f.nchunks);
     return f;
 }
+}  // namespace spz
 
 extern "C" uint64_t spz_frame_nchunks(uint64_t len, uint16_t ndims, uint32_t chunk_rows)
 {
@@ -159,7 +132,6 @@ extern "C" uint64_t spz_frame_nchunks(uint64_t len, uint16_t ndims, uint32_t chu
     return frame_layout(len, ndims, chunk_rows).nchunks;
 }
 
-static inline uint64_t align32(uint64_t x) { return (x + 31ull) & ~31ull; }
 static uint64_t slot_stride_of(int elem_sz, uint64_t chunk_len, uint16_t ndims)
 {
     return align32(spz_max_compressed_bytes(elem_sz, chunk_len, ndims));      // whole sectors: 256-bit stores
@@ -172,20 +144,24 @@ extern "C" uint64_t spz_frame_max_bytes(int elem_sz, uint64_t len, uint16_t ndim
     return f.payload_off + f.nchunks * slot_stride_of(elem_sz, f.chunk_len, ndims) + 16;
 }
 
-// workspace = [tile_state | ticket | meta | slots]
-struct WorkLayout { uint64_t off_state, off_ticket, off_meta, off_slots, slot_stride, total; };
-static WorkLayout work_layout(int elem_sz, uint64_t len, uint16_t ndims, uint32_t chunk_rows)
+namespace spz {
+// workspace = [scan tile states, per slab | tickets | running payload totals | error word | meta | slots]
+WorkLayout work_layout(int elem_sz, uint64_t len, uint16_t ndims, uint32_t chunk_rows)
 {
     const FrameLayout f = frame_layout(len, ndims, chunk_rows);
     WorkLayout w;
     w.off_state = 0;
-    w.off_ticket = align16(8 * chase_tiles(f.nchunks));           // >= scan_tiles: either directory kernel fits; ticket at +0, error flag at +4
-    w.off_meta = w.off_ticket + 16;
+    w.state_words = scan_tiles(f.nchunks) + kMaxSlabs;             // every slab rounds its tile count up
+    w.off_ticket = align16(8 * w.state_words);
+    w.off_tot = align16(w.off_ticket + 4 * kMaxSlabs);
+    w.off_err = align16(w.off_tot + 8 * (kMaxSlabs + 1));
+    w.off_meta = w.off_err + 16;
     w.off_slots = align32(w.off_meta + sizeof(ChunkMeta) * f.nchunks);
     w.slot_stride = slot_stride_of(elem_sz, f.chunk_len < len || len == 0 ? f.chunk_len : len, ndims);
     w.total = w.off_slots + f.nchunks * w.slot_stride + 16;
     return w;
 }
+}  // namespace spz
 
 extern "C" uint64_t spz_frame_workspace_bytes(int elem_sz, uint64_t len, uint16_t ndims, uint32_t chunk_rows)
 {
@@ -248,103 +224,202 @@ static int decompress_dev_impl(uint32_t variant, int predictor, int elem_sz, con
     return SPZ_OK;
 }
 
-// second stream + events of the overlapped frame encode; one per process (one process per GPU)
-namespace {
-struct SideStream {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev_begin = nullptr, ev_done = nullptr;
-    cudaError_t init()
-    {
-        if (stream) return cudaSuccess;
+// ------------------------------------------------------------------ the slab-pipelined frame encoder (spz_host.h)
+
+namespace spz {
+
+cudaError_t SidePipe::init(int nslabs)
+{
+    cudaError_t e;
+    if (!side) {
         int lo = 0, hi = 0;
-        cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        if (e != cudaSuccess) return e;
-        e = cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, hi);     // highest priority: its few CTAs get SM slots first
-        if (e != cudaSuccess) return e;
-        e = cudaEventCreateWithFlags(&ev_begin, cudaEventDisableTiming);
-        if (e != cudaSuccess) return e;
-        return cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming);
+        if ((e = cudaDeviceGetStreamPriorityRange(&lo, &hi)) != cudaSuccess) return e;
+        // highest priority: the few CTAs of the directory scan / compaction get SM slots as soon as encoder CTAs retire
+        if ((e = cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&ev_begin, cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming)) != cudaSuccess) return e;
     }
-} g_side;
-int g_overlap_mode = 0;             // 1: overlap directory + compaction with the lane encoders (experimental); 0: run them afterwards
-int g_last_encode_overlapped = 0;
+    for (; nev < nslabs && nev < (int)kMaxSlabs; nev++)
+        if ((e = cudaEventCreateWithFlags(&ev_enc[nev], cudaEventDisableTiming)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+SidePipe& side_pipe() { static SidePipe p; return p; }
+
+}  // namespace spz
+
+namespace {
+std::mutex g_pipe_mu;                       // one call at a time enqueues on the shared side stream
+std::atomic<int> g_pipeline_slabs{0};       // 0: automatic; 1: classic (scan + compaction after the encoder); n: n slabs
+thread_local int g_last_encode_slabs = 1;
 }  // namespace
 
-extern "C" int spz_set_encode_overlap(int on)
+extern "C" int spz_set_encode_pipeline(int slabs)
 {
-    const int old = g_overlap_mode;
-    g_overlap_mode = on == 2 ? 2 : (on ? 1 : 0);      // 2: no tile cap (UNVERIFIED above 148 tiles; tools/overlap_probe.py)
+    const int old = g_pipeline_slabs.load();
+    if (slabs >= 0 && slabs <= (int)kMaxSlabs) g_pipeline_slabs.store(slabs);
     return old;
 }
-extern "C" int spz_last_encode_overlapped(void) { return g_last_encode_overlapped; }
+extern "C" int spz_last_encode_slabs(void) { return g_last_encode_slabs; }
+
+namespace spz {
+
+int frame_job_init(FrameJob& j, int predictor, int elem_sz, const void* d_src, uint64_t len, uint16_t ndims,
+                   uint32_t chunk_rows, void* d_frame, uint64_t frame_cap, void* d_work, uint64_t work_bytes,
+                   uint64_t* d_frame_bytes, uint64_t slab_chunks)
+{
+    if (!valid_frame_codec(predictor, elem_sz) || ndims == 0 || chunk_rows == 0) return SPZ_E_ARG;
+    if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
+    j.predictor = predictor; j.elem_sz = elem_sz; j.ndims = ndims; j.chunk_rows = chunk_rows; j.len = len;
+    j.f = frame_layout(len, ndims, chunk_rows);
+    if (j.f.chunk_len > 0xffffffffull) return SPZ_E_ARG;           // a chunk is one reference stream: uint32_t len
+    j.w = work_layout(elem_sz, len, ndims, chunk_rows);
+    if (work_bytes < j.w.total) return SPZ_E_CAPACITY;
+    if (frame_cap < spz_frame_max_bytes(elem_sz, len, ndims, chunk_rows)) return SPZ_E_CAPACITY;
+    j.d_src = (const uint8_t*)d_src; j.d_frame = (uint8_t*)d_frame; j.work = (uint8_t*)d_work; j.d_frame_bytes = d_frame_bytes;
+    memset(&j.h, 0, sizeof(j.h));
+    j.h.magic = SPZ_FRAME_MAGIC; j.h.version = 1; j.h.elem_sz = (uint8_t)elem_sz; j.h.predictor = (uint8_t)predictor;
+    j.h.ndims = ndims; j.h.chunk_rows = chunk_rows; j.h.len = len; j.h.nchunks = j.f.nchunks; j.h.payload_off = j.f.payload_off;
+
+    // kernel family + machine round, decided ONCE on the whole frame
+    EncParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = j.d_src; p.dst = j.work + j.w.off_slots; p.meta = (ChunkMeta*)(j.work + j.w.off_meta);
+    p.len = len; p.chunk_len = j.f.chunk_len; p.nchunks = j.f.nchunks; p.slot_stride = j.w.slot_stride;
+    p.ndims = ndims; p.write_size = 1;
+    const EncodeProbe pr = probe_encode(elem_sz, predictor, p);
+    if (pr.family < 0) return fail_msg(SPZ_E_CUDA, "probe_encode failed");
+    j.family = pr.family;
+    if (slab_chunks == 0) {
+        // Automatic: slabs of whole machine rounds (every resident lane / team finishes its chunk at about the same
+        // time, so a slab that fills the machine exactly k times drains without a tail), at least ~1/16 of the frame
+        // so the per-slab launches stay negligible, and a single slab when the frame is only a few rounds long.
+        const int want = g_pipeline_slabs.load();
+        if (want > 1) slab_chunks = (j.f.nchunks + want - 1) / want;            // forced (tests, tuning)
+        else if (want == 1 || pr.round_chunks == 0 || j.f.nchunks < 3 * pr.round_chunks) slab_chunks = j.f.nchunks;
+        else {
+            uint64_t rounds = j.f.nchunks / pr.round_chunks;          // >= 3
+            uint64_t per = rounds > 16 ? (rounds + 15) / 16 : 1;      // rounds per slab
+            slab_chunks = per * pr.round_chunks;
+        }
+    }
+    if (slab_chunks == 0) slab_chunks = 1;
+    j.slab_chunks = slab_chunks;
+    j.nslabs = (j.f.nchunks + slab_chunks - 1) / slab_chunks;
+    if (j.nslabs > kMaxSlabs) { j.slab_chunks = (j.f.nchunks + kMaxSlabs - 1) / kMaxSlabs; j.nslabs = (j.f.nchunks + j.slab_chunks - 1) / j.slab_chunks; }
+    j.tiles_per_slab = scan_tiles(j.slab_chunks);
+    if (j.tiles_per_slab * j.nslabs > j.w.state_words) return SPZ_E_CAPACITY;     // cannot happen: state_words = tiles + kMaxSlabs
+    return SPZ_OK;
+}
+
+int frame_job_reset(const FrameJob& j, cudaStream_t st)
+{
+    CK(cudaMemsetAsync(j.work, 0, j.w.off_meta, st));             // scan tile states, tickets, totals, error word
+    return SPZ_OK;
+}
+
+int frame_job_encode_slab(const FrameJob& j, uint64_t k, cudaStream_t st)
+{
+    uint64_t c0, nc, e0, ne;
+    j.slab(k, c0, nc, e0, ne);
+    EncParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = j.d_src + e0 * j.elem_sz; p.dst = j.work + j.w.off_slots + c0 * j.w.slot_stride;
+    p.meta = (ChunkMeta*)(j.work + j.w.off_meta) + c0;
+    p.len = ne; p.chunk_len = j.f.chunk_len; p.nchunks = nc; p.slot_stride = j.w.slot_stride;
+    p.ndims = j.ndims; p.write_size = 1;
+    p.family_pin = (uint32_t)j.family + 1u;
+    CK(launch_encode(j.elem_sz, j.predictor, p, st));
+    return SPZ_OK;
+}
+
+int frame_job_compact_slab(const FrameJob& j, uint64_t k, cudaStream_t st)
+{
+    uint64_t c0, nc, e0, ne;
+    j.slab(k, c0, nc, e0, ne);
+    ChunkMeta* meta = (ChunkMeta*)(j.work + j.w.off_meta);
+    uint64_t* chunk_off = (uint64_t*)(j.d_frame + j.f.off_dir);
+    uint32_t* chunk_nbytes = (uint32_t*)(j.d_frame + j.f.off_sizes);
+    CK(launch_scan_sizes(meta + c0, nc, chunk_off + c0, chunk_nbytes + c0,
+                         (unsigned long long*)(j.work + j.w.off_state) + k * j.tiles_per_slab,
+                         (unsigned int*)(j.work + j.w.off_ticket) + k, j.d_tot() + k, j.d_tot() + k + 1,
+                         k + 1 == j.nslabs, (spz_frame_header*)j.d_frame, j.h, k + 1 == j.nslabs ? j.d_frame_bytes : nullptr,
+                         j.d_err(), st));
+    CK(launch_gather(j.work + j.w.off_slots + c0 * j.w.slot_stride, j.w.slot_stride, nc, chunk_off + c0, chunk_nbytes + c0,
+                     j.d_frame + j.f.payload_off, st));
+    return SPZ_OK;
+}
+
+}  // namespace spz
 
 extern "C" int spz_frame_encode_dev(int predictor, int elem_sz, const void* d_src, uint64_t len, uint16_t ndims,
                                     uint32_t chunk_rows, void* d_frame, uint64_t frame_cap,
                                     void* d_work, uint64_t work_bytes, uint64_t* d_frame_bytes, spz_stream_t stream_)
 {
-    if (!valid_frame_codec(predictor, elem_sz) || ndims == 0 || chunk_rows == 0) return SPZ_E_ARG;
-    if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
     cudaStream_t stream = (cudaStream_t)stream_;
-    const FrameLayout f = frame_layout(len, ndims, chunk_rows);
-    if (f.chunk_len > 0xffffffffull) return SPZ_E_ARG;           // a chunk is one reference stream: uint32_t len
-    const WorkLayout w = work_layout(elem_sz, len, ndims, chunk_rows);
-    if (work_bytes < w.total) return SPZ_E_CAPACITY;
-    if (frame_cap < spz_frame_max_bytes(elem_sz, len, ndims, chunk_rows)) return SPZ_E_CAPACITY;
+    FrameJob j;
+    const int rc = frame_job_init(j, predictor, elem_sz, d_src, len, ndims, chunk_rows, d_frame, frame_cap, d_work,
+                                  work_bytes, d_frame_bytes, 0);
+    if (rc != SPZ_OK) return rc;
+    g_last_encode_slabs = (int)j.nslabs;
+    if (frame_job_reset(j, stream) != SPZ_OK) return SPZ_E_CUDA;
 
-    uint8_t* work = (uint8_t*)d_work;
-    uint8_t* frame = (uint8_t*)d_frame;
-
-    EncParams p;
-    memset(&p, 0, sizeof(p));
-    p.src = (const uint8_t*)d_src; p.dst = work + w.off_slots; p.meta = (ChunkMeta*)(work + w.off_meta);
-    p.len = len; p.chunk_len = f.chunk_len; p.nchunks = f.nchunks; p.slot_stride = w.slot_stride;
-    p.ndims = ndims; p.write_size = 1;
-
-    spz_frame_header h;
-    memset(&h, 0, sizeof(h));
-    h.magic = SPZ_FRAME_MAGIC; h.version = 1; h.elem_sz = (uint8_t)elem_sz; h.predictor = (uint8_t)predictor;
-    h.ndims = ndims; h.chunk_rows = chunk_rows; h.len = len; h.nchunks = f.nchunks; h.payload_off = f.payload_off;
-    uint64_t* chunk_off = (uint64_t*)(frame + f.off_dir);
-    uint32_t* chunk_nbytes = (uint32_t*)(frame + f.off_sizes);
-
-    // EXPERIMENTAL, off by default (spz_set_encode_overlap): overlapped directory + compaction (spz_chase_kernel), only
-    // behind the lane encoders (they publish every chunk record with a release) and only for frames of up to 148
-    // tiles of 128 chunks, where every chase CTA owns one tile -- the configuration that is verified bit-exact
-    // (tests/test_zy_overlap_gpu.py).  Larger frames take the classic path: with several tiles per CTA the waits ran into
-    // their bounds on BASELINE-sized frames and the cause is not isolated yet.
-    g_last_encode_overlapped = 0;
-    if (g_overlap_mode != 0 && (chase_tiles(f.nchunks) <= 148 || g_overlap_mode == 2) && encode_uses_lane(elem_sz, predictor, p)) {
-        CK(g_side.init());
-        CK(cudaMemsetAsync(work, 0, w.off_slots, stream));        // tile states, error flag AND the chunk records (nbytes == 0: not ready)
-        CK(cudaEventRecord(g_side.ev_begin, stream));
-        CK(cudaStreamWaitEvent(g_side.stream, g_side.ev_begin, 0));
-        CK(launch_chase(p.meta, f.nchunks, work + w.off_slots, w.slot_stride, chunk_off, chunk_nbytes, frame + f.payload_off,
-                        (unsigned long long*)(work + w.off_state), (spz_frame_header*)frame, h, d_frame_bytes,
-                        (unsigned int*)(work + w.off_ticket + 4), g_overlap_mode == 2, g_side.stream));
-        CK(cudaEventRecord(g_side.ev_done, g_side.stream));
+    if (j.nslabs == 1) {            // classic: codec kernel, directory scan, compaction back to back on the caller's stream
         PROF_MARK(0);
-        CK(launch_encode(elem_sz, predictor, p, stream));
+        if (int r = frame_job_encode_slab(j, 0, stream)) return r;
         PROF_MARK(1);
+        uint64_t c0, nc, e0, ne;
+        j.slab(0, c0, nc, e0, ne);
+        ChunkMeta* meta = (ChunkMeta*)(j.work + j.w.off_meta);
+        uint64_t* chunk_off = (uint64_t*)(j.d_frame + j.f.off_dir);
+        uint32_t* chunk_nbytes = (uint32_t*)(j.d_frame + j.f.off_sizes);
+        CK(launch_scan_sizes(meta, nc, chunk_off, chunk_nbytes, (unsigned long long*)(j.work + j.w.off_state),
+                             (unsigned int*)(j.work + j.w.off_ticket), nullptr, j.d_tot() + 1, 1,
+                             (spz_frame_header*)j.d_frame, j.h, d_frame_bytes, j.d_err(), stream));
         PROF_MARK(2);
-        CK(cudaStreamWaitEvent(stream, g_side.ev_done, 0));       // the exposed remainder of the copy (last wave of chunks)
+        CK(launch_gather(j.work + j.w.off_slots, j.w.slot_stride, nc, chunk_off, chunk_nbytes, j.d_frame + j.f.payload_off, stream));
         PROF_MARK(3);
         PROF_NEXT();
-        g_last_encode_overlapped = 1;
         return SPZ_OK;
     }
 
-    CK(cudaMemsetAsync(work, 0, w.off_meta, stream));             // scan tile states + ticket
+    // pipelined: slab k's scan + compaction run on the side stream while slab k+1 is being encoded
+    std::lock_guard<std::mutex> lk(g_pipe_mu);
+    SidePipe& sp = side_pipe();
+    CK(sp.init((int)j.nslabs));
+    CK(cudaEventRecord(sp.ev_begin, stream));
+    CK(cudaStreamWaitEvent(sp.side, sp.ev_begin, 0));              // the reset above, and whatever the caller queued before
     PROF_MARK(0);
-    CK(launch_encode(elem_sz, predictor, p, stream));
+    for (uint64_t k = 0; k < j.nslabs; k++) {
+        if (int r = frame_job_encode_slab(j, k, stream)) return r;
+        CK(cudaEventRecord(sp.ev_enc[k], stream));
+        CK(cudaStreamWaitEvent(sp.side, sp.ev_enc[k], 0));
+        if (int r = frame_job_compact_slab(j, k, sp.side)) return r;
+    }
     PROF_MARK(1);
-    CK(launch_scan_sizes(p.meta, f.nchunks, chunk_off, chunk_nbytes,
-                         (unsigned long long*)(work + w.off_state), (unsigned int*)(work + w.off_ticket),
-                         nullptr, nullptr, 1, (spz_frame_header*)frame, h, d_frame_bytes, stream));
     PROF_MARK(2);
-    CK(launch_gather(work + w.off_slots, w.slot_stride, f.nchunks, chunk_off, chunk_nbytes,
-                     frame + f.payload_off, stream));
+    CK(cudaEventRecord(sp.ev_done, sp.side));
+    CK(cudaStreamWaitEvent(stream, sp.ev_done, 0));               // the exposed remainder: the last slab's compaction
     PROF_MARK(3);
     PROF_NEXT();
+    return SPZ_OK;
+}
+
+// The directory of a frame is input from outside: it is validated on the device before any decoder runs, and the
+// decoders bound every chunk by its directory span.  *d_err (optional) is OR-ed with 1 when the directory is bad.
+static int frame_decode_params(DecParams& p, int predictor, int elem_sz, const void* d_frame, uint64_t frame_bytes,
+                               uint64_t len, uint16_t ndims, uint32_t chunk_rows, void* d_dest, spz_chunk_meta* d_status)
+{
+    if (!valid_frame_codec(predictor, elem_sz) || ndims == 0 || chunk_rows == 0) return SPZ_E_ARG;
+    if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
+    const FrameLayout f = frame_layout(len, ndims, chunk_rows);
+    if (frame_bytes < f.payload_off + 16) return SPZ_E_STREAM;
+    const uint8_t* frame = (const uint8_t*)d_frame;
+    memset(&p, 0, sizeof(p));
+    p.src = frame + f.payload_off; p.offsets = (const uint64_t*)(frame + f.off_dir);
+    p.dst = (uint8_t*)d_dest; p.meta = (ChunkMeta*)d_status;
+    p.len = len; p.chunk_len = f.chunk_len; p.nchunks = f.nchunks; p.dst_cap = len;
+    p.ndims = ndims; p.has_meta = 1;
+    p.src_end = frame + frame_bytes;
     return SPZ_OK;
 }
 
@@ -352,19 +427,10 @@ extern "C" int spz_frame_decode_dev(int predictor, int elem_sz, const void* d_fr
                                     uint64_t len, uint16_t ndims, uint32_t chunk_rows, void* d_dest,
                                     uint64_t dest_cap_elems, spz_chunk_meta* d_status, spz_stream_t stream)
 {
-    if (!valid_frame_codec(predictor, elem_sz) || ndims == 0 || chunk_rows == 0) return SPZ_E_ARG;
-    if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
     if (dest_cap_elems < len) return SPZ_E_CAPACITY;
-    const FrameLayout f = frame_layout(len, ndims, chunk_rows);
-    const uint8_t* frame = (const uint8_t*)d_frame;
     DecParams p;
-    memset(&p, 0, sizeof(p));
-    p.src = frame + f.payload_off; p.offsets = (const uint64_t*)(frame + f.off_dir);
-    p.dst = (uint8_t*)d_dest; p.meta = (ChunkMeta*)d_status;
-    p.len = len; p.chunk_len = f.chunk_len; p.nchunks = f.nchunks; p.dst_cap = len;
-    p.ndims = ndims; p.has_meta = 1;
-    if (frame_bytes < f.payload_off + 16) return SPZ_E_STREAM;
-    p.src_end = frame + frame_bytes;
+    const int rc = frame_decode_params(p, predictor, elem_sz, d_frame, frame_bytes, len, ndims, chunk_rows, d_dest, d_status);
+    if (rc != SPZ_OK) return rc;
     CK(launch_decode(elem_sz, predictor, p, (cudaStream_t)stream));
     return SPZ_OK;
 }
@@ -756,7 +822,7 @@ extern "C" int spz_forecast_decode_dev(int order, int elem_sz, const void* d_src
     if (((uintptr_t)d_src & (elem_sz - 1)) || ((uintptr_t)d_dest & (elem_sz - 1)) || ((uintptr_t)d_work & 7)) return SPZ_E_ARG;
     if (work_bytes < forecast_workspace_bytes(len, ndims)) return SPZ_E_CAPACITY;
     CK(launch_forecast_decode(order, elem_sz, (const uint8_t*)d_src, (uint8_t*)d_dest, len, ndims,
-                              (unsigned long long*)d_work, (cudaStream_t)stream));
+                              (unsigned long long*)d_work, nullptr, (cudaStream_t)stream));
     return SPZ_OK;
 }
 
@@ -802,7 +868,7 @@ extern "C" int64_t spz_decode_forecast_host(int order, int elem_sz, const void* 
     if (bytes) {
         CK(cudaMemcpyAsync(g_cache.buf[0], src, bytes, cudaMemcpyHostToDevice, st));
         CK(launch_forecast_decode(order, elem_sz, (const uint8_t*)g_cache.buf[0], (uint8_t*)g_cache.buf[1], len, ndims,
-                                  (unsigned long long*)g_cache.buf[2], st));
+                                  (unsigned long long*)g_cache.buf[2], nullptr, st));
         CK(cudaMemcpyAsync(dest, g_cache.buf[1], bytes, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
     }
@@ -860,6 +926,39 @@ extern "C" uint32_t spz_decode_doubledelta_rowmajor_8b(const int8_t* s, uint32_t
 extern "C" uint32_t spz_encode_doubledelta_rowmajor_16b(const uint16_t* s, uint32_t n, int16_t* d, uint16_t nd, int ws) { return (uint32_t)spz_encode_forecast_host(2, 2, s, n, d, nd, ws); }
 extern "C" uint32_t spz_decode_doubledelta_rowmajor_16b(const int16_t* s, uint32_t n, uint16_t* d, uint16_t nd) { return (uint32_t)spz_decode_forecast_host(2, 2, s, n, d, nd); }
 
+// ------------------------------------------------------------------ float -> integer quantiser
+// python/datasets/compress_bench.py:45-60 (_quantize, axis = 0); kernels in spz_quant.cu.
+
+extern "C" uint64_t spz_quantize_workspace_bytes(uint16_t ndims) { return quantize_workspace_bytes(ndims); }
+
+extern "C" int spz_quantize_dev(int elem_sz, int src_f64, const void* d_src, uint64_t len, uint16_t ndims, void* d_dest,
+                                void* d_work, uint64_t work_bytes, spz_stream_t stream)
+{
+    if ((elem_sz != 1 && elem_sz != 2) || ndims == 0 || (len && (!d_src || !d_dest))) return SPZ_E_ARG;
+    if (!d_work || ((uintptr_t)d_work & 7) || work_bytes < quantize_workspace_bytes(ndims)) return SPZ_E_CAPACITY;
+    CK(launch_quantize(elem_sz, src_f64 ? 1 : 0, d_src, len, ndims, d_dest, d_work, (cudaStream_t)stream));
+    return SPZ_OK;
+}
+
+extern "C" int64_t spz_quantize_host(int elem_sz, int src_f64, const void* src, uint64_t len, uint16_t ndims, void* dest)
+{
+    if ((elem_sz != 1 && elem_sz != 2) || ndims == 0) return SPZ_E_ARG;
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    cudaStream_t st;
+    CK(g_cache.get_stream(&st));
+    const uint64_t in_bytes = len * (src_f64 ? 8ull : 4ull);
+    CK(g_cache.ensure(0, in_bytes + 16));
+    CK(g_cache.ensure(1, len * elem_sz + 16));
+    CK(g_cache.ensure(2, quantize_workspace_bytes(ndims) + 16));
+    if (len) {
+        CK(cudaMemcpyAsync(g_cache.buf[0], src, in_bytes, cudaMemcpyHostToDevice, st));
+        CK(launch_quantize(elem_sz, src_f64 ? 1 : 0, g_cache.buf[0], len, ndims, g_cache.buf[1], g_cache.buf[2], st));
+        CK(cudaMemcpyAsync(dest, g_cache.buf[1], len * elem_sz, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return (int64_t)len;
+}
+
 // ------------------------------------------------------------------ frame, host buffers
 //
 // Both calls are software pipelines over SLABS of whole chunks on three streams (upload / kernels /
@@ -875,10 +974,11 @@ constexpr uint64_t kSlabBytes = 64ull << 20;     // raw bytes per pipeline slab
 
 struct Pipe {
     cudaStream_t up = nullptr, run = nullptr, down = nullptr;
-    static constexpr int kMaxSlabs = 4096;
-    cudaEvent_t ev_up[kMaxSlabs], ev_run[kMaxSlabs];
+    static constexpr int kMaxPipe = (int)kMaxSlabs;
+    cudaEvent_t ev_up[kMaxPipe], ev_run[kMaxPipe];
     int nev = 0;
     unsigned long long* h_tot = nullptr;          // pinned: running payload offset after each slab
+    unsigned int* h_err = nullptr;                // pinned: the encode job's error word
     cudaError_t init(int nslabs)
     {
         cudaError_t e;
@@ -886,13 +986,20 @@ struct Pipe {
             if ((e = cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking)) != cudaSuccess) return e;
             if ((e = cudaStreamCreateWithFlags(&run, cudaStreamNonBlocking)) != cudaSuccess) return e;
             if ((e = cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking)) != cudaSuccess) return e;
-            if ((e = cudaMallocHost(&h_tot, sizeof(unsigned long long) * kMaxSlabs)) != cudaSuccess) return e;
+            if ((e = cudaMallocHost(&h_tot, sizeof(unsigned long long) * kMaxPipe)) != cudaSuccess) return e;
+            if ((e = cudaMallocHost(&h_err, 64)) != cudaSuccess) return e;
         }
-        for (; nev < nslabs; nev++) {
+        for (; nev < nslabs && nev < kMaxPipe; nev++) {
             if ((e = cudaEventCreateWithFlags(&ev_up[nev], cudaEventDisableTiming)) != cudaSuccess) return e;
             if ((e = cudaEventCreateWithFlags(&ev_run[nev], cudaEventDisableTiming)) != cudaSuccess) return e;
         }
         return cudaSuccess;
+    }
+    // every exit of the host frame calls goes through here: nothing may still be reading the caller's buffers or
+    // the cached device buffers once the call returns and the lock is released
+    void drain()
+    {
+        if (up) { cudaStreamSynchronize(up); cudaStreamSynchronize(run); cudaStreamSynchronize(down); }
     }
     void release()
     {
@@ -900,9 +1007,11 @@ struct Pipe {
         nev = 0;
         if (up) { cudaStreamDestroy(up); cudaStreamDestroy(run); cudaStreamDestroy(down); up = run = down = nullptr; }
         if (h_tot) { cudaFreeHost(h_tot); h_tot = nullptr; }
+        if (h_err) { cudaFreeHost(h_err); h_err = nullptr; }
     }
 };
 Pipe g_pipe;
+struct DrainOnExit { ~DrainOnExit() { g_pipe.drain(); } };
 }  // namespace
 
 extern "C" int64_t spz_frame_compress_host(int predictor, int elem_sz, const void* src_, uint64_t len, uint16_t ndims,
@@ -918,68 +1027,42 @@ extern "C" int64_t spz_frame_compress_host(int predictor, int elem_sz, const voi
     const WorkLayout w = work_layout(elem_sz, len, ndims, chunk_rows);
     const uint64_t in_bytes = len * (uint64_t)elem_sz;
     const uint64_t fmax = spz_frame_max_bytes(elem_sz, len, ndims, chunk_rows);
+    if (frame_cap < f.payload_off + 16) return SPZ_E_CAPACITY;
     const uint64_t chunk_bytes = f.chunk_len * elem_sz;
     uint64_t slab_chunks = kSlabBytes / (chunk_bytes ? chunk_bytes : 1);
     if (slab_chunks == 0) slab_chunks = 1;
-    uint64_t nslabs = (f.nchunks + slab_chunks - 1) / slab_chunks;
-    if (nslabs > (uint64_t)Pipe::kMaxSlabs) { slab_chunks = (f.nchunks + Pipe::kMaxSlabs - 1) / Pipe::kMaxSlabs; nslabs = (f.nchunks + slab_chunks - 1) / slab_chunks; }
-    const uint64_t tiles_per_slab = scan_tiles(slab_chunks);
-    // workspace: per-slab scan states + tickets + running totals, then meta + slots as in work_layout
-    const uint64_t off_state = 0;
-    const uint64_t off_ticket = align16(8 * tiles_per_slab * nslabs);
-    const uint64_t off_tot = align16(off_ticket + 4 * nslabs);
-    const uint64_t off_meta = align16(off_tot + 8 * (nslabs + 1));
-    const uint64_t off_slots = align32(off_meta + sizeof(ChunkMeta) * f.nchunks);
-    const uint64_t wtotal = off_slots + f.nchunks * w.slot_stride + 16;
-    CK(g_pipe.init((int)nslabs));
     CK(g_cache.ensure(0, in_bytes + 16));
     CK(g_cache.ensure(1, fmax + 16));
-    CK(g_cache.ensure(2, wtotal + 16));
+    CK(g_cache.ensure(2, w.total + 16));
     uint8_t* d_in = (uint8_t*)g_cache.buf[0];
     uint8_t* d_frame = (uint8_t*)g_cache.buf[1];
-    uint8_t* work = (uint8_t*)g_cache.buf[2];
-    if (frame_cap < f.payload_off + 16) return SPZ_E_CAPACITY;
-
-    CK(cudaMemsetAsync(work, 0, off_meta, g_pipe.run));
-    spz_frame_header h;
-    memset(&h, 0, sizeof(h));
-    h.magic = SPZ_FRAME_MAGIC; h.version = 1; h.elem_sz = (uint8_t)elem_sz; h.predictor = (uint8_t)predictor;
-    h.ndims = ndims; h.chunk_rows = chunk_rows; h.len = len; h.nchunks = f.nchunks; h.payload_off = f.payload_off;
-    uint64_t* chunk_off = (uint64_t*)(d_frame + f.off_dir);
-    uint32_t* chunk_nbytes = (uint32_t*)(d_frame + f.off_sizes);
-    unsigned long long* d_tot = (unsigned long long*)(work + off_tot);     // d_tot[k] = payload offset before slab k
-    ChunkMeta* meta = (ChunkMeta*)(work + off_meta);
+    FrameJob j;
+    int rc = frame_job_init(j, predictor, elem_sz, d_in, len, ndims, chunk_rows, d_frame, fmax + 16, g_cache.buf[2], w.total + 16,
+                            nullptr, slab_chunks);
+    if (rc != SPZ_OK) return rc;
+    CK(g_pipe.init((int)j.nslabs));
+    DrainOnExit drain;                                  // error exits included
+    if ((rc = frame_job_reset(j, g_pipe.run)) != SPZ_OK) return rc;
 
     uint64_t copied = 0;        // payload bytes already on their way to the host
-    int rc_cap = SPZ_OK;
-    for (uint64_t k = 0; k <= nslabs; k++) {
-        if (k < nslabs) {
-            const uint64_t c0 = k * slab_chunks;
-            const uint64_t nc = (c0 + slab_chunks <= f.nchunks) ? slab_chunks : (f.nchunks - c0);
-            const uint64_t e0 = c0 * f.chunk_len;
-            const uint64_t ne = (e0 + nc * f.chunk_len <= len) ? nc * f.chunk_len : (len - e0);
+    for (uint64_t k = 0; k <= j.nslabs; k++) {
+        if (k < j.nslabs) {
+            uint64_t c0, nc, e0, ne;
+            j.slab(k, c0, nc, e0, ne);
             if (ne) CK(cudaMemcpyAsync(d_in + e0 * elem_sz, src + e0 * elem_sz, ne * elem_sz, cudaMemcpyHostToDevice, g_pipe.up));
             CK(cudaEventRecord(g_pipe.ev_up[k], g_pipe.up));
             CK(cudaStreamWaitEvent(g_pipe.run, g_pipe.ev_up[k], 0));
-            EncParams p;
-            memset(&p, 0, sizeof(p));
-            p.src = d_in + e0 * elem_sz; p.dst = work + off_slots + c0 * w.slot_stride; p.meta = meta + c0;
-            p.len = ne; p.chunk_len = f.chunk_len; p.nchunks = nc; p.slot_stride = w.slot_stride;
-            p.ndims = ndims; p.write_size = 1;
-            CK(launch_encode(elem_sz, predictor, p, g_pipe.run));
-            CK(launch_scan_sizes(meta + c0, nc, chunk_off + c0, chunk_nbytes + c0,
-                                 (unsigned long long*)(work + off_state) + k * tiles_per_slab,
-                                 (unsigned int*)(work + off_ticket) + k, d_tot + k, d_tot + k + 1,
-                                 k + 1 == nslabs, (spz_frame_header*)d_frame, h, nullptr, g_pipe.run));
-            CK(launch_gather(work + off_slots + c0 * w.slot_stride, w.slot_stride, nc, chunk_off + c0, chunk_nbytes + c0,
-                             d_frame + f.payload_off, g_pipe.run));
-            CK(cudaMemcpyAsync(&g_pipe.h_tot[k], d_tot + k + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, g_pipe.run));
+            if ((rc = frame_job_encode_slab(j, k, g_pipe.run)) != SPZ_OK) return rc;
+            if ((rc = frame_job_compact_slab(j, k, g_pipe.run)) != SPZ_OK) return rc;
+            CK(cudaMemcpyAsync(&g_pipe.h_tot[k], j.d_tot() + k + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, g_pipe.run));
+            if (k + 1 == j.nslabs)
+                CK(cudaMemcpyAsync(g_pipe.h_err, j.d_err(), sizeof(unsigned int), cudaMemcpyDeviceToHost, g_pipe.run));
             CK(cudaEventRecord(g_pipe.ev_run[k], g_pipe.run));
         }
         if (k >= 1) {       // slab k-1 is compacted: its payload range can leave while slab k runs
             CK(cudaEventSynchronize(g_pipe.ev_run[k - 1]));
             const uint64_t upto = g_pipe.h_tot[k - 1];
-            if (f.payload_off + upto + 16 > frame_cap) { rc_cap = SPZ_E_CAPACITY; break; }
+            if (f.payload_off + upto + 16 > frame_cap) return SPZ_E_CAPACITY;
             CK(cudaStreamWaitEvent(g_pipe.down, g_pipe.ev_run[k - 1], 0));
             if (upto > copied)
                 CK(cudaMemcpyAsync(hframe + f.payload_off + copied, d_frame + f.payload_off + copied, upto - copied,
@@ -987,7 +1070,7 @@ extern "C" int64_t spz_frame_compress_host(int predictor, int elem_sz, const voi
             copied = upto;
         }
     }
-    if (rc_cap != SPZ_OK) { cudaDeviceSynchronize(); return rc_cap; }
+    if (*g_pipe.h_err != 0) return fail_msg(SPZ_E_CAPACITY, "a chunk encoder overflowed its slot");
     // header + directory (written by the last slab's scan) and the 16 bytes of read slack
     CK(cudaMemcpyAsync(hframe, d_frame, f.payload_off, cudaMemcpyDeviceToHost, g_pipe.down));
     CK(cudaStreamSynchronize(g_pipe.down));
@@ -1006,16 +1089,22 @@ extern "C" int64_t spz_frame_decompress_host(const void* frame_, uint64_t frame_
     if (h.magic != SPZ_FRAME_MAGIC || h.frame_bytes > frame_bytes || !valid_frame_codec(h.predictor, h.elem_sz) ||
         h.ndims == 0 || h.ndims > SPZ_MAX_NDIMS || h.chunk_rows == 0) return SPZ_E_STREAM;
     if (dest_cap_elems < h.len) return SPZ_E_CAPACITY;
+    if (h.len > (1ull << 48)) return SPZ_E_STREAM;                  // keeps the layout arithmetic far from overflow
     const FrameLayout f = frame_layout(h.len, (uint16_t)h.ndims, h.chunk_rows);
-    if (f.nchunks != h.nchunks || f.payload_off != h.payload_off || h.frame_bytes < f.payload_off + 16) return SPZ_E_STREAM;
-    const uint64_t* hoff = (const uint64_t*)(hframe + f.off_dir);      // the directory is readable on the host
+    if (f.nchunks != h.nchunks || f.payload_off != h.payload_off || h.frame_bytes < f.payload_off + 16 ||
+        h.payload_bytes != h.frame_bytes - f.payload_off - 16) return SPZ_E_STREAM;
+    // the directory is input from outside: every entry 16-byte aligned, non-decreasing, inside the payload
+    const uint64_t* hoff = (const uint64_t*)(hframe + f.off_dir);
+    if (hoff[0] != 0 || hoff[f.nchunks] != h.payload_bytes) return SPZ_E_STREAM;
+    for (uint64_t c = 0; c < f.nchunks; c++)
+        if ((hoff[c] & 15ull) || hoff[c + 1] < hoff[c] || hoff[c + 1] > h.payload_bytes) return SPZ_E_STREAM;
     std::lock_guard<std::mutex> lk(g_cache.mu);
     const int esz = h.elem_sz;
     const uint64_t chunk_bytes = f.chunk_len * esz;
     uint64_t slab_chunks = kSlabBytes / (chunk_bytes ? chunk_bytes : 1);
     if (slab_chunks == 0) slab_chunks = 1;
     uint64_t nslabs = (f.nchunks + slab_chunks - 1) / slab_chunks;
-    if (nslabs > (uint64_t)Pipe::kMaxSlabs) { slab_chunks = (f.nchunks + Pipe::kMaxSlabs - 1) / Pipe::kMaxSlabs; nslabs = (f.nchunks + slab_chunks - 1) / slab_chunks; }
+    if (nslabs > (uint64_t)Pipe::kMaxPipe) { slab_chunks = (f.nchunks + Pipe::kMaxPipe - 1) / Pipe::kMaxPipe; nslabs = (f.nchunks + slab_chunks - 1) / slab_chunks; }
     CK(g_pipe.init((int)nslabs));
     CK(g_cache.ensure(0, h.len * esz + 16));
     CK(g_cache.ensure(1, h.frame_bytes + 32));
@@ -1023,7 +1112,7 @@ extern "C" int64_t spz_frame_decompress_host(const void* frame_, uint64_t frame_
     uint8_t* d_out = (uint8_t*)g_cache.buf[0];
     uint8_t* d_frame = (uint8_t*)g_cache.buf[1];
     spz_chunk_meta* d_status = (spz_chunk_meta*)g_cache.buf[2];
-    if (hoff[f.nchunks] + f.payload_off + 16 > h.frame_bytes) return SPZ_E_STREAM;
+    DrainOnExit drain;                                  // error exits included
 
     // header + directory first (small), then payload slabs
     CK(cudaMemcpyAsync(d_frame, hframe, f.payload_off, cudaMemcpyHostToDevice, g_pipe.up));
@@ -1031,7 +1120,6 @@ extern "C" int64_t spz_frame_decompress_host(const void* frame_, uint64_t frame_
         const uint64_t c0 = k * slab_chunks;
         const uint64_t nc = (c0 + slab_chunks <= f.nchunks) ? slab_chunks : (f.nchunks - c0);
         const uint64_t b0 = hoff[c0], b1 = hoff[c0 + nc] + (k + 1 == nslabs ? 16 : 0);
-        if (b1 < b0 || f.payload_off + b1 > h.frame_bytes) return SPZ_E_STREAM;
         CK(cudaMemcpyAsync(d_frame + f.payload_off + b0, hframe + f.payload_off + b0, b1 - b0, cudaMemcpyHostToDevice, g_pipe.up));
         CK(cudaEventRecord(g_pipe.ev_up[k], g_pipe.up));
         CK(cudaStreamWaitEvent(g_pipe.run, g_pipe.ev_up[k], 0));
@@ -1043,7 +1131,7 @@ extern "C" int64_t spz_frame_decompress_host(const void* frame_, uint64_t frame_
         p.dst = d_out + e0 * esz; p.meta = (ChunkMeta*)(d_status + c0);
         p.len = ne; p.chunk_len = f.chunk_len; p.nchunks = nc; p.dst_cap = ne;
         p.ndims = h.ndims; p.has_meta = 1;
-        p.src_end = d_frame + f.payload_off + b1;
+        p.src_end = d_frame + f.payload_off + hoff[c0 + nc] + 16;      // 16 bytes of read slack: the next slab's first bytes or the frame's own slack
         CK(launch_decode(esz, h.predictor, p, g_pipe.run));
         CK(cudaEventRecord(g_pipe.ev_run[k], g_pipe.run));
         CK(cudaStreamWaitEvent(g_pipe.down, g_pipe.ev_run[k], 0));

@@ -51,6 +51,7 @@ struct EncParams {
     uint32_t       out_cap;   // staging capacity (bytes)
     uint32_t       teams_per_cta;
     uint32_t       variant;   // 0: RLE codecs (sprintz.h) | 1: compress_rowmajor_delta_* | 2: compress_rowmajor_* (no RLE, 6-byte metadata)
+    uint32_t       family_pin;// 0: the launcher picks the kernel family | f + 1: family f was chosen for the whole frame (slabs must not re-decide)
 };
 
 struct DecParams {

@@ -12,7 +12,7 @@
 //   runs     delta: repeat the previous row; FIRE: free-run the predictor with err = 0
 //            (sprintz_delta_rle.cpp:640-667, sprintz_xff_rle.cpp:828-958 -- but with the *correct*
 //            coefficients)
-#include "spz_common.cuh"
+#include "spz_host.h"
 
 namespace spz {
 
@@ -47,7 +47,12 @@ __global__ void __launch_bounds__(kThreads) spz_decode_kernel(const DecParams p)
         s_pv[k * TEAM + t] = 0; s_pd[k * TEAM + t] = 0; s_ct[k * TEAM + t] = 0;
     }
 
-    const uint8_t* __restrict__ stream = p.src + (p.offsets ? p.offsets[c] : c * p.slot_stride);
+    // Streams and directories are input from outside: every read below is bounded by `avail`, the readable bytes
+    // from the chunk's first byte to src_end (the contract: the source covers the stream plus 8 bytes of slack).
+    const uint64_t soff = p.offsets ? p.offsets[c] : c * p.slot_stride;
+    const uint64_t src_bytes = p.src_end ? (uint64_t)(p.src_end - p.src) : ~0ull;
+    const uint64_t avail = soff <= src_bytes ? src_bytes - soff : 0;
+    const uint8_t* __restrict__ stream = p.src + (avail ? soff : 0);
     const uint64_t first = c * p.chunk_len;
     uint_t* __restrict__ out = reinterpret_cast<uint_t*>(p.dst) + first;
     // elements this chunk may write
@@ -57,7 +62,9 @@ __global__ void __launch_bounds__(kThreads) spz_decode_kernel(const DecParams p)
     uint32_t ngroups, remaining, status = kStatusOk;
     uint64_t pos = 0;                   // byte cursor in the stream (team-uniform)
     const uint32_t variant = p.variant; // 1 / 2: non-RLE sibling codecs (see spz_encode.cu)
-    if (variant) {                      // format.h:75-85: [u32 len][u16 ndims]; ngroups is implied
+    if (avail < (variant ? (variant == 3u ? 8u : 6u) : (p.has_meta ? 8u : 0u))) {
+        ngroups = 0; remaining = 0; status = kStatusTruncated;
+    } else if (variant) {               // format.h:75-85: [u32 len][u16 ndims]; ngroups is implied
         const uint32_t len32 = (uint32_t)stream[0] | ((uint32_t)stream[1] << 8) | ((uint32_t)stream[2] << 16) | ((uint32_t)stream[3] << 24);
         const uint32_t at = variant == 3u ? 6u : 4u;          // variant 3: [u48 len][u16 ndims] (sprintz_xff.cpp:64-69)
         const uint32_t nd = (uint32_t)stream[at] | ((uint32_t)stream[at + 1] << 8);
@@ -85,6 +92,7 @@ __global__ void __launch_bounds__(kThreads) spz_decode_kernel(const DecParams p)
 
     if (status == kStatusOk && (variant ? ngroups != 0 : !(ngroups == 0 && remaining < kMinDataSize))) {
         for (uint32_t g = 0; g < ngroups && status == kStatusOk; g++) {
+            if (pos + H + 8 > avail) { status = kStatusTruncated; break; }      // header fields are read as aligned word pairs
             const uint8_t* hdr = stream + pos;
             pos += H;
             for (uint32_t s = 0; s < 2; s++) {
@@ -104,6 +112,7 @@ __global__ void __launch_bounds__(kThreads) spz_decode_kernel(const DecParams p)
 
                 if (total == 0 && variant == 0u) {
                     // ---- run slot (sprintz_delta_rle.cpp:640-667)
+                    if (pos + 2 > avail) { status = kStatusTruncated; break; }
                     uint32_t nrun = stream[pos] & 0x7f;
                     if (stream[pos] & 0x80) { nrun |= (uint32_t)stream[pos + 1] << 7; pos += 2; } else { pos += 1; }
                     const uint64_t nrows = (uint64_t)nrun * kBlockRows;
@@ -135,6 +144,7 @@ __global__ void __launch_bounds__(kThreads) spz_decode_kernel(const DecParams p)
                 // ---- data slot
                 if (o + B > cap) { status = kStatusOverflow; break; }
                 const uint32_t row_bytes = (total + 7u) >> 3;
+                if (pos + (LOW ? total : row_bytes * kBlockRows) + 8 > avail) { status = kStatusTruncated; break; }
                 const uint8_t* pay = stream + pos;
                 for (int k = 0; k < DPL; k++) {
                     const int d = k * TEAM + t;
@@ -182,6 +192,8 @@ __global__ void __launch_bounds__(kThreads) spz_decode_kernel(const DecParams p)
     if (status == kStatusOk) {
         if (o + remaining > cap) {
             status = kStatusOverflow;
+        } else if (pos + (uint64_t)remaining * ESZ > avail) {
+            status = kStatusTruncated;
         } else {
             const uint8_t* tsrc = stream + pos;
             uint8_t* tdst = reinterpret_cast<uint8_t*>(out + o);
@@ -204,6 +216,7 @@ static cudaError_t launch_one(const DecParams& p, uint32_t grid, size_t smem, cu
     cudaError_t e = cudaFuncSetAttribute(spz_decode_kernel<W, FIRE, LOW>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    count_launch();
     spz_decode_kernel<W, FIRE, LOW><<<grid, p.teams_per_cta * p.team, smem, stream>>>(p);
     return cudaGetLastError();
 }
@@ -214,7 +227,7 @@ cudaError_t launch_decode_hd(int elem_sz, int predictor, DecParams p, cudaStream
 cudaError_t launch_decode_lane(int elem_sz, int predictor, DecParams p, cudaStream_t stream);
 cudaError_t launch_decode_lowlane(int elem_sz, int predictor, DecParams p, cudaStream_t stream);
 
-static int g_last_decode_family = 0;     // 0 generic team kernel, 1 fast team kernel (hd), 2 lane kernel
+static thread_local int g_last_decode_family = 0;     // 0 generic team kernel, 1 fast team kernel (hd), 2 lane kernel, 3 wide-row kernel
 int last_decode_family() { return g_last_decode_family; }
 
 cudaError_t launch_decode(int elem_sz, int predictor, DecParams p, cudaStream_t stream)

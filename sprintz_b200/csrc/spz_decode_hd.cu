@@ -20,7 +20,7 @@
 //
 // Reference behaviour restated: sprintz_delta_rle.cpp:417-772, sprintz_xff_rle.cpp:568-1179 (high-dim only;
 // the low-dim column-major variants stay on the generic kernel).
-#include "spz_common.cuh"
+#include "spz_host.h"
 
 namespace spz {
 
@@ -69,7 +69,11 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
     const uint32_t OCAP = p.out_cap;
 
     // ---- input: byte offsets are relative to `abase`, the 16-byte aligned-down stream start
-    const uint8_t* const gstream = p.src + (p.offsets ? p.offsets[c] : c * p.slot_stride);
+    // the directory is input from outside: an offset past the source makes the chunk "truncated", never a wild read
+    const uint64_t soff = p.offsets ? p.offsets[c] : c * p.slot_stride;
+    const uint64_t src_bytes = (uint64_t)(p.src_end - p.src);
+    const bool bad_off = soff > src_bytes || src_bytes - soff < 8u;
+    const uint8_t* const gstream = p.src + (bad_off ? 0 : soff);
     const uint32_t mis_in = (uint32_t)((uintptr_t)gstream & 15);
     const uint8_t* const abase = gstream - mis_in;
     const uint64_t lim64 = (uint64_t)(p.src_end - abase);
@@ -192,6 +196,13 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
         ngroups = p.meta[c].ngroups;
         remaining = p.meta[c].remaining & 0xffffu;
     }
+    if (bad_off) { status = kStatusTruncated; remaining = 0; }
+    {   // a group is at least H + 2 bytes: a group count the chunk's own span cannot hold is corrupt (and would spin)
+        const uint64_t next = p.offsets ? p.offsets[c + 1] : src_bytes;
+        const uint64_t cspan = (next > soff && next <= src_bytes) ? next - soff : (src_bytes > soff ? src_bytes - soff : 0);
+        const uint64_t hmin = ((2ull * (uint64_t)D * HB + 7ull) >> 3) + 2ull;
+        if ((uint64_t)ngroups * hmin > cspan) { status = kStatusTruncated; remaining = 0; }
+    }
     if (!valid || status != kStatusOk) ngroups = 0;
 
     uint32_t o = 0;                     // output element cursor (team-uniform)
@@ -202,6 +213,7 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
 
     const uint32_t gmax = __reduce_max_sync(kFull, ngroups);
     for (uint32_t g = 0; g < gmax; g++) {
+        if (g < ngroups && pos > limit) status = kStatusTruncated;     // ran past the readable bytes (the ring was fed zeros)
         const bool act = g < ngroups && status == kStatusOk;
         ensure(pos + max_group + 8, act);
 
@@ -421,6 +433,8 @@ __global__ void __launch_bounds__(kThreads) spz_decode_hd_kernel(const DecParams
     if (valid && status == kStatusOk) {
         if ((uint64_t)o + remaining > cap) {
             status = kStatusOverflow;
+        } else if ((uint64_t)pos + (uint64_t)remaining * ESZ > (uint64_t)limit) {
+            status = kStatusTruncated;              // the raw tail is read straight from the source
         } else {
             const uint8_t* tsrc = abase + pos;
             uint8_t* tdst = reinterpret_cast<uint8_t*>(out + o);
@@ -449,6 +463,7 @@ static cudaError_t launch_hd(const DecParams& p, uint32_t grid, size_t smem, cud
     cudaError_t e = cudaFuncSetAttribute(spz_decode_hd_kernel<W, FIRE, TEAM, DPL, FULLD>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    count_launch();
     spz_decode_hd_kernel<W, FIRE, TEAM, DPL, FULLD><<<grid, kThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }

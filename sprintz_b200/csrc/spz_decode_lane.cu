@@ -27,7 +27,9 @@
 //   runs / tail / errors   plain divergent scalar code, as in the reference's decoder
 //
 // Reference behaviour restated: sprintz_delta_rle.cpp:417-772, sprintz_xff_rle.cpp:568-1179 (high-dim).
-#include "spz_common.cuh"
+#include <atomic>
+
+#include "spz_host.h"
 
 namespace spz {
 
@@ -70,7 +72,10 @@ __global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_k
     const uint32_t rboff = (threadIdx.x >> 5) * kLaneWarpSmem + (threadIdx.x & 31) * 4u;
 
     // ---- input ring
-    const uint8_t* const gstream = p.src + (p.offsets ? p.offsets[c] : c * p.slot_stride);
+    // the directory is input from outside: an offset past the source makes the chunk "truncated", never a wild read
+    const uint64_t soff = p.offsets ? p.offsets[c] : c * p.slot_stride;
+    const bool bad_off = soff > (uint64_t)(p.src_end - p.src) || (uint64_t)(p.src_end - p.src) - soff < 8u;
+    const uint8_t* const gstream = p.src + (bad_off ? 0 : soff);
     const uint32_t mis = (uint32_t)((uintptr_t)gstream & 31);
     const uint8_t* base32 = gstream - mis;
     asm volatile("" : "+l"(base32));                // keep the pointer in registers (no rematerialisation per fill)
@@ -260,6 +265,13 @@ __global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_k
         ngroups = p.meta[c].ngroups;
         remaining = p.meta[c].remaining & 0xffffu;
     }
+    if (bad_off) { status = kStatusTruncated; remaining = 0; }
+    {   // a group is at least H + 2 bytes: a group count the chunk's own span cannot hold is corrupt (and would spin)
+        const uint64_t src_bytes = (uint64_t)(p.src_end - p.src);
+        const uint64_t next = p.offsets ? p.offsets[c + 1] : src_bytes;
+        const uint64_t cspan = (next > soff && next <= src_bytes) ? next - soff : (src_bytes > soff ? src_bytes - soff : 0);
+        if ((uint64_t)ngroups * (H + 2u) > cspan) { status = kStatusTruncated; remaining = 0; }
+    }
     if (status != kStatusOk) ngroups = 0;
 
     uint32_t o = 0;                                  // output element cursor of the chunk
@@ -416,6 +428,8 @@ __global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_k
     if (status == kStatusOk) {
         if ((uint64_t)o + remaining > cap) {
             status = kStatusOverflow;
+        } else if ((uint64_t)(pos >> 3) + (uint64_t)remaining * ESZ > (uint64_t)limit) {
+            status = kStatusTruncated;              // the raw tail is read straight from the source
         } else {
             const uint8_t* tsrc = base32 + (pos >> 3);
             if (Q) {
@@ -483,9 +497,9 @@ __global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_k
 
 // ------------------------------------------------------------------ launch
 
-static int g_force_path = 0;       // 0 auto, 1 team kernels only, 2 lane kernels whenever the shape allows
-void set_force_path(int v) { g_force_path = v; }
-int get_force_path() { return g_force_path; }
+static std::atomic<int> g_force_path{0};       // 0 auto, 1 team kernels only, 2 lane kernels whenever the shape allows (process-wide test switch)
+void set_force_path(int v) { g_force_path.store(v); }
+int get_force_path() { return g_force_path.load(); }
 
 template <int W, bool FIRE, int D, int Q>
 static cudaError_t launch_lane_q(const DecParams& p, cudaStream_t stream)
@@ -493,6 +507,7 @@ static cudaError_t launch_lane_q(const DecParams& p, cudaStream_t stream)
     const uint64_t threads = p.nchunks * (uint64_t)(D / 8);
     const uint64_t grid64 = (threads + kLaneThreads - 1) / kLaneThreads;
     if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
+    count_launch();
     spz_decode_lane_kernel<W, FIRE, D, Q><<<(uint32_t)grid64, kLaneThreads, 0, stream>>>(p);
     return cudaGetLastError();
 }
@@ -505,6 +520,7 @@ static cudaError_t launch_lane(const DecParams& p, cudaStream_t stream)
     const uint64_t threads = p.nchunks * (uint64_t)(D / 8);
     const uint64_t grid64 = (threads + kLaneThreads - 1) / kLaneThreads;
     if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
+    count_launch();
     spz_decode_lane_kernel<W, FIRE, D, 0><<<(uint32_t)grid64, kLaneThreads, 0, stream>>>(p);
     return cudaGetLastError();
 }
@@ -512,13 +528,14 @@ static cudaError_t launch_lane(const DecParams& p, cudaStream_t stream)
 // Returns cudaErrorNotSupported when the shape is not covered (caller continues with the team kernels).
 cudaError_t launch_decode_lane(int elem_sz, int predictor, DecParams p, cudaStream_t stream)
 {
-    if (g_force_path == 1) return cudaErrorNotSupported;
+    const int force = get_force_path();
+    if (force == 1) return cudaErrorNotSupported;
     if (p.ndims != 8 && p.ndims != 16) return cudaErrorNotSupported;
     if (p.src_end == nullptr || p.src_end <= p.src) return cudaErrorNotSupported;
     // a lane is a whole scalar decoder: only worth it when there are enough lane tasks to fill the machine (one wave
     // is 148 SMs x 4 CTAs x 128 lanes = 75 776).  Measured crossover against the team kernels at 1024-row chunks
     // (gpurun s43, 64..512 MiB frames): ~20-28 Ki lane tasks for int8, ~50 Ki for int16.
-    if (g_force_path != 2 && p.nchunks * (p.ndims / 8) < (elem_sz == 1 ? 24576u : 49152u)) return cudaErrorNotSupported;
+    if (force != 2 && p.nchunks * (p.ndims / 8) < (elem_sz == 1 ? 24576u : 49152u)) return cudaErrorNotSupported;
     // vector stores: every chunk's output must start 16-byte aligned
     if (!p.qop && ((uintptr_t)p.dst & 15) != 0) return cudaErrorNotSupported;
     if (!p.qop && p.nchunks > 1 && ((p.chunk_len * (uint64_t)elem_sz) & 15) != 0) return cudaErrorNotSupported;

@@ -9,7 +9,7 @@
 // fill ahead, predictor state lives in registers left-aligned, and a block (8 rows x ndims) leaves as 64/128-bit
 // stores.  A column is one 64-bit segment (8-bit) / two 64-bit segments (16-bit) of the ring; every field is
 // "mask the low bits, shift the segment by its width".
-#include "spz_common.cuh"
+#include "spz_host.h"
 
 namespace spz {
 
@@ -45,7 +45,10 @@ __global__ void __launch_bounds__(kLowLaneThreads, (D * W <= 16) ? 7 : 5) spz_de
     const uint32_t rboff = (threadIdx.x >> 5) * kLowLaneWarpSmem + (threadIdx.x & 31) * 4u;
 
     // ---- input ring
-    const uint8_t* const gstream = p.src + (p.offsets ? p.offsets[c] : c * p.slot_stride);
+    // the directory is input from outside: an offset past the source makes the chunk "truncated", never a wild read
+    const uint64_t soff = p.offsets ? p.offsets[c] : c * p.slot_stride;
+    const bool bad_off = soff > (uint64_t)(p.src_end - p.src) || (uint64_t)(p.src_end - p.src) - soff < 8u;
+    const uint8_t* const gstream = p.src + (bad_off ? 0 : soff);
     const uint32_t mis = (uint32_t)((uintptr_t)gstream & 31);
     const uint8_t* base32 = gstream - mis;
     asm volatile("" : "+l"(base32));                // keep the pointer in registers (no rematerialisation per fill)
@@ -229,6 +232,13 @@ __global__ void __launch_bounds__(kLowLaneThreads, (D * W <= 16) ? 7 : 5) spz_de
         ngroups = p.meta[c].ngroups;
         remaining = p.meta[c].remaining & 0xffffu;
     }
+    if (bad_off) { status = kStatusTruncated; remaining = 0; }
+    {   // a group is at least H + 2 bytes: a group count the chunk's own span cannot hold is corrupt (and would spin)
+        const uint64_t src_bytes = (uint64_t)(p.src_end - p.src);
+        const uint64_t next = p.offsets ? p.offsets[c + 1] : src_bytes;
+        const uint64_t cspan = (next > soff && next <= src_bytes) ? next - soff : (src_bytes > soff ? src_bytes - soff : 0);
+        if ((uint64_t)ngroups * (H + 2u) > cspan) { status = kStatusTruncated; remaining = 0; }
+    }
     if (status != kStatusOk) ngroups = 0;
 
     uint32_t o = 0;                                  // output element cursor of the chunk
@@ -338,6 +348,8 @@ __global__ void __launch_bounds__(kLowLaneThreads, (D * W <= 16) ? 7 : 5) spz_de
     if (status == kStatusOk) {
         if ((uint64_t)o + remaining > cap) {
             status = kStatusOverflow;
+        } else if ((uint64_t)(pos >> 3) + (uint64_t)remaining * ESZ > (uint64_t)limit) {
+            status = kStatusTruncated;              // the raw tail is read straight from the source
         } else {
             const uint8_t* tsrc = base32 + (pos >> 3);
             if (Q) {                                 // raw tail elements go straight to the result (short, rare)
@@ -410,6 +422,7 @@ static cudaError_t launch_lowlane(const DecParams& p, cudaStream_t stream)
 {
     const uint64_t grid64 = (p.nchunks + kLowLaneThreads - 1) / kLowLaneThreads;
     if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
+    count_launch();
     if (p.qop == 1) spz_decode_lowlane_kernel<W, FIRE, D, 1><<<(uint32_t)grid64, kLowLaneThreads, 0, stream>>>(p);
     else if (p.qop == 2) spz_decode_lowlane_kernel<W, FIRE, D, 2><<<(uint32_t)grid64, kLowLaneThreads, 0, stream>>>(p);
     else spz_decode_lowlane_kernel<W, FIRE, D, 0><<<(uint32_t)grid64, kLowLaneThreads, 0, stream>>>(p);

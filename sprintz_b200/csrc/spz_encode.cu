@@ -12,7 +12,7 @@
 //   flush    128-bit coalesced copies of finished groups to HBM
 //
 // No tensor cores: this is integer bit-twiddling, bounded by instruction issue and HBM.
-#include "spz_common.cuh"
+#include "spz_host.h"
 
 namespace spz {
 
@@ -351,6 +351,8 @@ static cudaError_t launch_one(const EncParams& p, uint32_t grid, size_t smem, cu
     cudaError_t e = cudaFuncSetAttribute(spz_encode_kernel<W, FIRE, LOW>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    if (g_enc_probe) return probe_fill(g_enc_probe, 0, spz_encode_kernel<W, FIRE, LOW>, (int)(p.teams_per_cta * p.team), smem, p.teams_per_cta);
+    count_launch();
     spz_encode_kernel<W, FIRE, LOW><<<grid, p.teams_per_cta * p.team, smem, stream>>>(p);
     return cudaGetLastError();
 }
@@ -381,39 +383,40 @@ cudaError_t launch_encode_hd(int elem_sz, int predictor, EncParams p, cudaStream
 cudaError_t launch_encode_lane(int elem_sz, int predictor, EncParams p, cudaStream_t stream);
 cudaError_t launch_encode_lowlane(int elem_sz, int predictor, EncParams p, cudaStream_t stream);
 
-extern bool g_encode_dry_run;
-static int g_last_encode_family = 0;     // 0 generic team kernel, 1 fast team kernel (hd), 2 lane kernel
+thread_local EncodeProbe* g_enc_probe = nullptr;      // set by probe_encode(): launchers describe instead of launching
+static thread_local int g_last_encode_family = 0;    // 0 generic team kernel, 1 fast team kernel (hd), 2 lane kernel, 3 wide-row kernel
 int last_encode_family() { return g_last_encode_family; }
 
-// Will launch_encode() run a LANE encoder for this call?  (Those publish each chunk record with a release after the
-// chunk's last byte, which is what the overlapped scan-and-copy kernel of spz_frame.cu waits on.)
-bool encode_uses_lane(int elem_sz, int predictor, EncParams p)
+// What launch_encode() would do for this call (kernel family, chunks per machine round); launches nothing.
+EncodeProbe probe_encode(int elem_sz, int predictor, EncParams p)
 {
-    if (predictor >= 2) { p.variant = (uint32_t)predictor - 1u; }
-    if (p.variant) predictor = (p.variant == 3u) ? 1 : 0;
-    g_encode_dry_run = true;
-    cudaError_t e = launch_encode_lane(elem_sz, predictor, p, nullptr);
-    const bool low = p.variant ? false : (elem_sz == 1 ? (p.ndims <= 4) : (p.ndims <= 2));
-    if (e == cudaErrorNotSupported && low) e = launch_encode_lowlane(elem_sz, predictor, p, nullptr);
-    g_encode_dry_run = false;
-    return e == cudaSuccess;
+    EncodeProbe pr{0, 0};
+    const int keep = g_last_encode_family;
+    g_enc_probe = &pr;
+    const cudaError_t e = launch_encode(elem_sz, predictor, p, nullptr);
+    g_enc_probe = nullptr;
+    g_last_encode_family = keep;
+    if (e != cudaSuccess) { (void)cudaGetLastError(); pr.family = -1; pr.round_chunks = 0; }
+    return pr;
 }
 
 cudaError_t launch_encode(int elem_sz, int predictor, EncParams p, cudaStream_t stream)
 {
     if (predictor >= 2) { p.variant = (uint32_t)predictor - 1u; }                  // SPZ_RM_DELTA / SPZ_RM_PLAIN / SPZ_RM_XFF (frames)
     if (p.variant) predictor = (p.variant == 3u) ? 1 : 0;
+    const uint32_t pin = p.family_pin;           // family + 1 chosen for the whole frame, or 0
+    if (pin == 0 || pin == 3)
     {   // throughput path: frames with many chunks of 8 / 16 dims (spz_encode_lane.cu)
         const cudaError_t e = launch_encode_lane(elem_sz, predictor, p, stream);
         if (e != cudaErrorNotSupported) { g_last_encode_family = 2; return e; }
     }
-    if (p.variant == 0)
+    if (p.variant == 0 && (pin == 0 || pin == 2))
     {   // fast path for high-dim shapes; the generic kernel below covers everything else
         const cudaError_t e = launch_encode_hd(elem_sz, predictor, p, stream);
         if (e != cudaErrorNotSupported) { g_last_encode_family = 1; return e; }
     }
     const bool low = p.variant ? false : (elem_sz == 1 ? (p.ndims <= 4) : (p.ndims <= 2));
-    if (low)
+    if (low && (pin == 0 || pin == 3))
     {   // throughput path of the low-dim codecs: frames with many chunks (spz_encode_lowlane.cu)
         const cudaError_t e = launch_encode_lowlane(elem_sz, predictor, p, stream);
         if (e != cudaErrorNotSupported) { g_last_encode_family = 2; return e; }

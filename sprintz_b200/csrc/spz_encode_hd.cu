@@ -16,9 +16,10 @@
 //            multiply-add (multipliers 2^prefix precomputed per block), clusters are appended to the row with
 //            one 64-bit multiply-add each; header nibbles are gathered into words by a few lanes
 //   output   a double-buffered shared staging tile, flushed with 128-bit stores once per group
-#include "spz_common.cuh"
+#include "spz_host.h"
 
 namespace spz {
+
 
 constexpr unsigned kFullE = 0xffffffffu;
 
@@ -466,6 +467,8 @@ static cudaError_t launch_hd(const EncParams& p, uint32_t grid, size_t smem, cud
     cudaError_t e = cudaFuncSetAttribute(spz_encode_hd_kernel<W, FIRE, TEAM, DPL, FULLD>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    if (g_enc_probe) return probe_fill(g_enc_probe, 1, spz_encode_hd_kernel<W, FIRE, TEAM, DPL, FULLD>, kThreads, smem, kThreads / TEAM);
+    count_launch();
     spz_encode_hd_kernel<W, FIRE, TEAM, DPL, FULLD><<<grid, kThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }

@@ -22,12 +22,11 @@
 //            of its slots, so slot 1's fields are patched in afterwards (ring or HBM, wherever the bytes are).
 //
 // Reference behaviour restated: sprintz_delta_rle.cpp:54-404, sprintz_xff_rle.cpp:60-555 (high-dim).
-#include "spz_common.cuh"
+#include "spz_host.h"
 
 namespace spz {
 
 constexpr int kEncLaneThreads = 128;
-bool g_encode_dry_run = false;                             // launchers return without launching (single-threaded use under the API's call)
 
 template <int W, bool FIRE, int D>
 // int8 x 8 fits 5 CTAs per SM without spills (96 registers); the int16 shapes spill there and stay at 4
@@ -431,17 +430,12 @@ static cudaError_t launch_enc_lane(const EncParams& p, cudaStream_t stream)
     if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
     constexpr int NW = kEncLaneThreads / 32, NVEC = 8 * D * (W / 8) / 16;
     const size_t smem = 4096 + NW * 4096 + NW * NVEC * 512;            // alignment slack + rings + staging
-    // Eligibility probe of the overlapped frame encode: only once this instantiation has been launched before.  Its
-    // first launch loads the kernel lazily (and may synchronise the device), which must not happen while the chase
-    // kernel is already spinning on this encoder's output.
-    static bool warmed = false;
-    if (g_encode_dry_run) return warmed ? cudaSuccess : cudaErrorNotReady;
     cudaError_t e = cudaFuncSetAttribute(spz_encode_lane_kernel<W, FIRE, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    if (g_enc_probe) return probe_fill(g_enc_probe, 2, spz_encode_lane_kernel<W, FIRE, D>, kEncLaneThreads, smem, kEncLaneThreads);
+    count_launch();
     spz_encode_lane_kernel<W, FIRE, D><<<(uint32_t)grid64, kEncLaneThreads, smem, stream>>>(p);
-    e = cudaGetLastError();
-    if (e == cudaSuccess) warmed = true;
-    return e;
+    return cudaGetLastError();
 }
 
 // Returns cudaErrorNotSupported when the shape is not covered (caller continues with the team kernels).
@@ -453,7 +447,7 @@ cudaError_t launch_encode_lane(int elem_sz, int predictor, EncParams p, cudaStre
     if (p.meta == nullptr) return cudaErrorNotSupported;
     // a lane is a whole scalar encoder: only worth it when there are enough chunks to fill the machine
     // measured crossover against the team kernels (gpurun s43): 16 Ki chunks for 8 dims, ~24 Ki for int16 x 16
-    if (force != 2 && p.nchunks < (p.ndims == 16 ? 24576u : 16384u)) return cudaErrorNotSupported;
+    if (force != 2 && p.family_pin != 3u && p.nchunks < (p.ndims == 16 ? 24576u : 16384u)) return cudaErrorNotSupported;
     // 256-bit loads / stores: every chunk's input and output slot must start 32-byte aligned
     if (((uintptr_t)p.src & 31) != 0 || ((uintptr_t)p.dst & 31) != 0) return cudaErrorNotSupported;
     if (p.nchunks > 1 && (((p.chunk_len * (uint64_t)elem_sz) & 31) != 0 || (p.slot_stride & 31) != 0)) return cudaErrorNotSupported;

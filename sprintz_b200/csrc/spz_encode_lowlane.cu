@@ -9,12 +9,11 @@
 // continue-run test (sprintz_delta_lowdim.cpp:190, sprintz_xff_lowdim.cpp:234).
 // A block is 8..32 bytes: it lives in registers (fetched one block ahead), a column is built from its 8 fields with
 // shifts and appended to the bit writer as two (8-bit) or four (16-bit) <= 32-bit pieces.
-#include "spz_common.cuh"
+#include "spz_host.h"
 
 namespace spz {
 
 int get_force_path();
-extern bool g_encode_dry_run;
 
 constexpr int kEncLowThreads = 128;
 
@@ -324,12 +323,10 @@ static cudaError_t launch_enc_lowlane(const EncParams& p, cudaStream_t stream)
     const uint64_t grid64 = (p.nchunks + kEncLowThreads - 1) / kEncLowThreads;
     if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
     const size_t smem = 4096 + (kEncLowThreads / 32) * (4096 + 1024);          // alignment slack + rings + sector columns
-    static bool warmed = false;                                                // see launch_enc_lane (spz_encode_lane.cu)
-    if (g_encode_dry_run) return warmed ? cudaSuccess : cudaErrorNotReady;
+    if (g_enc_probe) return probe_fill(g_enc_probe, 2, spz_encode_lowlane_kernel<W, FIRE, D>, kEncLowThreads, smem, kEncLowThreads);
+    count_launch();
     spz_encode_lowlane_kernel<W, FIRE, D><<<(uint32_t)grid64, kEncLowThreads, smem, stream>>>(p);
-    const cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) warmed = true;
-    return e;
+    return cudaGetLastError();
 }
 
 // Returns cudaErrorNotSupported when the shape is not covered (caller continues with the generic kernel).
@@ -340,7 +337,7 @@ cudaError_t launch_encode_lowlane(int elem_sz, int predictor, EncParams p, cudaS
     if (!(elem_sz == 1 ? (p.ndims >= 1 && p.ndims <= 4) : (p.ndims >= 1 && p.ndims <= 2))) return cudaErrorNotSupported;
     if (p.meta == nullptr) return cudaErrorNotSupported;
     // a lane is a whole scalar encoder: only worth it when there are enough chunks to fill the machine
-    if (force != 2 && p.nchunks < 16384) return cudaErrorNotSupported;
+    if (force != 2 && p.family_pin != 3u && p.nchunks < 16384) return cudaErrorNotSupported;
     // 64-bit loads / 256-bit stores: chunk inputs 8-byte aligned, output slots 32-byte aligned
     if (((uintptr_t)p.src & 7) != 0 || ((uintptr_t)p.dst & 31) != 0) return cudaErrorNotSupported;
     if (p.nchunks > 1 && (((p.chunk_len * (uint64_t)elem_sz) & 7) != 0 || (p.slot_stride & 31) != 0)) return cudaErrorNotSupported;

@@ -12,7 +12,7 @@
 //        for the running state, then re-walks the tile (now L1/L2 resident) producing the output.  The state of
 //        the double-delta recurrence is the pair (delta, value); a tile of n rows maps (d0, x0) to
 //        (d0 + S1, x0 + n*d0 + S2) with S1 = sum y_k, S2 = sum (n-k)*y_k, which composes associatively.
-#include "spz_common.cuh"
+#include "spz_host.h"
 #include "spz_swar.cuh"
 #include "spz_xff_forecast.cuh"
 #include "../../include/sprintz_b200.h"
@@ -74,11 +74,16 @@ template <int W, int ORDER>
 __global__ void __launch_bounds__(kFcThreads) spz_forecast_decode_kernel(const uint8_t* __restrict__ src,
                                                                          uint8_t* __restrict__ dst, uint64_t len,
                                                                          uint32_t D, uint32_t tile_rows, uint64_t ntiles,
-                                                                         unsigned long long* state)
+                                                                         unsigned long long* state, unsigned int* ticket)
 {
     typedef typename Traits<W>::uint_t uint_t;
     constexpr uint32_t WM = (1u << W) - 1u;
-    const uint64_t g = (uint64_t)blockIdx.x * kFcThreads + threadIdx.x;
+    // Tiles are handed out by ticket, not by blockIdx: a look-back only ever waits for tiles whose CTA has already
+    // started, whatever order the hardware (or a serialising tool) schedules the blocks in.
+    __shared__ unsigned int s_vb;
+    if (threadIdx.x == 0) s_vb = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint64_t g = (uint64_t)s_vb * kFcThreads + threadIdx.x;
     const uint64_t tile = g / D;
     const uint32_t d = (uint32_t)(g % D);
     if (tile >= ntiles) return;
@@ -159,9 +164,11 @@ cudaError_t launch_xff_forecast(int enc, int elem_sz, const uint8_t* src, uint8_
     const int32_t nb = xffp_nblocks(len, D, elem_sz);
     const unsigned grid = (D + 127u) / 128u;
     if (elem_sz == 1) {
+        count_launch();
         if (enc) spz_xff_forecast_kernel<8, true><<<grid, 128, 0, stream>>>(src, dst, len, D, nb);
         else     spz_xff_forecast_kernel<8, false><<<grid, 128, 0, stream>>>(src, dst, len, D, nb);
     } else {
+        count_launch();
         if (enc) spz_xff_forecast_kernel<16, true><<<grid, 128, 0, stream>>>(src, dst, len, D, nb);
         else     spz_xff_forecast_kernel<16, false><<<grid, 128, 0, stream>>>(src, dst, len, D, nb);
     }
@@ -183,7 +190,7 @@ uint64_t forecast_workspace_bytes(uint64_t len, uint32_t D)
     const uint64_t rows = (len + D - 1) / D;
     const uint32_t tr = forecast_tile_rows(len, D);
     const uint64_t ntiles = (rows + tr - 1) / tr;
-    return 8 * (ntiles ? ntiles : 1) * D;
+    return 8 * (ntiles ? ntiles : 1) * D + 8;          // + the tile ticket
 }
 
 cudaError_t launch_forecast_encode(int order, int elem_sz, const uint8_t* src, uint8_t* dst, uint64_t len, uint32_t D,
@@ -195,6 +202,7 @@ cudaError_t launch_forecast_encode(int order, int elem_sz, const uint8_t* src, u
     const uint64_t grid = (units + kFcThreads - 1) / kFcThreads;
     if (grid > 0x7fffffffull) return cudaErrorInvalidValue;
     const uint64_t lag = (uint64_t)D * elem_sz;
+    count_launch();
 #define SPZ_FE(Wv, Ov) spz_forecast_encode_kernel<Wv, Ov><<<(unsigned)grid, kFcThreads, 0, stream>>>(src, dst, bytes, lag)
     if (elem_sz == 1) { if (order == 1) SPZ_FE(8, 1); else SPZ_FE(8, 2); }
     else              { if (order == 1) SPZ_FE(16, 1); else SPZ_FE(16, 2); }
@@ -203,18 +211,20 @@ cudaError_t launch_forecast_encode(int order, int elem_sz, const uint8_t* src, u
 }
 
 cudaError_t launch_forecast_decode(int order, int elem_sz, const uint8_t* src, uint8_t* dst, uint64_t len, uint32_t D,
-                                   unsigned long long* state, cudaStream_t stream)
+                                   unsigned long long* state, unsigned int* ticket, cudaStream_t stream)
 {
     if (len == 0) return cudaSuccess;
     const uint64_t rows = (len + D - 1) / D;
     const uint32_t tr = forecast_tile_rows(len, D);
     const uint64_t ntiles = (rows + tr - 1) / tr;
-    cudaError_t e = cudaMemsetAsync(state, 0, 8 * ntiles * D, stream);
+    if (ticket == nullptr) ticket = reinterpret_cast<unsigned int*>(state + ntiles * D);     // last word of the workspace
+    cudaError_t e = cudaMemsetAsync(state, 0, 8 * ntiles * D + 8, stream);
     if (e != cudaSuccess) return e;
     const uint64_t threads = ntiles * D;
     const uint64_t grid = (threads + kFcThreads - 1) / kFcThreads;
     if (grid > 0x7fffffffull) return cudaErrorInvalidValue;
-#define SPZ_FD(Wv, Ov) spz_forecast_decode_kernel<Wv, Ov><<<(unsigned)grid, kFcThreads, 0, stream>>>(src, dst, len, D, tr, ntiles, state)
+    count_launch();
+#define SPZ_FD(Wv, Ov) spz_forecast_decode_kernel<Wv, Ov><<<(unsigned)grid, kFcThreads, 0, stream>>>(src, dst, len, D, tr, ntiles, state, ticket)
     if (elem_sz == 1) { if (order == 1) SPZ_FD(8, 1); else SPZ_FD(8, 2); }
     else              { if (order == 1) SPZ_FD(16, 1); else SPZ_FD(16, 2); }
 #undef SPZ_FD

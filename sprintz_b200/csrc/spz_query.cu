@@ -12,7 +12,7 @@
 // spz_reduce_rows_kernel: a thread owns one 16-byte unit per sweep of S units, S * (16 / esz) a multiple of ndims,
 // so the dims of its 8 / 16 element positions never change and the accumulators are plain registers.  Threads fold
 // into per-CTA shared arrays, CTAs into the result with one atomic per dim.  HBM bound: N bytes read.
-#include "spz_common.cuh"
+#include "spz_host.h"
 
 namespace spz {
 
@@ -131,6 +131,7 @@ cudaError_t launch_reduce_rows(int op, int elem_sz, const uint8_t* src, uint64_t
     if (grid < min_grid) grid = min_grid;
     const uint64_t S = (grid * kRedThreads) / m * m;
     const size_t smem = 8ull * D;
+    count_launch();
 #define SPZ_RED(Wv, Ov) spz_reduce_rows_kernel<Wv, Ov><<<(unsigned)grid, kRedThreads, smem, stream>>>(src, len, D, S, result)
     if (elem_sz == 1) { if (op == 1) SPZ_RED(8, 1); else SPZ_RED(8, 2); }
     else              { if (op == 1) SPZ_RED(16, 1); else SPZ_RED(16, 2); }

@@ -25,7 +25,7 @@ def test_reference_arm_prints_one_contract_line(ref):
     assert d["impl"] == "reference" and d["metric"] == "encode+decode GB/s" and d["unit"] == "GB/s"
     assert d["higher_is_better"] is True and d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None
-    assert d["dtype"] == "u8" and d["data"] == "synthetic" and "workload" in d["config"]
+    assert d["dtype"] == "u16" and d["data"] == "synthetic" and d["config"]["workload"].startswith("c3")
     cb = d["cpu_baseline"]
     assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert cb["roundtrip_ok"] is True
