@@ -45,10 +45,13 @@ CONFIGS = {
     "c1": dict(desc="int8, 1-dim, delta+bitpack, 64 KB", esz=1, D=1, pred=0, nbytes=64 << 10, chunk_rows=2048),
     "c2": dict(desc="int8, 8-dim rowmajor, FIRE+bitpack, 1 GB synthetic AR(1)", esz=1, D=8, pred=1,
                nbytes=1 << 30, chunk_rows=512),
+    # chunk_rows: the lane kernels run whole chunks per lane, so run time is quantised in machine "rounds"; 512 rows give
+    # 6.9 (decode) rounds instead of 3.5 at 1024 -- decode 0.623 -> 0.644 of the roofline for 0.5 % of compression ratio
+    # (profiles/r2_rows_sweep_c3.jsonl)
     "c3": dict(desc="int16, 16-dim rowmajor, FIRE+bitpack, 4 GB synthetic AR(1)", esz=2, D=16, pred=1,
-               nbytes=4 << 30, chunk_rows=1024),
+               nbytes=4 << 30, chunk_rows=512),
     "c4": dict(desc="int8, 80-dim, delta+bitpack, 4 GB per GPU (32 GB over 8)", esz=1, D=80, pred=0,
-               nbytes=4 << 30, chunk_rows=1024),
+               nbytes=4 << 30, chunk_rows=512),
     # the non-RLE sibling codec compress_rowmajor_delta_8b (frame codec id 2)
     "f1": dict(desc="int8, 8-dim rowmajor, delta+bitpack without RLE (compress_rowmajor_delta_8b), 1 GB synthetic AR(1)",
                esz=1, D=8, pred=2, nbytes=1 << 30, chunk_rows=1024),
@@ -128,10 +131,13 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def make_stream(cfg, device, seed):
+GATHER_ROUNDS = 8       # stripes per rank of the streamed multi-GPU gather
+
+
+def make_stream(cfg, device, seed, multiple=16):
     from sprintz_b200.synth import ar1_stream
     rows = cfg["nbytes"] // (cfg["esz"] * cfg["D"])
-    rows -= rows % 16
+    rows -= rows % multiple
     return ar1_stream(rows, cfg["D"], cfg["esz"], seed=seed, device=device), rows
 
 
@@ -366,7 +372,9 @@ def measure_config(env, args, cfg_name, cfg, steps, warm, main):
     esz, D, pred = cfg["esz"], cfg["D"], cfg["pred"]
     chunk_rows = (args.chunk_rows if main and args.chunk_rows else 0) or cfg["chunk_rows"]
     world, rank, dev = env.world, env.rank, env.dev
-    x, rows = make_stream(cfg, dev, seed=12345 + rank)
+    # N > 1: every rank's shard is GATHER_ROUNDS whole stripes of whole chunks (the gathered frame needs whole chunks
+    # everywhere but at the end of the global stream)
+    x, rows = make_stream(cfg, dev, seed=12345 + rank, multiple=16 if world == 1 else chunk_rows * GATHER_ROUNDS)
     n = x.numel()
     raw = n * esz
     codec = spz.FrameCodec(pred, esz, n, D, chunk_rows, device=dev)
@@ -576,7 +584,7 @@ def measure_gather(env, args, codec, fr, x, out, cfg, chunk_rows, raw, payload, 
     import sprintz_b200 as spz
     world, rank, dev = env.world, env.rank, env.dev
     try:
-        g = spz.FrameGather(env.comm, codec, dst=0)
+        g = spz.FrameGather(env.comm, codec, dst=0, stripe_chunks=codec.nchunks // GATHER_ROUNDS)
         gf = g.gather(fr)                                   # warm-up + correctness
         torch.cuda.synchronize()
         ok = None

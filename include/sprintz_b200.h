@@ -223,11 +223,12 @@ int64_t spz_frame_decompress_host(const void* frame, uint64_t frame_bytes, void*
 int spz_profile_enable(int on);
 int spz_profile_collect(float* ms3, int* ncalls);
 
-/* spz_frame_encode_dev cuts long frames into SLABS of whole chunks and runs slab k's directory scan + compaction
- * on a second stream while slab k+1 is being encoded (the codec kernels are instruction-bound, the compaction is
- * HBM-bound).  The frame bytes do not depend on the slab count.  slabs: 0 = automatic (whole machine rounds, a
- * single slab for frames of only a few rounds), 1 = no pipelining (codec kernel, scan, compaction back to back),
- * n > 1 = n slabs.  Returns the previous setting; spz_last_encode_slabs() = slabs of this thread's last frame encode. */
+/* spz_frame_encode_dev can cut a frame into SLABS of whole chunks and run slab k's directory scan + compaction on a
+ * second stream while slab k+1 is being encoded.  The frame bytes do not depend on the slab count.  slabs: 0 or 1 =
+ * one slab (codec kernel, scan, compaction back to back: the default -- measured, slabs do not pay for device-resident
+ * input), n > 1 = n slabs.  The same slab machinery carries the host-buffer path (PCIe overlap)
+ * and the streamed multi-GPU gather (NVLink overlap), where it does pay.  Returns the previous setting;
+ * spz_last_encode_slabs() = slabs of this thread's last frame encode. */
 int spz_set_encode_pipeline(int slabs);
 int spz_last_encode_slabs(void);
 

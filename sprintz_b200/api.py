@@ -265,6 +265,8 @@ class Frame:
         return int(lib().spz_frame_nchunks(self.len, self.ndims, self.chunk_rows))
 
     def nbytes(self) -> int:
+        if self.nbytes_dev is None:
+            return int(self.header().frame_bytes)
         return int(self.nbytes_dev.item())
 
     def header(self) -> FrameHeader:
@@ -514,12 +516,9 @@ class FrameGather:
     def _frame(self, stripes):
         if self.comm.rank != self.dst:
             return None
-        nb = torch_scalar = None  # noqa: F841
-        torch = _torch()
-        nbytes = torch.zeros(1, dtype=torch.int64, device=self.buf.device)
         self.last_stripes = stripes
         self.last_frame = Frame(self.buf, self.codec.predictor, self.codec.elem_sz, self.total_len, self.codec.ndims,
-                                self.codec.chunk_rows, nbytes)
+                                self.codec.chunk_rows, None)
         return self.last_frame
 
     def gather(self, frame: Frame):

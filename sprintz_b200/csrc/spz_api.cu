@@ -290,17 +290,14 @@ int frame_job_init(FrameJob& j, int predictor, int elem_sz, const void* d_src, u
     if (pr.family < 0) return fail_msg(SPZ_E_CUDA, "probe_encode failed");
     j.family = pr.family;
     if (slab_chunks == 0) {
-        // Automatic: slabs of whole machine rounds (every resident lane / team finishes its chunk at about the same
-        // time, so a slab that fills the machine exactly k times drains without a tail), at least ~1/16 of the frame
-        // so the per-slab launches stay negligible, and a single slab when the frame is only a few rounds long.
         const int want = g_pipeline_slabs.load();
-        if (want > 1) slab_chunks = (j.f.nchunks + want - 1) / want;            // forced (tests, tuning)
-        else if (want == 1 || pr.round_chunks == 0 || j.f.nchunks < 3 * pr.round_chunks) slab_chunks = j.f.nchunks;
-        else {
-            uint64_t rounds = j.f.nchunks / pr.round_chunks;          // >= 3
-            uint64_t per = rounds > 16 ? (rounds + 15) / 16 : 1;      // rounds per slab
-            slab_chunks = per * pr.round_chunks;
-        }
+        // Measured (profiles/r2_pipeline_sweep.jsonl): splitting the device-resident frame encode into slabs does NOT
+        // pay -- the compaction CTAs displace encoder CTAs (the lane encoders run 4 CTAs per SM at 116 registers, nothing
+        // else fits beside them) and every slab boundary drains the machine, so c3 goes 3.46 -> 3.66 ms with 7 slabs.
+        // Automatic therefore means ONE slab; the slab machinery is what the host path (PCIe overlap) and the streamed
+        // multi-GPU gather (NVLink overlap) are built on, and `want` > 1 forces it here for tests and tuning.
+        if (want > 1) slab_chunks = (j.f.nchunks + want - 1) / want;
+        else slab_chunks = j.f.nchunks;
     }
     if (slab_chunks == 0) slab_chunks = 1;
     j.slab_chunks = slab_chunks;

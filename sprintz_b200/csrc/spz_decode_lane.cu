@@ -270,7 +270,8 @@ __global__ void __launch_bounds__(kLaneThreads, SPZ_LANE_MINB) spz_decode_lane_k
         const uint64_t src_bytes = (uint64_t)(p.src_end - p.src);
         const uint64_t next = p.offsets ? p.offsets[c + 1] : src_bytes;
         const uint64_t cspan = (next > soff && next <= src_bytes) ? next - soff : (src_bytes > soff ? src_bytes - soff : 0);
-        if ((uint64_t)ngroups * (H + 2u) > cspan) { status = kStatusTruncated; remaining = 0; }
+        // (the non-RLE siblings have no run slots: an all-zero block is a data slot with no payload at all)
+        if ((uint64_t)ngroups * (H + (variant ? 0u : 2u)) > cspan) { status = kStatusTruncated; remaining = 0; }
     }
     if (status != kStatusOk) ngroups = 0;
 

@@ -54,17 +54,18 @@ def test_slab_count_does_not_change_the_frame(spz):
         assert torch.equal(f, frames[0])
 
 
-def test_automatic_pipeline_engages_on_long_frames(spz):
-    """c3-shaped frame of 256 MiB at 256-row chunks: many machine rounds -> several slabs, same round trip."""
+def test_pipelined_long_frame_round_trip(spz):
+    """c3-shaped frame of 256 MiB at 256-row chunks in 7 slabs on the production (lane) kernels: same round trip."""
     import torch
     from sprintz_b200.synth import ar1_stream
-    spz.set_encode_pipeline(0)
+    spz.set_encode_pipeline(7)
     x = ar1_stream(1 << 23, 16, 2, seed=3, device="cuda")
     codec = spz.FrameCodec(XFF, 2, x.numel(), 16, 256)
     fr = codec.encode(x)
-    assert spz.last_encode_slabs() > 1
+    assert spz.last_encode_slabs() == 7
     out = torch.empty_like(x)
     codec.decode(fr, out)
     torch.cuda.synchronize()
     codec.check_status()
     assert torch.equal(out, x)
+    spz.set_encode_pipeline(0)
