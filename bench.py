@@ -432,7 +432,7 @@ def measure_config(env, args, cfg_name, cfg, steps, warm, main):
                               "decode_raw_gbs_kernel": raw / r["t_dec_kernel"] / 1e9,
                               "encode_raw_gbs_kernel": raw / r["t_enc_kernel"] / 1e9},
         "encode_breakdown_ms": {"codec_kernel": 1e3 * r["t_enc_kernel"], "directory_scan": 1e3 * r["t_scan"],
-                                "compaction": 1e3 * r["t_gather"], "pipelined": bool(L.spz_last_encode_overlapped())},
+                                "compaction": 1e3 * r["t_gather"], "slabs": int(L.spz_last_encode_slabs())},
         "gpu_launches": r["launches"],
     }
     dom_is_dec = r["t_dec_kernel"] >= r["t_enc_kernel"]

@@ -226,6 +226,7 @@ static inline uint32_t pow2_ceil(uint32_t x) { uint32_t p = 1; while (p < x) p <
 cudaError_t launch_decode_hd(int elem_sz, int predictor, DecParams p, cudaStream_t stream);
 cudaError_t launch_decode_lane(int elem_sz, int predictor, DecParams p, cudaStream_t stream);
 cudaError_t launch_decode_lowlane(int elem_sz, int predictor, DecParams p, cudaStream_t stream);
+cudaError_t launch_decode_wide(int elem_sz, int predictor, DecParams p, cudaStream_t stream);
 
 static thread_local int g_last_decode_family = 0;     // 0 generic team kernel, 1 fast team kernel (hd), 2 lane kernel, 3 wide-row kernel
 int last_decode_family() { return g_last_decode_family; }
@@ -237,6 +238,11 @@ cudaError_t launch_decode(int elem_sz, int predictor, DecParams p, cudaStream_t 
     {   // throughput path: frames with many chunks of 8 / 16 dims (spz_decode_lane.cu)
         const cudaError_t e = launch_decode_lane(elem_sz, predictor, p, stream);
         if (e != cudaErrorNotSupported) { g_last_decode_family = 2; return e; }
+    }
+    if (p.variant == 0)
+    {   // wide rows (ndims a multiple of 8, 24..256), 8-bit delta: SWAR octet teams (spz_decode_wide.cu)
+        const cudaError_t e = launch_decode_wide(elem_sz, predictor, p, stream);
+        if (e != cudaErrorNotSupported) { g_last_decode_family = 3; return e; }
     }
     if (p.variant == 0)
     {   // fast path for high-dim shapes; the generic kernel below covers everything else

@@ -104,6 +104,7 @@ spz_scan_sizes_kernel(const ChunkMeta* __restrict__ meta, uint64_t nchunks,
             uint8_t* gap = reinterpret_cast<uint8_t*>(chunk_nbytes + nchunks);
             uint8_t* pay = reinterpret_cast<uint8_t*>(hdr) + hdr_in.payload_off;
             while (gap < pay) *gap++ = 0;
+            for (int i = 0; i < 16; i++) pay[total + i] = 0;             // the frame's 16 bytes of read slack
             spz_frame_header h = hdr_in;
             h.payload_bytes = total;
             h.frame_bytes = h.payload_off + total + 16;
