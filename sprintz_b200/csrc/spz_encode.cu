@@ -382,6 +382,7 @@ static void enc_layout(int elem_sz, bool low, EncParams& p)
 cudaError_t launch_encode_hd(int elem_sz, int predictor, EncParams p, cudaStream_t stream);
 cudaError_t launch_encode_lane(int elem_sz, int predictor, EncParams p, cudaStream_t stream);
 cudaError_t launch_encode_lowlane(int elem_sz, int predictor, EncParams p, cudaStream_t stream);
+cudaError_t launch_encode_wide(int elem_sz, int predictor, EncParams p, cudaStream_t stream);
 
 thread_local EncodeProbe* g_enc_probe = nullptr;      // set by probe_encode(): launchers describe instead of launching
 static thread_local int g_last_encode_family = 0;    // 0 generic team kernel, 1 fast team kernel (hd), 2 lane kernel, 3 wide-row kernel
@@ -409,6 +410,11 @@ cudaError_t launch_encode(int elem_sz, int predictor, EncParams p, cudaStream_t 
     {   // throughput path: frames with many chunks of 8 / 16 dims (spz_encode_lane.cu)
         const cudaError_t e = launch_encode_lane(elem_sz, predictor, p, stream);
         if (e != cudaErrorNotSupported) { g_last_encode_family = 2; return e; }
+    }
+    if (p.variant == 0 && (pin == 0 || pin == 4))
+    {   // wide rows (ndims a multiple of 8, 24..256), 8-bit delta: SWAR octet teams (spz_encode_wide.cu)
+        const cudaError_t e = launch_encode_wide(elem_sz, predictor, p, stream);
+        if (e != cudaErrorNotSupported) { g_last_encode_family = 3; return e; }
     }
     if (p.variant == 0 && (pin == 0 || pin == 2))
     {   // fast path for high-dim shapes; the generic kernel below covers everything else

@@ -1,0 +1,421 @@
+// spz_encode_wide.cu -- wide-row ("octet team") encode kernel: 8-bit delta streams with ndims a multiple of 8, 24..256.
+//
+// BASELINE config 4 (int8 x 80 dims, delta) ran on the team kernel of spz_encode_hd.cu at 0.23 of the roofline: ncu
+// showed 26 thread instructions per sample (lane-per-dim forecasting of single bytes, a cluster multiply-add bit
+// emitter that re-reads every zigzagged byte and its multiplier from shared memory), LSU pipe 65 %, 22 % of the shared
+// wavefronts bank conflicts.  The delta predictor needs no multiply, so everything up to the bit packing runs
+// SIMD-within-a-register on FOUR samples per 32-bit word, and the per-dim packing constants live in registers:
+//
+//   mapping  one lane owns 8 consecutive dims (an OCTET = two words per row) of one chunk; a chunk is encoded by a team
+//            of ndims/8 lanes (10 for 80 dims), 32/(ndims/8) teams per warp, warp-synchronous like the team kernels
+//   input    a lane loads its 8 bytes of each of the block's 8 rows with 64-bit loads (a team's loads cover whole rows:
+//            coalesced), one block ahead in registers
+//   pass 1   packed subtract (delta), packed zigzag (one PRMT replicates the four sign bits), OR-mask: 9 instructions
+//            per 4 samples; widths of 4 dims at once (7 -> 8 promotion, bit smear, per-byte popcount)
+//   header   D % 8 == 0: an octet owns 3 whole header bytes per slot
+//   pack     a quad of fields is squeezed to <= 32 contiguous bits with three multiply-adds (byte 1 and byte 3 move next
+//            to bytes 0 and 2, then the high pair moves next to the low pair); two quads make the octet's <= 64-bit
+//            piece of the row
+//   rows     the pieces of a block go through shared memory ([row][octet], 64-bit); lane (team, row) then appends the
+//            team's pieces of ITS row with a scalar bit writer straight into the output staging tile -- no cross-lane
+//            bit merging, no atomics; rows only share their first / last partial word, written byte-wise
+//   control  the reference's run / group state machine (sprintz_delta_rle.cpp:134-312) as the per-team action generator
+//            of spz_encode_hd.cu, executed in lock-step passes
+//   output   double-buffered shared staging tile, flushed with 128-bit stores
+//
+// Reference behaviour restated: sprintz_delta_rle.cpp:54-404 (high-dim delta + RLE encode).
+#include "spz_host.h"
+#include "spz_swar.cuh"
+
+namespace spz {
+
+constexpr int kWideEncThreads = 128;
+constexpr unsigned kFullWE = 0xffffffffu;
+
+enum : uint32_t { WACT_NONE = 0, WACT_RUN = 1, WACT_PAD = 2, WACT_DATA = 3 };
+
+// per-byte zigzag (bitpack.h:302) of four int8 lanes: (d << 1) ^ (d >> 7)
+__device__ __forceinline__ uint32_t zigzag4(uint32_t d)
+{
+    uint32_t sign;
+    asm("prmt.b32 %0, %1, 0, 0xba98;" : "=r"(sign) : "r"(d));           // selector msb: replicate the byte's sign
+    return ((d + d) & 0xfefefefeu) ^ sign;
+}
+
+// OR-masks of four dims -> their field widths, one per byte: bit length with 7 -> 8 (bitpack.h:72-93) => 0..6, 8
+__device__ __forceinline__ uint32_t widths4(uint32_t m)
+{
+    m |= (m << 1) & 0x80808080u;                                        // bit 6 set => the width is 8
+    uint32_t v = m | ((m >> 1) & 0x7f7f7f7fu);
+    v |= (v >> 2) & 0x3f3f3f3fu;
+    v |= (v >> 4) & 0x0f0f0f0fu;                                        // 2^n - 1 in every byte
+    uint32_t n = v - ((v >> 1) & 0x55555555u);
+    n = (n & 0x33333333u) + ((n >> 2) & 0x33333333u);
+    return (n + (n >> 4)) & 0x0f0f0f0fu;
+}
+
+// four widths (one per byte) -> the 12 header bits of the quad; a width of 8 is stored as 7 (sprintz_delta_rle.cpp:199)
+__device__ __forceinline__ uint32_t header12(uint32_t n4)
+{
+    const uint32_t f = n4 - ((n4 >> 3) & 0x01010101u);
+    return (f & 7u) | ((f >> 5) & 0x38u) | ((f >> 10) & 0x1c0u) | ((f >> 15) & 0xe00u);
+}
+
+// multipliers that squeeze the four bytes of a zigzag word to contiguous fields
+struct PackC { uint32_t c1, c3, c23; };
+__device__ __forceinline__ void pack_consts(uint32_t n4, PackC& q)
+{
+    const uint32_t n0 = n4 & 0xffu, n1 = (n4 >> 8) & 0xffu, n2 = (n4 >> 16) & 0xffu;
+    q.c1 = (1u << n0) - 256u;                    // byte 1 moves from bit 8 to bit n0
+    q.c3 = ((1u << n2) - 256u) << 16;            // byte 3 moves from bit 24 to bit 16 + n2
+    q.c23 = (1u << (n0 + n1)) - 65536u;          // the high pair moves from bit 16 to bit n0 + n1
+}
+__device__ __forceinline__ uint32_t pack_quad(uint32_t w, const PackC& q)
+{
+    const uint32_t w1 = w + __byte_perm(w, 0, 0x4441) * q.c1;
+    const uint32_t w2 = w1 + (w >> 24) * q.c3;
+    return w2 + (w2 >> 16) * q.c23;
+}
+
+// p.team = lanes per chunk (ndims / 8), p.dpl = teams per warp; team shared memory:
+//   [piece buffers 2 x 64*NP][octet widths 2 x 32][2 staging tiles of out_cap bytes]
+template <int W>
+__global__ void __launch_bounds__(kWideEncThreads) spz_encode_wide_kernel(const EncParams p)
+{
+    static_assert(W == 8, "the SWAR wide-row encoder covers 8-bit elements");
+    constexpr int HB = Traits<W>::HB;
+    extern __shared__ __align__(16) uint8_t smem[];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t NP = p.team, TPW = p.dpl;
+    const uint32_t tw_raw = (uint32_t)lane / NP;
+    const bool lane_on = tw_raw < TPW;                  // lanes past the last whole team of the warp idle along
+    const uint32_t tw = lane_on ? tw_raw : 0u;
+    const uint32_t t = lane_on ? (uint32_t)lane - tw * NP : 0u;
+    const uint64_t c64 = ((uint64_t)blockIdx.x * (kWideEncThreads / 32) + warp) * TPW + tw;
+    const bool valid = lane_on && c64 < p.nchunks;
+    const uint64_t c = valid ? c64 : 0;
+    const uint32_t D = NP * 8u;
+    const uint32_t last_lane = tw * NP + NP - 1u;
+
+    // ---- shared memory of this team
+    const uint32_t TS = p.team_smem;
+    const uint32_t warp_base = (uint32_t)warp * TPW * TS;
+    uint8_t* const sm = smem + warp_base + tw * TS;
+    const uint32_t PB = 64u * NP;                       // one piece buffer: [8 rows][NP] x 8 bytes
+    const uint32_t wid_off = 2u * PB;
+    uint8_t* const stage0 = sm + p.out_off;
+    const uint32_t OCAP = p.out_cap;
+
+    // ---- this chunk
+    const uint64_t first = c * p.chunk_len;
+    const int64_t L = valid ? (int64_t)((first + p.chunk_len <= p.len) ? p.chunk_len : (p.len - first)) : 0;
+    const uint8_t* const gin = p.src + first;           // 8-byte aligned (checked on the host)
+    uint8_t* const gstream = p.dst + c * p.slot_stride;
+    const uint32_t B = (uint32_t)kBlockRows * D;
+    const int64_t G = 2 * (int64_t)B;
+    const uint32_t H = (2u * D * HB) >> 3;               // D % 8 == 0: whole bytes
+    const uint32_t SH = H >> 1;                          // header bytes of one slot
+    const uint32_t meta_bytes = p.write_size ? 8u : 0u;
+    const uint32_t max_group_bytes = H + 2u * B + 4u;
+
+    // ---- output staging (double buffered)
+    uint8_t* ob = stage0;
+    uint32_t ob_sel = 0;
+    uint8_t* gdst;
+    uint32_t ocur, oskip;
+    {
+        const uint32_t mis = (uint32_t)((uintptr_t)gstream & 15);
+        gdst = gstream - mis; ocur = mis; oskip = mis;
+    }
+    auto flush = [&](bool on_, bool final_flush) {
+        __syncwarp();
+        if (on_) {
+            ob_sel ^= 1u;
+            uint8_t* const nb = stage0 + ob_sel * OCAP;
+            const uint32_t hi = final_flush ? ocur : (ocur & ~15u);
+            if (hi > oskip) {
+                uint32_t a = (oskip + 15u) & ~15u;
+                if (a > hi) a = hi;
+                for (uint32_t b = oskip + t; b < a; b += NP) gdst[b] = ob[b];
+                const uint4* s4 = reinterpret_cast<const uint4*>(ob);
+                uint4* g4 = reinterpret_cast<uint4*>(gdst);
+                for (uint32_t u = (a >> 4) + t; u < (hi >> 4); u += NP) g4[u] = s4[u];
+                uint32_t tb = hi & ~15u;
+                if (tb < a) tb = a;
+                for (uint32_t b = tb + t; b < hi; b += NP) gdst[b] = ob[b];
+                const uint32_t rem = ocur - hi;
+                for (uint32_t b = t; b < rem; b += NP) nb[b] = ob[hi + b];
+                ob = nb; gdst += hi; ocur = rem; oskip = 0;
+            } else {
+                ob_sel ^= 1u;               // nothing left: stay on the current tile
+            }
+        }
+    };
+    if (lane_on && t == 0) for (uint32_t b = 0; b < meta_bytes; b++) ob[ocur + b] = 0;     // metadata placeholder
+    ocur += meta_bytes;
+
+    // ---- team-uniform encoder state (sprintz_delta_rle.cpp:132-158)
+    uint32_t xA = 0, xB = 0;                            // the previous row's values of my 8 dims
+    uint32_t ngroups = 0, nslots = 0, run = 0, blk = 0;
+    uint32_t hdr_off = 0;
+    int64_t tail = 0;
+    bool outer = true;
+    bool on = valid && L >= (int64_t)kMinDataSize;
+    // blk*B <= L-G  <=>  blk <= last_start ; blk*B < L-G  <=>  blk <= last_cont   (both -1 when L < G)
+    const int32_t last_start = (L >= G) ? (int32_t)((L - G) / B) : -1;
+    const int32_t last_cont = (L > G) ? (int32_t)((L - G - 1) / B) : -1;     // delta: strict `<` (sprintz_delta_rle.cpp:226)
+
+    // ---- input prefetch (registers), one block ahead
+    uint32_t nxa[kBlockRows], nxb[kBlockRows];
+    auto prefetch = [&](uint32_t b) {
+        const bool ok = on && (int64_t)(b + 1u) * B <= L;
+        const uint8_t* src = gin + (size_t)b * B + 8u * t;
+#pragma unroll
+        for (int r = 0; r < kBlockRows; r++) {
+            uint2 v = make_uint2(0u, 0u);
+            if (ok) v = __ldg(reinterpret_cast<const uint2*>(src + (uint32_t)r * D));
+            nxa[r] = v.x; nxb[r] = v.y;
+        }
+    };
+
+    // this block's zigzagged errors and layout
+    uint32_t za[kBlockRows], zb[kBlockRows];
+    uint32_t nA = 0, nB = 0, wA = 0, wo = 0, row_bytes = 0;
+    uint32_t info = 0;                                  // what the row lanes need from my team (lane 0 of the team is read)
+
+    // One slot of the open group (team-predicated by the caller).  Data slots leave their pieces in the piece buffer;
+    // emit_rows() turns them into payload bytes.
+    auto emit_slot = [&](uint32_t act, uint32_t run_len, uint32_t pbsel) -> bool {
+        const uint32_t sl = nslots & 1u;
+        if (sl == 0u) { hdr_off = ocur; ocur += H; ngroups++; }
+        uint32_t h24 = 0;
+        if (act == WACT_RUN) {       // zero header fields + 1..2 length bytes (sprintz_delta_rle.cpp:238-245)
+            const uint32_t two = run_len > 0x7fu ? 1u : 0u;
+            if (t == 0) {
+                ob[ocur] = (uint8_t)((run_len & 0x7fu) | (two << 7));
+                if (two) ob[ocur + 1] = (uint8_t)(run_len >> 7);
+            }
+            ocur += 1u + two;
+        } else if (act == WACT_PAD) {
+            if (t == 0) ob[ocur] = 0;
+            ocur += 1u;
+        } else {
+            h24 = header12(nA) | (header12(nB) << 12);
+            PackC qa, qb;
+            pack_consts(nA, qa);
+            pack_consts(nB, qb);
+            uint2* pb = reinterpret_cast<uint2*>(sm + pbsel * PB) + t;
+#pragma unroll
+            for (int r = 0; r < kBlockRows; r++) {
+                const uint32_t va = pack_quad(za[r], qa), vb = pack_quad(zb[r], qb);
+                // octet piece = va | vb << wA (wA <= 32: the clamping funnel shifts give 0 / vb at 32)
+                pb[(uint32_t)r * NP] = make_uint2(va | __funnelshift_lc(0u, vb, wA), __funnelshift_lc(vb, 0u, wA));
+            }
+            sm[wid_off + pbsel * 32u + t] = (uint8_t)wo;
+            info = 1u | (row_bytes << 1) | ((uint32_t)((ob + ocur) - smem) << 11);
+            ocur += kBlockRows * row_bytes;
+            blk++;
+        }
+        {   // my octet's 3 header bytes of this slot
+            uint8_t* hp = ob + hdr_off + sl * SH + 3u * t;
+            hp[0] = (uint8_t)h24; hp[1] = (uint8_t)(h24 >> 8); hp[2] = (uint8_t)(h24 >> 16);
+        }
+        nslots++;
+        return (nslots & 1u) == 0u;
+    };
+
+    // Payload rows of the data slots just emitted: lane (team, row) appends the team's NP pieces of its row.
+    // Warp-uniform call; `doit` = my team emitted a data slot in this pass.
+    auto emit_rows = [&](bool doit, uint32_t pbsel) {
+        if (!doit) info = 0;
+        __syncwarp();                                   // pieces, widths and header bytes are in shared memory
+        const uint32_t njobs = 8u * TPW;
+        for (uint32_t j0 = 0; j0 < njobs; j0 += 32u) {
+            const uint32_t j = j0 + (uint32_t)lane;
+            const uint32_t jt = (j >> 3) < TPW ? (j >> 3) : TPW - 1u;
+            const uint32_t inf = __shfl_sync(kFullWE, info, (int)(jt * NP));
+            if (j < njobs && (inf & 1u)) {
+                const uint32_t r = j & 7u;
+                const uint32_t rb = (inf >> 1) & 0x3ffu;
+                const uint32_t rowaddr = (inf >> 11) + r * rb;          // byte offset from smem[]
+                const uint32_t end = rowaddr + rb;
+                const uint8_t* tb = smem + warp_base + jt * TS;
+                const uint2* pc = reinterpret_cast<const uint2*>(tb + pbsel * PB) + r * NP;
+                const uint8_t* wd = tb + wid_off + pbsel * 32u;
+                uint32_t waddr = rowaddr & ~3u;
+                uint32_t fill = (rowaddr & 3u) * 8u;
+                uint32_t a0 = 0;
+                auto put = [&](uint32_t wa, uint32_t v) {
+                    if (wa >= rowaddr && wa + 4u <= end) {
+                        *reinterpret_cast<uint32_t*>(smem + wa) = v;
+                    } else {                                            // the row's first / last partial word
+#pragma unroll
+                        for (uint32_t i = 0; i < 4u; i++)
+                            if (wa + i >= rowaddr && wa + i < end) smem[wa + i] = (uint8_t)(v >> (8u * i));
+                    }
+                };
+                for (uint32_t u = 0; u < NP; u++) {
+                    const uint2 pv = pc[u];
+                    const uint32_t w = wd[u];
+                    a0 |= pv.x << fill;
+                    uint32_t a1 = __funnelshift_l(pv.x, pv.y, fill);
+                    const uint32_t a2 = __funnelshift_l(pv.y, 0u, fill);
+                    fill += w;
+                    if (fill >= 32u) {
+                        put(waddr, a0); waddr += 4u; a0 = a1; a1 = a2; fill -= 32u;
+                        if (fill >= 32u) { put(waddr, a0); waddr += 4u; a0 = a1; fill -= 32u; }
+                    }
+                }
+                if (waddr < end) put(waddr, a0);
+            }
+        }
+    };
+
+    // Group finished: the staging tile leaves for HBM when the next group might not fit.  Warp-uniform call.
+    auto close_group = [&](bool gc) {
+        const bool need = gc && ocur + max_group_bytes + 16u > OCAP;
+        if (__any_sync(kFullWE, need)) flush(need, false);
+    };
+
+    prefetch(0);
+    for (uint32_t it = 0;; it++) {
+        if (on && outer && (int32_t)blk > last_start) { tail = (int64_t)blk * B; on = false; }
+        if (!__any_sync(kFullWE, on)) break;
+        const uint32_t pbsel = it & 1u;
+
+        // ================= pass 1: packed delta -> zigzag -> OR-mask of this block (sprintz_delta_rle.cpp:161-201)
+        {
+            uint32_t a = xA, b = xB, ma = 0, mb = 0;
+#pragma unroll
+            for (int r = 0; r < kBlockRows; r++) {
+                const uint32_t va = nxa[r], vb = nxb[r];
+                za[r] = zigzag4(psub<8>(va, a)); ma |= za[r]; a = va;
+                zb[r] = zigzag4(psub<8>(vb, b)); mb |= zb[r]; b = vb;
+            }
+            if (on) { xA = a; xB = b; }
+            nA = widths4(ma); nB = widths4(mb);
+        }
+        prefetch(it + 1u);
+        wA = (nA * 0x01010101u) >> 24;
+        wo = wA + ((nB * 0x01010101u) >> 24);
+        uint32_t incl = wo;
+        for (uint32_t s = 1; s < NP; s <<= 1) {
+            const uint32_t y = __shfl_up_sync(kFullWE, incl, s);
+            if (t >= s) incl += y;
+        }
+        const uint32_t total = __shfl_sync(kFullWE, incl, (int)last_lane);
+        const bool zero = (total == 0);
+        row_bytes = (total + 7u) >> 3;
+
+        // ================= control
+        // Fast path: every live team has a plain data block (no run open, block not all-zero).
+        if (__all_sync(kFullWE, !on || (!zero && run == 0u))) {
+            bool gc = false;
+            if (on) { gc = emit_slot(WACT_DATA, 0u, pbsel); outer = gc; }
+            emit_rows(on, pbsel);
+            if (__any_sync(kFullWE, gc)) close_group(gc);
+            continue;
+        }
+        // General case: per-team action generator (run slot / pad / data slot), executed in lock-step passes.
+        // st: 0 = block just read; 1 = run flushed because the data ran out, maybe pad; 2 = finished; 3 = block consumed
+        uint32_t st = on ? 0u : 3u;
+        for (;;) {
+            uint32_t act = WACT_NONE, run_len = 0;
+            if (st == 0u) {
+                if (zero && run < kMaxRun) {
+                    run++; blk++;
+                    if ((int32_t)blk <= last_cont) { outer = false; st = 3u; }
+                    else { act = WACT_RUN; run_len = run; run = 0; st = 1u; }    // not enough data to finish the group
+                } else if (run > 0) {
+                    act = WACT_RUN; run_len = run; run = 0;                      // a run just ended; re-evaluate this block
+                } else {
+                    act = WACT_DATA; st = 3u;
+                }
+            } else if (st == 1u) {
+                if (nslots & 1u) { act = WACT_PAD; }
+                st = 2u;
+            }
+            if (st == 2u && act == WACT_NONE) { tail = (int64_t)blk * B; on = false; st = 3u; }
+            if (!__any_sync(kFullWE, act != WACT_NONE)) break;
+
+            bool gc = false;
+            if (act != WACT_NONE) {
+                gc = emit_slot(act, run_len, pbsel);
+                if (act == WACT_DATA) outer = gc;
+            }
+            if (__any_sync(kFullWE, act == WACT_DATA)) emit_rows(act == WACT_DATA, pbsel);
+            if (__any_sync(kFullWE, gc)) close_group(gc);
+        }
+    }
+
+    // ---- trailing raw elements (sprintz_delta_rle.cpp:398-403); also the whole input when L < 128
+    {
+        const int64_t rem_elems = valid ? (L - tail) : 0;
+        const uint8_t* tsrc = gin + tail;
+        uint32_t left = (uint32_t)rem_elems, done = 0;
+        while (__any_sync(kFullWE, left > 0)) {
+            const uint32_t space = OCAP - ocur;
+            const uint32_t take = left < space ? left : space;
+            for (uint32_t b = t; b < take; b += NP) ob[ocur + b] = tsrc[done + b];
+            ocur += take; done += take; left -= take;
+            flush(left > 0, false);
+        }
+        const uint32_t sbytes = (uint32_t)((gdst + ocur) - gstream);      // exact stream length
+        flush(valid, true);
+        __syncwarp();
+        if (valid && t == 0) {
+            if (p.write_size) {     // format.h:35-45, written last because ngroups is only known now
+                const uint32_t rem16 = (uint32_t)rem_elems & 0xffffu;
+                gstream[0] = (uint8_t)ngroups; gstream[1] = (uint8_t)(ngroups >> 8);
+                gstream[2] = (uint8_t)(ngroups >> 16); gstream[3] = (uint8_t)(ngroups >> 24);
+                gstream[4] = (uint8_t)rem16; gstream[5] = (uint8_t)(rem16 >> 8);
+                gstream[6] = (uint8_t)D; gstream[7] = (uint8_t)(D >> 8);
+            }
+            ChunkMeta m;
+            m.nbytes = sbytes;
+            m.ngroups = ngroups;
+            m.remaining = (uint32_t)rem_elems;
+            m.status = kStatusOk;
+            p.meta[c] = m;
+        }
+    }
+}
+
+static inline uint32_t up16w(uint32_t x) { return (x + 15u) & ~15u; }
+
+// Returns cudaErrorNotSupported when the shape is not covered (the caller continues with the team kernels).
+cudaError_t launch_encode_wide(int elem_sz, int predictor, EncParams p, cudaStream_t stream)
+{
+    if (get_force_path() == 1) return cudaErrorNotSupported;
+    if (elem_sz != 1 || predictor != 0 || p.variant != 0) return cudaErrorNotSupported;
+    if (p.ndims < 24 || p.ndims > 256 || (p.ndims & 7u)) return cudaErrorNotSupported;
+    if (p.chunk_len > 0x70000000ull) return cudaErrorNotSupported;      // 32-bit cursors inside one chunk
+    // 64-bit row loads: every row of every chunk must start 8-byte aligned
+    if (((uintptr_t)p.src & 7) || (p.nchunks > 1 && (p.chunk_len & 7))) return cudaErrorNotSupported;
+    const uint32_t NP = p.ndims / 8u, TPW = 32u / NP;
+    const uint32_t H = (2u * p.ndims * 3u) / 8u;
+    p.team = NP; p.dpl = TPW;
+    const uint32_t grp = H + 16u * p.ndims + 4u;
+    const uint32_t teams_per_cta = (kWideEncThreads / 32) * TPW;
+    p.teams_per_cta = teams_per_cta;
+    p.out_off = up16w(2u * 64u * NP + 64u);
+    // staging tiles hold up to 4 groups, fewer when that would cost occupancy (4 CTAs per SM need <= 56 KB each)
+    for (uint32_t ngrp = 4; ngrp >= 1; ngrp--) {
+        p.out_cap = up16w(32u + ngrp * grp + 16u);
+        p.team_smem = p.out_off + 2u * p.out_cap;
+        if ((size_t)teams_per_cta * p.team_smem <= 56u * 1024u) break;
+    }
+    const size_t smem = (size_t)teams_per_cta * p.team_smem;
+    if (smem > 200 * 1024) return cudaErrorNotSupported;
+    const uint64_t grid64 = (p.nchunks + teams_per_cta - 1) / teams_per_cta;
+    if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(spz_encode_wide_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (g_enc_probe) return probe_fill(g_enc_probe, 3, spz_encode_wide_kernel<8>, kWideEncThreads, smem, teams_per_cta);
+    count_launch();
+    spz_encode_wide_kernel<8><<<(uint32_t)grid64, kWideEncThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace spz
