@@ -12,7 +12,7 @@
 //   header   a lane reads its octet's 8 width fields as one 24-bit window, sums them with two multiplies and a popcount;
 //            one packed shuffle scan over the team gives both slots' bit offsets
 //   unpack   a quad of fields (<= 32 bits) is one window (2 LDS + funnel shift); field j is moved to byte j by a left
-//            shift of 8j - (bits before it) >= 0, the four shifted copies are merged with three bit-selects: 6
+//            shift of 8j - (bits before it) >= 0 (as a multiply: the ALU pipe is the binding one), the four shifted copies are merged with three bit-selects: 6
 //            instructions per 4 samples instead of 16
 //   predict  zigzag^-1 on four bytes at once (mask, multiply by 0xff, shift, select-xor) and the running sum as a
 //            carry-less byte-wise add: 9 instructions per 4 samples
@@ -28,7 +28,7 @@ constexpr int kWideThreads = 128;
 constexpr unsigned kFullW = 0xffffffffu;
 
 // per-quad constants of one slot: shifts that move field j to byte j, byte masks (split for the zigzag step)
-struct QuadC { uint32_t sl1, sl2, sl3, ones, half; };
+struct QuadC { uint32_t m1, m2, m3, ones, half; };      // m_j = 2^(8j - bits before field j): the shifts run as multiplies (FMA pipe)
 
 // f12: four 3-bit header fields.  Returns the quad's total width in bits.
 __device__ __forceinline__ uint32_t quad_consts8(uint32_t f12, QuadC& q)
@@ -37,7 +37,7 @@ __device__ __forceinline__ uint32_t quad_consts8(uint32_t f12, QuadC& q)
     const uint32_t n = f + (((f + 0x01010101u) >> 3) & 0x01010101u);      // width: 7 is stored for 8 (sprintz_delta_rle.cpp:199)
     const uint32_t pre = n * 0x01010100u;                                   // byte k = n_0 + ... + n_(k-1)  (<= 24)
     const uint32_t sl = 0x18100800u - pre;                                  // byte k = 8k - bits before field k  (>= 0)
-    q.sl1 = (sl >> 8) & 0xffu; q.sl2 = (sl >> 16) & 0xffu; q.sl3 = sl >> 24;
+    q.m1 = 1u << ((sl >> 8) & 0xffu); q.m2 = 1u << ((sl >> 16) & 0xffu); q.m3 = 1u << (sl >> 24);
     uint32_t m = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) m |= ((1u << ((n >> (8 * k)) & 0xffu)) - 1u) << (8 * k);
@@ -172,7 +172,6 @@ __global__ void __launch_bounds__(kWideThreads) spz_decode_wide_kernel(const Dec
 
     uint32_t o = 0;                                     // output element cursor (team-uniform)
     const uint32_t B = 8u * D;
-    const uint32_t max_group = H + 2u * B;
 
     // One data slot: unpack + inverse predictor for my octet, rows staged in a tile, tile flushed with whole sectors.
     // Warp-uniform call; `doit` = my team really has this slot (state and global memory only change then).
@@ -192,8 +191,8 @@ __global__ void __launch_bounds__(kWideThreads) spz_decode_wide_kernel(const Dec
             const uint32_t la = ring_bits(bitA);
             const uint32_t lb = ring_bits(bitA + wA);
             bitA += row_bits;
-            const uint32_t wa = bsel(bsel(la, la << qa.sl1, 0x000000ffu), bsel(la << qa.sl2, la << qa.sl3, 0x00ff0000u), 0x0000ffffu);
-            const uint32_t wb = bsel(bsel(lb, lb << qb.sl1, 0x000000ffu), bsel(lb << qb.sl2, lb << qb.sl3, 0x00ff0000u), 0x0000ffffu);
+            const uint32_t wa = bsel(bsel(la, la * qa.m1, 0x000000ffu), bsel(la * qa.m2, la * qa.m3, 0x00ff0000u), 0x0000ffffu);
+            const uint32_t wb = bsel(bsel(lb, lb * qb.m1, 0x000000ffu), bsel(lb * qb.m2, lb * qb.m3, 0x00ff0000u), 0x0000ffffu);
             // zigzag^-1 (bitpack.h:303) on four bytes: (u >> 1) ^ -(u & 1); bits above each field's width are masked off here
             const uint32_t da = ((wa >> 1) & qa.half) ^ ((wa & qa.ones) * 0xffu);
             const uint32_t db = ((wb >> 1) & qb.half) ^ ((wb & qb.ones) * 0xffu);
@@ -220,7 +219,7 @@ __global__ void __launch_bounds__(kWideThreads) spz_decode_wide_kernel(const Dec
     for (uint32_t g = 0; g < gmax; g++) {
         if (g < ngroups && pos > limit) status = kStatusTruncated;      // ran past the readable bytes (the ring was fed zeros)
         const bool act = g < ngroups && status == kStatusOk;
-        ensure(pos + max_group + 8, act);
+        ensure(pos + H + 8, act);                       // the ring holds one header or one slot at a time (occupancy: half the ring)
 
         // ---- both slots' widths: my octet's fields, one packed scan over the team for the bit offsets
         const uint32_t hbit = (pos & RMASK) * 8u;
@@ -239,7 +238,9 @@ __global__ void __launch_bounds__(kWideThreads) spz_decode_wide_kernel(const Dec
 
         // Fast path: every live team of the warp has two data slots that fit.
         if (__all_sync(kFullW, !lane_on || (act && tot0 != 0u && tot1 != 0u && o + 2u * B <= cap))) {
+            ensure(pos + ((tot0 + 7u) & ~7u) + 8, lane_on);
             data_slot(fw0, excl & 0xffffu, tot0, lane_on);
+            ensure(pos + ((tot1 + 7u) & ~7u) + 8, lane_on);
             data_slot(fw1, excl >> 16, tot1, lane_on);
             continue;
         }
@@ -248,6 +249,7 @@ __global__ void __launch_bounds__(kWideThreads) spz_decode_wide_kernel(const Dec
         for (uint32_t s = 0; s < 2; s++) {
             const uint32_t total = s ? tot1 : tot0;
             const bool is_run = act && status == kStatusOk && total == 0;
+            ensure(pos + (is_run ? 2u : ((total + 7u) & ~7u)) + 8, act && status == kStatusOk);
             if (is_run) {
                 // ---- run slot (sprintz_delta_rle.cpp:640-667): the previous row repeats nrun * 8 times; rare, divergent
                 uint32_t nrun = ring_byte(pos) & 0x7f;
@@ -306,9 +308,9 @@ cudaError_t launch_decode_wide(int elem_sz, int predictor, DecParams p, cudaStre
     if (p.chunk_len > 0x70000000ull) return cudaErrorNotSupported;      // 32-bit cursors inside one chunk
     const uint32_t NP = p.ndims / 8u, TPW = 32u / NP;
     const uint32_t H = (2u * p.ndims * 3u + 7u) / 8u;
-    const uint32_t max_group = H + 16u * p.ndims;
+    const uint32_t max_need = (H > 8u * p.ndims ? H : 8u * p.ndims) + 8u;      // one header or one slot, plus the window over-read
     p.team = NP; p.dpl = TPW;
-    p.ring_cap = pow2_ceil_w(max_group + 8u + NP * 32u + 32u);
+    p.ring_cap = pow2_ceil_w(max_need + NP * 32u + 32u);
     p.ring_mask4 = (p.ring_cap - 1u) & ~3u;
     const uint32_t tile = 64u * NP;
     p.team_smem = ((p.ring_cap + 32u + 128u + 2u * (tile + 128u) + p.ring_cap - 1u) / p.ring_cap) * p.ring_cap;

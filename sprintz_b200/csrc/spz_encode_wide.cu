@@ -227,6 +227,12 @@ __global__ void __launch_bounds__(kWideEncThreads) spz_encode_wide_kernel(const 
 
     // Payload rows of the data slots just emitted: lane (team, row) appends the team's NP pieces of its row.
     // Warp-uniform call; `doit` = my team emitted a data slot in this pass.
+    //
+    // Rows are byte aligned, the writer stores whole words: a row's first word is stored with ZERO low bytes (they
+    // belong to the previous row), so after a barrier the previous row's lane ORs its last partial word into it.  Row 0
+    // saves the bytes in front of the payload before and restores them after; row 7 stores its tail with zeros behind
+    // the payload (bytes that are only written later).  Rows shorter than 8 bytes (which may not own a whole word) take
+    // a byte-wise path.
     auto emit_rows = [&](bool doit, uint32_t pbsel) {
         if (!doit) info = 0;
         __syncwarp();                                   // pieces, widths and header bytes are in shared memory
@@ -235,25 +241,38 @@ __global__ void __launch_bounds__(kWideEncThreads) spz_encode_wide_kernel(const 
             const uint32_t j = j0 + (uint32_t)lane;
             const uint32_t jt = (j >> 3) < TPW ? (j >> 3) : TPW - 1u;
             const uint32_t inf = __shfl_sync(kFullWE, info, (int)(jt * NP));
-            if (j < njobs && (inf & 1u)) {
-                const uint32_t r = j & 7u;
-                const uint32_t rb = (inf >> 1) & 0x3ffu;
-                const uint32_t rowaddr = (inf >> 11) + r * rb;          // byte offset from smem[]
-                const uint32_t end = rowaddr + rb;
-                const uint8_t* tb = smem + warp_base + jt * TS;
-                const uint2* pc = reinterpret_cast<const uint2*>(tb + pbsel * PB) + r * NP;
-                const uint8_t* wd = tb + wid_off + pbsel * 32u;
-                uint32_t waddr = rowaddr & ~3u;
-                uint32_t fill = (rowaddr & 3u) * 8u;
-                uint32_t a0 = 0;
-                auto put = [&](uint32_t wa, uint32_t v) {
-                    if (wa >= rowaddr && wa + 4u <= end) {
-                        *reinterpret_cast<uint32_t*>(smem + wa) = v;
-                    } else {                                            // the row's first / last partial word
-#pragma unroll
-                        for (uint32_t i = 0; i < 4u; i++)
-                            if (wa + i >= rowaddr && wa + i < end) smem[wa + i] = (uint8_t)(v >> (8u * i));
+            const bool act = j < njobs && (inf & 1u);
+            const uint32_t r = j & 7u;
+            const uint32_t rb = (inf >> 1) & 0x3ffu;
+            const uint32_t rowaddr = (inf >> 11) + r * rb;              // byte offset from smem[]
+            const uint32_t end = rowaddr + rb;
+            const uint8_t* tb = smem + warp_base + jt * TS;
+            const uint2* pc = reinterpret_cast<const uint2*>(tb + pbsel * PB) + r * NP;
+            const uint8_t* wd = tb + wid_off + pbsel * 32u;
+            const bool fast = act && rb >= 8u;
+            uint32_t waddr = rowaddr & ~3u;
+            const uint32_t fill0 = (rowaddr & 3u) * 8u;
+            uint32_t fill = fill0;
+            uint32_t a0 = 0, old0 = 0;
+            if (fast) {
+                if (r == 0u && fill0) old0 = *reinterpret_cast<const uint32_t*>(smem + waddr) & ((1u << fill0) - 1u);
+                for (uint32_t u = 0; u < NP; u++) {
+                    const uint2 pv = pc[u];
+                    const uint32_t w = wd[u];
+                    a0 |= pv.x << fill;
+                    uint32_t a1 = __funnelshift_l(pv.x, pv.y, fill);
+                    const uint32_t a2 = __funnelshift_l(pv.y, 0u, fill);
+                    fill += w;
+                    if (fill >= 32u) {
+                        *reinterpret_cast<uint32_t*>(smem + waddr) = a0; waddr += 4u; a0 = a1; a1 = a2; fill -= 32u;
+                        if (fill >= 32u) { *reinterpret_cast<uint32_t*>(smem + waddr) = a0; waddr += 4u; a0 = a1; fill -= 32u; }
                     }
+                }
+            } else if (act) {
+                auto put = [&](uint32_t wa, uint32_t v) {
+#pragma unroll
+                    for (uint32_t i = 0; i < 4u; i++)
+                        if (wa + i >= rowaddr && wa + i < end) smem[wa + i] = (uint8_t)(v >> (8u * i));
                 };
                 for (uint32_t u = 0; u < NP; u++) {
                     const uint2 pv = pc[u];
@@ -269,7 +288,16 @@ __global__ void __launch_bounds__(kWideEncThreads) spz_encode_wide_kernel(const 
                 }
                 if (waddr < end) put(waddr, a0);
             }
+            __syncwarp();                               // every whole word of every row is stored
+            if (fast) {
+                if (waddr < end) {                      // last word: when the row ends inside it, it is the next row's (zero-padded) first word
+                    if (r < 7u && (end & 3u)) a0 |= *reinterpret_cast<const uint32_t*>(smem + waddr);
+                    *reinterpret_cast<uint32_t*>(smem + waddr) = a0;
+                }
+                if (r == 0u && fill0) *reinterpret_cast<uint32_t*>(smem + (rowaddr & ~3u)) |= old0;
+            }
         }
+        __syncwarp();                                   // rows are complete before anything is appended behind them
     };
 
     // Group finished: the staging tile leaves for HBM when the next group might not fit.  Warp-uniform call.
