@@ -21,7 +21,7 @@
 //            bit merging, no atomics; rows only share their first / last partial word, written byte-wise
 //   control  the reference's run / group state machine (sprintz_delta_rle.cpp:134-312) as the per-team action generator
 //            of spz_encode_hd.cu, executed in lock-step passes
-//   output   double-buffered shared staging tile, flushed with 128-bit stores
+//   output   shared staging tile, flushed with 128-bit stores
 //
 // Reference behaviour restated: sprintz_delta_rle.cpp:54-404 (high-dim delta + RLE encode).
 #include "spz_host.h"
@@ -78,9 +78,9 @@ __device__ __forceinline__ uint32_t pack_quad(uint32_t w, const PackC& q)
 }
 
 // p.team = lanes per chunk (ndims / 8), p.dpl = teams per warp; team shared memory:
-//   [piece buffers 2 x 64*NP][octet widths 2 x 32][2 staging tiles of out_cap bytes]
-template <int W>
-__global__ void __launch_bounds__(kWideEncThreads) spz_encode_wide_kernel(const EncParams p)
+//   [piece buffers 2 x 64*NP][octet widths 2 x 32][staging tile of out_cap bytes]
+template <int W, int MINB>
+__global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(const EncParams p)
 {
     static_assert(W == 8, "the SWAR wide-row encoder covers 8-bit elements");
     constexpr int HB = Traits<W>::HB;
@@ -119,9 +119,8 @@ __global__ void __launch_bounds__(kWideEncThreads) spz_encode_wide_kernel(const 
     const uint32_t meta_bytes = p.write_size ? 8u : 0u;
     const uint32_t max_group_bytes = H + 2u * B + 4u;
 
-    // ---- output staging (double buffered)
-    uint8_t* ob = stage0;
-    uint32_t ob_sel = 0;
+    // ---- output staging: one tile; whole 16-byte units leave, the (< 16 byte) remainder moves to the front
+    uint8_t* const ob = stage0;
     uint8_t* gdst;
     uint32_t ocur, oskip;
     {
@@ -130,9 +129,10 @@ __global__ void __launch_bounds__(kWideEncThreads) spz_encode_wide_kernel(const 
     }
     auto flush = [&](bool on_, bool final_flush) {
         __syncwarp();
+        uint32_t carry[5] = {0, 0, 0, 0, 0};            // NP >= 3: a lane moves at most 5 of the < 16 remaining bytes
+        uint32_t rem = 0;
+        bool moved = false;
         if (on_) {
-            ob_sel ^= 1u;
-            uint8_t* const nb = stage0 + ob_sel * OCAP;
             const uint32_t hi = final_flush ? ocur : (ocur & ~15u);
             if (hi > oskip) {
                 uint32_t a = (oskip + 15u) & ~15u;
@@ -144,12 +144,17 @@ __global__ void __launch_bounds__(kWideEncThreads) spz_encode_wide_kernel(const 
                 uint32_t tb = hi & ~15u;
                 if (tb < a) tb = a;
                 for (uint32_t b = tb + t; b < hi; b += NP) gdst[b] = ob[b];
-                const uint32_t rem = ocur - hi;
-                for (uint32_t b = t; b < rem; b += NP) nb[b] = ob[hi + b];
-                ob = nb; gdst += hi; ocur = rem; oskip = 0;
-            } else {
-                ob_sel ^= 1u;               // nothing left: stay on the current tile
+                rem = ocur - hi;
+#pragma unroll
+                for (int k = 0; k < 5; k++) if (t + k * NP < rem) carry[k] = ob[hi + t + k * NP];
+                gdst += hi; ocur = rem; oskip = 0;
+                moved = true;
             }
+        }
+        __syncwarp();                                   // the tile has been read
+        if (moved) {
+#pragma unroll
+            for (int k = 0; k < 5; k++) if (t + k * NP < rem) ob[t + k * NP] = (uint8_t)carry[k];
         }
     };
     if (lane_on && t == 0) for (uint32_t b = 0; b < meta_bytes; b++) ob[ocur + b] = 0;     // metadata placeholder
@@ -428,21 +433,24 @@ cudaError_t launch_encode_wide(int elem_sz, int predictor, EncParams p, cudaStre
     const uint32_t teams_per_cta = (kWideEncThreads / 32) * TPW;
     p.teams_per_cta = teams_per_cta;
     p.out_off = up16w(2u * 64u * NP + 64u);
-    // staging tiles hold up to 4 groups, fewer when that would cost occupancy (4 CTAs per SM need <= 56 KB each)
+    // the staging tile holds up to 4 groups, fewer when that would cost occupancy (6 CTAs per SM need <= 36 KB each)
     for (uint32_t ngrp = 4; ngrp >= 1; ngrp--) {
         p.out_cap = up16w(32u + ngrp * grp + 16u);
-        p.team_smem = p.out_off + 2u * p.out_cap;
-        if ((size_t)teams_per_cta * p.team_smem <= 56u * 1024u) break;
+        p.team_smem = p.out_off + p.out_cap;
+        if ((size_t)teams_per_cta * p.team_smem <= 36u * 1024u) break;
     }
     const size_t smem = (size_t)teams_per_cta * p.team_smem;
     if (smem > 200 * 1024) return cudaErrorNotSupported;
     const uint64_t grid64 = (p.nchunks + teams_per_cta - 1) / teams_per_cta;
     if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(spz_encode_wide_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // 96 registers / 5 CTAs per SM: measured equal to 127 registers / 4 CTAs (the kernel is issue-bound, not latency-bound);
+    // 80 registers / 6 CTAs spills and is 8 % slower
+    auto kernel = spz_encode_wide_kernel<8, 5>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    if (g_enc_probe) return probe_fill(g_enc_probe, 3, spz_encode_wide_kernel<8>, kWideEncThreads, smem, teams_per_cta);
+    if (g_enc_probe) return probe_fill(g_enc_probe, 3, kernel, kWideEncThreads, smem, teams_per_cta);
     count_launch();
-    spz_encode_wide_kernel<8><<<(uint32_t)grid64, kWideEncThreads, smem, stream>>>(p);
+    kernel<<<(uint32_t)grid64, kWideEncThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
