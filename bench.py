@@ -131,7 +131,8 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-GATHER_ROUNDS = 8       # stripes per rank of the streamed multi-GPU gather
+GATHER_ROUNDS = 8       # stripes per rank of the streamed multi-GPU gather (NCCL)
+P2P_ROUNDS = 16         # stripes per rank of the peer-memory gather (profiles/r2_p2p_probe_n2.jsonl: 16 > 8 > 4)
 
 
 def make_stream(cfg, device, seed, multiple=16):
@@ -374,7 +375,7 @@ def measure_config(env, args, cfg_name, cfg, steps, warm, main):
     world, rank, dev = env.world, env.rank, env.dev
     # N > 1: every rank's shard is GATHER_ROUNDS whole stripes of whole chunks (the gathered frame needs whole chunks
     # everywhere but at the end of the global stream)
-    x, rows = make_stream(cfg, dev, seed=12345 + rank, multiple=16 if world == 1 else chunk_rows * GATHER_ROUNDS)
+    x, rows = make_stream(cfg, dev, seed=12345 + rank, multiple=16 if world == 1 else chunk_rows * max(GATHER_ROUNDS, P2P_ROUNDS))
     n = x.numel()
     raw = n * esz
     codec = spz.FrameCodec(pred, esz, n, D, chunk_rows, device=dev)
@@ -610,13 +611,44 @@ def measure_gather(env, args, codec, fr, x, out, cfg, chunk_rows, raw, payload, 
         moved = (world - 1) * payload                       # bytes that crossed NVLink into rank 0 (payloads are ~equal)
         t_enc_step = r["t_enc"] / steps
         t_dec_step = r["t_dec"] / steps
-        return {"gather": {"ms": 1e3 * t_g, "payload_bytes_total": world * payload, "gbs_into_rank0": moved / t_g / 1e9,
-                           "backend": "ncclSend/ncclRecv grouped, libsprintz_b200.so (spz_frame_gather_dev)",
-                           "encode_plus_gather_ms": 1e3 * t_eg, "encode_ms": 1e3 * t_enc_step,
-                           "overlap_efficiency": max(t_enc_step, t_g) / t_eg,
-                           "gathered_frame_decodes_to_input": ok, "streamed_frame_decodes_to_input": ok2},
-                "value_with_gather": world * raw / (t_eg + t_dec_step) / 1e9,
-                "encode_with_gather_gbs": world * raw / t_eg / 1e9}
+        rec = {"gather": {"ms": 1e3 * t_g, "payload_bytes_total": world * payload, "gbs_into_rank0": moved / t_g / 1e9,
+                          "backend": "ncclSend/ncclRecv grouped, libsprintz_b200.so (spz_frame_gather_dev)",
+                          "encode_plus_gather_ms": 1e3 * t_eg, "encode_ms": 1e3 * t_enc_step,
+                          "overlap_efficiency": max(t_enc_step, t_g) / t_eg,
+                          "gathered_frame_decodes_to_input": ok, "streamed_frame_decodes_to_input": ok2},
+               "value_with_gather": world * raw / (t_eg + t_dec_step) / 1e9,
+               "encode_with_gather_gbs": world * raw / t_eg / 1e9}
+        # ---- the same exchange over peer memory: every stripe's compaction kernel stores straight into rank 0's frame
+        try:
+            g = spz.FrameGather(env.comm, codec, dst=0, stripe_chunks=codec.nchunks // P2P_ROUNDS)
+            g.enable_p2p()
+            g.encode_and_gather_p2p(x)                      # warm-up + correctness
+            torch.cuda.synchronize()
+            env.barrier()
+            ok3 = g.verify_against_shards(g.last_frame, x) if rank == 0 else None
+            env.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                g.encode_and_gather_p2p(x)
+            e1.record()
+            env.barrier()
+            t_p2p = env.max_over_ranks([e0.elapsed_time(e1) / reps / 1e3])[0]
+            ok4 = g.verify_against_shards(g.last_frame, x) if rank == 0 else None
+            # what bounds it: rank 0 ingress (the other ranks' payload over NVLink) or the encode itself
+            rec["gather_p2p"] = {"encode_plus_gather_ms": 1e3 * t_p2p, "gbs_into_rank0": moved / t_p2p / 1e9,
+                                 "backend": "fused compaction + NVLink peer stores (spz_frame_encode_gather_p2p_dev), no NCCL in the data path",
+                                 "overlap_efficiency": max(t_enc_step, t_g) / t_p2p, "stripes_per_rank": P2P_ROUNDS,
+                                 "frame_decodes_to_input": bool(ok3) and bool(ok4) if rank == 0 else None}
+            if t_p2p < t_eg:
+                rec["value_with_gather"] = world * raw / (t_p2p + t_dec_step) / 1e9
+                rec["encode_with_gather_gbs"] = world * raw / t_p2p / 1e9
+                rec["value_with_gather_backend"] = "p2p"
+            else:
+                rec["value_with_gather_backend"] = "nccl"
+        except Exception as e:  # noqa: BLE001
+            rec["gather_p2p"] = {"error": f"{type(e).__name__}: {e}"}
+        return rec
     except Exception as e:  # noqa: BLE001
         return {"gather": {"error": f"{type(e).__name__}: {e}"}}
 

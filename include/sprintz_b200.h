@@ -273,6 +273,19 @@ int spz_frame_encode_gather_dev(spz_comm_t comm, int dst, int predictor, int ele
                                 uint16_t ndims, uint32_t chunk_rows, uint32_t stripe_chunks, void* d_frame, uint64_t frame_cap,
                                 void* d_work, uint64_t work_bytes, void* d_gathered, uint64_t gathered_cap, spz_stream_t stream);
 
+/* Peer-memory form of the same exchange (NVLink stores, no NCCL in the data path).  spz_comm_shared_alloc is collective:
+ * every rank allocates a shared region (CUDA IPC, mapped by all peers) with room for a gathered frame of gathered_bytes
+ * (0 on ranks that never are the destination) and gets the address of that area in *d_gathered.
+ * spz_frame_encode_gather_p2p_dev encodes the rank's shard stripe by stripe; each stripe's compaction kernel writes the
+ * chunk streams and their directory entries straight to their final place in the DESTINATION's shared area while the
+ * next stripe is being encoded (sizes travel as tagged flag words in peer memory; no host synchronisation).  The
+ * gathered frame lands in dst's shared area (the pointer spz_comm_shared_alloc returned there); d_frame only receives
+ * the local directory.  Asynchronous on `stream`; a rank that fails leaves the gathered frame without magic. */
+int spz_comm_shared_alloc(spz_comm_t comm, uint64_t gathered_bytes, void** d_gathered);
+int spz_frame_encode_gather_p2p_dev(spz_comm_t comm, int dst, int predictor, int elem_sz, const void* d_src, uint64_t total_len,
+                                    uint16_t ndims, uint32_t chunk_rows, uint32_t stripe_chunks, void* d_frame, uint64_t frame_cap,
+                                    void* d_work, uint64_t work_bytes, spz_stream_t stream);
+
 /* ---------------------------------------------------------------- 5. float -> integer quantiser
  * python/datasets/compress_bench.py:45-60 (_quantize, axis = 0): the step that turns a float dataset (rows x ndims,
  * row-major) into the integer stream the codecs eat.  Per dim d, exactly the reference's arithmetic:

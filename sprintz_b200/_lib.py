@@ -95,6 +95,8 @@ SYMBOLS = {
     "spz_frame_gather_max_bytes": (_u64, [_i, _u64, _u16, _u32]),
     "spz_frame_gather_dev": (_i, [_vp, _i, _u64, _u32, _vp, _vp, _u64, _vp]),
     "spz_frame_encode_gather_dev": (_i, [_vp, _i, _i, _i, _vp, _u64, _u16, _u32, _u32, _vp, _u64, _vp, _u64, _vp, _u64, _vp]),
+    "spz_comm_shared_alloc": (_i, [_vp, _u64, C.POINTER(_vp)]),
+    "spz_frame_encode_gather_p2p_dev": (_i, [_vp, _i, _i, _i, _vp, _u64, _u16, _u32, _u32, _vp, _u64, _vp, _u64, _vp]),
     "spz_quantize_workspace_bytes": (_u64, [_u16]),
     "spz_quantize_dev": (_i, [_i, _i, _vp, _u64, _u16, _vp, _vp, _u64, _vp]),
     "spz_quantize_host": (_i64, [_i, _i, _vp, _u64, _u16, _vp]),

@@ -538,6 +538,35 @@ class FrameGather:
               "spz_frame_encode_gather_dev")
         return self._frame(self.stripe_chunks)
 
+    def enable_p2p(self):
+        """Collective: allocates the shared (CUDA IPC) regions; the gathered frame of encode_and_gather_p2p lands in the
+        destination's one."""
+        torch = _torch()
+        ptr = C.c_void_p(None)
+        need = self.cap if self.comm.rank == self.dst else 0
+        check(lib().spz_comm_shared_alloc(self.comm.handle, need, C.byref(ptr)), "spz_comm_shared_alloc")
+        self.p2p_buf = None
+        if need:
+            class _DevMem:                      # CUDA array interface over the library-owned allocation
+                pass
+            m = _DevMem()
+            m.__cuda_array_interface__ = {"shape": (need,), "typestr": "|u1", "data": (int(ptr.value), False), "version": 2}
+            self.p2p_buf = torch.as_tensor(m, device=self.codec.frame.device)
+        self.p2p = True
+
+    def encode_and_gather_p2p(self, x):
+        """streamed over peer memory: every stripe's compaction kernel stores straight into the destination's frame"""
+        c = self.codec
+        check(lib().spz_frame_encode_gather_p2p_dev(self.comm.handle, self.dst, c.predictor, c.elem_sz, x.data_ptr(),
+                                                    self.total_len, c.ndims, c.chunk_rows, self.stripe_chunks, c.frame.data_ptr(),
+                                                    c.frame_cap, c.work.data_ptr(), c.work_bytes, _stream_ptr()),
+              "spz_frame_encode_gather_p2p_dev")
+        if self.comm.rank != self.dst:
+            return None
+        self.last_stripes = self.stripe_chunks
+        self.last_frame = Frame(self.p2p_buf, c.predictor, c.elem_sz, self.total_len, c.ndims, c.chunk_rows, None)
+        return self.last_frame
+
     def shard_positions(self, rank: int, stripes: int):
         """[(global element lo, local element lo, count)] of `rank`'s pieces inside the global stream"""
         c = self.codec

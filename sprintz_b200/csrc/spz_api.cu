@@ -329,6 +329,22 @@ int frame_job_encode_slab(const FrameJob& j, uint64_t k, cudaStream_t st)
     return SPZ_OK;
 }
 
+// directory scan of slab k alone: local chunk_off / chunk_nbytes and the running payload total; no header, no compaction
+// (the peer-memory gather moves the streams itself, spz_comm.cu)
+int frame_job_scan_slab(const FrameJob& j, uint64_t k, cudaStream_t st)
+{
+    uint64_t c0, nc, e0, ne;
+    j.slab(k, c0, nc, e0, ne);
+    ChunkMeta* meta = (ChunkMeta*)(j.work + j.w.off_meta);
+    uint64_t* chunk_off = (uint64_t*)(j.d_frame + j.f.off_dir);
+    uint32_t* chunk_nbytes = (uint32_t*)(j.d_frame + j.f.off_sizes);
+    CK(launch_scan_sizes(meta + c0, nc, chunk_off + c0, chunk_nbytes + c0,
+                         (unsigned long long*)(j.work + j.w.off_state) + k * j.tiles_per_slab,
+                         (unsigned int*)(j.work + j.w.off_ticket) + k, j.d_tot() + k, j.d_tot() + k + 1,
+                         0, (spz_frame_header*)j.d_frame, j.h, nullptr, j.d_err(), st));
+    return SPZ_OK;
+}
+
 int frame_job_compact_slab(const FrameJob& j, uint64_t k, cudaStream_t st)
 {
     uint64_t c0, nc, e0, ne;

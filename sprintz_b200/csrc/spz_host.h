@@ -127,6 +127,7 @@ int frame_job_init(FrameJob& j, int predictor, int elem_sz, const void* d_src, u
                    uint64_t* d_frame_bytes, uint64_t slab_chunks);
 int frame_job_reset(const FrameJob& j, cudaStream_t st);                       // zeroes scan states / tickets / totals / error word
 int frame_job_encode_slab(const FrameJob& j, uint64_t k, cudaStream_t st);     // codec kernel of slab k
+int frame_job_scan_slab(const FrameJob& j, uint64_t k, cudaStream_t st);       // directory scan of slab k only (slab order!)
 int frame_job_compact_slab(const FrameJob& j, uint64_t k, cudaStream_t st);    // directory scan + compaction of slab k (slab order!)
 
 // side stream + events of the pipelined encode (one set per process, guarded by a mutex while a call enqueues)

@@ -59,7 +59,22 @@ def run_case(comm, rank, world, checker, pred, esz, D, chunk_rows, nrows, ragged
     cap = int(L.spz_frame_gather_max_bytes(esz, total, D, chunk_rows)) if rank == 0 else 0
     gbuf = torch.zeros(max(cap, 16), dtype=torch.uint8, device=dev)
     st = spz.api._stream_ptr()
-    if streamed:
+    if streamed == "p2p":
+        # peer-memory gather: the gathered frame lands in rank 0's shared (CUDA IPC) area
+        ptr = C.c_void_p(None)
+        spz._lib.check(L.spz_comm_shared_alloc(comm.handle, cap, C.byref(ptr)), "spz_comm_shared_alloc")
+        for rep in range(2):                    # twice: the epoch tags must make the flag words reusable
+            spz._lib.check(L.spz_frame_encode_gather_p2p_dev(comm.handle, 0, pred, esz, xt.data_ptr(), total, D, chunk_rows, S,
+                                                             codec.frame.data_ptr(), codec.frame_cap, codec.work.data_ptr(),
+                                                             codec.work_bytes, st), "spz_frame_encode_gather_p2p_dev")
+            torch.cuda.synchronize()
+        if rank == 0:
+            class _DevMem:
+                pass
+            m = _DevMem()
+            m.__cuda_array_interface__ = {"shape": (cap,), "typestr": "|u1", "data": (int(ptr.value), False), "version": 2}
+            gbuf = torch.as_tensor(m, device=dev)
+    elif streamed:
         spz._lib.check(L.spz_frame_encode_gather_dev(comm.handle, 0, pred, esz, xt.data_ptr(), total, D, chunk_rows, S,
                                                      codec.frame.data_ptr(), codec.frame_cap, codec.work.data_ptr(),
                                                      codec.work_bytes, gbuf.data_ptr() if rank == 0 else None, cap, st),
@@ -112,7 +127,8 @@ def main():
     for pred, esz, D, chunk_rows, nrows, ragged, force in shapes:
         nch = -(-(nrows * D - ragged) // (chunk_rows * D))
         for S, streamed in ((0, False), (max(7, -(-nch // (20 * world))), False), (max(1, nch // (3 * world)), True),
-                            (max(1, nch // (8 * world) + 1), True)):
+                            (max(1, nch // (8 * world) + 1), True), (max(1, nch // (3 * world)), "p2p"),
+                            (max(1, nch // (8 * world) + 1), "p2p")):
             run_case(comm, rank, world, checker, pred, esz, D, chunk_rows, nrows, ragged, S, streamed, force)
             ncases += 1
             dist.barrier()
