@@ -245,6 +245,26 @@ int spz_set_kernel_path(int path);
  * 3 = wide-row octet kernel (spz_*_wide_kernel).  Per calling thread. */
 int spz_last_kernel_family(int decode);
 
+/* ---------------------------------------------------------------- 3b. block-size axis (BASELINE config 5)
+ * The reference's block is a compile-time constant of 8 rows (sprintz_delta_rle.cpp:62-64, sprintz_xff_rle.cpp:78-82); its
+ * benchmark sweep names 16 / 32 / 64-row blocks.  These entry points run the RLE codecs (SPZ_DELTA / SPZ_XFF) with
+ * block_rows = 8 | 16 | 32 | 64: the same stream format with a block of block_rows rows, the reference's own derived
+ * constants (min_data_size = 8 * block_sz * 2, FIRE counter += grad_sum >> (log2_block_sz - 1)) and -- for more than 8
+ * rows -- the high-dim (row-major payload) layout at every ndims.  block_rows == 8 is exactly the calls above.  No
+ * reference build exists for the larger blocks: PARITY UNPINNED BEYOND BLOCK 8 (the oracle's generalisation is pinned to
+ * the reference at 8 and checked by round trips otherwise).  chunk_rows must be a multiple of 2 * block_rows.  A frame
+ * records block_rows in spz_frame_header.reserved (0 = 8). */
+int spz_compress_bs_dev(int predictor, int elem_sz, int block_rows, const void* d_src, uint32_t len, uint16_t ndims,
+                        int write_size, void* d_dest, spz_chunk_meta* d_meta, spz_stream_t stream);
+int spz_decompress_bs_dev(int predictor, int elem_sz, int block_rows, const void* d_src, uint64_t src_bytes, int has_meta,
+                          uint16_t ndims, void* d_dest, uint64_t dest_cap_elems, spz_chunk_meta* d_meta, spz_stream_t stream);
+int spz_frame_encode_bs_dev(int predictor, int elem_sz, int block_rows, const void* d_src, uint64_t len, uint16_t ndims,
+                            uint32_t chunk_rows, void* d_frame, uint64_t frame_cap, void* d_work, uint64_t work_bytes,
+                            uint64_t* d_frame_bytes, spz_stream_t stream);
+int spz_frame_decode_bs_dev(int predictor, int elem_sz, int block_rows, const void* d_frame, uint64_t frame_bytes, uint64_t len,
+                            uint16_t ndims, uint32_t chunk_rows, void* d_dest, uint64_t dest_cap_elems,
+                            spz_chunk_meta* d_status, spz_stream_t stream);
+
 /* ---------------------------------------------------------------- 4. multi-GPU: one process per GPU
  * No reference equivalent (the reference is single-threaded host code).  The path shards at chunk granularity with no
  * data-path collective; the one exchange step is gathering the ranks' compressed frames into ONE decodable frame on

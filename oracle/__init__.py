@@ -155,6 +155,28 @@ class Oracle(_Codec):
         dt = np.uint8 if esz == 1 else np.uint16
         return out[: n_out * esz].view(dt).copy(), int(ret)
 
+    def compress_bs(self, predictor, x, ndims, block_rows, write_size=True):
+        """Block-size axis (BASELINE config 5): block_rows in {8, 16, 32, 64}; 8 is oracle_compress itself."""
+        self.L.oracle_compress_bs.restype = C.c_int64
+        self.L.oracle_compress_bs.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint16, C.c_int,
+                                              C.c_void_p, C.c_int]
+        esz = x.dtype.itemsize
+        src = _as_u8(x)
+        buf = np.zeros(self.max_bytes(esz, x.size, ndims) + SLACK, np.uint8)
+        nb = C.c_uint64(0)
+        ret = self.L.oracle_compress_bs(predictor, esz, src.ctypes.data, x.size, buf.ctypes.data, ndims, int(write_size),
+                                        C.byref(nb), block_rows)
+        return buf[: nb.value].copy(), int(ret)
+
+    def decompress_bs(self, predictor, esz, stream, n_out, block_rows):
+        self.L.oracle_decompress_bs.restype = C.c_int64
+        self.L.oracle_decompress_bs.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        src = np.concatenate([_as_u8(stream), np.zeros(SLACK, np.uint8)])
+        out = np.full((n_out + 64) * esz + SLACK, 0xAA, np.uint8)
+        ret = self.L.oracle_decompress_bs(predictor, esz, src.ctypes.data, out.ctypes.data, block_rows)
+        dt = np.uint8 if esz == 1 else np.uint16
+        return out[: n_out * esz].view(dt).copy(), int(ret)
+
     def query(self, predictor, esz, stream, n_out, op):
         """-> (result uint64[ndims], decoded elements, returned count)"""
         self.L.oracle_query.restype = C.c_int64

@@ -43,6 +43,8 @@ typedef struct {
     int low;    /* low-dim variant? (sprintz.cpp:69-85) */
     int D;
     uint32_t H; /* header bytes per group */
+    int R;      /* rows per block: 8 in the reference (sprintz_delta_rle.cpp:62, sprintz_xff_rle.cpp:78-82 block_sz) */
+    int gshift; /* FIRE: counter += grad_sum >> (log2_block_sz - log2_learning_downsample) (sprintz_xff_rle.cpp:271-275) */
 } cfg_t;
 
 typedef struct {
@@ -71,6 +73,7 @@ static cfg_t make_cfg(int predictor, int elem_sz, int D)
     c.low = (elem_sz == 1) ? (D <= 4) : (D <= 2);
     c.D = D;
     c.H = (uint32_t)((2u * (uint32_t)D * (uint32_t)c.hb + 7u) / 8u);
+    c.R = BLOCK_SZ; c.gshift = 2;
     return c;
 }
 
@@ -130,7 +133,7 @@ static uint32_t encode_block(const cfg_t* c, state_t* st, const uint8_t* src, ui
         int32_t coef = c->fire ? fire_coef(c, st->counter[d]) : 0;
         uint32_t mask = 0, pv = st->prev_val[d];
         int32_t pd = st->prev_delta[d], gs = 0;
-        for (int r = 0; r < BLOCK_SZ; r++) {
+        for (int r = 0; r < c->R; r++) {
             uint32_t v = load_elem(src, first_elem + (uint64_t)r * D + d, c->esz);
             int32_t delta = (int32_t)sx((int64_t)v - (int64_t)pv, w);
             int32_t err = delta;
@@ -149,7 +152,7 @@ static uint32_t encode_block(const cfg_t* c, state_t* st, const uint8_t* src, ui
         }
         st->prev_val[d] = pv; st->prev_delta[d] = pd;
         if (c->fire)  /* counter += grad_sum >> 2, counter_t wraps (sprintz_xff_rle.cpp:273-275) */
-            st->counter[d] = (int32_t)sx((int64_t)st->counter[d] + (gs >> 2), c->cb);
+            st->counter[d] = (int32_t)sx((int64_t)st->counter[d] + (gs >> c->gshift), c->cb);
         nbits[d] = (uint8_t)nbits_rule(c, mask);
         total += nbits[d];
     }
@@ -210,19 +213,19 @@ static void emit_data(const cfg_t* c, emitter_t* e, const uint32_t* zz, const ui
         put_bits(e->hdr, (uint64_t)(s * (uint32_t)D + (uint32_t)d) * c->hb, field, c->hb);
     }
     if (c->low) {
-        memset(e->dest, 0, total);
+        memset(e->dest, 0, (size_t)total * (c->R / 8));    /* a column is R fields of nbits bits = nbits * R / 8 bytes */
         uint64_t bit = 0;
         for (int d = 0; d < D; d++)
-            for (int r = 0; r < BLOCK_SZ; r++) { put_bits(e->dest, bit, zz[r * D + d], nbits[d]); bit += nbits[d]; }
-        e->dest += total;
+            for (int r = 0; r < c->R; r++) { put_bits(e->dest, bit, zz[r * D + d], nbits[d]); bit += nbits[d]; }
+        e->dest += (size_t)total * (c->R / 8);
     } else {
         uint32_t row_bytes = (total + 7) / 8;
-        memset(e->dest, 0, (size_t)row_bytes * BLOCK_SZ);
-        for (int r = 0; r < BLOCK_SZ; r++) {
+        memset(e->dest, 0, (size_t)row_bytes * c->R);
+        for (int r = 0; r < c->R; r++) {
             uint64_t bit = (uint64_t)r * row_bytes * 8;
             for (int d = 0; d < D; d++) { put_bits(e->dest, bit, zz[r * D + d], nbits[d]); bit += nbits[d]; }
         }
-        e->dest += (size_t)row_bytes * BLOCK_SZ;
+        e->dest += (size_t)row_bytes * c->R;
     }
     e->nslots++;
 }
@@ -234,18 +237,34 @@ static void write_meta(uint8_t* p, uint16_t ndims, uint32_t ngroups, uint16_t re
     p[6] = (uint8_t)ndims; p[7] = (uint8_t)(ndims >> 8);
 }
 
-int64_t oracle_compress(int predictor, int elem_sz, const void* src_, uint32_t len, void* dest_,
-                        uint16_t ndims, int write_size, uint64_t* true_nbytes)
+/* block_rows: rows per block.  8 is the reference's constant; 16 / 32 / 64 apply the reference's own derived constants
+ * (min_data_size = 8 * block_sz * group_sz_blocks, shift_to_get_mean = log2_block_sz - log2_learning_downsample) to a
+ * larger block_sz -- BASELINE config 5's block-size axis, which no reference build can check ("parity unpinned"). */
+static int set_block_rows(cfg_t* c, int block_rows)
+{
+    int lg = 0;
+    while ((1 << lg) < block_rows) lg++;
+    if ((1 << lg) != block_rows || block_rows < 8 || block_rows > 64) return -1;
+    c->R = block_rows; c->gshift = lg - 1;
+    if (block_rows > 8) c->low = 0;    /* the column-major low-dim layout is tied to 8-row blocks: larger blocks use the
+                                        * high-dim layout, width rule, coefficient rule and continue-run test at every ndims */
+    return 0;
+}
+
+int64_t oracle_compress_bs(int predictor, int elem_sz, const void* src_, uint32_t len, void* dest_,
+                           uint16_t ndims, int write_size, uint64_t* true_nbytes, int block_rows)
 {
     if (ndims == 0) return -1;                 /* sprintz.cpp:71 */
     const uint8_t* src = (const uint8_t*)src_;
     uint8_t* const orig = (uint8_t*)dest_;
     cfg_t c = make_cfg(predictor, elem_sz, ndims);
+    if (set_block_rows(&c, block_rows)) return -1;
     const int D = c.D;
-    const int64_t B = (int64_t)BLOCK_SZ * D, G = 2 * B, L = len;
+    const int BLOCK_ROWS = c.R;
+    const int64_t B = (int64_t)BLOCK_ROWS * D, G = 2 * B, L = len;
     uint8_t* dest = orig;
 
-    if (len < MIN_DATA_SIZE) {                 /* sprintz_delta_rle.cpp:101-109 */
+    if (len < (uint32_t)(8 * BLOCK_ROWS * 2)) {    /* min_data_size, sprintz_delta_rle.cpp:71,101-109 */
         if (write_size) { write_meta(dest, ndims, 0, (uint16_t)len); dest += 8; }
         memcpy(dest, src, (size_t)len * c.esz);
         dest += (size_t)len * c.esz;
@@ -258,7 +277,7 @@ int64_t oracle_compress(int predictor, int elem_sz, const void* src_, uint32_t l
     st.prev_val = (uint32_t*)calloc(D, sizeof(uint32_t));
     st.prev_delta = (int32_t*)calloc(D, sizeof(int32_t));
     st.counter = (int32_t*)calloc(D, sizeof(int32_t));
-    uint32_t* zz = (uint32_t*)malloc(sizeof(uint32_t) * BLOCK_SZ * D);
+    uint32_t* zz = (uint32_t*)malloc(sizeof(uint32_t) * BLOCK_ROWS * D);
     uint8_t* nbits = (uint8_t*)malloc(D);
 
     /* continue-run test: `<` for delta and all low-dim codecs, `<=` for high-dim FIRE
@@ -307,19 +326,27 @@ int64_t oracle_compress(int predictor, int elem_sz, const void* src_, uint32_t l
     return (int64_t)(dest - orig) / c.esz;      /* pointer difference in int_t units */
 }
 
+int64_t oracle_compress(int predictor, int elem_sz, const void* src, uint32_t len, void* dest,
+                        uint16_t ndims, int write_size, uint64_t* true_nbytes)
+{
+    return oracle_compress_bs(predictor, elem_sz, src, len, dest, ndims, write_size, true_nbytes, BLOCK_SZ);
+}
+
 /* ------------------------------------------------------------------ decode */
 
-int64_t oracle_decompress_raw(int predictor, int elem_sz, const void* src_, void* dest_,
-                              uint16_t ndims, uint32_t ngroups, uint16_t remaining_len)
+int64_t oracle_decompress_raw_bs(int predictor, int elem_sz, const void* src_, void* dest_,
+                                 uint16_t ndims, uint32_t ngroups, uint16_t remaining_len, int block_rows)
 {
     const uint8_t* src = (const uint8_t*)src_;
     uint8_t* out = (uint8_t*)dest_;
-    if (ngroups == 0 && remaining_len < MIN_DATA_SIZE) {   /* sprintz_xff_rle.cpp:623-629 */
+    if (ngroups == 0 && remaining_len < (uint32_t)(8 * block_rows * 2)) {   /* sprintz_xff_rle.cpp:623-629 */
         memcpy(out, src, (size_t)remaining_len * elem_sz);
         return remaining_len;
     }
     if (ndims == 0) return 0;                              /* sprintz_delta_rle.cpp:475-478 */
     cfg_t c = make_cfg(predictor, elem_sz, ndims);
+    if (set_block_rows(&c, block_rows)) return -1;
+    const int BLOCK_ROWS = c.R;
     const int D = c.D, w = c.w;
     const uint32_t wmask = (1u << w) - 1u;
 
@@ -345,7 +372,7 @@ int64_t oracle_decompress_raw(int predictor, int elem_sz, const void* src_, void
                 uint32_t n = src[0] & 0x7f;
                 if (src[0] & 0x80) { n |= (uint32_t)src[1] << 7; src += 2; } else { src += 1; }
                 for (int d = 0; d < D; d++) coef[d] = c.fire ? fire_coef(&c, st.counter[d]) : 0;
-                for (uint64_t r = 0; r < (uint64_t)n * BLOCK_SZ; r++) {
+                for (uint64_t r = 0; r < (uint64_t)n * BLOCK_ROWS; r++) {
                     for (int d = 0; d < D; d++) {
                         if (c.fire) {   /* free-run the predictor with err = 0; counters untouched */
                             int32_t pred = fire_predict(&c, st.prev_delta[d], coef[d]);
@@ -363,7 +390,7 @@ int64_t oracle_decompress_raw(int predictor, int elem_sz, const void* src_, void
             uint64_t colbit = 0;    /* low-dim: start bit of dim d's column */
             uint32_t rowoff = 0;    /* high-dim: bit offset of dim d inside a row */
             for (int d = 0; d < D; d++) {
-                for (int r = 0; r < BLOCK_SZ; r++) {
+                for (int r = 0; r < BLOCK_ROWS; r++) {
                     uint64_t bit = c.low ? colbit + (uint64_t)r * nbits[d]
                                          : (uint64_t)r * row_bytes * 8 + rowoff;
                     uint32_t u = get_bits(src, bit, nbits[d]);
@@ -382,12 +409,12 @@ int64_t oracle_decompress_raw(int predictor, int elem_sz, const void* src_, void
                     st.prev_val[d] = (st.prev_val[d] + (uint32_t)delta) & wmask;
                     store_elem(out, o + (uint64_t)r * D + d, c.esz, st.prev_val[d]);
                 }
-                if (c.fire) st.counter[d] = (int32_t)sx((int64_t)st.counter[d] + (gs[d] >> 2), c.cb);
-                colbit += (uint64_t)BLOCK_SZ * nbits[d];
+                if (c.fire) st.counter[d] = (int32_t)sx((int64_t)st.counter[d] + (gs[d] >> c.gshift), c.cb);
+                colbit += (uint64_t)BLOCK_ROWS * nbits[d];
                 rowoff += nbits[d];
             }
-            src += c.low ? total : row_bytes * BLOCK_SZ;
-            o += (uint64_t)BLOCK_SZ * D;
+            src += c.low ? total * (uint32_t)(BLOCK_ROWS / 8) : row_bytes * (uint32_t)BLOCK_ROWS;
+            o += (uint64_t)BLOCK_ROWS * D;
         }
     }
     memcpy(out + o * c.esz, src, (size_t)remaining_len * c.esz);
@@ -395,6 +422,21 @@ int64_t oracle_decompress_raw(int predictor, int elem_sz, const void* src_, void
 
     free(st.prev_val); free(st.prev_delta); free(st.counter); free(nbits); free(gs); free(coef);
     return (int64_t)o;
+}
+
+int64_t oracle_decompress_raw(int predictor, int elem_sz, const void* src, void* dest,
+                              uint16_t ndims, uint32_t ngroups, uint16_t remaining_len)
+{
+    return oracle_decompress_raw_bs(predictor, elem_sz, src, dest, ndims, ngroups, remaining_len, BLOCK_SZ);
+}
+
+int64_t oracle_decompress_bs(int predictor, int elem_sz, const void* src_, void* dest, int block_rows)
+{
+    const uint8_t* p = (const uint8_t*)src_;
+    uint32_t ngroups = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+    uint16_t rem = (uint16_t)(p[4] | (p[5] << 8));
+    uint16_t ndims = (uint16_t)(p[6] | (p[7] << 8));
+    return oracle_decompress_raw_bs(predictor, elem_sz, p + 8, dest, ndims, ngroups, rem, block_rows);
 }
 
 int64_t oracle_decompress(int predictor, int elem_sz, const void* src_, void* dest)

@@ -34,6 +34,15 @@ int64_t oracle_decompress(int predictor, int elem_sz, const void* src, void* des
 int64_t oracle_decompress_raw(int predictor, int elem_sz, const void* src, void* dest,
                               uint16_t ndims, uint32_t ngroups, uint16_t remaining_len);
 
+/* Block-size axis (BASELINE config 5): the same codecs with block_rows = 8 | 16 | 32 | 64 rows per block.  8 is the
+ * reference (the functions above call these with 8); the other sizes apply the reference's own derived constants to a
+ * larger block_sz and have NO reference build to check against: parity unpinned beyond block 8. */
+int64_t oracle_compress_bs(int predictor, int elem_sz, const void* src, uint32_t len, void* dest, uint16_t ndims,
+                           int write_size, uint64_t* true_nbytes, int block_rows);
+int64_t oracle_decompress_bs(int predictor, int elem_sz, const void* src, void* dest, int block_rows);
+int64_t oracle_decompress_raw_bs(int predictor, int elem_sz, const void* src, void* dest, uint16_t ndims,
+                                 uint32_t ngroups, uint16_t remaining_len, int block_rows);
+
 /* Non-RLE sibling codecs: kind 1 = compress_rowmajor_delta_{8b,16b}, kind 2 =
  * compress_rowmajor_{8b,16b} (sprintz_delta.h:27-44). 6-byte metadata [u32 len][u16 ndims]. */
 int64_t oracle_compress_rowmajor(int kind, int elem_sz, const void* src, uint32_t len, void* dest,

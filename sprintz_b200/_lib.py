@@ -112,6 +112,10 @@ SYMBOLS = {
     "spz_frame_workspace_bytes": (_u64, [_i, _u64, _u16, _u32]),
     "spz_frame_encode_dev": (_i, [_i, _i, _vp, _u64, _u16, _u32, _vp, _u64, _vp, _u64, _vp, _vp]),
     "spz_frame_decode_dev": (_i, [_i, _i, _vp, _u64, _u64, _u16, _u32, _vp, _u64, _vp, _vp]),
+    "spz_compress_bs_dev": (_i, [_i, _i, _i, _vp, _u32, _u16, _i, _vp, _vp, _vp]),
+    "spz_decompress_bs_dev": (_i, [_i, _i, _i, _vp, _u64, _i, _u16, _vp, _u64, _vp, _vp]),
+    "spz_frame_encode_bs_dev": (_i, [_i, _i, _i, _vp, _u64, _u16, _u32, _vp, _u64, _vp, _u64, _vp, _vp]),
+    "spz_frame_decode_bs_dev": (_i, [_i, _i, _i, _vp, _u64, _u64, _u16, _u32, _vp, _u64, _vp, _vp]),
     "spz_frame_read_header": (_i, [_vp, C.POINTER(FrameHeader), _vp]),
     "spz_frame_compress_host": (_i64, [_i, _i, _vp, _u64, _u16, _u32, _vp, _u64]),
     "spz_frame_decompress_host": (_i64, [_vp, _u64, _vp, _u64]),

@@ -222,27 +222,36 @@ def _stream_ptr(stream=None):
     return C.c_void_p(s.cuda_stream)
 
 
-def compress_dev(predictor: int, x, ndims: int, write_size: bool = True):
-    """Single reference stream from a CUDA tensor (uint8 / int16-viewable). -> (uint8 CUDA tensor, ChunkMeta)."""
+def compress_dev(predictor: int, x, ndims: int, write_size: bool = True, block_rows: int = 8):
+    """Single reference stream from a CUDA tensor (uint8 / int16-viewable). -> (uint8 CUDA tensor, ChunkMeta).
+    block_rows != 8: BASELINE config 5's block-size axis (spz_compress_bs_dev)."""
     torch = _torch()
     esz = x.element_size()
     n = x.numel()
     out = torch.empty(max_compressed_bytes(esz, n, ndims), dtype=torch.uint8, device=x.device)
     meta = torch.zeros(4, dtype=torch.int32, device=x.device)
-    check(lib().spz_compress_dev(predictor, esz, x.data_ptr(), n, ndims, int(write_size), out.data_ptr(),
-                                 meta.data_ptr(), _stream_ptr()), "spz_compress_dev")
+    if block_rows != 8:
+        check(lib().spz_compress_bs_dev(predictor, esz, block_rows, x.data_ptr(), n, ndims, int(write_size), out.data_ptr(),
+                                        meta.data_ptr(), _stream_ptr()), "spz_compress_bs_dev")
+    else:
+        check(lib().spz_compress_dev(predictor, esz, x.data_ptr(), n, ndims, int(write_size), out.data_ptr(),
+                                     meta.data_ptr(), _stream_ptr()), "spz_compress_dev")
     m = meta.cpu().numpy().view(np.uint32)
     return out[: int(m[0])], ChunkMeta(int(m[0]), int(m[1]), int(m[2]), int(m[3]))
 
 
-def decompress_dev(predictor: int, esz: int, stream, ndims: int, n_out: int):
+def decompress_dev(predictor: int, esz: int, stream, ndims: int, n_out: int, block_rows: int = 8):
     torch = _torch()
     src = torch.zeros(stream.numel() + 16, dtype=torch.uint8, device=stream.device)
     src[: stream.numel()] = stream
     out = torch.empty(n_out, dtype=torch.uint8 if esz == 1 else torch.int16, device=stream.device)
     meta = torch.zeros(4, dtype=torch.int32, device=stream.device)
-    check(lib().spz_decompress_dev(predictor, esz, src.data_ptr(), src.numel(), 1, ndims, out.data_ptr(), n_out,
-                                   meta.data_ptr(), _stream_ptr()), "spz_decompress_dev")
+    if block_rows != 8:
+        check(lib().spz_decompress_bs_dev(predictor, esz, block_rows, src.data_ptr(), src.numel(), 1, ndims, out.data_ptr(),
+                                          n_out, meta.data_ptr(), _stream_ptr()), "spz_decompress_bs_dev")
+    else:
+        check(lib().spz_decompress_dev(predictor, esz, src.data_ptr(), src.numel(), 1, ndims, out.data_ptr(), n_out,
+                                       meta.data_ptr(), _stream_ptr()), "spz_decompress_dev")
     m = meta.cpu().numpy().view(np.uint32)
     if int(m[3]) != 0:
         raise SprintzError(f"decode status {int(m[3])}")
@@ -259,6 +268,7 @@ class Frame:
     ndims: int
     chunk_rows: int
     nbytes_dev: "object"     # 1-element int64 CUDA tensor: frame size in bytes
+    block_rows: int = 8      # rows per block (8 = the reference's format; 16 / 32 / 64 = BASELINE config 5's axis)
 
     @property
     def nchunks(self) -> int:
@@ -292,10 +302,11 @@ class Frame:
 class FrameCodec:
     """Pre-allocated buffers for repeated frame encode/decode of one (codec, shape): the measured path."""
 
-    def __init__(self, predictor: int, elem_sz: int, length: int, ndims: int, chunk_rows: int, device="cuda"):
+    def __init__(self, predictor: int, elem_sz: int, length: int, ndims: int, chunk_rows: int, device="cuda", block_rows: int = 8):
         torch = _torch()
         L = lib()
         self.predictor, self.elem_sz, self.len, self.ndims, self.chunk_rows = predictor, elem_sz, length, ndims, chunk_rows
+        self.block_rows = block_rows
         self.frame_cap = int(L.spz_frame_max_bytes(elem_sz, length, ndims, chunk_rows))
         self.work_bytes = int(L.spz_frame_workspace_bytes(elem_sz, length, ndims, chunk_rows))
         self.nchunks = int(L.spz_frame_nchunks(length, ndims, chunk_rows))
@@ -306,17 +317,29 @@ class FrameCodec:
 
     def encode(self, x) -> Frame:
         assert x.numel() == self.len and x.element_size() == self.elem_sz and x.is_cuda
-        check(lib().spz_frame_encode_dev(self.predictor, self.elem_sz, x.data_ptr(), self.len, self.ndims,
-                                         self.chunk_rows, self.frame.data_ptr(), self.frame_cap,
-                                         self.work.data_ptr(), self.work_bytes, self.nbytes_dev.data_ptr(),
-                                         _stream_ptr()), "spz_frame_encode_dev")
-        return Frame(self.frame, self.predictor, self.elem_sz, self.len, self.ndims, self.chunk_rows, self.nbytes_dev)
+        if self.block_rows != 8:
+            check(lib().spz_frame_encode_bs_dev(self.predictor, self.elem_sz, self.block_rows, x.data_ptr(), self.len, self.ndims,
+                                                self.chunk_rows, self.frame.data_ptr(), self.frame_cap,
+                                                self.work.data_ptr(), self.work_bytes, self.nbytes_dev.data_ptr(),
+                                                _stream_ptr()), "spz_frame_encode_bs_dev")
+        else:
+            check(lib().spz_frame_encode_dev(self.predictor, self.elem_sz, x.data_ptr(), self.len, self.ndims,
+                                             self.chunk_rows, self.frame.data_ptr(), self.frame_cap,
+                                             self.work.data_ptr(), self.work_bytes, self.nbytes_dev.data_ptr(),
+                                             _stream_ptr()), "spz_frame_encode_dev")
+        return Frame(self.frame, self.predictor, self.elem_sz, self.len, self.ndims, self.chunk_rows, self.nbytes_dev,
+                     self.block_rows)
 
     def decode(self, frame: Frame, out):
         assert out.numel() >= self.len and out.element_size() == self.elem_sz and out.is_cuda
-        check(lib().spz_frame_decode_dev(frame.predictor, frame.elem_sz, frame.buf.data_ptr(), frame.buf.numel(),
-                                         frame.len, frame.ndims, frame.chunk_rows, out.data_ptr(), out.numel(),
-                                         self.status.data_ptr(), _stream_ptr()), "spz_frame_decode_dev")
+        if frame.block_rows != 8:
+            check(lib().spz_frame_decode_bs_dev(frame.predictor, frame.elem_sz, frame.block_rows, frame.buf.data_ptr(),
+                                                frame.buf.numel(), frame.len, frame.ndims, frame.chunk_rows, out.data_ptr(),
+                                                out.numel(), self.status.data_ptr(), _stream_ptr()), "spz_frame_decode_bs_dev")
+        else:
+            check(lib().spz_frame_decode_dev(frame.predictor, frame.elem_sz, frame.buf.data_ptr(), frame.buf.numel(),
+                                             frame.len, frame.ndims, frame.chunk_rows, out.data_ptr(), out.numel(),
+                                             self.status.data_ptr(), _stream_ptr()), "spz_frame_decode_dev")
         return out
 
     def check_status(self):
@@ -326,8 +349,8 @@ class FrameCodec:
             raise SprintzError(f"{bad} chunk(s) failed to decode")
 
 
-def frame_encode(predictor: int, x, ndims: int, chunk_rows: int) -> Frame:
-    codec = FrameCodec(predictor, x.element_size(), x.numel(), ndims, chunk_rows, device=x.device)
+def frame_encode(predictor: int, x, ndims: int, chunk_rows: int, block_rows: int = 8) -> Frame:
+    codec = FrameCodec(predictor, x.element_size(), x.numel(), ndims, chunk_rows, device=x.device, block_rows=block_rows)
     return codec.encode(x)
 
 

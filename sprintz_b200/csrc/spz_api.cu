@@ -172,7 +172,8 @@ extern "C" uint64_t spz_frame_workspace_bytes(int elem_sz, uint64_t len, uint16_
 // ------------------------------------------------------------------ device entry points
 
 static int compress_dev_impl(uint32_t variant, int predictor, int elem_sz, const void* d_src, uint32_t len, uint16_t ndims,
-                             int write_size, void* d_dest, spz_chunk_meta* d_meta, spz_stream_t stream);
+                             int write_size, void* d_dest, spz_chunk_meta* d_meta, spz_stream_t stream, uint32_t block_rows = 8);
+static bool valid_block_rows(int r) { return r == 8 || r == 16 || r == 32 || r == 64; }
 
 extern "C" int spz_compress_dev(int predictor, int elem_sz, const void* d_src, uint32_t len, uint16_t ndims,
                                 int write_size, void* d_dest, spz_chunk_meta* d_meta, spz_stream_t stream)
@@ -180,14 +181,21 @@ extern "C" int spz_compress_dev(int predictor, int elem_sz, const void* d_src, u
     return compress_dev_impl(0, predictor, elem_sz, d_src, len, ndims, write_size, d_dest, d_meta, stream);
 }
 
+extern "C" int spz_compress_bs_dev(int predictor, int elem_sz, int block_rows, const void* d_src, uint32_t len, uint16_t ndims,
+                                   int write_size, void* d_dest, spz_chunk_meta* d_meta, spz_stream_t stream)
+{
+    if (!valid_block_rows(block_rows)) return SPZ_E_ARG;
+    return compress_dev_impl(0, predictor, elem_sz, d_src, len, ndims, write_size, d_dest, d_meta, stream, (uint32_t)block_rows);
+}
+
 static int compress_dev_impl(uint32_t variant, int predictor, int elem_sz, const void* d_src, uint32_t len, uint16_t ndims,
-                             int write_size, void* d_dest, spz_chunk_meta* d_meta, spz_stream_t stream)
+                             int write_size, void* d_dest, spz_chunk_meta* d_meta, spz_stream_t stream, uint32_t block_rows)
 {
     if (!valid_codec(predictor, elem_sz) || ndims == 0) return SPZ_E_ARG;
     if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
     EncParams p;
     memset(&p, 0, sizeof(p));
-    p.variant = variant;
+    p.variant = variant; p.block_rows = block_rows;
     p.src = (const uint8_t*)d_src; p.dst = (uint8_t*)d_dest; p.meta = (ChunkMeta*)d_meta;
     p.len = len; p.chunk_len = len ? len : 1; p.nchunks = 1; p.slot_stride = 0;
     p.ndims = ndims; p.write_size = write_size ? 1 : 0;
@@ -197,7 +205,7 @@ static int compress_dev_impl(uint32_t variant, int predictor, int elem_sz, const
 
 static int decompress_dev_impl(uint32_t variant, int predictor, int elem_sz, const void* d_src, uint64_t src_bytes, int has_meta,
                                uint16_t ndims, void* d_dest, uint64_t dest_cap_elems, spz_chunk_meta* d_meta,
-                               spz_stream_t stream);
+                               spz_stream_t stream, uint32_t block_rows = 8);
 
 extern "C" int spz_decompress_dev(int predictor, int elem_sz, const void* d_src, uint64_t src_bytes, int has_meta,
                                   uint16_t ndims, void* d_dest, uint64_t dest_cap_elems, spz_chunk_meta* d_meta,
@@ -206,16 +214,25 @@ extern "C" int spz_decompress_dev(int predictor, int elem_sz, const void* d_src,
     return decompress_dev_impl(0, predictor, elem_sz, d_src, src_bytes, has_meta, ndims, d_dest, dest_cap_elems, d_meta, stream);
 }
 
+extern "C" int spz_decompress_bs_dev(int predictor, int elem_sz, int block_rows, const void* d_src, uint64_t src_bytes,
+                                     int has_meta, uint16_t ndims, void* d_dest, uint64_t dest_cap_elems,
+                                     spz_chunk_meta* d_meta, spz_stream_t stream)
+{
+    if (!valid_block_rows(block_rows)) return SPZ_E_ARG;
+    return decompress_dev_impl(0, predictor, elem_sz, d_src, src_bytes, has_meta, ndims, d_dest, dest_cap_elems, d_meta, stream,
+                               (uint32_t)block_rows);
+}
+
 static int decompress_dev_impl(uint32_t variant, int predictor, int elem_sz, const void* d_src, uint64_t src_bytes, int has_meta,
                                uint16_t ndims, void* d_dest, uint64_t dest_cap_elems, spz_chunk_meta* d_meta,
-                               spz_stream_t stream)
+                               spz_stream_t stream, uint32_t block_rows)
 {
     if (!valid_codec(predictor, elem_sz) || ndims == 0) return SPZ_E_ARG;
     if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
     if (!has_meta && !d_meta) return SPZ_E_ARG;
     DecParams p;
     memset(&p, 0, sizeof(p));
-    p.variant = variant;
+    p.variant = variant; p.block_rows = block_rows;
     p.src = (const uint8_t*)d_src; p.offsets = nullptr; p.dst = (uint8_t*)d_dest; p.meta = (ChunkMeta*)d_meta;
     p.len = dest_cap_elems; p.chunk_len = dest_cap_elems ? dest_cap_elems : 1; p.nchunks = 1; p.slot_stride = 0;
     p.dst_cap = dest_cap_elems; p.ndims = ndims; p.has_meta = has_meta ? 1 : 0;
@@ -265,9 +282,11 @@ namespace spz {
 
 int frame_job_init(FrameJob& j, int predictor, int elem_sz, const void* d_src, uint64_t len, uint16_t ndims,
                    uint32_t chunk_rows, void* d_frame, uint64_t frame_cap, void* d_work, uint64_t work_bytes,
-                   uint64_t* d_frame_bytes, uint64_t slab_chunks)
+                   uint64_t* d_frame_bytes, uint64_t slab_chunks, uint32_t block_rows)
 {
     if (!valid_frame_codec(predictor, elem_sz) || ndims == 0 || chunk_rows == 0) return SPZ_E_ARG;
+    if (block_rows != 8 && (predictor > 1 || !valid_block_rows((int)block_rows))) return SPZ_E_ARG;
+    j.block_rows = block_rows;
     if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
     j.predictor = predictor; j.elem_sz = elem_sz; j.ndims = ndims; j.chunk_rows = chunk_rows; j.len = len;
     j.f = frame_layout(len, ndims, chunk_rows);
@@ -279,13 +298,14 @@ int frame_job_init(FrameJob& j, int predictor, int elem_sz, const void* d_src, u
     memset(&j.h, 0, sizeof(j.h));
     j.h.magic = SPZ_FRAME_MAGIC; j.h.version = 1; j.h.elem_sz = (uint8_t)elem_sz; j.h.predictor = (uint8_t)predictor;
     j.h.ndims = ndims; j.h.chunk_rows = chunk_rows; j.h.len = len; j.h.nchunks = j.f.nchunks; j.h.payload_off = j.f.payload_off;
+    j.h.reserved = block_rows == 8 ? 0 : block_rows;           // 0: the reference's 8-row blocks
 
     // kernel family + machine round, decided ONCE on the whole frame
     EncParams p;
     memset(&p, 0, sizeof(p));
     p.src = j.d_src; p.dst = j.work + j.w.off_slots; p.meta = (ChunkMeta*)(j.work + j.w.off_meta);
     p.len = len; p.chunk_len = j.f.chunk_len; p.nchunks = j.f.nchunks; p.slot_stride = j.w.slot_stride;
-    p.ndims = ndims; p.write_size = 1;
+    p.ndims = ndims; p.write_size = 1; p.block_rows = block_rows;
     const EncodeProbe pr = probe_encode(elem_sz, predictor, p);
     if (pr.family < 0) return fail_msg(SPZ_E_CUDA, "probe_encode failed");
     j.family = pr.family;
@@ -323,7 +343,7 @@ int frame_job_encode_slab(const FrameJob& j, uint64_t k, cudaStream_t st)
     p.src = j.d_src + e0 * j.elem_sz; p.dst = j.work + j.w.off_slots + c0 * j.w.slot_stride;
     p.meta = (ChunkMeta*)(j.work + j.w.off_meta) + c0;
     p.len = ne; p.chunk_len = j.f.chunk_len; p.nchunks = nc; p.slot_stride = j.w.slot_stride;
-    p.ndims = j.ndims; p.write_size = 1;
+    p.ndims = j.ndims; p.write_size = 1; p.block_rows = j.block_rows;
     p.family_pin = (uint32_t)j.family + 1u;
     CK(launch_encode(j.elem_sz, j.predictor, p, st));
     return SPZ_OK;
@@ -364,14 +384,35 @@ int frame_job_compact_slab(const FrameJob& j, uint64_t k, cudaStream_t st)
 
 }  // namespace spz
 
+static int frame_encode_impl(int predictor, int elem_sz, uint32_t block_rows, const void* d_src, uint64_t len, uint16_t ndims,
+                             uint32_t chunk_rows, void* d_frame, uint64_t frame_cap, void* d_work, uint64_t work_bytes,
+                             uint64_t* d_frame_bytes, spz_stream_t stream_);
+
 extern "C" int spz_frame_encode_dev(int predictor, int elem_sz, const void* d_src, uint64_t len, uint16_t ndims,
                                     uint32_t chunk_rows, void* d_frame, uint64_t frame_cap,
-                                    void* d_work, uint64_t work_bytes, uint64_t* d_frame_bytes, spz_stream_t stream_)
+                                    void* d_work, uint64_t work_bytes, uint64_t* d_frame_bytes, spz_stream_t stream)
+{
+    return frame_encode_impl(predictor, elem_sz, 8, d_src, len, ndims, chunk_rows, d_frame, frame_cap, d_work, work_bytes,
+                             d_frame_bytes, stream);
+}
+
+extern "C" int spz_frame_encode_bs_dev(int predictor, int elem_sz, int block_rows, const void* d_src, uint64_t len, uint16_t ndims,
+                                       uint32_t chunk_rows, void* d_frame, uint64_t frame_cap,
+                                       void* d_work, uint64_t work_bytes, uint64_t* d_frame_bytes, spz_stream_t stream)
+{
+    if (!valid_block_rows(block_rows) || chunk_rows % (2u * (uint32_t)block_rows) != 0) return SPZ_E_ARG;     // whole groups per chunk
+    return frame_encode_impl(predictor, elem_sz, (uint32_t)block_rows, d_src, len, ndims, chunk_rows, d_frame, frame_cap, d_work,
+                             work_bytes, d_frame_bytes, stream);
+}
+
+static int frame_encode_impl(int predictor, int elem_sz, uint32_t block_rows, const void* d_src, uint64_t len, uint16_t ndims,
+                             uint32_t chunk_rows, void* d_frame, uint64_t frame_cap, void* d_work, uint64_t work_bytes,
+                             uint64_t* d_frame_bytes, spz_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     FrameJob j;
     const int rc = frame_job_init(j, predictor, elem_sz, d_src, len, ndims, chunk_rows, d_frame, frame_cap, d_work,
-                                  work_bytes, d_frame_bytes, 0);
+                                  work_bytes, d_frame_bytes, 0, block_rows);
     if (rc != SPZ_OK) return rc;
     g_last_encode_slabs = (int)j.nslabs;
     if (frame_job_reset(j, stream) != SPZ_OK) return SPZ_E_CUDA;
@@ -444,6 +485,20 @@ extern "C" int spz_frame_decode_dev(int predictor, int elem_sz, const void* d_fr
     DecParams p;
     const int rc = frame_decode_params(p, predictor, elem_sz, d_frame, frame_bytes, len, ndims, chunk_rows, d_dest, d_status);
     if (rc != SPZ_OK) return rc;
+    CK(launch_decode(elem_sz, predictor, p, (cudaStream_t)stream));
+    return SPZ_OK;
+}
+
+extern "C" int spz_frame_decode_bs_dev(int predictor, int elem_sz, int block_rows, const void* d_frame, uint64_t frame_bytes,
+                                       uint64_t len, uint16_t ndims, uint32_t chunk_rows, void* d_dest,
+                                       uint64_t dest_cap_elems, spz_chunk_meta* d_status, spz_stream_t stream)
+{
+    if (dest_cap_elems < len) return SPZ_E_CAPACITY;
+    if (!valid_block_rows(block_rows) || (block_rows != 8 && predictor > 1)) return SPZ_E_ARG;
+    DecParams p;
+    const int rc = frame_decode_params(p, predictor, elem_sz, d_frame, frame_bytes, len, ndims, chunk_rows, d_dest, d_status);
+    if (rc != SPZ_OK) return rc;
+    p.block_rows = (uint32_t)block_rows;
     CK(launch_decode(elem_sz, predictor, p, (cudaStream_t)stream));
     return SPZ_OK;
 }

@@ -52,6 +52,7 @@ struct EncParams {
     uint32_t       teams_per_cta;
     uint32_t       variant;   // 0: RLE codecs (sprintz.h) | 1: compress_rowmajor_delta_* | 2: compress_rowmajor_* (no RLE, 6-byte metadata)
     uint32_t       family_pin;// 0: the launcher picks the kernel family | f + 1: family f was chosen for the whole frame (slabs must not re-decide)
+    uint32_t       block_rows;// rows per block: 0 / 8 = the reference's format; 16 / 32 / 64 = BASELINE config 5's block-size axis (generic kernels)
 };
 
 struct DecParams {
@@ -77,6 +78,7 @@ struct DecParams {
     uint32_t        variant;   // as EncParams::variant
     uint32_t        qop;       // query-on-compressed (lane kernels only): 0 decode | 1 per-dim max | 2 per-dim sum; dst unused
     unsigned long long* qresult;   // [ndims] u64, zero-initialised by the caller
+    uint32_t        block_rows;// as EncParams::block_rows
 };
 
 template <int W> struct Traits;

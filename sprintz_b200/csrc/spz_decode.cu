@@ -16,7 +16,8 @@
 
 namespace spz {
 
-template <int W, bool FIRE, bool LOW>
+// R = rows per block (8 = the reference's format; 16 / 32 / 64 = BASELINE config 5's block-size axis, see spz_encode.cu)
+template <int W, bool FIRE, bool LOW, int R>
 __global__ void __launch_bounds__(kThreads) spz_decode_kernel(const DecParams p)
 {
     typedef typename Traits<W>::uint_t uint_t;
@@ -24,6 +25,9 @@ __global__ void __launch_bounds__(kThreads) spz_decode_kernel(const DecParams p)
     constexpr int HB = Traits<W>::HB;
     constexpr int CB = Traits<W>::CB;
     constexpr uint32_t WMASK = (1u << W) - 1u;
+    static_assert(R == 8 || !LOW, "the low-dim (column-major) layout exists for 8-row blocks only");
+    constexpr int GSH = (R == 8) ? 2 : (R == 16) ? 3 : (R == 32) ? 4 : 5;      // log2(R) - 1
+    constexpr uint32_t kMinData = 16u * R;
 
     extern __shared__ __align__(16) uint8_t smem[];
 
@@ -69,7 +73,7 @@ __global__ void __launch_bounds__(kThreads) spz_decode_kernel(const DecParams p)
         const uint32_t at = variant == 3u ? 6u : 4u;          // variant 3: [u48 len][u16 ndims] (sprintz_xff.cpp:64-69)
         const uint32_t nd = (uint32_t)stream[at] | ((uint32_t)stream[at + 1] << 8);
         pos = at + 2;
-        if (len32 < kMinDataSize) { ngroups = 0; remaining = len32; }
+        if (len32 < kMinData) { ngroups = 0; remaining = len32; }
         else {
             if (nd != (uint32_t)D) status = kStatusBadDims;
             ngroups = len32 / (16u * (uint32_t)D);
@@ -88,9 +92,9 @@ __global__ void __launch_bounds__(kThreads) spz_decode_kernel(const DecParams p)
 
     uint64_t o = 0;                     // output element cursor (team-uniform)
     const uint32_t H = (2u * (uint32_t)D * HB + 7u) >> 3;
-    const uint64_t B = (uint64_t)kBlockRows * D;
+    const uint64_t B = (uint64_t)R * D;
 
-    if (status == kStatusOk && (variant ? ngroups != 0 : !(ngroups == 0 && remaining < kMinDataSize))) {
+    if (status == kStatusOk && (variant ? ngroups != 0 : !(ngroups == 0 && remaining < kMinData))) {
         for (uint32_t g = 0; g < ngroups && status == kStatusOk; g++) {
             if (pos + H + 8 > avail) { status = kStatusTruncated; break; }      // header fields are read as aligned word pairs
             const uint8_t* hdr = stream + pos;
@@ -115,7 +119,7 @@ __global__ void __launch_bounds__(kThreads) spz_decode_kernel(const DecParams p)
                     if (pos + 2 > avail) { status = kStatusTruncated; break; }
                     uint32_t nrun = stream[pos] & 0x7f;
                     if (stream[pos] & 0x80) { nrun |= (uint32_t)stream[pos + 1] << 7; pos += 2; } else { pos += 1; }
-                    const uint64_t nrows = (uint64_t)nrun * kBlockRows;
+                    const uint64_t nrows = (uint64_t)nrun * R;
                     if (o + nrows * D > cap) { status = kStatusOverflow; break; }
                     for (int k = 0; k < DPL; k++) {
                         const int d = k * TEAM + t;
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(kThreads) spz_decode_kernel(const DecParams p)
                 // ---- data slot
                 if (o + B > cap) { status = kStatusOverflow; break; }
                 const uint32_t row_bytes = (total + 7u) >> 3;
-                if (pos + (LOW ? total : row_bytes * kBlockRows) + 8 > avail) { status = kStatusTruncated; break; }
+                if (pos + (LOW ? total : row_bytes * R) + 8 > avail) { status = kStatusTruncated; break; }
                 const uint8_t* pay = stream + pos;
                 for (int k = 0; k < DPL; k++) {
                     const int d = k * TEAM + t;
@@ -155,34 +159,37 @@ __global__ void __launch_bounds__(kThreads) spz_decode_kernel(const DecParams p)
                         // high-dim: row r's field at bit r*row_bytes*8 + off; low-dim: column at byte `off`, field r at r*n
                         const uint32_t bit0 = LOW ? off * 8u : off;
                         const uint32_t stride = LOW ? n : row_bytes * 8u;
-                        uint32_t u[kBlockRows];
-#pragma unroll
-                        for (int r = 0; r < kBlockRows; r++) u[r] = load_bits32(pay, bit0 + (uint32_t)r * stride) & fmask;
-
                         uint32_t pv = (uint32_t)s_pv[d];
                         int32_t pd = 0, coef = 0, gs = 0;
                         if (FIRE) { pd = s_pd[d]; coef = fire_coef<W, LOW>(s_ct[d]); }
                         uint_t* op = out + o + d;
+#pragma unroll 1
+                        for (int sb = 0; sb < R / kBlockRows; sb++) {   // 8 rows at a time (R == 8: once)
+                            uint32_t u[kBlockRows];
 #pragma unroll
-                        for (int r = 0; r < kBlockRows; r++) {
-                            const int32_t err = zigzag_dec<W>(u[r]);
-                            int32_t delta = err;
-                            if (FIRE) {
-                                delta = sx<W>(err + fire_predict<W>(pd, coef));
-                                if (r & 1) gs += fire_grad<W>(err, pd);
+                            for (int r = 0; r < kBlockRows; r++)
+                                u[r] = load_bits32(pay, bit0 + (uint32_t)(sb * kBlockRows + r) * stride) & fmask;
+#pragma unroll
+                            for (int r = 0; r < kBlockRows; r++) {
+                                const int32_t err = zigzag_dec<W>(u[r]);
+                                int32_t delta = err;
+                                if (FIRE) {
+                                    delta = sx<W>(err + fire_predict<W>(pd, coef));
+                                    if (r & 1) gs += fire_grad<W>(err, pd);
+                                }
+                                pd = delta;
+                                pv = (variant == 2u) ? u[r] : ((pv + (uint32_t)delta) & WMASK);
+                                op[(size_t)(sb * kBlockRows + r) * D] = (uint_t)pv;
                             }
-                            pd = delta;
-                            pv = (variant == 2u) ? u[r] : ((pv + (uint32_t)delta) & WMASK);
-                            op[r * D] = (uint_t)pv;
                         }
                         s_pv[d] = (int32_t)pv;
                         if (FIRE) {
                             s_pd[d] = pd;
-                            s_ct[d] = sx<CB>(s_ct[d] + (sx<W>(gs) >> 2));
+                            s_ct[d] = sx<CB>(s_ct[d] + (sx<W>(gs) >> GSH));
                         }
                     }
                 }
-                pos += LOW ? total : row_bytes * kBlockRows;
+                pos += LOW ? total : row_bytes * R;
                 o += B;
             }
         }
@@ -210,14 +217,14 @@ __global__ void __launch_bounds__(kThreads) spz_decode_kernel(const DecParams p)
 
 // ------------------------------------------------------------------ launch
 
-template <int W, bool FIRE, bool LOW>
+template <int W, bool FIRE, bool LOW, int R = 8>
 static cudaError_t launch_one(const DecParams& p, uint32_t grid, size_t smem, cudaStream_t stream)
 {
-    cudaError_t e = cudaFuncSetAttribute(spz_decode_kernel<W, FIRE, LOW>,
+    cudaError_t e = cudaFuncSetAttribute(spz_decode_kernel<W, FIRE, LOW, R>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     count_launch();
-    spz_decode_kernel<W, FIRE, LOW><<<grid, p.teams_per_cta * p.team, smem, stream>>>(p);
+    spz_decode_kernel<W, FIRE, LOW, R><<<grid, p.teams_per_cta * p.team, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -235,6 +242,30 @@ cudaError_t launch_decode(int elem_sz, int predictor, DecParams p, cudaStream_t 
 {
     if (predictor >= 2) { p.variant = (uint32_t)predictor - 1u; }                  // SPZ_RM_DELTA / SPZ_RM_PLAIN / SPZ_RM_XFF (frames)
     if (p.variant) predictor = (p.variant == 3u) ? 1 : 0;
+    const uint32_t R = p.block_rows ? p.block_rows : 8u;
+    if (R != 8u) {
+        // block-size axis (16 / 32 / 64 rows per block): generic kernels, high-dim layout for every ndims, RLE codecs only
+        if (p.variant != 0 || (R != 16u && R != 32u && R != 64u)) return cudaErrorInvalidValue;
+        g_last_decode_family = 0;
+        p.team = p.ndims >= 32 ? 32 : pow2_ceil(p.ndims);
+        p.dpl = (p.ndims + p.team - 1) / p.team;
+        p.team_smem = (4u * 4u * p.team * p.dpl + 15u) & ~15u;
+        uint32_t tpc = kThreads / p.team;
+        while (tpc > 1 && (size_t)tpc * p.team_smem > 200 * 1024) tpc >>= 1;
+        p.teams_per_cta = tpc;
+        const size_t smem = (size_t)tpc * p.team_smem;
+        const uint64_t grid64 = (p.nchunks + tpc - 1) / tpc;
+        if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
+        const uint32_t grid = (uint32_t)grid64;
+#define SPZ_BS(Rv) \
+        if (R == Rv) { \
+            if (elem_sz == 1) return predictor ? launch_one<8, true, false, Rv>(p, grid, smem, stream) : launch_one<8, false, false, Rv>(p, grid, smem, stream); \
+            return predictor ? launch_one<16, true, false, Rv>(p, grid, smem, stream) : launch_one<16, false, false, Rv>(p, grid, smem, stream); \
+        }
+        SPZ_BS(16) SPZ_BS(32) SPZ_BS(64)
+#undef SPZ_BS
+        return cudaErrorInvalidValue;
+    }
     {   // throughput path: frames with many chunks of 8 / 16 dims (spz_decode_lane.cu)
         const cudaError_t e = launch_decode_lane(elem_sz, predictor, p, stream);
         if (e != cudaErrorNotSupported) { g_last_decode_family = 2; return e; }

@@ -59,13 +59,19 @@ struct BitPacker {
 
 }  // namespace
 
-template <int W, bool FIRE, bool LOW>
+// R = rows per block: 8 is the reference's format (sprintz_delta_rle.cpp:62); 16 / 32 / 64 are BASELINE config 5's
+// block-size axis with the reference's derived constants (min_data_size = 8 * block_sz * 2, the FIRE counter update
+// shifts by log2_block_sz - 1: sprintz_xff_rle.cpp:78-82,271-275) and always the high-dim layout.
+template <int W, bool FIRE, bool LOW, int R>
 __global__ void __launch_bounds__(kThreads) spz_encode_kernel(const EncParams p)
 {
     typedef typename Traits<W>::uint_t uint_t;
     constexpr int ESZ = W / 8;
     constexpr int HB = Traits<W>::HB;
     constexpr int CB = Traits<W>::CB;
+    static_assert(R == 8 || !LOW, "the low-dim (column-major) layout exists for 8-row blocks only");
+    constexpr int GSH = (R == 8) ? 2 : (R == 16) ? 3 : (R == 32) ? 4 : 5;      // log2(R) - 1
+    constexpr int64_t kMinData = 16 * R;
 
     extern __shared__ __align__(16) uint8_t smem[];
 
@@ -101,7 +107,7 @@ __global__ void __launch_bounds__(kThreads) spz_encode_kernel(const EncParams p)
     const int64_t L = (int64_t)((first + p.chunk_len <= p.len) ? p.chunk_len : (p.len - first));
     const uint_t* __restrict__ src = reinterpret_cast<const uint_t*>(p.src) + first;
     uint8_t* const gstream = p.dst + c * p.slot_stride;
-    const int64_t B = (int64_t)kBlockRows * D, G = 2 * B;
+    const int64_t B = (int64_t)R * D, G = 2 * B;
     const uint32_t H = (2u * (uint32_t)D * HB + 7u) >> 3;
     // variant 1 / 2: the non-RLE sibling codecs compress_rowmajor_delta_* / compress_rowmajor_*
     // (sprintz_delta.cpp:776-1017, :64-392): 6-byte metadata [u32 len][u16 ndims] (format.h:65-73), every block
@@ -145,7 +151,7 @@ __global__ void __launch_bounds__(kThreads) spz_encode_kernel(const EncParams p)
         end_slot();
     };
 
-    if (L >= (int64_t)kMinDataSize) {
+    if (L >= kMinData) {
         const bool strict = !(FIRE && !LOW);   // `<` vs `<=` in the continue-run test (sprintz_xff_rle.cpp:362)
         for (;;) {
             if (outer && i * B > L - G) { tail = i * B; break; }
@@ -160,37 +166,40 @@ __global__ void __launch_bounds__(kThreads) spz_encode_kernel(const EncParams p)
                 uint32_t n = 0;
                 uint32_t zz[kBlockRows];
                 if (d < D) {
-                    uint32_t x[kBlockRows];
-#pragma unroll
-                    for (int r = 0; r < kBlockRows; r++) x[r] = blk[r * D + d];
                     uint32_t pv = (uint32_t)s_pv[d];
                     int32_t pd = 0, coef = 0, gs = 0;
                     if (FIRE) { pd = s_pd[d]; coef = fire_coef<W, LOW>(s_ct[d]); }
                     uint32_t mask = 0;
+#pragma unroll 1
+                    for (int sb = 0; sb < R / kBlockRows; sb++) {       // 8 rows at a time (R == 8: once)
+                        uint32_t x[kBlockRows];
 #pragma unroll
-                    for (int r = 0; r < kBlockRows; r++) {
-                        const int32_t delta = sx<W>((int32_t)(x[r] - pv));
-                        int32_t err = delta;
-                        if (FIRE) {
-                            err = sx<W>(delta - fire_predict<W>(pd, coef));
-                            if (r & 1) gs += fire_grad<W>(err, pd);
+                        for (int r = 0; r < kBlockRows; r++) x[r] = blk[(sb * kBlockRows + r) * D + d];
+#pragma unroll
+                        for (int r = 0; r < kBlockRows; r++) {
+                            const int32_t delta = sx<W>((int32_t)(x[r] - pv));
+                            int32_t err = delta;
+                            if (FIRE) {
+                                err = sx<W>(delta - fire_predict<W>(pd, coef));
+                                if (r & 1) gs += fire_grad<W>(err, pd);
+                            }
+                            zz[r] = (variant == 2u) ? x[r] : zigzag_enc<W>(err);
+                            mask |= zz[r];
+                            pv = x[r]; pd = delta;
                         }
-                        zz[r] = (variant == 2u) ? x[r] : zigzag_enc<W>(err);
-                        mask |= zz[r];
-                        pv = x[r]; pd = delta;
+                        if (!LOW) {
+#pragma unroll
+                            for (int r = 0; r < kBlockRows; r++)
+                                reinterpret_cast<uint_t*>(s_tile + (sb * kBlockRows + r) * tile_stride)[d] = (uint_t)zz[r];
+                        }
                     }
                     s_pv[d] = (int32_t)pv;
                     if (FIRE) {
                         s_pd[d] = pd;
-                        s_ct[d] = sx<CB>(s_ct[d] + (sx<W>(gs) >> 2));     // sprintz_xff_rle.cpp:273-275
+                        s_ct[d] = sx<CB>(s_ct[d] + (sx<W>(gs) >> GSH));   // sprintz_xff_rle.cpp:271-275
                     }
                     n = nbits_rule<W, LOW>(mask);
                     s_nb[d] = (uint8_t)n;
-                    if (!LOW) {
-#pragma unroll
-                        for (int r = 0; r < kBlockRows; r++)
-                            reinterpret_cast<uint_t*>(s_tile + r * tile_stride)[d] = (uint_t)zz[r];
-                    }
                 }
                 const uint32_t incl = team_incl_scan(n, t, TEAM, tmask);
                 if (LOW) {
@@ -251,7 +260,7 @@ __global__ void __launch_bounds__(kThreads) spz_encode_kernel(const EncParams p)
                 const uint32_t s = nslots & 1u;
                 const uint32_t pay = o.cur;                         // staging offset of the payload
                 const uint32_t row_bytes = (total + 7u) >> 3;
-                const uint32_t pay_bytes = LOW ? total : row_bytes * kBlockRows;
+                const uint32_t pay_bytes = LOW ? total : row_bytes * R;
                 if (LOW) {
                     // each lane copies its packed column (n bytes) to its byte offset
                     const int d = t;
@@ -274,10 +283,10 @@ __global__ void __launch_bounds__(kThreads) spz_encode_kernel(const EncParams p)
                         bp.finish();
                     }
                 } else {
-                    // jobs 0..7 = the 8 payload rows, job 8 = this slot's header fields
-                    for (int j = t; j < kBlockRows + 1; j += TEAM) {
+                    // jobs 0..R-1 = the payload rows, job R = this slot's header fields
+                    for (int j = t; j < R + 1; j += TEAM) {
                         BitPacker bp;
-                        if (j < kBlockRows) {
+                        if (j < R) {
                             bp.init(o.buf + pay + (uint32_t)j * row_bytes, 0, 0);
                             const uint_t* trow = reinterpret_cast<const uint_t*>(s_tile + j * tile_stride);
                             for (int dd = 0; dd < D; dd++) bp.put(trow[dd], s_nb[dd]);
@@ -345,22 +354,22 @@ stream_done:
 
 // ------------------------------------------------------------------ launch
 
-template <int W, bool FIRE, bool LOW>
+template <int W, bool FIRE, bool LOW, int R = 8>
 static cudaError_t launch_one(const EncParams& p, uint32_t grid, size_t smem, cudaStream_t stream)
 {
-    cudaError_t e = cudaFuncSetAttribute(spz_encode_kernel<W, FIRE, LOW>,
+    cudaError_t e = cudaFuncSetAttribute(spz_encode_kernel<W, FIRE, LOW, R>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    if (g_enc_probe) return probe_fill(g_enc_probe, 0, spz_encode_kernel<W, FIRE, LOW>, (int)(p.teams_per_cta * p.team), smem, p.teams_per_cta);
+    if (g_enc_probe) return probe_fill(g_enc_probe, 0, spz_encode_kernel<W, FIRE, LOW, R>, (int)(p.teams_per_cta * p.team), smem, p.teams_per_cta);
     count_launch();
-    spz_encode_kernel<W, FIRE, LOW><<<grid, p.teams_per_cta * p.team, smem, stream>>>(p);
+    spz_encode_kernel<W, FIRE, LOW, R><<<grid, p.teams_per_cta * p.team, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
 static inline uint32_t pow2_ceil(uint32_t x) { uint32_t p = 1; while (p < x) p <<= 1; return p; }
 
 // Shared-memory layout of one team (all regions 16-byte aligned).
-static void enc_layout(int elem_sz, bool low, EncParams& p)
+static void enc_layout(int elem_sz, bool low, EncParams& p, uint32_t R = 8)
 {
     const uint32_t Dp = p.team * p.dpl;
     const uint32_t hb = elem_sz == 1 ? 3 : 4;
@@ -370,9 +379,9 @@ static void enc_layout(int elem_sz, bool low, EncParams& p)
     off += (Dp + 15u) & ~15u;
     p.tile_off = off;
     p.tile_stride = low ? 0u : ((((Dp * (uint32_t)elem_sz + 3u) >> 2) | 1u) * 4u);   // odd #words: conflict-free rows
-    off += low ? 16u * Dp : ((8u * p.tile_stride + 15u) & ~15u);
+    off += low ? 16u * Dp : ((R * p.tile_stride + 15u) & ~15u);
     p.out_off = off;
-    uint32_t cap = 32 + H + 2 * (8 * p.ndims * (uint32_t)elem_sz) + 16;   // skip + one full group + slack
+    uint32_t cap = 32 + H + 2 * (R * p.ndims * (uint32_t)elem_sz) + 16;   // skip + one full group + slack
     cap = (cap + 15u) & ~15u;
     if (cap < 256) cap = 256;
     p.out_cap = cap;
@@ -406,6 +415,31 @@ cudaError_t launch_encode(int elem_sz, int predictor, EncParams p, cudaStream_t 
     if (predictor >= 2) { p.variant = (uint32_t)predictor - 1u; }                  // SPZ_RM_DELTA / SPZ_RM_PLAIN / SPZ_RM_XFF (frames)
     if (p.variant) predictor = (p.variant == 3u) ? 1 : 0;
     const uint32_t pin = p.family_pin;           // family + 1 chosen for the whole frame, or 0
+    const uint32_t R = p.block_rows ? p.block_rows : 8u;
+    if (R != 8u) {
+        // block-size axis (16 / 32 / 64 rows per block): generic kernels, high-dim layout for every ndims, RLE codecs only
+        if (p.variant != 0 || (R != 16u && R != 32u && R != 64u)) return cudaErrorInvalidValue;
+        g_last_encode_family = 0;
+        p.team = p.ndims >= 32 ? 32 : pow2_ceil(p.ndims);
+        p.dpl = (p.ndims + p.team - 1) / p.team;
+        enc_layout(elem_sz, false, p, R);
+        uint32_t tpc = kThreads / p.team;
+        while (tpc > 1 && (size_t)tpc * p.team_smem > 200 * 1024) tpc >>= 1;
+        p.teams_per_cta = tpc;
+        const size_t smem = (size_t)tpc * p.team_smem;
+        if (smem > 227 * 1024) return cudaErrorInvalidValue;
+        const uint64_t grid64 = (p.nchunks + tpc - 1) / tpc;
+        if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
+        const uint32_t grid = (uint32_t)grid64;
+#define SPZ_BS(Rv) \
+        if (R == Rv) { \
+            if (elem_sz == 1) return predictor ? launch_one<8, true, false, Rv>(p, grid, smem, stream) : launch_one<8, false, false, Rv>(p, grid, smem, stream); \
+            return predictor ? launch_one<16, true, false, Rv>(p, grid, smem, stream) : launch_one<16, false, false, Rv>(p, grid, smem, stream); \
+        }
+        SPZ_BS(16) SPZ_BS(32) SPZ_BS(64)
+#undef SPZ_BS
+        return cudaErrorInvalidValue;
+    }
     if (pin == 0 || pin == 3)
     {   // throughput path: frames with many chunks of 8 / 16 dims (spz_encode_lane.cu)
         const cudaError_t e = launch_encode_lane(elem_sz, predictor, p, stream);

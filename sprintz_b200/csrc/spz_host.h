@@ -104,6 +104,7 @@ struct FrameJob {
     FrameLayout f;
     WorkLayout w;
     uint64_t slab_chunks, nslabs, tiles_per_slab;
+    uint32_t block_rows;                 // rows per block (8 = the reference's format)
     int family;                          // kernel family chosen for the WHOLE frame (slabs must not re-decide)
     const uint8_t* d_src;
     uint8_t* d_frame;
@@ -124,7 +125,7 @@ struct FrameJob {
 // slab_chunks == 0: pick automatically (whole machine rounds of the codec kernel; one slab for small frames)
 int frame_job_init(FrameJob& j, int predictor, int elem_sz, const void* d_src, uint64_t len, uint16_t ndims,
                    uint32_t chunk_rows, void* d_frame, uint64_t frame_cap, void* d_work, uint64_t work_bytes,
-                   uint64_t* d_frame_bytes, uint64_t slab_chunks);
+                   uint64_t* d_frame_bytes, uint64_t slab_chunks, uint32_t block_rows = 8);
 int frame_job_reset(const FrameJob& j, cudaStream_t st);                       // zeroes scan states / tickets / totals / error word
 int frame_job_encode_slab(const FrameJob& j, uint64_t k, cudaStream_t st);     // codec kernel of slab k
 int frame_job_scan_slab(const FrameJob& j, uint64_t k, cudaStream_t st);       // directory scan of slab k only (slab order!)
