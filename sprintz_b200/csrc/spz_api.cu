@@ -185,6 +185,7 @@ extern "C" int spz_compress_bs_dev(int predictor, int elem_sz, int block_rows, c
                                    int write_size, void* d_dest, spz_chunk_meta* d_meta, spz_stream_t stream)
 {
     if (!valid_block_rows(block_rows)) return SPZ_E_ARG;
+    if (block_rows != 8 && 2ull * (uint64_t)block_rows * ndims + ndims > 0xffffull) return SPZ_E_UNSUPPORTED;     // u16 tail length
     return compress_dev_impl(0, predictor, elem_sz, d_src, len, ndims, write_size, d_dest, d_meta, stream, (uint32_t)block_rows);
 }
 
@@ -286,6 +287,7 @@ int frame_job_init(FrameJob& j, int predictor, int elem_sz, const void* d_src, u
 {
     if (!valid_frame_codec(predictor, elem_sz) || ndims == 0 || chunk_rows == 0) return SPZ_E_ARG;
     if (block_rows != 8 && (predictor > 1 || !valid_block_rows((int)block_rows))) return SPZ_E_ARG;
+    if (block_rows != 8 && 2ull * block_rows * ndims + ndims > 0xffffull) return SPZ_E_UNSUPPORTED;   // the tail length is a u16 (format.h:35-45)
     j.block_rows = block_rows;
     if (ndims > SPZ_MAX_NDIMS) return SPZ_E_UNSUPPORTED;
     j.predictor = predictor; j.elem_sz = elem_sz; j.ndims = ndims; j.chunk_rows = chunk_rows; j.len = len;
