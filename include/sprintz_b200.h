@@ -319,6 +319,22 @@ int spz_quantize_dev(int elem_sz, int src_f64, const void* d_src, uint64_t len, 
                      void* d_work, uint64_t work_bytes, spz_stream_t stream);
 int64_t spz_quantize_host(int elem_sz, int src_f64, const void* src, uint64_t len, uint16_t ndims, void* dest);
 
+/* ---------------------------------------------------------------- 6. entropy stage (BASELINE config 3)
+ * The paper's "SprintzFIRE+Huf" entropy-codes the bit-packed bytes with Huff0, which is NOT in the reference tree
+ * (cpp/Compress/entropy.cpp:46-58 is a stub; README.md:29,45 points to the un-vendored lzbench fork).  PARITY UNPINNED:
+ * this is OUR byte-wise canonical Huffman stage -- order-0 Huffman over bytes, 11-bit length limit, one table per
+ * container, independently decodable 4096-byte segments behind a directory (one lane per segment) -- specified byte for
+ * byte by oracle/huff_oracle.c.  It runs over any device buffer (16-byte aligned), typically a frame's payload.
+ * Container: [64 B header][256 x 4-bit code lengths][u64 seg_off[nsegs+1]][u32 seg_nbytes[nsegs]][pad 16][streams][16 B].
+ * Asynchronous on `stream`.  *d_cont_bytes (device, optional) receives the container size; *d_status (device) receives 0
+ * or a bit set: 1 bad table | 2 bad header | 4 bad directory | 8 corrupt / truncated segment. */
+uint64_t spz_huff_max_bytes(uint64_t raw_bytes);
+uint64_t spz_huff_workspace_bytes(uint64_t raw_bytes);
+int spz_huff_encode_dev(const void* d_src, uint64_t raw_bytes, void* d_cont, uint64_t cont_cap, void* d_work,
+                        uint64_t work_bytes, uint64_t* d_cont_bytes, spz_stream_t stream);
+int spz_huff_decode_dev(const void* d_cont, uint64_t cont_bytes, uint64_t raw_bytes, void* d_dest, uint64_t dest_cap,
+                        void* d_work, uint64_t work_bytes, unsigned int* d_status, spz_stream_t stream);
+
 /* releases the cached device workspaces of the host-buffer entry points */
 void spz_release_workspaces(void);
 

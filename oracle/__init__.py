@@ -155,6 +155,33 @@ class Oracle(_Codec):
         dt = np.uint8 if esz == 1 else np.uint16
         return out[: n_out * esz].view(dt).copy(), int(ret)
 
+    # ---- entropy stage (oracle/huff_oracle.c): OUR container, parity unpinned
+    def huff_lengths(self, counts):
+        cnt = np.ascontiguousarray(counts, dtype=np.uint64)
+        out = np.zeros(256, np.uint8)
+        self.L.oracle_huff_lengths.restype = None
+        self.L.oracle_huff_lengths.argtypes = [C.c_void_p, C.c_void_p]
+        self.L.oracle_huff_lengths(cnt.ctypes.data, out.ctypes.data)
+        return out
+
+    def huff_encode(self, x):
+        src = np.ascontiguousarray(_as_u8(x))
+        self.L.oracle_huff_max_bytes.restype = C.c_uint64
+        self.L.oracle_huff_max_bytes.argtypes = [C.c_uint64]
+        self.L.oracle_huff_encode.restype = C.c_int64
+        self.L.oracle_huff_encode.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        buf = np.zeros(int(self.L.oracle_huff_max_bytes(src.size)), np.uint8)
+        n = self.L.oracle_huff_encode(src.ctypes.data, src.size, buf.ctypes.data)
+        return buf[: int(n)].copy()
+
+    def huff_decode(self, cont, n):
+        src = np.ascontiguousarray(_as_u8(cont))
+        self.L.oracle_huff_decode.restype = C.c_int64
+        self.L.oracle_huff_decode.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        out = np.zeros(max(n, 1), np.uint8)
+        r = self.L.oracle_huff_decode(src.ctypes.data, src.size, out.ctypes.data, n)
+        return out[:n], int(r)
+
     def compress_bs(self, predictor, x, ndims, block_rows, write_size=True):
         """Block-size axis (BASELINE config 5): block_rows in {8, 16, 32, 64}; 8 is oracle_compress itself."""
         self.L.oracle_compress_bs.restype = C.c_int64

@@ -64,6 +64,13 @@ int64_t oracle_decode_xff_forecast(int elem_sz, const void* src, uint32_t len, v
  * result[ndims]; returns the decoded element count. */
 int64_t oracle_query(int predictor, int elem_sz, const void* src, void* dest, int op, uint64_t* result);
 
+/* Entropy stage, oracle/huff_oracle.c: OUR byte-wise canonical Huffman container -- PARITY UNPINNED (Huff0
+ * is not in the reference tree).  encode returns the container bytes; decode returns n or -1 for a malformed container. */
+void oracle_huff_lengths(const uint64_t* count256, uint8_t* len256);
+uint64_t oracle_huff_max_bytes(uint64_t n);
+int64_t oracle_huff_encode(const uint8_t* src, uint64_t n, uint8_t* dst);
+int64_t oracle_huff_decode(const uint8_t* cont, uint64_t cont_bytes, uint8_t* dst, uint64_t n);
+
 /* Worst-case stream size in bytes for `len` elements (our own bound, used by tests
  * to size buffers; the reference has no capacity arguments). */
 uint64_t oracle_max_compressed_bytes(int elem_sz, uint64_t len, uint16_t ndims);

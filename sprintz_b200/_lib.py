@@ -95,6 +95,10 @@ SYMBOLS = {
     "spz_frame_gather_max_bytes": (_u64, [_i, _u64, _u16, _u32]),
     "spz_frame_gather_dev": (_i, [_vp, _i, _u64, _u32, _vp, _vp, _u64, _vp]),
     "spz_frame_encode_gather_dev": (_i, [_vp, _i, _i, _i, _vp, _u64, _u16, _u32, _u32, _vp, _u64, _vp, _u64, _vp, _u64, _vp]),
+    "spz_huff_max_bytes": (_u64, [_u64]),
+    "spz_huff_workspace_bytes": (_u64, [_u64]),
+    "spz_huff_encode_dev": (_i, [_vp, _u64, _vp, _u64, _vp, _u64, _vp, _vp]),
+    "spz_huff_decode_dev": (_i, [_vp, _u64, _u64, _vp, _u64, _vp, _u64, _vp, _vp]),
     "spz_comm_shared_alloc": (_i, [_vp, _u64, C.POINTER(_vp)]),
     "spz_frame_encode_gather_p2p_dev": (_i, [_vp, _i, _i, _i, _vp, _u64, _u16, _u32, _u32, _vp, _u64, _vp, _u64, _vp]),
     "spz_quantize_workspace_bytes": (_u64, [_u16]),

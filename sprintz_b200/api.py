@@ -29,6 +29,7 @@ __all__ = [
     "encode_forecast", "decode_forecast", "forecast_encode_dev", "forecast_decode_dev",
     "encode_xff_forecast", "decode_xff_forecast",
     "set_encode_pipeline", "last_encode_slabs", "kernel_launches", "Communicator", "FrameGather", "shard_len",
+    "HuffCodec", "huff_encode_dev", "huff_decode_dev",
     "quantize", "quantize_dev", "Q_NOOP", "Q_MAX", "Q_SUM", "query", "frame_query", "reduce_rows_dev", "last_query_fused",
 ]
 
@@ -475,6 +476,61 @@ def quantize_dev(x, ndims: int, elem_sz: int):
     check(lib().spz_quantize_dev(elem_sz, int(x.dtype == torch.float64), x.data_ptr(), x.numel(), ndims, out.data_ptr(),
                                  work.data_ptr(), wb, _stream_ptr()), "spz_quantize_dev")
     return out
+
+
+# ------------------------------------------------------------------ entropy stage (include/sprintz_b200.h section 6)
+
+class HuffCodec:
+    """Pre-allocated buffers for the byte-wise Huffman stage over `nbytes` device bytes (parity unpinned: our container)."""
+
+    def __init__(self, nbytes: int, device="cuda"):
+        torch = _torch()
+        L = lib()
+        self.nbytes = nbytes
+        self.cap = int(L.spz_huff_max_bytes(nbytes))
+        self.work_bytes = int(L.spz_huff_workspace_bytes(nbytes))
+        self.cont = torch.empty(self.cap, dtype=torch.uint8, device=device)
+        self.work = torch.empty(self.work_bytes, dtype=torch.uint8, device=device)
+        self.cont_bytes = torch.zeros(1, dtype=torch.int64, device=device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def encode(self, x):
+        """x: uint8 CUDA tensor of nbytes (16-byte aligned). -> the container tensor (self.cont[: size()])"""
+        assert x.is_cuda and x.element_size() == 1 and x.numel() == self.nbytes
+        check(lib().spz_huff_encode_dev(x.data_ptr(), self.nbytes, self.cont.data_ptr(), self.cap, self.work.data_ptr(),
+                                        self.work_bytes, self.cont_bytes.data_ptr(), _stream_ptr()), "spz_huff_encode_dev")
+        return self.cont
+
+    def size(self) -> int:
+        return int(self.cont_bytes.item())
+
+    def decode(self, cont, out, cont_bytes=None):
+        assert out.is_cuda and out.numel() >= self.nbytes
+        check(lib().spz_huff_decode_dev(cont.data_ptr(), cont.numel() if cont_bytes is None else cont_bytes, self.nbytes,
+                                        out.data_ptr(), out.numel(), self.work.data_ptr(), self.work_bytes,
+                                        self.status.data_ptr(), _stream_ptr()), "spz_huff_decode_dev")
+        return out
+
+    def check_status(self):
+        st = int(self.status.item())
+        if st:
+            raise SprintzError(f"huffman decode status {st}")
+
+
+def huff_encode_dev(x):
+    """-> uint8 CUDA tensor holding exactly the container"""
+    h = HuffCodec(x.numel(), device=x.device)
+    h.encode(x)
+    return h.cont[: h.size()].clone()
+
+
+def huff_decode_dev(cont, nbytes: int):
+    torch = _torch()
+    h = HuffCodec(nbytes, device=cont.device)
+    out = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=cont.device)
+    h.decode(cont, out)
+    h.check_status()
+    return out[:nbytes]
 
 
 # ------------------------------------------------------------------ multi-GPU: one process per GPU (include/sprintz_b200.h section 4)
