@@ -13,11 +13,15 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "smsp__warps_eligible.avg.per_cycle_active", "sm__cycles_elapsed.avg.per_second"]
 out_csv, out_json = sys.argv[1], sys.argv[2]
-traffic = {"how": "ncu --set full --clock-control none -k regex:spz_.*_lane -s 6 -c 2 python bench.py --config <c> --steps 2 "
-                  "--warmup 3 (full BASELINE sizes); per launch", "configs": {}}
+traffic = {"how": "ncu --set full --clock-control none --import-source on -k regex:spz_(en|de)code_(lane|wide) -s 2 -c 2 python bench.py "
+                  "--config <c> --no-sub --no-cpu-baseline --steps 1 --warmup 3 (full BASELINE sizes, tools/final_run.sh); per launch",
+           "configs": {}}
 with open(out_csv, "w") as f:
     for arg in sys.argv[3:]:
         cfg, rep = arg.split("=")
+        chunk_rows = 512
+        if ":" in cfg:
+            cfg, cr = cfg.split(":"); chunk_rows = int(cr)
         txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(txt)))
         hdr, units = rows[0], rows[1]
@@ -38,7 +42,7 @@ with open(out_csv, "w") as f:
                 return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[u]
             rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
             du, dv = units[hdr.index("gpu__time_duration.sum")], float(r[hdr.index("gpu__time_duration.sum")])
-            traffic["configs"].setdefault(cfg, {})[short] = {
+            traffic["configs"].setdefault(cfg, {"chunk_rows": chunk_rows})[short] = {
                 "dram_bytes_read": rd, "dram_bytes_write": wr, "traffic": rd + wr,
                 "ncu_duration_us": dv * {"ms": 1e3, "us": 1, "ns": 1e-3, "s": 1e6}[du], "kernel": name}
 with open(out_json, "w") as f:
