@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
     const bool valid = lane_on && c64 < p.nchunks;
     const uint64_t c = valid ? c64 : 0;
     const uint32_t D = NP * 8u;
-    const uint32_t last_lane = tw * NP + NP - 1u;
+    // my team's lanes (an idle lane is a team of its own): every team-wide reduction names exactly these
+    const uint32_t tmask = lane_on ? ((NP == 32u ? 0xffffffffu : ((1u << NP) - 1u)) << (tw * NP)) : (1u << lane);
 
     // ---- shared memory of this team
     const uint32_t TS = p.team_smem;
@@ -129,8 +130,7 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
     }
     auto flush = [&](bool on_, bool final_flush) {
         __syncwarp();
-        uint32_t carry[5] = {0, 0, 0, 0, 0};            // NP >= 3: a lane moves at most 5 of the < 16 remaining bytes
-        uint32_t rem = 0;
+        uint32_t carry0 = 0, carry1 = 0;                // the < 16 remaining bytes move to the front as (up to) 4 words
         bool moved = false;
         if (on_) {
             const uint32_t hi = final_flush ? ocur : (ocur & ~15u);
@@ -144,17 +144,21 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
                 uint32_t tb = hi & ~15u;
                 if (tb < a) tb = a;
                 for (uint32_t b = tb + t; b < hi; b += NP) gdst[b] = ob[b];
-                rem = ocur - hi;
-#pragma unroll
-                for (int k = 0; k < 5; k++) if (t + k * NP < rem) carry[k] = ob[hi + t + k * NP];
+                const uint32_t rem = ocur - hi;         // < 16 (0 on the final flush)
+                {   // hi is a multiple of 16: whole words; the bytes of the last word past the cursor are don't-care
+                    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(ob + hi);
+                    if (4u * t < rem) carry0 = w32[t];
+                    if (4u * (t + NP) < rem) carry1 = w32[t + NP];
+                }
                 gdst += hi; ocur = rem; oskip = 0;
-                moved = true;
+                moved = rem != 0u;
             }
         }
         __syncwarp();                                   // the tile has been read
         if (moved) {
-#pragma unroll
-            for (int k = 0; k < 5; k++) if (t + k * NP < rem) ob[t + k * NP] = (uint8_t)carry[k];
+            uint32_t* w32 = reinterpret_cast<uint32_t*>(ob);
+            if (4u * t < ocur) w32[t] = carry0;
+            if (4u * (t + NP) < ocur) w32[t + NP] = carry1;
         }
     };
     if (lane_on && t == 0) for (uint32_t b = 0; b < meta_bytes; b++) ob[ocur + b] = 0;     // metadata placeholder
@@ -265,13 +269,16 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
                     const uint2 pv = pc[u];
                     const uint32_t w = wd[u];
                     a0 |= pv.x << fill;
-                    uint32_t a1 = __funnelshift_l(pv.x, pv.y, fill);
+                    const uint32_t a1 = __funnelshift_l(pv.x, pv.y, fill);
                     const uint32_t a2 = __funnelshift_l(pv.y, 0u, fill);
                     fill += w;
-                    if (fill >= 32u) {
-                        *reinterpret_cast<uint32_t*>(smem + waddr) = a0; waddr += 4u; a0 = a1; a1 = a2; fill -= 32u;
-                        if (fill >= 32u) { *reinterpret_cast<uint32_t*>(smem + waddr) = a0; waddr += 4u; a0 = a1; fill -= 32u; }
-                    }
+                    // 0, 1 or 2 whole words are complete: predicated stores and selects, no branches
+                    const bool p1 = fill >= 32u, p2 = fill >= 64u;
+                    if (p1) *reinterpret_cast<uint32_t*>(smem + waddr) = a0;
+                    if (p2) *reinterpret_cast<uint32_t*>(smem + waddr + 4u) = a1;
+                    a0 = p2 ? a2 : (p1 ? a1 : a0);
+                    waddr += (fill >> 5) * 4u;
+                    fill &= 31u;
                 }
             } else if (act) {
                 auto put = [&](uint32_t wa, uint32_t v) {
@@ -332,12 +339,7 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
         prefetch(it + 1u);
         wA = (nA * 0x01010101u) >> 24;
         wo = wA + ((nB * 0x01010101u) >> 24);
-        uint32_t incl = wo;
-        for (uint32_t s = 1; s < NP; s <<= 1) {
-            const uint32_t y = __shfl_up_sync(kFullWE, incl, s);
-            if (t >= s) incl += y;
-        }
-        const uint32_t total = __shfl_sync(kFullWE, incl, (int)last_lane);
+        const uint32_t total = __reduce_add_sync(tmask, wo);            // one REDUX per team (disjoint masks, same instruction)
         const bool zero = (total == 0);
         row_bytes = (total + 7u) >> 3;
 
