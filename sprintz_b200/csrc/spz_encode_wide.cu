@@ -78,8 +78,10 @@ __device__ __forceinline__ uint32_t pack_quad(uint32_t w, const PackC& q)
 }
 
 // p.team = lanes per chunk (ndims / 8), p.dpl = teams per warp; team shared memory:
-//   [piece buffers 2 x 64*NP][octet widths 2 x 32][staging tile of out_cap bytes]
-template <int W, int MINB>
+//   [piece buffers 2 x 64*NP][octet widths 2 x 32][row bit offsets of the octets 2 x 32 x u16][staging tile of out_cap bytes]
+// LSEG: log2 of the segments a row is cut into for the row writers (0 with >= 3 teams per warp, 1 with two, 2 with one);
+// RDX: the team total is one REDUX (three teams per warp) instead of a shuffle scan
+template <int W, int MINB, int LSEG_, bool RDX>
 __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(const EncParams p)
 {
     static_assert(W == 8, "the SWAR wide-row encoder covers 8-bit elements");
@@ -96,7 +98,8 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
     const bool valid = lane_on && c64 < p.nchunks;
     const uint64_t c = valid ? c64 : 0;
     const uint32_t D = NP * 8u;
-    // my team's lanes (an idle lane is a team of its own): every team-wide reduction names exactly these
+    const uint32_t last_lane = tw * NP + NP - 1u;
+    // my team's lanes (an idle lane is a team of its own): a team-wide REDUX names exactly these
     const uint32_t tmask = lane_on ? ((NP == 32u ? 0xffffffffu : ((1u << NP) - 1u)) << (tw * NP)) : (1u << lane);
 
     // ---- shared memory of this team
@@ -104,7 +107,12 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
     const uint32_t warp_base = (uint32_t)warp * TPW * TS;
     uint8_t* const sm = smem + warp_base + tw * TS;
     const uint32_t PB = 64u * NP;                       // one piece buffer: [8 rows][NP] x 8 bytes
-    const uint32_t wid_off = 2u * PB;
+    const uint32_t wid_off = 2u * PB;                   // [2][32] octet widths (u8), then [2][32] bit offsets of the octets in a row (u16)
+    const uint32_t pre_off = wid_off + 64u;
+    // rows are written by one lane each; with one or two teams per warp a row is cut into SEG segments of whole pieces
+    // so that all 32 lanes work in that phase (ndims >= 88)
+    constexpr uint32_t LSEG = LSEG_;                    // log2(SEG): every division by SEG is a shift
+    constexpr uint32_t SEG = 1u << LSEG;
     uint8_t* const stage0 = sm + p.out_off;
     const uint32_t OCAP = p.out_cap;
 
@@ -190,7 +198,7 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
 
     // this block's zigzagged errors and layout
     uint32_t za[kBlockRows], zb[kBlockRows];
-    uint32_t nA = 0, nB = 0, wA = 0, wo = 0, row_bytes = 0;
+    uint32_t nA = 0, nB = 0, wA = 0, wo = 0, row_bytes = 0, excl = 0;
     uint32_t info = 0;                                  // what the row lanes need from my team (lane 0 of the team is read)
 
     // One slot of the open group (team-predicated by the caller).  Data slots leave their pieces in the piece buffer;
@@ -222,6 +230,7 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
                 pb[(uint32_t)r * NP] = make_uint2(va | __funnelshift_lc(0u, vb, wA), __funnelshift_lc(vb, 0u, wA));
             }
             sm[wid_off + pbsel * 32u + t] = (uint8_t)wo;
+            if (SEG > 1u) reinterpret_cast<uint16_t*>(sm + pre_off)[pbsel * 32u + t] = (uint16_t)excl;
             info = 1u | (row_bytes << 1) | ((uint32_t)((ob + ocur) - smem) << 11);
             ocur += kBlockRows * row_bytes;
             blk++;
@@ -244,28 +253,55 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
     // a byte-wise path.
     auto emit_rows = [&](bool doit, uint32_t pbsel) {
         if (!doit) info = 0;
-        __syncwarp();                                   // pieces, widths and header bytes are in shared memory
-        const uint32_t njobs = 8u * TPW;
+        __syncwarp();                                   // pieces, widths, offsets and header bytes are in shared memory
+        const uint32_t njobs = 8u * TPW * SEG;          // job = (team, row, segment): consecutive lanes are consecutive in the stream
         for (uint32_t j0 = 0; j0 < njobs; j0 += 32u) {
             const uint32_t j = j0 + (uint32_t)lane;
-            const uint32_t jt = (j >> 3) < TPW ? (j >> 3) : TPW - 1u;
+            const uint32_t jt_raw = j >> (3u + LSEG);
+            const uint32_t jt = jt_raw < TPW ? jt_raw : TPW - 1u;
             const uint32_t inf = __shfl_sync(kFullWE, info, (int)(jt * NP));
             const bool act = j < njobs && (inf & 1u);
-            const uint32_t r = j & 7u;
+            const uint32_t r = (j >> LSEG) & 7u;
+            uint32_t seg = j & (SEG - 1u);
             const uint32_t rb = (inf >> 1) & 0x3ffu;
             const uint32_t rowaddr = (inf >> 11) + r * rb;              // byte offset from smem[]
             const uint32_t end = rowaddr + rb;
             const uint8_t* tb = smem + warp_base + jt * TS;
-            const uint2* pc = reinterpret_cast<const uint2*>(tb + pbsel * PB) + r * NP;
             const uint8_t* wd = tb + wid_off + pbsel * 32u;
-            const bool fast = act && rb >= 8u;
-            uint32_t waddr = rowaddr & ~3u;
-            const uint32_t fill0 = (rowaddr & 3u) * 8u;
+            const uint16_t* pre = reinterpret_cast<const uint16_t*>(tb + pre_off) + pbsel * 32u;
+            // my pieces [u0, u1) and their bit range [s0, s1) inside the row; a segmented row needs >= 64 bits per segment
+            // (every job must complete the word it starts in), else lane `seg == 0` writes the whole row
+            uint32_t u0 = 0, u1 = NP, s0 = 0, s1 = rb * 8u;
+            bool last = true, mine = true;
+            if (SEG > 1u) {
+                bool segok = act;
+                uint32_t lo = 0;
+                for (uint32_t k = 1; k <= SEG && segok; k++) {
+                    const uint32_t hi = k < SEG ? (uint32_t)pre[(k * NP) >> LSEG] : rb * 8u;
+                    segok = hi - lo >= 64u;
+                    lo = hi;
+                }
+                if (segok) {
+                    u0 = (seg * NP) >> LSEG; u1 = ((seg + 1u) * NP) >> LSEG;
+                    s0 = pre[u0];
+                    last = seg == SEG - 1u;
+                    if (!last) s1 = pre[u1];
+                } else {
+                    mine = seg == 0u;
+                    seg = 0u;
+                }
+            }
+            const bool fast = act && mine && rb >= 8u;
+            const uint32_t bit0 = rowaddr * 8u + s0;
+            uint32_t waddr = (bit0 >> 5) << 2;
+            const uint32_t fill0 = bit0 & 31u;
             uint32_t fill = fill0;
             uint32_t a0 = 0, old0 = 0;
+            const bool first_job = r == 0u && seg == 0u;   // the bytes in front of the payload are saved and restored
+            const uint2* pc = reinterpret_cast<const uint2*>(tb + pbsel * PB) + r * NP;
             if (fast) {
-                if (r == 0u && fill0) old0 = *reinterpret_cast<const uint32_t*>(smem + waddr) & ((1u << fill0) - 1u);
-                for (uint32_t u = 0; u < NP; u++) {
+                if (first_job && fill0) old0 = *reinterpret_cast<const uint32_t*>(smem + waddr) & ((1u << fill0) - 1u);
+                for (uint32_t u = u0; u < u1; u++) {
                     const uint2 pv = pc[u];
                     const uint32_t w = wd[u];
                     a0 |= pv.x << fill;
@@ -280,7 +316,7 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
                     waddr += (fill >> 5) * 4u;
                     fill &= 31u;
                 }
-            } else if (act) {
+            } else if (act && mine) {
                 auto put = [&](uint32_t wa, uint32_t v) {
 #pragma unroll
                     for (uint32_t i = 0; i < 4u; i++)
@@ -300,13 +336,17 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
                 }
                 if (waddr < end) put(waddr, a0);
             }
-            __syncwarp();                               // every whole word of every row is stored
+            __syncwarp();                               // every whole word of every job is stored
             if (fast) {
-                if (waddr < end) {                      // last word: when the row ends inside it, it is the next row's (zero-padded) first word
-                    if (r < 7u && (end & 3u)) a0 |= *reinterpret_cast<const uint32_t*>(smem + waddr);
+                // my last, partial word: the job behind me (next segment / next row) stored it with ZERO low bits when
+                // my range ends inside it.  The last job of the slot stores zeros behind the payload.
+                const bool tail = last ? (waddr < end) : (fill != 0u);
+                if (tail) {
+                    const bool shared = last ? (r < 7u && (end & 3u)) : true;
+                    if (shared) a0 |= *reinterpret_cast<const uint32_t*>(smem + waddr);
                     *reinterpret_cast<uint32_t*>(smem + waddr) = a0;
                 }
-                if (r == 0u && fill0) *reinterpret_cast<uint32_t*>(smem + (rowaddr & ~3u)) |= old0;
+                if (first_job && fill0) *reinterpret_cast<uint32_t*>(smem + ((rowaddr * 8u) >> 5 << 2)) |= old0;
             }
         }
         __syncwarp();                                   // rows are complete before anything is appended behind them
@@ -339,7 +379,22 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
         prefetch(it + 1u);
         wA = (nA * 0x01010101u) >> 24;
         wo = wA + ((nB * 0x01010101u) >> 24);
-        const uint32_t total = __reduce_add_sync(tmask, wo);            // one REDUX per team (disjoint masks, same instruction)
+        // team total of the widths (and, for segmented rows, the bit offset of my octet inside a row).  Three teams per warp:
+        // one REDUX per team with the team's own mask (the hardware reduces one mask at a time, so this only pays with few
+        // teams and a full machine: c4 2.54 -> 2.39 ms; with 10 teams per warp it costs 20 %).  Otherwise a shuffle scan.
+        uint32_t total;
+        excl = 0;
+        if (RDX) {
+            total = __reduce_add_sync(tmask, wo);
+        } else {
+            uint32_t incl = wo;
+            for (uint32_t sft = 1; sft < NP; sft <<= 1) {
+                const uint32_t y = __shfl_up_sync(kFullWE, incl, sft);
+                if (t >= sft) incl += y;
+            }
+            excl = incl - wo;
+            total = __shfl_sync(kFullWE, incl, (int)last_lane);
+        }
         const bool zero = (total == 0);
         row_bytes = (total + 7u) >> 3;
 
@@ -434,7 +489,7 @@ cudaError_t launch_encode_wide(int elem_sz, int predictor, EncParams p, cudaStre
     const uint32_t grp = H + 16u * p.ndims + 4u;
     const uint32_t teams_per_cta = (kWideEncThreads / 32) * TPW;
     p.teams_per_cta = teams_per_cta;
-    p.out_off = up16w(2u * 64u * NP + 64u);
+    p.out_off = up16w(2u * 64u * NP + 64u + 128u);       // piece buffers | widths | row bit offsets
     // the staging tile holds up to 4 groups, fewer when that would cost occupancy (6 CTAs per SM need <= 36 KB each)
     for (uint32_t ngrp = 4; ngrp >= 1; ngrp--) {
         p.out_cap = up16w(32u + ngrp * grp + 16u);
@@ -447,13 +502,18 @@ cudaError_t launch_encode_wide(int elem_sz, int predictor, EncParams p, cudaStre
     if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
     // 96 registers / 5 CTAs per SM: measured equal to 127 registers / 4 CTAs (the kernel is issue-bound, not latency-bound);
     // 80 registers / 6 CTAs spills and is 8 % slower
-    auto kernel = spz_encode_wide_kernel<8, 5>;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    if (g_enc_probe) return probe_fill(g_enc_probe, 3, kernel, kWideEncThreads, smem, teams_per_cta);
-    count_launch();
-    kernel<<<(uint32_t)grid64, kWideEncThreads, smem, stream>>>(p);
-    return cudaGetLastError();
+    auto go = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (g_enc_probe) return probe_fill(g_enc_probe, 3, kernel, kWideEncThreads, smem, teams_per_cta);
+        count_launch();
+        kernel<<<(uint32_t)grid64, kWideEncThreads, smem, stream>>>(p);
+        return cudaGetLastError();
+    };
+    if (TPW == 1u) return go(spz_encode_wide_kernel<8, 5, 2, false>);
+    if (TPW == 2u) return go(spz_encode_wide_kernel<8, 5, 1, false>);
+    if (TPW == 3u) return go(spz_encode_wide_kernel<8, 5, 0, true>);
+    return go(spz_encode_wide_kernel<8, 5, 0, false>);
 }
 
 }  // namespace spz
