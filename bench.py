@@ -629,9 +629,9 @@ def measure_gather(env, args, codec, fr, x, out, cfg, chunk_rows, raw, payload, 
         g = spz.FrameGather(env.comm, codec, dst=0, stripe_chunks=codec.nchunks // GATHER_ROUNDS)
         gf = g.gather(fr)                                   # warm-up + correctness
         torch.cuda.synchronize()
-        ok = None
-        if rank == 0:
-            ok = g.verify_against_shards(gf, x)             # decodes the gathered frame; shard 0 == x on rank 0
+        env.barrier()
+        # rank 0 decodes the gathered frame: its own shard element by element, every other rank's through checksums
+        ok = g.verify_against_shards(gf if rank == 0 else None, x, all_ranks=True)
         env.barrier()
         reps = max(3, min(steps, 10))
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -646,9 +646,7 @@ def measure_gather(env, args, codec, fr, x, out, cfg, chunk_rows, raw, payload, 
         t_g = ev[0].elapsed_time(ev[1]) / reps / 1e3
         t_eg = ev[1].elapsed_time(ev[2]) / reps / 1e3
         t_g, t_eg = env.max_over_ranks([t_g, t_eg])
-        ok2 = None
-        if rank == 0:
-            ok2 = g.verify_against_shards(g.last_frame, x)
+        ok2 = g.verify_against_shards(g.last_frame if rank == 0 else None, x, all_ranks=True)
         moved = (world - 1) * payload                       # bytes that crossed NVLink into rank 0 (payloads are ~equal)
         t_enc_step = r["t_enc"] / steps
         t_dec_step = r["t_dec"] / steps
@@ -661,12 +659,14 @@ def measure_gather(env, args, codec, fr, x, out, cfg, chunk_rows, raw, payload, 
                "encode_with_gather_gbs": world * raw / t_eg / 1e9}
         # ---- the same exchange over peer memory: every stripe's compaction kernel stores straight into rank 0's frame
         try:
-            g = spz.FrameGather(env.comm, codec, dst=0, stripe_chunks=codec.nchunks // P2P_ROUNDS)
+            del g, gf                                       # the NCCL destination buffer (a whole gathered frame) goes first
+            torch.cuda.empty_cache()                        # the shared regions are cudaMalloc'ed by the library, outside torch's pool
+            g = spz.FrameGather(env.comm, codec, dst=0, stripe_chunks=codec.nchunks // P2P_ROUNDS, alloc=False)
             g.enable_p2p()
             g.encode_and_gather_p2p(x)                      # warm-up + correctness
             torch.cuda.synchronize()
             env.barrier()
-            ok3 = g.verify_against_shards(g.last_frame, x) if rank == 0 else None
+            ok3 = g.verify_against_shards(g.last_frame if rank == 0 else None, x, all_ranks=True)
             env.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -675,7 +675,7 @@ def measure_gather(env, args, codec, fr, x, out, cfg, chunk_rows, raw, payload, 
             e1.record()
             env.barrier()
             t_p2p = env.max_over_ranks([e0.elapsed_time(e1) / reps / 1e3])[0]
-            ok4 = g.verify_against_shards(g.last_frame, x) if rank == 0 else None
+            ok4 = g.verify_against_shards(g.last_frame if rank == 0 else None, x, all_ranks=True)
             # what bounds it: rank 0 ingress (the other ranks' payload over NVLink) or the encode itself
             rec["gather_p2p"] = {"encode_plus_gather_ms": 1e3 * t_p2p, "gbs_into_rank0": moved / t_p2p / 1e9,
                                  "backend": "fused compaction + NVLink peer stores (spz_frame_encode_gather_p2p_dev), no NCCL in the data path",

@@ -576,7 +576,7 @@ class FrameGather:
     """Gathers every rank's frame of one codec shape into ONE decodable frame of the global stream on rank `dst`
     (spz_frame_gather_dev / spz_frame_encode_gather_dev).  All ranks hold shards of equal length here."""
 
-    def __init__(self, comm: Communicator, codec: FrameCodec, dst: int = 0, stripe_chunks: int = 0):
+    def __init__(self, comm: Communicator, codec: FrameCodec, dst: int = 0, stripe_chunks: int = 0, alloc: bool = True):
         torch = _torch()
         L = lib()
         self.comm, self.codec, self.dst, self.stripe_chunks = comm, codec, dst, stripe_chunks
@@ -588,7 +588,8 @@ class FrameGather:
         self.buf = None
         if comm.rank == dst:
             self.cap = int(L.spz_frame_gather_max_bytes(codec.elem_sz, self.total_len, codec.ndims, codec.chunk_rows))
-            self.buf = torch.empty(self.cap, dtype=torch.uint8, device=codec.frame.device)
+            if alloc:                               # alloc=False: only the peer-memory gather is used (its buffer is the library's)
+                self.buf = torch.empty(self.cap, dtype=torch.uint8, device=codec.frame.device)
         self.last_frame = None
         self.last_stripes = 0
 
@@ -660,12 +661,44 @@ class FrameGather:
             k += 1
         return out
 
-    def verify_against_shards(self, gframe: Frame, x) -> bool:
-        """dst: decodes the gathered frame and compares this rank's pieces with x (the other ranks' pieces are checked
-        through per-piece checksums by the harness: tests/mgpu_worker.py)."""
-        out = frame_decode(gframe)
-        ok = True
-        for glo, llo, n in self.shard_positions(self.comm.rank, self.last_stripes):
-            ok = ok and bool(_torch().equal(out[glo: glo + n], x[llo: llo + n]))
-        self.decoded = out
+    @staticmethod
+    def _checksum(t):
+        """position-weighted 64-bit checksum of a 1-D integer tensor (wraps; computed in slabs, no large temporaries)"""
+        torch = _torch()
+        acc = torch.zeros(2, dtype=torch.int64, device=t.device)
+        step = 1 << 25
+        for a in range(0, t.numel(), step):
+            v = t[a: a + step].to(torch.int64)
+            w = (torch.arange(a, a + v.numel(), device=t.device, dtype=torch.int64) % 65521) + 1
+            acc[0] += v.sum()
+            acc[1] += (v * w).sum()
+        return acc
+
+    def verify_against_shards(self, gframe, x, all_ranks: bool = False) -> bool:
+        """Collective when all_ranks: dst decodes the gathered frame; its own pieces are compared element by element with
+        x, every other rank's pieces through position-weighted checksums exchanged over torch.distributed.  Returns the
+        verdict on dst (None elsewhere)."""
+        torch = _torch()
+        out = frame_decode(gframe) if self.comm.rank == self.dst else None
+        ok = None
+        if out is not None:
+            ok = True
+            for glo, llo, n in self.shard_positions(self.comm.rank, self.last_stripes):
+                ok = ok and bool(torch.equal(out[glo: glo + n], x[llo: llo + n]))
+        if all_ranks and self.comm.world > 1:
+            import torch.distributed as dist
+            stripes = self.last_stripes if self.comm.rank == self.dst else None
+            box = [stripes]
+            dist.broadcast_object_list(box, src=self.dst)
+            stripes = box[0]
+            mine = torch.stack([self._checksum(x[llo: llo + n]) for _, llo, n in self.shard_positions(self.comm.rank, stripes)])
+            allsums = [torch.zeros_like(mine) for _ in range(self.comm.world)]
+            dist.all_gather(allsums, mine)
+            if out is not None:
+                for r in range(self.comm.world):
+                    if r == self.dst:
+                        continue
+                    for k, (glo, _, n) in enumerate(self.shard_positions(r, stripes)):
+                        ok = ok and bool(torch.equal(self._checksum(out[glo: glo + n]), allsums[r][k]))
+        del out
         return ok
