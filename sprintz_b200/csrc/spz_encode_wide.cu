@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
             if (4u * t < ocur) w32[t] = carry0;
             if (4u * (t + NP) < ocur) w32[t + NP] = carry1;
         }
+        __syncwarp();                                   // the carried words hold don't-care bytes past the cursor: later writers come after
     };
     if (lane_on && t == 0) for (uint32_t b = 0; b < meta_bytes; b++) ob[ocur + b] = 0;     // metadata placeholder
     ocur += meta_bytes;
