@@ -441,6 +441,31 @@ def measure_config(env, args, cfg_name, cfg, steps, warm, main):
     if clocks is not None:
         rec["clocks"] = clocks
 
+    # ---- the slab-pipelined frame encode (three slabs, thin compaction CTAs beside the next slab's codec kernel): it pays for
+    # the wide-row encoder (many machine rounds of small CTAs), not for the lane encoders -- reported beside the classic time
+    old_slabs = spz.set_encode_pipeline(3)
+    try:
+        for _ in range(2):
+            codec.encode(x)
+        pe = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        env.barrier()
+        pe[0].record()
+        for _ in range(5):
+            fr_p = codec.encode(x)
+        pe[1].record()
+        env.barrier()
+        codec.decode(fr_p, out)
+        torch.cuda.synchronize()
+        t_pipe = env.max_over_ranks([pe[0].elapsed_time(pe[1]) / 5e3])[0]
+        rec["encode_pipelined"] = {"slabs": int(L.spz_last_encode_slabs()), "ms": 1e3 * t_pipe, "encode_gbs": world * raw / t_pipe / 1e9,
+                                   "classic_ms": 1e3 * r["t_enc"] / steps, "roundtrip_ok": bool(torch.equal(out, x))}
+    except Exception as e:  # noqa: BLE001
+        rec["encode_pipelined"] = {"error": f"{type(e).__name__}: {e}"}
+    finally:
+        spz.set_encode_pipeline(old_slabs)
+        fr = codec.encode(x)                                # the classic frame again (what the checks below read)
+        torch.cuda.synchronize()
+
     # ---- the frame on the host, for the parity check (before the buffers go away)
     want_parity = rank == 0 and not args.no_cpu_baseline
     host_frame = frame_to_host(fr, hdr) if want_parity else None

@@ -256,6 +256,9 @@ cudaError_t SidePipe::init(int nslabs)
         if ((e = cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi)) != cudaSuccess) return e;
         if ((e = cudaEventCreateWithFlags(&ev_begin, cudaEventDisableTiming)) != cudaSuccess) return e;
         if ((e = cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming)) != cudaSuccess) return e;
+        int dev = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     }
     for (; nev < nslabs && nev < (int)kMaxSlabs; nev++)
         if ((e = cudaEventCreateWithFlags(&ev_enc[nev], cudaEventDisableTiming)) != cudaSuccess) return e;
@@ -317,7 +320,10 @@ int frame_job_init(FrameJob& j, int predictor, int elem_sz, const void* d_src, u
         // pay -- the compaction CTAs displace encoder CTAs (the lane encoders run 4 CTAs per SM at 116 registers, nothing
         // else fits beside them) and every slab boundary drains the machine, so c3 goes 3.46 -> 3.66 ms with 7 slabs.
         // Automatic therefore means ONE slab; the slab machinery is what the host path (PCIe overlap) and the streamed
-        // multi-GPU gather (NVLink overlap) are built on, and `want` > 1 forces it here for tests and tuning.
+        // multi-GPU gather (NVLink overlap) are built on, and `want` > 1 forces it here for tests and tuning.  With the
+        // thin (one-warp) compaction CTAs of this round three slabs DO pay for the wide-row encoder (c4: 3.08 -> 2.87 ms,
+        // it runs 12 machine rounds of small CTAs) but still not for the lane encoders (c3: 3.50 -> 3.70 ms at best, also
+        // with slabs cut at machine rounds): the bench reports the pipelined time beside the classic one.
         if (want > 1) slab_chunks = (j.f.nchunks + want - 1) / want;
         else slab_chunks = j.f.nchunks;
     }
@@ -367,7 +373,7 @@ int frame_job_scan_slab(const FrameJob& j, uint64_t k, cudaStream_t st)
     return SPZ_OK;
 }
 
-int frame_job_compact_slab(const FrameJob& j, uint64_t k, cudaStream_t st)
+int frame_job_compact_slab(const FrameJob& j, uint64_t k, cudaStream_t st, int thin_ctas)
 {
     uint64_t c0, nc, e0, ne;
     j.slab(k, c0, nc, e0, ne);
@@ -379,8 +385,12 @@ int frame_job_compact_slab(const FrameJob& j, uint64_t k, cudaStream_t st)
                          (unsigned int*)(j.work + j.w.off_ticket) + k, j.d_tot() + k, j.d_tot() + k + 1,
                          k + 1 == j.nslabs, (spz_frame_header*)j.d_frame, j.h, k + 1 == j.nslabs ? j.d_frame_bytes : nullptr,
                          j.d_err(), st));
-    CK(launch_gather(j.work + j.w.off_slots + c0 * j.w.slot_stride, j.w.slot_stride, nc, chunk_off + c0, chunk_nbytes + c0,
-                     j.d_frame + j.f.payload_off, st));
+    if (thin_ctas > 0)
+        CK(launch_gather_thin(j.work + j.w.off_slots + c0 * j.w.slot_stride, j.w.slot_stride, nc, chunk_off + c0, chunk_nbytes + c0,
+                              j.d_frame + j.f.payload_off, (uint32_t)thin_ctas, st));
+    else
+        CK(launch_gather(j.work + j.w.off_slots + c0 * j.w.slot_stride, j.w.slot_stride, nc, chunk_off + c0, chunk_nbytes + c0,
+                         j.d_frame + j.f.payload_off, st));
     return SPZ_OK;
 }
 
@@ -449,7 +459,9 @@ static int frame_encode_impl(int predictor, int elem_sz, uint32_t block_rows, co
         if (int r = frame_job_encode_slab(j, k, stream)) return r;
         CK(cudaEventRecord(sp.ev_enc[k], stream));
         CK(cudaStreamWaitEvent(sp.side, sp.ev_enc[k], 0));
-        if (int r = frame_job_compact_slab(j, k, sp.side)) return r;
+        // every slab but the last is compacted by one-warp CTAs that fit beside the next slab's codec kernel (four per
+        // SM); the last slab's compaction runs alone at full width
+        if (int r = frame_job_compact_slab(j, k, sp.side, (k + 1 < j.nslabs) ? 4 * sp.sms : 0)) return r;
     }
     PROF_MARK(1);
     PROF_MARK(2);

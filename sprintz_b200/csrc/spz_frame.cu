@@ -149,6 +149,50 @@ spz_gather_kernel(const uint8_t* __restrict__ slots, uint64_t slot_stride, uint6
     }
 }
 
+// The same compaction as ONE-warp CTAs with eight 128-bit loads in flight per lane (~70 registers x 32 threads): thin
+// enough to sit in the registers the codec kernels leave free (the lane encoders fill 59 of the 64 K registers of an SM
+// with 4 CTAs), so a slab's compaction can run BESIDE the next slab's codec kernel instead of displacing its CTAs.
+__global__ void __launch_bounds__(32)
+spz_gather_thin_kernel(const uint8_t* __restrict__ slots, uint64_t slot_stride, uint64_t nchunks,
+                       const uint64_t* __restrict__ chunk_off, const uint32_t* __restrict__ chunk_nbytes,
+                       uint8_t* __restrict__ payload)
+{
+    const int lane = threadIdx.x;
+    for (uint64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const uint32_t nb = chunk_nbytes[c];
+        const uint32_t units = (nb + 15u) >> 4;
+        const uint4* __restrict__ s4 = reinterpret_cast<const uint4*>(slots + c * slot_stride);
+        uint4* __restrict__ d4 = reinterpret_cast<uint4*>(payload + chunk_off[c]);
+        for (uint32_t u0 = 0; u0 < units; u0 += 256u) {
+            uint4 x[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint32_t u = u0 + (uint32_t)lane + 32u * k;
+                if (u < units) x[k] = s4[u];
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint32_t u = u0 + (uint32_t)lane + 32u * k;
+                if (u < units) {
+                    uint4 v = x[k];
+                    if (u == units - 1 && (nb & 15u)) {
+                        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                        const uint32_t keep = nb & 15u;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const uint32_t lo = 4u * q;
+                            if (keep <= lo) w[q] = 0;
+                            else if (keep < lo + 4) w[q] &= (1u << (8 * (keep - lo))) - 1u;
+                        }
+                        v = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                    d4[u] = v;
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ directory of a gathered frame (multi-GPU)
 // After the ranks' directory slices have landed in the destination frame, entry c still holds the offset inside its
 // OWNER's payload.  Segment s covers global chunks [seg_lo[s], seg_lo[s+1]) and moved by seg_delta[s] bytes.
@@ -202,6 +246,16 @@ cudaError_t launch_scan_sizes(const ChunkMeta* meta, uint64_t nchunks, uint64_t*
 }
 
 uint64_t scan_tiles(uint64_t nchunks) { return (nchunks + kScanTile - 1) / kScanTile; }
+
+cudaError_t launch_gather_thin(const uint8_t* slots, uint64_t slot_stride, uint64_t nchunks, const uint64_t* chunk_off,
+                               const uint32_t* chunk_nbytes, uint8_t* payload, uint32_t ctas, cudaStream_t stream)
+{
+    if (ctas > nchunks) ctas = (uint32_t)nchunks;
+    if (ctas == 0) return cudaSuccess;
+    count_launch();
+    spz_gather_thin_kernel<<<ctas, 32, 0, stream>>>(slots, slot_stride, nchunks, chunk_off, chunk_nbytes, payload);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_gather(const uint8_t* slots, uint64_t slot_stride, uint64_t nchunks, const uint64_t* chunk_off,
                           const uint32_t* chunk_nbytes, uint8_t* payload, cudaStream_t stream)

@@ -23,6 +23,8 @@ cudaError_t launch_gather(const uint8_t* slots, uint64_t slot_stride, uint64_t n
 cudaError_t launch_rebase_directory(uint64_t* chunk_off, uint64_t nchunks, const uint64_t* seg_lo, const int64_t* seg_delta,
                                     uint32_t nsegs, uint64_t total_payload, uint32_t* chunk_nbytes, spz_frame_header* hdr,
                                     const spz_frame_header& hdr_in, cudaStream_t stream);
+cudaError_t launch_gather_thin(const uint8_t* slots, uint64_t slot_stride, uint64_t nchunks, const uint64_t* chunk_off,
+                               const uint32_t* chunk_nbytes, uint8_t* payload, uint32_t ctas, cudaStream_t stream);
 uint64_t scan_tiles(uint64_t nchunks);
 // What launch_encode() would do for this call: kernel family (0 generic, 1 team, 2 lane, 3 wide) and how many chunks
 // fill the machine once (resident CTAs x chunks per CTA); nothing is launched.
@@ -129,7 +131,7 @@ int frame_job_init(FrameJob& j, int predictor, int elem_sz, const void* d_src, u
 int frame_job_reset(const FrameJob& j, cudaStream_t st);                       // zeroes scan states / tickets / totals / error word
 int frame_job_encode_slab(const FrameJob& j, uint64_t k, cudaStream_t st);     // codec kernel of slab k
 int frame_job_scan_slab(const FrameJob& j, uint64_t k, cudaStream_t st);       // directory scan of slab k only (slab order!)
-int frame_job_compact_slab(const FrameJob& j, uint64_t k, cudaStream_t st);    // directory scan + compaction of slab k (slab order!)
+int frame_job_compact_slab(const FrameJob& j, uint64_t k, cudaStream_t st, int thin_ctas = 0);   // directory scan + compaction of slab k (slab order!); thin_ctas > 0: one-warp CTAs that fit beside a running codec kernel
 
 // side stream + events of the pipelined encode (one set per process, guarded by a mutex while a call enqueues)
 struct SidePipe {
@@ -137,6 +139,7 @@ struct SidePipe {
     cudaEvent_t ev_enc[kMaxSlabs];
     cudaEvent_t ev_done = nullptr, ev_begin = nullptr;
     int nev = 0;
+    int sms = 0;                         // SMs of the device the pipe was created on
     cudaError_t init(int nslabs);
 };
 SidePipe& side_pipe();
