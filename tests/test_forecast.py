@@ -172,3 +172,27 @@ def test_gpu_forecast_named_entry_points_vs_live_reference(ref):
         dec = np.zeros(x.size, x.dtype)
         n = getattr(L, "spz_decode_" + name)(out.ctypes.data + 6, x.size, dec.ctypes.data, D)
         assert n == x.size and np.array_equal(dec, x)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("esz,D", [(1, 8), (2, 4), (1, 16), (2, 8), (2, 16), (1, 80), (1, 48), (2, 40)])
+def test_gpu_delta_decode_vector_path(oracle, esz, D):
+    """Rows of 8 / 16 / k*16 bytes with a whole number of 16-byte units take the vectorised chained scan
+    (spz_delta_decode_vec_kernel): one tile, tile edges, many tiles per column, many CTAs -- against the oracle on the small
+    sizes and against an exact cumulative sum everywhere."""
+    import torch
+    import sprintz_b200 as spz
+    udt = np.uint8 if esz == 1 else np.uint16
+    row_bytes = D * esz
+    unit_rows = 2 if row_bytes == 8 else 1
+    rng = np.random.default_rng(D + esz)
+    for nrows in (unit_rows, 2 * unit_rows, 62, 64, 66, 128, 130, 64 * 7 + 2, 4096, 300000):
+        nrows -= nrows % unit_rows
+        y = rng.integers(0, 1 << (8 * esz), size=(nrows, D), dtype=np.uint32).astype(udt)
+        want = np.cumsum(y.astype(np.uint64), axis=0).astype(udt)            # mod 2^w
+        yt = torch.from_numpy(y.reshape(-1).view(np.uint8 if esz == 1 else np.int16)).cuda()
+        got = spz.forecast_decode_dev(1, yt, D).cpu().numpy().view(udt).reshape(nrows, D)
+        assert np.array_equal(got, want), (esz, D, nrows)
+        if nrows <= 4096:
+            od, n = oracle.decode_forecast(1, esz, y.reshape(-1), D)
+            assert n == y.size and np.array_equal(od.reshape(nrows, D), want)
