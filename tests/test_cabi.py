@@ -96,3 +96,34 @@ def test_reference_named_wrappers_exist():
         for p in ("delta", "xff"):
             assert callable(getattr(spz, f"sprintz_compress_{p}_{w}"))
             assert callable(getattr(spz, f"sprintz_decompress_{p}_{w}"))
+
+
+def test_shard_plan_partitions_the_stream():
+    """spz_shard_len (the partition the multi-GPU gathers use, spz_comm.cu make_plan) on the CPU: contiguous ranges and
+    round-robin stripes cover the global stream exactly once, only the last global stripe is short, and the lengths
+    agree with a Python model of the rule (tests/mgpu_worker.py uses the same model on the GPU box)."""
+    import sprintz_b200 as spz
+    L = spz.lib()
+
+    def model(total, D, chunk_rows, S, world, rank):
+        clen = chunk_rows * D
+        nch = max(1, -(-total // clen))
+        if S == 0:
+            base, extra = divmod(nch, world)
+            lo = sum(base + (1 if r < extra else 0) for r in range(rank))
+            n = base + (1 if rank < extra else 0)
+            return max(0, min(total, (lo + n) * clen) - min(total, lo * clen))
+        nstripes = -(-nch // S)
+        return sum(min(total, (j + 1) * S * clen) - j * S * clen for j in range(rank, nstripes, world))
+
+    for total, D, chunk_rows in ((1 << 20, 8, 512), (1000003, 5, 16), (80 * 64 * 37 + 16, 80, 64), (17, 16, 512)):
+        for world in (1, 2, 3, 8):
+            for S in (0, 1, 7, 64):
+                lens = [int(L.spz_shard_len(total, D, chunk_rows, S, world, r)) for r in range(world)]
+                nch = max(1, -(-total // (chunk_rows * D)))
+                if S and -(-(-(-nch // S)) // world) > 62:              # more than 62 stripes per rank: not a supported plan
+                    assert lens == [0] * world
+                    continue
+                assert sum(lens) == total, (total, D, chunk_rows, S, world, lens)
+                assert lens == [model(total, D, chunk_rows, S, world, r) for r in range(world)]
+    assert L.spz_shard_len(100, 0, 16, 0, 2, 0) == 0 and L.spz_shard_len(100, 4, 16, 0, 2, 5) == 0
