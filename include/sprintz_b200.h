@@ -225,9 +225,11 @@ int spz_profile_collect(float* ms3, int* ncalls);
 
 /* spz_frame_encode_dev can cut a frame into SLABS of whole chunks and run slab k's directory scan + compaction on a
  * second stream while slab k+1 is being encoded.  The frame bytes do not depend on the slab count.  slabs: 0 or 1 =
- * one slab (codec kernel, scan, compaction back to back: the default -- measured, slabs do not pay for device-resident
- * input), n > 1 = n slabs.  The same slab machinery carries the host-buffer path (PCIe overlap)
- * and the streamed multi-GPU gather (NVLink overlap), where it does pay.  Returns the previous setting;
+ * one slab (codec kernel, scan, compaction back to back: the default), n > 1 = n slabs, every slab but the last
+ * compacted by one-warp CTAs that fit beside the next slab's codec kernel.  Measured: three slabs
+ * pay for the wide-row encoder (int8 x 80 delta: 3.08 -> 2.84 ms) and not for the lane encoders, hence the default.  The
+ * same slab machinery carries the host-buffer path (PCIe overlap) and the multi-GPU gathers (NVLink overlap), where it
+ * does pay.  Returns the previous setting;
  * spz_last_encode_slabs() = slabs of this thread's last frame encode. */
 int spz_set_encode_pipeline(int slabs);
 int spz_last_encode_slabs(void);

@@ -17,8 +17,10 @@
 //            to bytes 0 and 2, then the high pair moves next to the low pair); two quads make the octet's <= 64-bit
 //            piece of the row
 //   rows     the pieces of a block go through shared memory ([row][octet], 64-bit); lane (team, row) then appends the
-//            team's pieces of ITS row with a scalar bit writer straight into the output staging tile -- no cross-lane
-//            bit merging, no atomics; rows only share their first / last partial word, written byte-wise
+//            team's pieces of ITS row with a branch-free scalar bit writer straight into the output staging tile -- no
+//            cross-lane bit merging, no atomics.  Whole-word stores only: a row's first word is stored with zero low
+//            bytes, after a barrier the lane in front ORs its last partial word into it.  With one or two teams per warp
+//            a row is cut into 4 / 2 segments of whole pieces handed over the same way, so all 32 lanes write rows.
 //   control  the reference's run / group state machine (sprintz_delta_rle.cpp:134-312) as the per-team action generator
 //            of spz_encode_hd.cu, executed in lock-step passes
 //   output   shared staging tile, flushed with 128-bit stores
