@@ -14,3 +14,4 @@ done
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:spz_ -c 120 --csv \
     --log-file $O/${T}_launches_c3.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 --no-sub > $O/${T}_launch_bench.log 2>&1
 ls -la $O | grep ${T}_
+timeout 600 python tools/dims_sweep.py --blocks 8 > $O/${T}_dims_sweep_block8.jsonl 2> $O/${T}_dims_sweep.err; wc -l $O/${T}_dims_sweep_block8.jsonl
