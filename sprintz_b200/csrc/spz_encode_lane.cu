@@ -156,6 +156,16 @@ __global__ void __launch_bounds__(kEncLaneThreads, (W == 8) ? 5 : 4) spz_encode_
         *reinterpret_cast<uint4*>(stg + (2 * s) * 512) = make_uint4(v[0], v[1], v[2], v[3]);
         *reinterpret_cast<uint4*>(stg + (2 * s + 1) * 512) = make_uint4(v[4], v[5], v[6], v[7]);
     };
+    // The NEXT block's sector s goes straight from HBM / L2 into the staging column with two 16-byte asynchronous copies
+    // (LDGSTS, no registers) issued as soon as the current block's sector s has been emitted; nobody waits for them before
+    // the next block's pass 1.  (Through registers -- load before a sector's emission, store after it -- the store waited
+    // for the load: 28 % of the kernel's stall samples at c3, profiles/r2_ncu_summary.csv.)
+    auto async_sector = [&](int s, const uint8_t* g) {
+        const uint32_t a = (uint32_t)__cvta_generic_to_shared(stg + (2 * s) * 512);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(g) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a + 512u), "l"(g + 16) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     auto load_block = [&](int32_t blk) {                   // plain (latency-exposed) load: first block, zero blocks
         const uint8_t* g = gin + (size_t)blk * BLKB;
 #pragma unroll
@@ -191,6 +201,9 @@ __global__ void __launch_bounds__(kEncLaneThreads, (W == 8) ? 5 : 4) spz_encode_
         uint32_t mulp[NCL * (W == 16 ? 1 : 3)];            // cluster multipliers (see pass 2)
         uint32_t cbits[NCL];                               // bits per cluster
         uint32_t hlo = 0, hhi = 0, total = 0;              // this block's header fields (D*HB bits), sum of widths
+        // the block's first half of sectors has landed (asynchronous copies complete in order); the second half is awaited
+        // where pass 1 first touches it
+        asm volatile("cp.async.wait_group %0;" ::"n"(NSEC / 2) : "memory");
 #pragma unroll
         for (int oc = 0; oc < NO; oc++) {
             int32_t coef[8], gsh[8];
@@ -236,6 +249,7 @@ __global__ void __launch_bounds__(kEncLaneThreads, (W == 8) ? 5 : 4) spz_encode_
                 for (int rp = 0; rp < 8; rp += 2)
 #pragma unroll
                 for (int r1 = 0; r1 < 2; r1++) {
+                    if (oc == 0 && r1 == 0 && rp == 2) asm volatile("cp.async.wait_all;" ::: "memory");   // row 3 fetches row 4 ahead
                     const int r = r1;                                          // only the parity matters to elem()
                     uint8_t* vp = stg + ((rp + r1) * NO + oc) * 512;
                     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
@@ -253,6 +267,7 @@ __global__ void __launch_bounds__(kEncLaneThreads, (W == 8) ? 5 : 4) spz_encode_
             } else {
 #pragma unroll
                 for (int v = 0; v < 4; v++) {              // a vector holds rows 2v, 2v+1 (8 bytes each)
+                    if (v == 2) asm volatile("cp.async.wait_all;" ::: "memory");     // the block's second sector
                     uint8_t* vp = stg + v * 512;
                     const uint4 q = *reinterpret_cast<const uint4*>(vp);
                     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
@@ -352,8 +367,6 @@ __global__ void __launch_bounds__(kEncLaneThreads, (W == 8) ? 5 : 4) spz_encode_
             uint4 qb = *reinterpret_cast<const uint4*>(stg + 512);
 #pragma unroll(NSEC > 2 ? 2 : NSEC)
             for (int s = 0; s < NSEC; s++) {
-                uint32_t nx[8];
-                load_sector(gnext + s * 32, nx);                               // lands while this sector is emitted
                 uint4 na = qa, nb4 = qb;
                 if (s + 1 < NSEC) {
                     na = *reinterpret_cast<const uint4*>(stg + (2 * s + 2) * 512);
@@ -378,7 +391,7 @@ __global__ void __launch_bounds__(kEncLaneThreads, (W == 8) ? 5 : 4) spz_encode_
                     // flush checks every 32 bytes of worst-case output (a row is at most ROWB bytes)
                     if (ROWB == 32 || (ROWB == 16 && (rr & 1)) || rr == RPS - 1) maybe_flush();
                 }
-                store_sector(s, nx);
+                async_sector(s, gnext + s * 32);                               // this sector's words are in registers: its slot is free
                 qa = na; qb = nb4;
             }
             nslots++;
@@ -393,6 +406,7 @@ __global__ void __launch_bounds__(kEncLaneThreads, (W == 8) ? 5 : 4) spz_encode_
     }
 
     // ---- finish: remaining ring words, the partial word, the raw tail, the metadata
+    asm volatile("cp.async.wait_all;" ::: "memory");
     uint32_t nbytes = cur_bytes();
     {
         const uint32_t nw = wcount - flushed;
