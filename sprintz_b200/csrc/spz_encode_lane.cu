@@ -8,9 +8,9 @@
 // shared-memory traffic is to lane-private columns, conflict-free by construction.
 //
 //   input    a block (8 rows) lives in a lane-private staging column ([vec][lane] 16-byte interleave: 128-bit
-//            accesses never conflict).  The NEXT block is fetched with one 256-bit load per 32 bytes issued
-//            before a sector of the current block is emitted and stored over it once that sector has been
-//            consumed, so HBM/L2 latency hides behind the bit emit; an L2 prefetch runs two blocks ahead.
+//            accesses never conflict).  The NEXT block's sectors are copied asynchronously (cp.async, 2 x 16 bytes)
+//            over the sectors of the current block as soon as those have been emitted, so HBM/L2 latency hides
+//            behind the rest of the bit emit and nobody holds the data in registers; an L2 prefetch runs one block ahead.
 //   pass 1   octet-major: 8 dims x 8 rows at a time; values, deltas and FIRE errors stay left-aligned
 //            (prediction = one IMAD.HI, error = one IMAD, natural W-bit wrap), zigzag, OR-masks packed 2 or 4
 //            dims per register; the zigzagged errors overwrite the raw block in place
