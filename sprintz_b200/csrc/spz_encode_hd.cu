@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(kThreads) spz_encode_hd_kernel(const EncParams
             }
             pend = 0;
         }
+        __syncwarp();       // the row jobs have read the zigzag tile: the next block's phase 1 may overwrite it (racecheck)
         // several groups accumulate in the staging tile; it leaves for HBM when the next group might not fit
         const bool need = gc && ocur + max_group_bytes + 16u > OCAP;
         if (__any_sync(kFullE, need)) flush(need, false);
