@@ -58,11 +58,17 @@ __device__ __forceinline__ uint32_t octet_width8(uint32_t fw)
 __device__ __forceinline__ uint32_t bsel(uint32_t a, uint32_t b, uint32_t c) { return (a & c) | (b & ~c); }   // one LOP3
 
 // p.team = lanes per chunk (ndims / 8), p.dpl = teams per warp, p.ring_cap / p.team_smem as in spz_decode_hd.cu
-template <int W>
-__global__ void __launch_bounds__(kWideThreads) spz_decode_wide_kernel(const DecParams p)
+// FIRE: the inverse forecaster needs a multiply per sample, so a data slot is unpacked and predicted per element on
+// left-aligned values exactly like the lane kernel's (spz_decode_lane.cu: one window per quad, one shift per field,
+// zigzag^-1 and icopysign as multiply-adds) and the row is re-packed four samples to a word; stream ring, header scan,
+// tiles and control are shared with the delta form.
+template <int W, bool FIRE>
+__global__ void __launch_bounds__(kWideThreads, FIRE ? 4 : 1) spz_decode_wide_kernel(const DecParams p)
 {
     static_assert(W == 8, "the SWAR wide-row decoder covers 8-bit elements");
     constexpr int HB = Traits<W>::HB;
+    constexpr int CB = Traits<W>::CB;
+    constexpr int UP = 32 - W;
     extern __shared__ __align__(16) uint8_t smem[];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -146,6 +152,15 @@ __global__ void __launch_bounds__(kWideThreads) spz_decode_wide_kernel(const Dec
     uint32_t tsel = 0;                                  // which tile the next data slot uses
 
     uint32_t xA = 0, xB = 0;                            // the previous row's values of my 8 dims (4 bytes per word)
+    uint32_t pvh[FIRE ? 8 : 1];                         // FIRE: previous values / deltas left-aligned, counters (sprintz_xff_rle.cpp:505-520)
+    int32_t pdh[FIRE ? 8 : 1], ct[FIRE ? 8 : 1];
+#pragma unroll
+    for (int j = 0; j < (FIRE ? 8 : 1); j++) { pvh[j] = 0; pdh[j] = 0; ct[j] = 0; }
+    auto row_words = [&]() -> uint2 {                   // the top bytes of my 8 left-aligned values, four to a word
+        const uint32_t a0 = __byte_perm(pvh[0], pvh[FIRE ? 1 : 0], 0x0073), a1 = __byte_perm(pvh[FIRE ? 2 : 0], pvh[FIRE ? 3 : 0], 0x0073);
+        const uint32_t b0 = __byte_perm(pvh[FIRE ? 4 : 0], pvh[FIRE ? 5 : 0], 0x0073), b1 = __byte_perm(pvh[FIRE ? 6 : 0], pvh[FIRE ? 7 : 0], 0x0073);
+        return make_uint2(__byte_perm(a0, a1, 0x5410), __byte_perm(b0, b1, 0x5410));
+    };
 
     prefetch();
     uint32_t pos = mis_in;                              // consume offset from abase (team-uniform)
@@ -176,6 +191,66 @@ __global__ void __launch_bounds__(kWideThreads) spz_decode_wide_kernel(const Dec
     // One data slot: unpack + inverse predictor for my octet, rows staged in a tile, tile flushed with whole sectors.
     // Warp-uniform call; `doit` = my team really has this slot (state and global memory only change then).
     auto data_slot = [&](uint32_t fw, uint32_t offA, uint32_t total, bool doit) {
+        if (FIRE) {
+            const uint32_t row_bytes = (total + 7u) >> 3;
+            uint8_t* const tile = tile0 + tsel * (TILE + 128u);
+            if (doit) {
+                uint32_t nb[8], fm[8];
+                int32_t coef[8], gsh[8];
+                uint32_t wA = 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t f = (fw >> (j * HB)) & 7u;
+                    const uint32_t n = f + (f == 7u ? 1u : 0u);      // 7 is stored for 8 (sprintz_xff_rle.cpp:287)
+                    nb[j] = n;
+                    if (j < 4) wA += n;
+                    fm[j] = (1u << n) - 1u;
+                    coef[j] = fire_coef<W, false>(ct[j]);
+                    gsh[j] = 0;
+                }
+                const uint32_t row_bits = row_bytes * 8u;
+                uint32_t bitA = (pos & RMASK) * 8u + offA;
+                uint8_t* trow = tile + t * 8u;
+#pragma unroll
+                for (uint32_t r = 0; r < 8; r++) {
+                    uint32_t lo = ring_bits(bitA);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        if (j == 4) lo = ring_bits(bitA + wA);
+                        // zigzag^-1 in doubled form: m = u ^ -(u & 1) == 2 * err; with b = u & 1 and tt = 1 - 2b, m = u * tt - b
+                        const uint32_t u = lo & fm[j];
+                        const uint32_t b = lo & fm[j] & 1u;
+                        if (j != 7 && j != 3) lo >>= nb[j];
+                        int32_t tt, mi;
+                        asm("mad.lo.s32 %0, %1, -2, 1;" : "=r"(tt) : "r"(b));
+                        asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(mi) : "r"(u), "r"(tt), "r"(0u - b));
+                        if (r & 1u) { if (mi != 0) gsh[j] += pdh[j] * tt; }          // icopysign(err, prev_delta) (util.h:63-68)
+                        // delta = ((prev_delta * coef) >> W) + err (sprintz_xff_rle.cpp:225), everything left-aligned
+                        const int32_t th = __mulhi(pdh[j], coef[j]);
+                        int32_t ths;
+                        asm("mad.lo.s32 %0, %1, %2, 0;" : "=r"(ths) : "r"(th), "n"(1 << UP));
+                        asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(pdh[j]) : "r"(mi), "n"(1 << (UP - 1)), "r"(ths));
+                        pvh[j] += (uint32_t)pdh[j];
+                    }
+                    bitA += row_bits;
+                    *reinterpret_cast<uint2*>(trow) = row_words();
+                    trow += D;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++) ct[j] = sx<CB>(ct[j] + ((gsh[j] >> UP) >> 2));   // sprintz_xff_rle.cpp:273-275
+            }
+            __syncwarp();                               // the tile is complete
+            if (doit) {
+                const uint4* s4 = reinterpret_cast<const uint4*>(tile);
+                uint4* g4 = reinterpret_cast<uint4*>(out + o);
+#pragma unroll
+                for (int i = 0; i < 4; i++) g4[t + i * NP] = s4[t + i * NP];
+                pos += row_bytes * 8u;
+                o += B;
+                tsel ^= 1u;
+            }
+            return;
+        }
         QuadC qa, qb;
         const uint32_t wA = quad_consts8(fw & 0xfffu, qa);
         (void)quad_consts8((fw >> 12) & 0xfffu, qb);
@@ -258,7 +333,24 @@ __global__ void __launch_bounds__(kWideThreads) spz_decode_wide_kernel(const Dec
                 if ((uint64_t)o + (uint64_t)nrows * D > cap) { status = kStatusOverflow; }
                 else {
                     uint8_t* op = out + o + t * 8u;
-                    for (uint32_t r = 0; r < nrows; r++) { *reinterpret_cast<uint2*>(op) = make_uint2(xA, xB); op += D; }
+                    if (FIRE) {     // errors of 0: every delta is its own prediction (sprintz_xff_rle.cpp:828-958); counters rest
+                        int32_t coef[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) coef[j] = fire_coef<W, false>(ct[j]);
+#pragma unroll 1
+                        for (uint32_t r = 0; r < nrows; r++) {
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const int32_t pred = __mulhi(pdh[j], coef[j]);
+                                pdh[j] = (int32_t)((uint32_t)pred << UP);
+                                pvh[j] += (uint32_t)pdh[j];
+                            }
+                            *reinterpret_cast<uint2*>(op) = row_words();
+                            op += D;
+                        }
+                    } else {
+                        for (uint32_t r = 0; r < nrows; r++) { *reinterpret_cast<uint2*>(op) = make_uint2(xA, xB); op += D; }
+                    }
                     o += nrows * D;
                 }
             }
@@ -298,7 +390,7 @@ static inline uint32_t pow2_ceil_w(uint32_t x) { uint32_t v = 1; while (v < x) v
 cudaError_t launch_decode_wide(int elem_sz, int predictor, DecParams p, cudaStream_t stream)
 {
     if (get_force_path() == 1) return cudaErrorNotSupported;
-    if (elem_sz != 1 || predictor != 0 || p.variant != 0 || p.qop != 0) return cudaErrorNotSupported;
+    if (elem_sz != 1 || (predictor != 0 && predictor != 1) || p.variant != 0 || p.qop != 0) return cudaErrorNotSupported;
     if (p.ndims < 24 || p.ndims > 256 || (p.ndims & 7u)) return cudaErrorNotSupported;
     if (p.src_end == nullptr || p.src_end <= p.src) return cudaErrorNotSupported;
     // 128-bit tile flushes: every block of every chunk must start 16-byte aligned in the output
@@ -319,11 +411,14 @@ cudaError_t launch_decode_wide(int elem_sz, int predictor, DecParams p, cudaStre
     if (smem > 200 * 1024) return cudaErrorNotSupported;
     const uint64_t grid64 = (p.nchunks + teams_per_cta - 1) / teams_per_cta;
     if (grid64 == 0 || grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(spz_decode_wide_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    count_launch();
-    spz_decode_wide_kernel<8><<<(uint32_t)grid64, kWideThreads, smem, stream>>>(p);
-    return cudaGetLastError();
+    auto go = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        count_launch();
+        kernel<<<(uint32_t)grid64, kWideThreads, smem, stream>>>(p);
+        return cudaGetLastError();
+    };
+    return predictor == 1 ? go(spz_decode_wide_kernel<8, true>) : go(spz_decode_wide_kernel<8, false>);
 }
 
 }  // namespace spz

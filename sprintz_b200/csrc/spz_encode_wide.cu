@@ -83,11 +83,16 @@ __device__ __forceinline__ uint32_t pack_quad(uint32_t w, const PackC& q)
 //   [piece buffers 2 x 64*NP][octet widths 2 x 32][row bit offsets of the octets 2 x 32 x u16][staging tile of out_cap bytes]
 // LSEG: log2 of the segments a row is cut into for the row writers (0 with >= 3 teams per warp, 1 with two, 2 with one);
 // RDX: the team total is one REDUX (three teams per warp) instead of a shuffle scan
-template <int W, int MINB, int LSEG_, bool RDX>
+// FIRE: the forecaster needs a multiply per sample, so pass 1 runs per element on left-aligned values exactly like the
+// lane kernel's (spz_encode_lane.cu) and re-packs the zigzagged errors four to a word; everything behind pass 1 (widths,
+// header, multiply-add packing, row writers, control) is shared with the delta form.
+template <int W, bool FIRE, int MINB, int LSEG_, bool RDX>
 __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(const EncParams p)
 {
     static_assert(W == 8, "the SWAR wide-row encoder covers 8-bit elements");
     constexpr int HB = Traits<W>::HB;
+    constexpr int CB = Traits<W>::CB;
+    constexpr int UP = 32 - W;
     extern __shared__ __align__(16) uint8_t smem[];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -177,6 +182,10 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
 
     // ---- team-uniform encoder state (sprintz_delta_rle.cpp:132-158)
     uint32_t xA = 0, xB = 0;                            // the previous row's values of my 8 dims
+    uint32_t xprev[FIRE ? 8 : 1];                       // FIRE: previous values / deltas left-aligned, counters (sprintz_xff_rle.cpp:150-158)
+    int32_t dprev[FIRE ? 8 : 1], ct[FIRE ? 8 : 1];
+#pragma unroll
+    for (int e = 0; e < (FIRE ? 8 : 1); e++) { xprev[e] = 0; dprev[e] = 0; ct[e] = 0; }
     uint32_t ngroups = 0, nslots = 0, run = 0, blk = 0;
     uint32_t hdr_off = 0;
     int64_t tail = 0;
@@ -184,7 +193,8 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
     bool on = valid && L >= (int64_t)kMinDataSize;
     // blk*B <= L-G  <=>  blk <= last_start ; blk*B < L-G  <=>  blk <= last_cont   (both -1 when L < G)
     const int32_t last_start = (L >= G) ? (int32_t)((L - G) / B) : -1;
-    const int32_t last_cont = (L > G) ? (int32_t)((L - G - 1) / B) : -1;     // delta: strict `<` (sprintz_delta_rle.cpp:226)
+    // delta: strict `<` (sprintz_delta_rle.cpp:226); FIRE: `<=` (sprintz_xff_rle.cpp:362)
+    const int32_t last_cont = FIRE ? last_start : ((L > G) ? (int32_t)((L - G - 1) / B) : -1);
 
     // ---- input prefetch (registers), one block ahead
     uint32_t nxa[kBlockRows], nxb[kBlockRows];
@@ -368,7 +378,48 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
         const uint32_t pbsel = it & 1u;
 
         // ================= pass 1: packed delta -> zigzag -> OR-mask of this block (sprintz_delta_rle.cpp:161-201)
-        {
+        if (FIRE) {
+            // sprintz_xff_rle.cpp:205-275: prediction = (prev_delta * coef) >> W, error = delta - prediction; the counter
+            // moves by the block's sum of icopysign(err, prev_delta) over the odd rows
+            int32_t coef[8], gsh[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) { coef[e] = fire_coef<W, false>(ct[e]); gsh[e] = 0; }
+            auto elem = [&](uint32_t vh, int e, int r) -> uint32_t {   // left-aligned value in, left-aligned zigzagged error out
+                const int32_t dh = (int32_t)(vh - xprev[e]);
+                xprev[e] = vh;
+                const int32_t pred = __mulhi(dprev[e], coef[e]);
+                int32_t eh;
+                asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(eh) : "r"(pred), "n"(-(1 << UP)), "r"(dh));
+                const int32_t sg = eh >> 31;
+                if (r & 1) {
+                    int32_t cs;
+                    asm("mad.lo.s32 %0, %1, 2, 1;" : "=r"(cs) : "r"(sg));
+                    if (eh != 0) gsh[e] += dprev[e] * cs;
+                }
+                dprev[e] = dh;
+                int32_t e2;
+                asm("mad.lo.s32 %0, %1, 2, 0;" : "=r"(e2) : "r"(eh));
+                return (uint32_t)e2 ^ (uint32_t)sg;
+            };
+            uint32_t ma = 0, mb = 0;
+#pragma unroll
+            for (int r = 0; r < kBlockRows; r++) {
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    const uint32_t x = k ? nxb[r] : nxa[r];
+                    const uint32_t z0 = elem(x << 24, 4 * k + 0, r);
+                    const uint32_t z1 = elem(__byte_perm(x, 0, 0x1444), 4 * k + 1, r);
+                    const uint32_t z2 = elem(__byte_perm(x, 0, 0x2444), 4 * k + 2, r);
+                    const uint32_t z3 = elem(x & 0xff000000u, 4 * k + 3, r);
+                    const uint32_t a = __byte_perm(z0, z1, 0x0073), b = __byte_perm(z2, z3, 0x0073);
+                    const uint32_t z = __byte_perm(a, b, 0x5410);
+                    if (k) { zb[r] = z; mb |= z; } else { za[r] = z; ma |= z; }
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; e++) ct[e] = sx<CB>(ct[e] + ((gsh[e] >> UP) >> 2));       // sprintz_xff_rle.cpp:273-275
+            nA = widths4(ma); nB = widths4(mb);
+        } else {
             uint32_t a = xA, b = xB, ma = 0, mb = 0;
 #pragma unroll
             for (int r = 0; r < kBlockRows; r++) {
@@ -481,7 +532,7 @@ static inline uint32_t up16w(uint32_t x) { return (x + 15u) & ~15u; }
 cudaError_t launch_encode_wide(int elem_sz, int predictor, EncParams p, cudaStream_t stream)
 {
     if (get_force_path() == 1) return cudaErrorNotSupported;
-    if (elem_sz != 1 || predictor != 0 || p.variant != 0) return cudaErrorNotSupported;
+    if (elem_sz != 1 || (predictor != 0 && predictor != 1) || p.variant != 0) return cudaErrorNotSupported;
     if (p.ndims < 24 || p.ndims > 256 || (p.ndims & 7u)) return cudaErrorNotSupported;
     if (p.chunk_len > 0x70000000ull) return cudaErrorNotSupported;      // 32-bit cursors inside one chunk
     // 64-bit row loads: every row of every chunk must start 8-byte aligned
@@ -513,10 +564,16 @@ cudaError_t launch_encode_wide(int elem_sz, int predictor, EncParams p, cudaStre
         kernel<<<(uint32_t)grid64, kWideEncThreads, smem, stream>>>(p);
         return cudaGetLastError();
     };
-    if (TPW == 1u) return go(spz_encode_wide_kernel<8, 5, 2, false>);
-    if (TPW == 2u) return go(spz_encode_wide_kernel<8, 5, 1, false>);
-    if (TPW == 3u) return go(spz_encode_wide_kernel<8, 5, 0, true>);
-    return go(spz_encode_wide_kernel<8, 5, 0, false>);
+    if (predictor == 1) {    // FIRE keeps 24 more registers of state per lane: 4 CTAs per SM
+        if (TPW == 1u) return go(spz_encode_wide_kernel<8, true, 4, 2, false>);
+        if (TPW == 2u) return go(spz_encode_wide_kernel<8, true, 4, 1, false>);
+        if (TPW == 3u) return go(spz_encode_wide_kernel<8, true, 4, 0, true>);
+        return go(spz_encode_wide_kernel<8, true, 4, 0, false>);
+    }
+    if (TPW == 1u) return go(spz_encode_wide_kernel<8, false, 5, 2, false>);
+    if (TPW == 2u) return go(spz_encode_wide_kernel<8, false, 5, 1, false>);
+    if (TPW == 3u) return go(spz_encode_wide_kernel<8, false, 5, 0, true>);
+    return go(spz_encode_wide_kernel<8, false, 5, 0, false>);
 }
 
 }  // namespace spz
