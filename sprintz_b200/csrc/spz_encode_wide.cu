@@ -63,6 +63,13 @@ __device__ __forceinline__ uint32_t header12(uint32_t n4)
     return (f & 7u) | ((f >> 5) & 0x38u) | ((f >> 10) & 0x1c0u) | ((f >> 15) & 0xe00u);
 }
 
+// four widths (one per byte) -> the 16 header bits of a 16-bit quad; a width of 16 is stored as 15
+__device__ __forceinline__ uint32_t header16(uint32_t n4)
+{
+    const uint32_t f = n4 - ((n4 >> 4) & 0x01010101u);
+    return (f & 0xfu) | ((f >> 4) & 0xf0u) | ((f >> 8) & 0xf00u) | ((f >> 12) & 0xf000u);
+}
+
 // multipliers that squeeze the four bytes of a zigzag word to contiguous fields
 struct PackC { uint32_t c1, c3, c23; };
 __device__ __forceinline__ void pack_consts(uint32_t n4, PackC& q)
@@ -89,10 +96,15 @@ __device__ __forceinline__ uint32_t pack_quad(uint32_t w, const PackC& q)
 template <int W, bool FIRE, int MINB, int LSEG_, bool RDX>
 __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(const EncParams p)
 {
-    static_assert(W == 8, "the SWAR wide-row encoder covers 8-bit elements");
+    static_assert(W == 8 || W == 16, "8- and 16-bit elements");
     constexpr int HB = Traits<W>::HB;
     constexpr int CB = Traits<W>::CB;
     constexpr int UP = 32 - W;
+    constexpr uint32_t ESZ = W / 8;
+    constexpr uint32_t NQ = W / 8;                      // <= 64-bit pieces per octet and row: the octet (8-bit), its two quads (16-bit)
+    constexpr int NXW = 2 * (W / 8);                    // words of an octet's row
+    constexpr bool ELEM = FIRE || W == 16;              // pass 1 runs per element (left-aligned values)
+    constexpr uint32_t WCAP = 32u * NQ;                 // pieces of a row, at most
     extern __shared__ __align__(16) uint8_t smem[];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -113,9 +125,10 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
     const uint32_t TS = p.team_smem;
     const uint32_t warp_base = (uint32_t)warp * TPW * TS;
     uint8_t* const sm = smem + warp_base + tw * TS;
-    const uint32_t PB = 64u * NP;                       // one piece buffer: [8 rows][NP] x 8 bytes
-    const uint32_t wid_off = 2u * PB;                   // [2][32] octet widths (u8), then [2][32] bit offsets of the octets in a row (u16)
-    const uint32_t pre_off = wid_off + 64u;
+    const uint32_t NPC = NP * NQ;                       // pieces of a row
+    const uint32_t PB = 64u * NPC;                      // one piece buffer: [8 rows][NPC] x 8 bytes
+    const uint32_t wid_off = 2u * PB;                   // [2][WCAP] piece widths (u8), then [2][WCAP] bit offsets of the pieces in a row (u16)
+    const uint32_t pre_off = wid_off + 2u * WCAP;
     // rows are written by one lane each; with one or two teams per warp a row is cut into SEG segments of whole pieces
     // so that all 32 lanes work in that phase (ndims >= 88)
     constexpr uint32_t LSEG = LSEG_;                    // log2(SEG): every division by SEG is a shift
@@ -126,14 +139,14 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
     // ---- this chunk
     const uint64_t first = c * p.chunk_len;
     const int64_t L = valid ? (int64_t)((first + p.chunk_len <= p.len) ? p.chunk_len : (p.len - first)) : 0;
-    const uint8_t* const gin = p.src + first;           // 8-byte aligned (checked on the host)
+    const uint8_t* const gin = p.src + first * ESZ;     // octet rows are 8 / 16-byte aligned (checked on the host)
     uint8_t* const gstream = p.dst + c * p.slot_stride;
     const uint32_t B = (uint32_t)kBlockRows * D;
     const int64_t G = 2 * (int64_t)B;
     const uint32_t H = (2u * D * HB) >> 3;               // D % 8 == 0: whole bytes
     const uint32_t SH = H >> 1;                          // header bytes of one slot
     const uint32_t meta_bytes = p.write_size ? 8u : 0u;
-    const uint32_t max_group_bytes = H + 2u * B + 4u;
+    const uint32_t max_group_bytes = H + 2u * B * ESZ + 4u;
 
     // ---- output staging: one tile; whole 16-byte units leave, the (< 16 byte) remainder moves to the front
     uint8_t* const ob = stage0;
@@ -182,10 +195,12 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
 
     // ---- team-uniform encoder state (sprintz_delta_rle.cpp:132-158)
     uint32_t xA = 0, xB = 0;                            // the previous row's values of my 8 dims
-    uint32_t xprev[FIRE ? 8 : 1];                       // FIRE: previous values / deltas left-aligned, counters (sprintz_xff_rle.cpp:150-158)
+    uint32_t xprev[ELEM ? 8 : 1];                       // per-element form: previous values / deltas left-aligned, FIRE counters (sprintz_xff_rle.cpp:150-158)
     int32_t dprev[FIRE ? 8 : 1], ct[FIRE ? 8 : 1];
 #pragma unroll
-    for (int e = 0; e < (FIRE ? 8 : 1); e++) { xprev[e] = 0; dprev[e] = 0; ct[e] = 0; }
+    for (int e = 0; e < (ELEM ? 8 : 1); e++) xprev[e] = 0;
+#pragma unroll
+    for (int e = 0; e < (FIRE ? 8 : 1); e++) { dprev[e] = 0; ct[e] = 0; }
     uint32_t ngroups = 0, nslots = 0, run = 0, blk = 0;
     uint32_t hdr_off = 0;
     int64_t tail = 0;
@@ -197,20 +212,27 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
     const int32_t last_cont = FIRE ? last_start : ((L > G) ? (int32_t)((L - G - 1) / B) : -1);
 
     // ---- input prefetch (registers), one block ahead
-    uint32_t nxa[kBlockRows], nxb[kBlockRows];
+    uint32_t nx[kBlockRows][NXW];
     auto prefetch = [&](uint32_t b) {
         const bool ok = on && (int64_t)(b + 1u) * B <= L;
-        const uint8_t* src = gin + (size_t)b * B + 8u * t;
+        const uint8_t* src = gin + ((size_t)b * B + 8u * t) * ESZ;
 #pragma unroll
         for (int r = 0; r < kBlockRows; r++) {
-            uint2 v = make_uint2(0u, 0u);
-            if (ok) v = __ldg(reinterpret_cast<const uint2*>(src + (uint32_t)r * D));
-            nxa[r] = v.x; nxb[r] = v.y;
+            if (W == 8) {
+                uint2 v = make_uint2(0u, 0u);
+                if (ok) v = __ldg(reinterpret_cast<const uint2*>(src + (uint32_t)r * D));
+                nx[r][0] = v.x; nx[r][1] = v.y;
+            } else {
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (ok) v = __ldg(reinterpret_cast<const uint4*>(src + (uint32_t)r * D * ESZ));
+                nx[r][0] = v.x; nx[r][1] = v.y; nx[r][NXW - 2] = v.z; nx[r][NXW - 1] = v.w;
+            }
         }
     };
 
-    // this block's zigzagged errors and layout
-    uint32_t za[kBlockRows], zb[kBlockRows];
+    // this block's zigzagged errors (four 8-bit / two 16-bit to a word) and layout; nA / nB: the widths of my dims 0..3 /
+    // 4..7, one per byte
+    uint32_t zz[kBlockRows][NXW];
     uint32_t nA = 0, nB = 0, wA = 0, wo = 0, row_bytes = 0, excl = 0;
     uint32_t info = 0;                                  // what the row lanes need from my team (lane 0 of the team is read)
 
@@ -231,26 +253,50 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
             if (t == 0) ob[ocur] = 0;
             ocur += 1u;
         } else {
-            h24 = header12(nA) | (header12(nB) << 12);
-            PackC qa, qb;
-            pack_consts(nA, qa);
-            pack_consts(nB, qb);
-            uint2* pb = reinterpret_cast<uint2*>(sm + pbsel * PB) + t;
+            if (W == 8) {
+                h24 = header12(nA) | (header12(nB) << 12);
+                PackC qa, qb;
+                pack_consts(nA, qa);
+                pack_consts(nB, qb);
+                uint2* pb = reinterpret_cast<uint2*>(sm + pbsel * PB) + t;
 #pragma unroll
-            for (int r = 0; r < kBlockRows; r++) {
-                const uint32_t va = pack_quad(za[r], qa), vb = pack_quad(zb[r], qb);
-                // octet piece = va | vb << wA (wA <= 32: the clamping funnel shifts give 0 / vb at 32)
-                pb[(uint32_t)r * NP] = make_uint2(va | __funnelshift_lc(0u, vb, wA), __funnelshift_lc(vb, 0u, wA));
+                for (int r = 0; r < kBlockRows; r++) {
+                    const uint32_t va = pack_quad(zz[r][0], qa), vb = pack_quad(zz[r][1], qb);
+                    // octet piece = va | vb << wA (wA <= 32: the clamping funnel shifts give 0 / vb at 32)
+                    pb[(uint32_t)r * NP] = make_uint2(va | __funnelshift_lc(0u, vb, wA), __funnelshift_lc(vb, 0u, wA));
+                }
+                sm[wid_off + pbsel * WCAP + t] = (uint8_t)wo;
+                if (SEG > 1u) reinterpret_cast<uint16_t*>(sm + pre_off)[pbsel * WCAP + t] = (uint16_t)excl;
+            } else {
+                h24 = header16(nA) | (header16(nB) << 16);
+                // a pair of fields p = lo | hi << 16 closes up as p + (p >> 16) * (2^n_lo - 2^16); two pairs make a quad's
+                // <= 64-bit piece
+                const uint32_t mA0 = (1u << (nA & 0xffu)) - 65536u, mA1 = (1u << ((nA >> 16) & 0xffu)) - 65536u;
+                const uint32_t mB0 = (1u << (nB & 0xffu)) - 65536u, mB1 = (1u << ((nB >> 16) & 0xffu)) - 65536u;
+                const uint32_t cA0 = (nA & 0xffu) + ((nA >> 8) & 0xffu), cB0 = (nB & 0xffu) + ((nB >> 8) & 0xffu);
+                uint2* pb = reinterpret_cast<uint2*>(sm + pbsel * PB) + 2u * t;
+#pragma unroll
+                for (int r = 0; r < kBlockRows; r++) {
+                    const uint32_t a0 = zz[r][0] + (zz[r][0] >> 16) * mA0, a1 = zz[r][1] + (zz[r][1] >> 16) * mA1;
+                    const uint32_t b0 = zz[r][NXW - 2] + (zz[r][NXW - 2] >> 16) * mB0, b1 = zz[r][NXW - 1] + (zz[r][NXW - 1] >> 16) * mB1;
+                    pb[(uint32_t)r * NPC] = make_uint2(a0 | __funnelshift_lc(0u, a1, cA0), __funnelshift_lc(a1, 0u, cA0));
+                    pb[(uint32_t)r * NPC + 1u] = make_uint2(b0 | __funnelshift_lc(0u, b1, cB0), __funnelshift_lc(b1, 0u, cB0));
+                }
+                sm[wid_off + pbsel * WCAP + 2u * t] = (uint8_t)wA;
+                sm[wid_off + pbsel * WCAP + 2u * t + 1u] = (uint8_t)(wo - wA);
+                if (SEG > 1u) {
+                    uint16_t* pre = reinterpret_cast<uint16_t*>(sm + pre_off) + pbsel * WCAP + 2u * t;
+                    pre[0] = (uint16_t)excl; pre[1] = (uint16_t)(excl + wA);
+                }
             }
-            sm[wid_off + pbsel * 32u + t] = (uint8_t)wo;
-            if (SEG > 1u) reinterpret_cast<uint16_t*>(sm + pre_off)[pbsel * 32u + t] = (uint16_t)excl;
             info = 1u | (row_bytes << 1) | ((uint32_t)((ob + ocur) - smem) << 11);
             ocur += kBlockRows * row_bytes;
             blk++;
         }
-        {   // my octet's 3 header bytes of this slot
-            uint8_t* hp = ob + hdr_off + sl * SH + 3u * t;
+        {   // my octet's 3 / 4 header bytes of this slot
+            uint8_t* hp = ob + hdr_off + sl * SH + (uint32_t)HB * t;
             hp[0] = (uint8_t)h24; hp[1] = (uint8_t)(h24 >> 8); hp[2] = (uint8_t)(h24 >> 16);
+            if (W == 16) hp[HB - 1] = (uint8_t)(h24 >> 24);
         }
         nslots++;
         return (nslots & 1u) == 0u;
@@ -280,22 +326,22 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
             const uint32_t rowaddr = (inf >> 11) + r * rb;              // byte offset from smem[]
             const uint32_t end = rowaddr + rb;
             const uint8_t* tb = smem + warp_base + jt * TS;
-            const uint8_t* wd = tb + wid_off + pbsel * 32u;
-            const uint16_t* pre = reinterpret_cast<const uint16_t*>(tb + pre_off) + pbsel * 32u;
+            const uint8_t* wd = tb + wid_off + pbsel * WCAP;
+            const uint16_t* pre = reinterpret_cast<const uint16_t*>(tb + pre_off) + pbsel * WCAP;
             // my pieces [u0, u1) and their bit range [s0, s1) inside the row; a segmented row needs >= 64 bits per segment
             // (every job must complete the word it starts in), else lane `seg == 0` writes the whole row
-            uint32_t u0 = 0, u1 = NP, s0 = 0, s1 = rb * 8u;
+            uint32_t u0 = 0, u1 = NPC, s0 = 0, s1 = rb * 8u;
             bool last = true, mine = true;
             if (SEG > 1u) {
                 bool segok = act;
                 uint32_t lo = 0;
                 for (uint32_t k = 1; k <= SEG && segok; k++) {
-                    const uint32_t hi = k < SEG ? (uint32_t)pre[(k * NP) >> LSEG] : rb * 8u;
+                    const uint32_t hi = k < SEG ? (uint32_t)pre[(k * NPC) >> LSEG] : rb * 8u;
                     segok = hi - lo >= 64u;
                     lo = hi;
                 }
                 if (segok) {
-                    u0 = (seg * NP) >> LSEG; u1 = ((seg + 1u) * NP) >> LSEG;
+                    u0 = (seg * NPC) >> LSEG; u1 = ((seg + 1u) * NPC) >> LSEG;
                     s0 = pre[u0];
                     last = seg == SEG - 1u;
                     if (!last) s1 = pre[u1];
@@ -311,7 +357,7 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
             uint32_t fill = fill0;
             uint32_t a0 = 0, old0 = 0;
             const bool first_job = r == 0u && seg == 0u;   // the bytes in front of the payload are saved and restored
-            const uint2* pc = reinterpret_cast<const uint2*>(tb + pbsel * PB) + r * NP;
+            const uint2* pc = reinterpret_cast<const uint2*>(tb + pbsel * PB) + r * NPC;
             if (fast) {
                 if (first_job && fill0) old0 = *reinterpret_cast<const uint32_t*>(smem + waddr) & ((1u << fill0) - 1u);
                 for (uint32_t u = u0; u < u1; u++) {
@@ -335,7 +381,7 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
                     for (uint32_t i = 0; i < 4u; i++)
                         if (wa + i >= rowaddr && wa + i < end) smem[wa + i] = (uint8_t)(v >> (8u * i));
                 };
-                for (uint32_t u = 0; u < NP; u++) {
+                for (uint32_t u = 0; u < NPC; u++) {
                     const uint2 pv = pc[u];
                     const uint32_t w = wd[u];
                     a0 |= pv.x << fill;
@@ -378,54 +424,76 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
         const uint32_t pbsel = it & 1u;
 
         // ================= pass 1: packed delta -> zigzag -> OR-mask of this block (sprintz_delta_rle.cpp:161-201)
-        if (FIRE) {
-            // sprintz_xff_rle.cpp:205-275: prediction = (prev_delta * coef) >> W, error = delta - prediction; the counter
-            // moves by the block's sum of icopysign(err, prev_delta) over the odd rows
-            int32_t coef[8], gsh[8];
+        if (ELEM) {
+            // per element on left-aligned values.  FIRE (sprintz_xff_rle.cpp:205-275): prediction = (prev_delta * coef) >> W,
+            // error = delta - prediction; the counter moves by the block's sum of icopysign(err, prev_delta) over the odd rows
+            int32_t coef[FIRE ? 8 : 1], gsh[FIRE ? 8 : 1];
 #pragma unroll
-            for (int e = 0; e < 8; e++) { coef[e] = fire_coef<W, false>(ct[e]); gsh[e] = 0; }
+            for (int e = 0; e < (FIRE ? 8 : 1); e++) { coef[e] = fire_coef<W, false>(ct[e]); gsh[e] = 0; }
             auto elem = [&](uint32_t vh, int e, int r) -> uint32_t {   // left-aligned value in, left-aligned zigzagged error out
                 const int32_t dh = (int32_t)(vh - xprev[e]);
                 xprev[e] = vh;
-                const int32_t pred = __mulhi(dprev[e], coef[e]);
-                int32_t eh;
-                asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(eh) : "r"(pred), "n"(-(1 << UP)), "r"(dh));
-                const int32_t sg = eh >> 31;
-                if (r & 1) {
-                    int32_t cs;
-                    asm("mad.lo.s32 %0, %1, 2, 1;" : "=r"(cs) : "r"(sg));
-                    if (eh != 0) gsh[e] += dprev[e] * cs;
+                int32_t eh = dh;
+                if (FIRE) {
+                    const int f = FIRE ? e : 0;
+                    const int32_t pred = __mulhi(dprev[f], coef[f]);
+                    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(eh) : "r"(pred), "n"(-(1 << UP)), "r"(dh));
+                    const int32_t sg = eh >> 31;
+                    if (r & 1) {
+                        int32_t cs;
+                        asm("mad.lo.s32 %0, %1, 2, 1;" : "=r"(cs) : "r"(sg));
+                        if (eh != 0) gsh[f] += dprev[f] * cs;
+                    }
+                    dprev[f] = dh;
                 }
-                dprev[e] = dh;
+                const int32_t sg = eh >> 31;
                 int32_t e2;
                 asm("mad.lo.s32 %0, %1, 2, 0;" : "=r"(e2) : "r"(eh));
                 return (uint32_t)e2 ^ (uint32_t)sg;
             };
-            uint32_t ma = 0, mb = 0;
+            uint32_t mk[NXW];
+#pragma unroll
+            for (int k = 0; k < NXW; k++) mk[k] = 0;
 #pragma unroll
             for (int r = 0; r < kBlockRows; r++) {
 #pragma unroll
-                for (int k = 0; k < 2; k++) {
-                    const uint32_t x = k ? nxb[r] : nxa[r];
-                    const uint32_t z0 = elem(x << 24, 4 * k + 0, r);
-                    const uint32_t z1 = elem(__byte_perm(x, 0, 0x1444), 4 * k + 1, r);
-                    const uint32_t z2 = elem(__byte_perm(x, 0, 0x2444), 4 * k + 2, r);
-                    const uint32_t z3 = elem(x & 0xff000000u, 4 * k + 3, r);
-                    const uint32_t a = __byte_perm(z0, z1, 0x0073), b = __byte_perm(z2, z3, 0x0073);
-                    const uint32_t z = __byte_perm(a, b, 0x5410);
-                    if (k) { zb[r] = z; mb |= z; } else { za[r] = z; ma |= z; }
+                for (int k = 0; k < NXW; k++) {
+                    const uint32_t x = nx[r][k];
+                    uint32_t z;
+                    if (W == 8) {
+                        const uint32_t z0 = elem(x << 24, 4 * k + 0, r);
+                        const uint32_t z1 = elem(__byte_perm(x, 0, 0x1444), 4 * k + 1, r);
+                        const uint32_t z2 = elem(__byte_perm(x, 0, 0x2444), 4 * k + 2, r);
+                        const uint32_t z3 = elem(x & 0xff000000u, 4 * k + 3, r);
+                        const uint32_t a = __byte_perm(z0, z1, 0x0073), b = __byte_perm(z2, z3, 0x0073);
+                        z = __byte_perm(a, b, 0x5410);
+                    } else {
+                        const uint32_t z0 = elem(x << 16, (2 * k + 0) & 7, r);
+                        const uint32_t z1 = elem(x & 0xffff0000u, (2 * k + 1) & 7, r);
+                        z = __byte_perm(z0, z1, 0x7632);
+                    }
+                    zz[r][k] = z; mk[k] |= z;
                 }
             }
+            if (FIRE) {
 #pragma unroll
-            for (int e = 0; e < 8; e++) ct[e] = sx<CB>(ct[e] + ((gsh[e] >> UP) >> 2));       // sprintz_xff_rle.cpp:273-275
-            nA = widths4(ma); nB = widths4(mb);
+                for (int e = 0; e < (FIRE ? 8 : 1); e++) ct[e] = sx<CB>(ct[e] + ((gsh[e] >> UP) >> 2));   // sprintz_xff_rle.cpp:273-275
+            }
+            if (W == 8) {
+                nA = widths4(mk[0]); nB = widths4(mk[1]);
+            } else {    // bit length with 7 -> 8 and 15 -> 16 (sprintz_delta_rle.cpp:177-187), one width per byte
+                nA = nbits_rule<16, false>(mk[0] & 0xffffu) | (nbits_rule<16, false>(mk[0] >> 16) << 8) |
+                     (nbits_rule<16, false>(mk[1] & 0xffffu) << 16) | (nbits_rule<16, false>(mk[1] >> 16) << 24);
+                nB = nbits_rule<16, false>(mk[NXW - 2] & 0xffffu) | (nbits_rule<16, false>(mk[NXW - 2] >> 16) << 8) |
+                     (nbits_rule<16, false>(mk[NXW - 1] & 0xffffu) << 16) | (nbits_rule<16, false>(mk[NXW - 1] >> 16) << 24);
+            }
         } else {
             uint32_t a = xA, b = xB, ma = 0, mb = 0;
 #pragma unroll
             for (int r = 0; r < kBlockRows; r++) {
-                const uint32_t va = nxa[r], vb = nxb[r];
-                za[r] = zigzag4(psub<8>(va, a)); ma |= za[r]; a = va;
-                zb[r] = zigzag4(psub<8>(vb, b)); mb |= zb[r]; b = vb;
+                const uint32_t va = nx[r][0], vb = nx[r][1];
+                zz[r][0] = zigzag4(psub<8>(va, a)); ma |= zz[r][0]; a = va;
+                zz[r][1] = zigzag4(psub<8>(vb, b)); mb |= zz[r][1]; b = vb;
             }
             if (on) { xA = a; xB = b; }
             nA = widths4(ma); nB = widths4(mb);
@@ -496,8 +564,8 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
     // ---- trailing raw elements (sprintz_delta_rle.cpp:398-403); also the whole input when L < 128
     {
         const int64_t rem_elems = valid ? (L - tail) : 0;
-        const uint8_t* tsrc = gin + tail;
-        uint32_t left = (uint32_t)rem_elems, done = 0;
+        const uint8_t* tsrc = gin + tail * ESZ;
+        uint32_t left = (uint32_t)rem_elems * ESZ, done = 0;
         while (__any_sync(kFullWE, left > 0)) {
             const uint32_t space = OCAP - ocur;
             const uint32_t take = left < space ? left : space;
@@ -532,23 +600,26 @@ static inline uint32_t up16w(uint32_t x) { return (x + 15u) & ~15u; }
 cudaError_t launch_encode_wide(int elem_sz, int predictor, EncParams p, cudaStream_t stream)
 {
     if (get_force_path() == 1) return cudaErrorNotSupported;
-    if (elem_sz != 1 || (predictor != 0 && predictor != 1) || p.variant != 0) return cudaErrorNotSupported;
+    if ((elem_sz != 1 && elem_sz != 2) || (predictor != 0 && predictor != 1) || p.variant != 0) return cudaErrorNotSupported;
     if (p.ndims < 24 || p.ndims > 256 || (p.ndims & 7u)) return cudaErrorNotSupported;
-    if (p.chunk_len > 0x70000000ull) return cudaErrorNotSupported;      // 32-bit cursors inside one chunk
-    // 64-bit row loads: every row of every chunk must start 8-byte aligned
-    if (((uintptr_t)p.src & 7) || (p.nchunks > 1 && (p.chunk_len & 7))) return cudaErrorNotSupported;
-    const uint32_t NP = p.ndims / 8u, TPW = 32u / NP;
-    const uint32_t H = (2u * p.ndims * 3u) / 8u;
+    if (p.chunk_len > 0x30000000ull) return cudaErrorNotSupported;      // 32-bit cursors inside one chunk
+    // 64 / 128-bit row loads: every octet row of every chunk must start 8 / 16-byte aligned
+    const uint32_t esz = (uint32_t)elem_sz, amask = 8u * esz - 1u;
+    if (((uintptr_t)p.src & amask) || (p.nchunks > 1 && ((p.chunk_len * esz) & amask))) return cudaErrorNotSupported;
+    const uint32_t NP = p.ndims / 8u, TPW = 32u / NP, NPC = NP * esz;
+    const uint32_t H = (2u * p.ndims * (esz == 1 ? 3u : 4u)) / 8u;
     p.team = NP; p.dpl = TPW;
-    const uint32_t grp = H + 16u * p.ndims + 4u;
+    const uint32_t grp = H + 16u * p.ndims * esz + 4u;
     const uint32_t teams_per_cta = (kWideEncThreads / 32) * TPW;
     p.teams_per_cta = teams_per_cta;
-    p.out_off = up16w(2u * 64u * NP + 64u + 128u);       // piece buffers | widths | row bit offsets
-    // the staging tile holds up to 4 groups, fewer when that would cost occupancy (6 CTAs per SM need <= 36 KB each)
+    p.out_off = up16w(2u * 64u * NPC + 64u * esz + 128u * esz);     // piece buffers | piece widths | row bit offsets
+    // the staging tile holds up to 4 groups, fewer when that would cost occupancy (6 CTAs per SM need <= 36 KB each; the
+    // 16-bit and FIRE forms run 4 CTAs per SM: <= 56 KB)
+    const uint32_t budget = (esz == 2 || predictor == 1) ? 56u * 1024u : 36u * 1024u;
     for (uint32_t ngrp = 4; ngrp >= 1; ngrp--) {
         p.out_cap = up16w(32u + ngrp * grp + 16u);
         p.team_smem = p.out_off + p.out_cap;
-        if ((size_t)teams_per_cta * p.team_smem <= 36u * 1024u) break;
+        if ((size_t)teams_per_cta * p.team_smem <= budget) break;
     }
     const size_t smem = (size_t)teams_per_cta * p.team_smem;
     if (smem > 200 * 1024) return cudaErrorNotSupported;
@@ -564,6 +635,18 @@ cudaError_t launch_encode_wide(int elem_sz, int predictor, EncParams p, cudaStre
         kernel<<<(uint32_t)grid64, kWideEncThreads, smem, stream>>>(p);
         return cudaGetLastError();
     };
+    if (esz == 2u) {         // twice the registers per row: 4 CTAs per SM
+        if (predictor == 1) {
+            if (TPW == 1u) return go(spz_encode_wide_kernel<16, true, 4, 2, false>);
+            if (TPW == 2u) return go(spz_encode_wide_kernel<16, true, 4, 1, false>);
+            if (TPW == 3u) return go(spz_encode_wide_kernel<16, true, 4, 0, true>);
+            return go(spz_encode_wide_kernel<16, true, 4, 0, false>);
+        }
+        if (TPW == 1u) return go(spz_encode_wide_kernel<16, false, 4, 2, false>);
+        if (TPW == 2u) return go(spz_encode_wide_kernel<16, false, 4, 1, false>);
+        if (TPW == 3u) return go(spz_encode_wide_kernel<16, false, 4, 0, true>);
+        return go(spz_encode_wide_kernel<16, false, 4, 0, false>);
+    }
     if (predictor == 1) {    // FIRE keeps 24 more registers of state per lane: 4 CTAs per SM
         if (TPW == 1u) return go(spz_encode_wide_kernel<8, true, 4, 2, false>);
         if (TPW == 2u) return go(spz_encode_wide_kernel<8, true, 4, 1, false>);

@@ -6,7 +6,7 @@ Prints one JSON line per point (kernel family, GB/s of raw data, roofline fracti
 block_rows 8 is the reference's format (bit-exact with the reference); 16 / 32 / 64 are the block-size axis: the oracle's
 generalisation, PARITY UNPINNED (no reference build exists), generic kernels.
 
-usage: [torchrun --nproc-per-node N] python tools/dims_sweep.py [--mb 256] [--dims 8,16] [--blocks 8,16,32,64] [--force 0|1|2]
+usage: [torchrun --nproc-per-node N] python tools/dims_sweep.py [--mb 256] [--dims 8,16] [--blocks 8,16,32,64] [--force 0|1|2] [--chunk-rows 1024]
        > profiles/<round>_dims_sweep[_nN].jsonl"""
 import json
 import os
@@ -29,6 +29,7 @@ mb = int(arg("--mb", 256))
 dims = [int(v) for v in arg("--dims", "1,2,3,4,5,8,16,24,32,48,64,80,128,256").split(",")]
 blocks = [int(v) for v in arg("--blocks", "8").split(",")]
 force = int(arg("--force", 0))          # spz_set_kernel_path
+chunk_rows = int(arg("--chunk-rows", 1024))
 env = bench.Env()
 if env.world > 1:
     import torch.distributed as dist
@@ -49,7 +50,7 @@ for R in blocks:
             raw = n * esz
             out = torch.empty_like(x)
             for pred, pname in ((0, "delta"), (1, "xff")):
-                codec = spz.FrameCodec(pred, esz, n, D, 1024, device=dev, block_rows=R)
+                codec = spz.FrameCodec(pred, esz, n, D, chunk_rows, device=dev, block_rows=R)
                 for _ in range(2):
                     fr = codec.encode(x); codec.decode(fr, out)
                 torch.cuda.synchronize()
@@ -71,7 +72,7 @@ for R in blocks:
                 alg = raw + payload
                 if env.rank == 0:
                     print(json.dumps({"block_rows": R, "elem_bits": 8 * esz, "ndims": D, "predictor": pname, "n_gpus": env.world,
-                                      "raw_mib_per_gpu": raw >> 20, "nchunks_per_gpu": codec.nchunks, "kernel_path": force,
+                                      "raw_mib_per_gpu": raw >> 20, "nchunks_per_gpu": codec.nchunks, "chunk_rows": chunk_rows, "kernel_path": force,
                                       "ratio": round(raw / payload, 4), "roundtrip_ok": nok == 0.0,
                                       "parity": "bit-exact with the reference" if R == 8 else "unpinned (oracle generalisation)",
                                       "encode_kernels": FAM[L.spz_last_kernel_family(0)], "decode_kernels": FAM[L.spz_last_kernel_family(1)],
