@@ -70,7 +70,7 @@ __device__ __forceinline__ uint32_t octet_width16(uint32_t fw)
 // left-aligned values exactly like the lane kernel's (spz_decode_lane.cu: one window per quad, one shift per field,
 // zigzag^-1 and icopysign as multiply-adds) and the row is re-packed four samples to a word; stream ring, header scan,
 // tiles and control are shared with the delta form.
-template <int W, bool FIRE>
+template <int W, bool FIRE, bool HALF>
 __global__ void __launch_bounds__(kWideThreads, (FIRE || W == 16) ? 4 : 1) spz_decode_wide_kernel(const DecParams p)
 {
     static_assert(W == 8 || W == 16, "8- and 16-bit elements");
@@ -220,26 +220,21 @@ __global__ void __launch_bounds__(kWideThreads, (FIRE || W == 16) ? 4 : 1) spz_d
     // Warp-uniform call; `doit` = my team really has this slot (state and global memory only change then).
     auto data_slot = [&](uint32_t fw, uint32_t offA, uint32_t total, bool doit) {
         if (ELEM) {
+            // one tile; a 16-bit slot is pulled through the ring in two halves of 4 rows (the ring stays as small as the
+            // 8-bit one: shared memory bounds the occupancy of this kernel)
             const uint32_t row_bytes = (total + 7u) >> 3;
-            uint8_t* const tile = tile0 + tsel * (TILE + 128u);
-            if (doit) {
-                uint32_t nb[8], fm[8];
-                int32_t coef[FIRE ? 8 : 1], gsh[FIRE ? 8 : 1];
-                uint32_t wA = 0;
+            const uint32_t row_bits = row_bytes * 8u;
+            uint8_t* const tile = tile0;
+            uint32_t nb[8], fm[8];
+            int32_t coef[FIRE ? 8 : 1], gsh[FIRE ? 8 : 1];
+            uint32_t wA = 0;
+            uint32_t bitA = (pos & RMASK) * 8u + offA;
+            uint8_t* trow = tile + t * 8u * ESZ;
+            __syncwarp();                               // the previous slot's tile has left
+            auto rows4 = [&](uint32_t r0) {
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const uint32_t f = (fw >> (j * HB)) & FMASK;
-                    const uint32_t n = f + (f == FMASK ? 1u : 0u);   // W - 1 is stored for W (sprintz_xff_rle.cpp:287)
-                    nb[j] = n;
-                    if (j < 4) wA += n;
-                    fm[j] = (1u << n) - 1u;
-                    if (FIRE) { coef[j] = fire_coef<W, false>(ct[j]); gsh[j] = 0; }
-                }
-                const uint32_t row_bits = row_bytes * 8u;
-                uint32_t bitA = (pos & RMASK) * 8u + offA;
-                uint8_t* trow = tile + t * 8u * ESZ;
-#pragma unroll
-                for (uint32_t r = 0; r < 8; r++) {
+                for (uint32_t r4 = 0; r4 < 4; r4++) {
+                    const uint32_t r = r0 + r4;
                     // 8-bit: one 32-bit window per quad of fields; 16-bit: one 64-bit window
                     uint32_t lo, hi = 0;
                     if (W == 16) ring_seg(bitA, lo, hi); else lo = ring_bits(bitA);
@@ -272,6 +267,22 @@ __global__ void __launch_bounds__(kWideThreads, (FIRE || W == 16) ? 4 : 1) spz_d
                     store_row(trow);
                     trow += D * ESZ;
                 }
+            };
+            if (doit) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t f = (fw >> (j * HB)) & FMASK;
+                    const uint32_t n = f + (f == FMASK ? 1u : 0u);   // W - 1 is stored for W (sprintz_xff_rle.cpp:287)
+                    nb[j] = n;
+                    if (j < 4) wA += n;
+                    fm[j] = (1u << n) - 1u;
+                    if (FIRE) { coef[FIRE ? j : 0] = fire_coef<W, false>(ct[FIRE ? j : 0]); gsh[FIRE ? j : 0] = 0; }
+                }
+                rows4(0);
+            }
+            if (HALF) ensure(pos + row_bytes * 8u + 16u, doit);     // second half of the slot (the caller staged the first)
+            if (doit) {
+                rows4(4);
                 if (FIRE) {
 #pragma unroll
                     for (int j = 0; j < (FIRE ? 8 : 1); j++) ct[j] = sx<CB>(ct[j] + ((gsh[j] >> UP) >> 2));   // sprintz_xff_rle.cpp:273-275
@@ -285,7 +296,6 @@ __global__ void __launch_bounds__(kWideThreads, (FIRE || W == 16) ? 4 : 1) spz_d
                 for (uint32_t i = 0; i < 4u * ESZ; i++) g4[t + i * NP] = s4[t + i * NP];
                 pos += row_bytes * 8u;
                 o += B;
-                tsel ^= 1u;
             }
             return;
         }
@@ -328,6 +338,11 @@ __global__ void __launch_bounds__(kWideThreads, (FIRE || W == 16) ? 4 : 1) spz_d
         }
     };
 
+    // stream bytes a data slot of `tot` bits per row needs staged before data_slot(): the slot plus the window over-read;
+    // 16-bit slots are staged in two halves (the second inside data_slot)
+    auto slot_need = [&](uint32_t tot) -> uint32_t {
+        return HALF ? ((tot + 7u) >> 3) * 4u + 16u : ((tot + 7u) & ~7u) + 16u;
+    };
     const uint32_t gmax = __reduce_max_sync(kFullW, ngroups);
     for (uint32_t g = 0; g < gmax; g++) {
         if (g < ngroups && pos > limit) status = kStatusTruncated;      // ran past the readable bytes (the ring was fed zeros)
@@ -351,9 +366,9 @@ __global__ void __launch_bounds__(kWideThreads, (FIRE || W == 16) ? 4 : 1) spz_d
 
         // Fast path: every live team of the warp has two data slots that fit.
         if (__all_sync(kFullW, !lane_on || (act && tot0 != 0u && tot1 != 0u && o + 2u * B <= cap))) {
-            ensure(pos + ((tot0 + 7u) & ~7u) + 8, lane_on);
+            ensure(pos + slot_need(tot0), lane_on);
             data_slot(fw0, excl & 0xffffu, tot0, lane_on);
-            ensure(pos + ((tot1 + 7u) & ~7u) + 8, lane_on);
+            ensure(pos + slot_need(tot1), lane_on);
             data_slot(fw1, excl >> 16, tot1, lane_on);
             continue;
         }
@@ -362,7 +377,7 @@ __global__ void __launch_bounds__(kWideThreads, (FIRE || W == 16) ? 4 : 1) spz_d
         for (uint32_t s = 0; s < 2; s++) {
             const uint32_t total = s ? tot1 : tot0;
             const bool is_run = act && status == kStatusOk && total == 0;
-            ensure(pos + (is_run ? 2u : ((total + 7u) & ~7u)) + 8, act && status == kStatusOk);
+            ensure(pos + (is_run ? 10u : slot_need(total)), act && status == kStatusOk);
             if (is_run) {
                 // ---- run slot (sprintz_delta_rle.cpp:640-667): the previous row repeats nrun * 8 times; rare, divergent
                 uint32_t nrun = ring_byte(pos) & 0x7f;
@@ -432,8 +447,10 @@ cudaError_t launch_decode_wide(int elem_sz, int predictor, DecParams p, cudaStre
 {
     if (get_force_path() == 1) return cudaErrorNotSupported;
     if ((elem_sz != 1 && elem_sz != 2) || (predictor != 0 && predictor != 1) || p.variant != 0 || p.qop != 0) return cudaErrorNotSupported;
-    // 24 dims (three lanes per chunk): the team kernel measured faster (delta 1952 vs 1720 GB/s, FIRE 1328 vs 1287)
-    if (p.ndims < (elem_sz == 1 ? 32u : 24u) || p.ndims > 256 || (p.ndims & 7u)) return cudaErrorNotSupported;
+    // 24 dims (three lanes per chunk, shared memory limits the occupancy): the team kernel measured faster (8-bit delta 1952
+    // vs 1720 GB/s, FIRE 1328 vs 1287; 16-bit delta 1712 vs 840)
+    if (p.ndims < 32u || p.ndims > 256 || (p.ndims & 7u)) return cudaErrorNotSupported;
+    if (elem_sz == 2 && p.ndims == 32u) return cudaErrorNotSupported;   // one dim per lane of a full warp: team kernel 2739 vs 2060 GB/s
     if (p.src_end == nullptr || p.src_end <= p.src) return cudaErrorNotSupported;
     const uint32_t esz = (uint32_t)elem_sz;
     // 128-bit tile flushes: every block of every chunk must start 16-byte aligned in the output
@@ -443,13 +460,17 @@ cudaError_t launch_decode_wide(int elem_sz, int predictor, DecParams p, cudaStre
     if (p.chunk_len > 0x30000000ull) return cudaErrorNotSupported;      // 32-bit cursors inside one chunk
     const uint32_t NP = p.ndims / 8u, TPW = 32u / NP;
     const uint32_t H = (2u * p.ndims * (esz == 1 ? 3u : 4u) + 7u) / 8u;
-    const uint32_t slot = 8u * p.ndims * esz;
-    const uint32_t max_need = (H > slot ? H : slot) + 8u + 8u;      // one header or one slot, plus the window over-read
+    // 16-bit delta slots are staged in two halves (D = 80: 2165 -> 2456 GB/s, D = 256: 1986 -> 2865); the FIRE form would spill
+    // the state it has to hold across the refill (1961 -> 1344 at D = 80)
+    const bool half = esz == 2u && predictor == 0;
+    const uint32_t slot = half ? 8u * p.ndims : 8u * p.ndims * esz; // 8 rows of 8-bit, 4 rows of 16-bit elements
+    const uint32_t max_need = (H > slot ? H : slot) + 8u + 8u;      // one header or one (half) slot, plus the window over-read
     p.team = NP; p.dpl = TPW;
     p.ring_cap = pow2_ceil_w(max_need + NP * 32u + 32u);
     p.ring_mask4 = (p.ring_cap - 1u) & ~3u;
     const uint32_t tile = 64u * NP * esz;
-    p.team_smem = ((p.ring_cap + 32u + 128u + 2u * (tile + 128u) + p.ring_cap - 1u) / p.ring_cap) * p.ring_cap;
+    const uint32_t ntiles = (esz == 2u || predictor == 1) ? 1u : 2u;  // the per-element forms synchronise instead of alternating tiles
+    p.team_smem = ((p.ring_cap + 32u + 128u + ntiles * (tile + 128u) + p.ring_cap - 1u) / p.ring_cap) * p.ring_cap;
     const uint32_t teams_per_cta = (kWideThreads / 32) * TPW;
     const size_t smem = (size_t)teams_per_cta * p.team_smem;
     if (smem > 200 * 1024) return cudaErrorNotSupported;
@@ -462,8 +483,9 @@ cudaError_t launch_decode_wide(int elem_sz, int predictor, DecParams p, cudaStre
         kernel<<<(uint32_t)grid64, kWideThreads, smem, stream>>>(p);
         return cudaGetLastError();
     };
-    if (esz == 2u) return predictor == 1 ? go(spz_decode_wide_kernel<16, true>) : go(spz_decode_wide_kernel<16, false>);
-    return predictor == 1 ? go(spz_decode_wide_kernel<8, true>) : go(spz_decode_wide_kernel<8, false>);
+    if (esz == 2u && half) return predictor == 1 ? go(spz_decode_wide_kernel<16, true, true>) : go(spz_decode_wide_kernel<16, false, true>);
+    if (esz == 2u) return predictor == 1 ? go(spz_decode_wide_kernel<16, true, false>) : go(spz_decode_wide_kernel<16, false, false>);
+    return predictor == 1 ? go(spz_decode_wide_kernel<8, true, false>) : go(spz_decode_wide_kernel<8, false, false>);
 }
 
 }  // namespace spz

@@ -498,7 +498,9 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
             if (on) { xA = a; xB = b; }
             nA = widths4(ma); nB = widths4(mb);
         }
-        prefetch(it + 1u);
+        // 8-bit: the next block's loads are issued now and land during the rest of the iteration; 16-bit rows are twice the
+        // registers, so they are issued once the zigzagged block has gone to shared memory
+        if (W == 8) prefetch(it + 1u);
         wA = (nA * 0x01010101u) >> 24;
         wo = wA + ((nB * 0x01010101u) >> 24);
         // team total of the widths (and, for segmented rows, the bit offset of my octet inside a row).  Three teams per warp:
@@ -525,6 +527,7 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
         if (__all_sync(kFullWE, !on || (!zero && run == 0u))) {
             bool gc = false;
             if (on) { gc = emit_slot(WACT_DATA, 0u, pbsel); outer = gc; }
+            if (W == 16) prefetch(it + 1u);
             emit_rows(on, pbsel);
             if (__any_sync(kFullWE, gc)) close_group(gc);
             continue;
@@ -559,6 +562,7 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
             if (__any_sync(kFullWE, act == WACT_DATA)) emit_rows(act == WACT_DATA, pbsel);
             if (__any_sync(kFullWE, gc)) close_group(gc);
         }
+        if (W == 16) prefetch(it + 1u);
     }
 
     // ---- trailing raw elements (sprintz_delta_rle.cpp:398-403); also the whole input when L < 128
@@ -601,7 +605,7 @@ cudaError_t launch_encode_wide(int elem_sz, int predictor, EncParams p, cudaStre
 {
     if (get_force_path() == 1) return cudaErrorNotSupported;
     if ((elem_sz != 1 && elem_sz != 2) || (predictor != 0 && predictor != 1) || p.variant != 0) return cudaErrorNotSupported;
-    if (p.ndims < 24 || p.ndims > 256 || (p.ndims & 7u)) return cudaErrorNotSupported;
+    if (p.ndims < 16u || p.ndims > 256 || (p.ndims & 7u)) return cudaErrorNotSupported;
     if (p.chunk_len > 0x30000000ull) return cudaErrorNotSupported;      // 32-bit cursors inside one chunk
     // 64 / 128-bit row loads: every octet row of every chunk must start 8 / 16-byte aligned
     const uint32_t esz = (uint32_t)elem_sz, amask = 8u * esz - 1u;
