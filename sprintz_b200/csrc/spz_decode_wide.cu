@@ -1,4 +1,6 @@
-// spz_decode_wide.cu -- wide-row ("octet team") decode kernel: 8-bit delta streams with ndims a multiple of 8, 24..256.
+// spz_decode_wide.cu -- wide-row ("octet team") decode kernel: ndims a multiple of 8, 32..256; 8- and 16-bit elements,
+// delta and FIRE.  The text below describes the 8-bit delta form (SIMD within a register); the FIRE and 16-bit forms share
+// everything but the unpack / inverse predictor of a data slot (see the comment at the kernel).
 //
 // BASELINE config 4 (int8 x 80 dims, delta) ran on the team kernel of spz_decode_hd.cu at 0.38 of the roofline: ncu
 // showed 26 thread instructions per sample, LSU pipe 65 % (a byte store per sample, two LDS + a funnel shift per

@@ -1,4 +1,6 @@
-// spz_encode_wide.cu -- wide-row ("octet team") encode kernel: 8-bit delta streams with ndims a multiple of 8, 24..256.
+// spz_encode_wide.cu -- wide-row ("octet team") encode kernel: ndims a multiple of 8, 16..256; 8- and 16-bit elements,
+// delta and FIRE.  The text below describes the 8-bit delta form (SIMD within a register); the FIRE and 16-bit forms share
+// everything but the arithmetic of pass 1 and the field packing (see the comment at the kernel).
 //
 // BASELINE config 4 (int8 x 80 dims, delta) ran on the team kernel of spz_encode_hd.cu at 0.23 of the roofline: ncu
 // showed 26 thread instructions per sample (lane-per-dim forecasting of single bytes, a cluster multiply-add bit
