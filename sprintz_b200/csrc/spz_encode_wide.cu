@@ -129,8 +129,11 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
     uint8_t* const sm = smem + warp_base + tw * TS;
     const uint32_t NPC = NP * NQ;                       // pieces of a row
     const uint32_t PB = 64u * NPC;                      // one piece buffer: [8 rows][NPC] x 8 bytes
-    const uint32_t wid_off = 2u * PB;                   // [2][WCAP] piece widths (u8), then [2][WCAP] bit offsets of the pieces in a row (u16)
-    const uint32_t pre_off = wid_off + 2u * WCAP;
+    // 8-bit: two piece buffers used in turn; 16-bit: one (emit_rows() ends with a barrier, and shared memory bounds the
+    // occupancy of the 16-bit form: 80 dims 3 -> 4 CTAs per SM)
+    constexpr uint32_t NBUF = W == 16 ? 1u : 2u;
+    const uint32_t wid_off = NBUF * PB;                 // [NBUF][WCAP] piece widths (u8), then [NBUF][WCAP] bit offsets of the pieces in a row (u16)
+    const uint32_t pre_off = wid_off + NBUF * WCAP;
     // rows are written by one lane each; with one or two teams per warp a row is cut into SEG segments of whole pieces
     // so that all 32 lanes work in that phase (ndims >= 88)
     constexpr uint32_t LSEG = LSEG_;                    // log2(SEG): every division by SEG is a shift
@@ -423,7 +426,7 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
     for (uint32_t it = 0;; it++) {
         if (on && outer && (int32_t)blk > last_start) { tail = (int64_t)blk * B; on = false; }
         if (!__any_sync(kFullWE, on)) break;
-        const uint32_t pbsel = it & 1u;
+        const uint32_t pbsel = NBUF == 2u ? (it & 1u) : 0u;
 
         // ================= pass 1: packed delta -> zigzag -> OR-mask of this block (sprintz_delta_rle.cpp:161-201)
         if (ELEM) {
@@ -618,7 +621,8 @@ cudaError_t launch_encode_wide(int elem_sz, int predictor, EncParams p, cudaStre
     const uint32_t grp = H + 16u * p.ndims * esz + 4u;
     const uint32_t teams_per_cta = (kWideEncThreads / 32) * TPW;
     p.teams_per_cta = teams_per_cta;
-    p.out_off = up16w(2u * 64u * NPC + 64u * esz + 128u * esz);     // piece buffers | piece widths | row bit offsets
+    const uint32_t nbuf = esz == 2u ? 1u : 2u;
+    p.out_off = up16w(nbuf * (64u * NPC + 32u * esz + 64u * esz));  // piece buffers | piece widths | row bit offsets
     // the staging tile holds up to 4 groups, fewer when that would cost occupancy (6 CTAs per SM need <= 36 KB each; the
     // 16-bit and FIRE forms run 4 CTAs per SM: <= 56 KB)
     const uint32_t budget = (esz == 2 || predictor == 1) ? 56u * 1024u : 36u * 1024u;
