@@ -95,7 +95,10 @@ __device__ __forceinline__ uint32_t pack_quad(uint32_t w, const PackC& q)
 // FIRE: the forecaster needs a multiply per sample, so pass 1 runs per element on left-aligned values exactly like the
 // lane kernel's (spz_encode_lane.cu) and re-packs the zigzagged errors four to a word; everything behind pass 1 (widths,
 // header, multiply-add packing, row writers, control) is shared with the delta form.
-template <int W, bool FIRE, int MINB, int LSEG_, bool RDX>
+// PART: any ndims -- the last lane of a team owns a partial octet (its missing dims read as constant zeros: width 0, no
+// bits), rows are not 8 / 16-byte aligned (two aligned loads and a byte funnel per row), and an octet's header fields are
+// not whole bytes (they are OR-ed into the zeroed header with shared-memory atomics, two per lane and slot).
+template <int W, bool FIRE, int MINB, int LSEG_, bool RDX, bool PART>
 __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(const EncParams p)
 {
     static_assert(W == 8 || W == 16, "8- and 16-bit elements");
@@ -106,7 +109,6 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
     constexpr uint32_t NQ = W / 8;                      // <= 64-bit pieces per octet and row: the octet (8-bit), its two quads (16-bit)
     constexpr int NXW = 2 * (W / 8);                    // words of an octet's row
     constexpr bool ELEM = FIRE || W == 16;              // pass 1 runs per element (left-aligned values)
-    constexpr uint32_t WCAP = 32u * NQ;                 // pieces of a row, at most
     extern __shared__ __align__(16) uint8_t smem[];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -118,7 +120,8 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
     const uint64_t c64 = ((uint64_t)blockIdx.x * (kWideEncThreads / 32) + warp) * TPW + tw;
     const bool valid = lane_on && c64 < p.nchunks;
     const uint64_t c = valid ? c64 : 0;
-    const uint32_t D = NP * 8u;
+    const uint32_t D = PART ? p.ndims : NP * 8u;
+    const uint32_t dl = PART ? (D - 8u * t < 8u ? D - 8u * t : 8u) : 8u;     // dims of my octet
     const uint32_t last_lane = tw * NP + NP - 1u;
     // my team's lanes (an idle lane is a team of its own): a team-wide REDUX names exactly these
     const uint32_t tmask = lane_on ? ((NP == 32u ? 0xffffffffu : ((1u << NP) - 1u)) << (tw * NP)) : (1u << lane);
@@ -128,6 +131,7 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
     const uint32_t warp_base = (uint32_t)warp * TPW * TS;
     uint8_t* const sm = smem + warp_base + tw * TS;
     const uint32_t NPC = NP * NQ;                       // pieces of a row
+    const uint32_t WCAP = (NPC + 3u) & ~3u;             // entries of a width / offset array
     // row stride of the piece buffer, in pieces: a multiple of 16 pieces (128 bytes) would put the 8 row jobs of a team on
     // the same banks, so such rows are padded by one piece
     const uint32_t NPS = NPC + ((NPC & 15u) ? 0u : 1u);
@@ -151,7 +155,7 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
     uint8_t* const gstream = p.dst + c * p.slot_stride;
     const uint32_t B = (uint32_t)kBlockRows * D;
     const int64_t G = 2 * (int64_t)B;
-    const uint32_t H = (2u * D * HB) >> 3;               // D % 8 == 0: whole bytes
+    const uint32_t H = (2u * D * HB + 7u) >> 3;          // D % 8 == 0: an octet's fields are whole bytes
     const uint32_t SH = H >> 1;                          // header bytes of one slot
     const uint32_t meta_bytes = p.write_size ? 8u : 0u;
     const uint32_t max_group_bytes = H + 2u * B * ESZ + 4u;
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
     }
     auto flush = [&](bool on_, bool final_flush) {
         __syncwarp();
-        uint32_t carry0 = 0, carry1 = 0;                // the < 16 remaining bytes move to the front as (up to) 4 words
+        uint32_t carry[4] = {0, 0, 0, 0};               // the < 16 remaining bytes move to the front as (up to) 4 words
         bool moved = false;
         if (on_) {
             const uint32_t hi = final_flush ? ocur : (ocur & ~15u);
@@ -183,8 +187,9 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
                 const uint32_t rem = ocur - hi;         // < 16 (0 on the final flush)
                 {   // hi is a multiple of 16: whole words; the bytes of the last word past the cursor are don't-care
                     const uint32_t* w32 = reinterpret_cast<const uint32_t*>(ob + hi);
-                    if (4u * t < rem) carry0 = w32[t];
-                    if (4u * (t + NP) < rem) carry1 = w32[t + NP];
+#pragma unroll
+                    for (uint32_t k = 0; k < 4u; k++)
+                        if (4u * (t + k * NP) < rem) carry[k] = w32[t + k * NP];
                 }
                 gdst += hi; ocur = rem; oskip = 0;
                 moved = rem != 0u;
@@ -193,8 +198,9 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
         __syncwarp();                                   // the tile has been read
         if (moved) {
             uint32_t* w32 = reinterpret_cast<uint32_t*>(ob);
-            if (4u * t < ocur) w32[t] = carry0;
-            if (4u * (t + NP) < ocur) w32[t + NP] = carry1;
+#pragma unroll
+            for (uint32_t k = 0; k < 4u; k++)
+                if (4u * (t + k * NP) < ocur) w32[t + k * NP] = carry[k];
         }
         __syncwarp();                                   // the carried words hold don't-care bytes past the cursor: later writers come after
     };
@@ -221,12 +227,53 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
 
     // ---- input prefetch (registers), one block ahead
     uint32_t nx[kBlockRows][NXW];
+    // PART: which bytes of my octet's row exist
+    uint32_t vmask[NXW];
+#pragma unroll
+    for (int k = 0; k < NXW; k++) {
+        const uint32_t per = 4u / ESZ;                  // dims per word
+        const uint32_t have = dl > (uint32_t)k * per ? dl - (uint32_t)k * per : 0u;
+        vmask[k] = have >= per ? 0xffffffffu : ((1u << (8u * ESZ * have)) - 1u);
+    }
     auto prefetch = [&](uint32_t b) {
         const bool ok = on && (int64_t)(b + 1u) * B <= L;
         const uint8_t* src = gin + ((size_t)b * B + 8u * t) * ESZ;
 #pragma unroll
         for (int r = 0; r < kBlockRows; r++) {
-            if (W == 8) {
+            if (PART) {
+                // the 8 * ESZ bytes at an arbitrary address: the two aligned vectors around it, shifted by whole words
+                // (selects) and by bytes (PRMT); the second vector is only read when my dims reach into it
+                const uint8_t* a = src + (uint32_t)r * D * ESZ;
+                const uint32_t o = (uint32_t)((uintptr_t)a & (8u * ESZ - 1u));
+                const uint8_t* base = a - o;
+                const bool two = ok && o + dl * ESZ > 8u * ESZ;
+                uint32_t w[2 * NXW + 1];
+                if (W == 8) {
+                    uint2 q0 = make_uint2(0u, 0u), q1 = make_uint2(0u, 0u);
+                    if (ok) q0 = __ldg(reinterpret_cast<const uint2*>(base));
+                    if (two) q1 = __ldg(reinterpret_cast<const uint2*>(base + 8));
+                    w[0] = q0.x; w[1] = q0.y; w[2] = q1.x; w[3] = q1.y; w[4] = 0u;
+                } else {
+                    uint4 q0 = make_uint4(0u, 0u, 0u, 0u), q1 = make_uint4(0u, 0u, 0u, 0u);
+                    if (ok) q0 = __ldg(reinterpret_cast<const uint4*>(base));
+                    if (two) q1 = __ldg(reinterpret_cast<const uint4*>(base + 16));
+                    constexpr int S = W == 16 ? 1 : 0;  // (this branch is dead code for 8-bit elements: keep its indices in range)
+                    w[0] = q0.x; w[1] = q0.y; w[2 * S] = q0.z; w[3 * S] = q0.w;
+                    w[4 * S] = q1.x; w[5 * S] = q1.y; w[6 * S] = q1.z; w[7 * S] = q1.w; w[8 * S] = 0u;
+                }
+                const uint32_t kw = o >> 2;             // whole words to skip: 0..NXW-1
+                if (W == 16 && (kw & 2u)) {
+#pragma unroll
+                    for (int i = 0; i + 2 <= 2 * NXW; i++) w[i] = w[i + 2];
+                }
+                if (kw & 1u) {
+#pragma unroll
+                    for (int i = 0; i + 1 <= 2 * NXW; i++) w[i] = w[i + 1];
+                }
+                const uint32_t sel = 0x3210u + 0x1111u * (o & 3u);
+#pragma unroll
+                for (int k = 0; k < NXW; k++) nx[r][k] = __byte_perm(w[k], w[k + 1], sel) & vmask[k];
+            } else if (W == 8) {
                 uint2 v = make_uint2(0u, 0u);
                 if (ok) v = __ldg(reinterpret_cast<const uint2*>(src + (uint32_t)r * D));
                 nx[r][0] = v.x; nx[r][1] = v.y;
@@ -248,7 +295,13 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
     // emit_rows() turns them into payload bytes.
     auto emit_slot = [&](uint32_t act, uint32_t run_len, uint32_t pbsel) -> bool {
         const uint32_t sl = nslots & 1u;
-        if (sl == 0u) { hdr_off = ocur; ocur += H; ngroups++; }
+        if (sl == 0u) {
+            hdr_off = ocur; ocur += H; ngroups++;
+            if (PART) {                                 // the fields are OR-ed in
+                for (uint32_t b = t; b < H; b += NP) ob[hdr_off + b] = 0;
+                __syncwarp(tmask);
+            }
+        }
         uint32_t h24 = 0;
         if (act == WACT_RUN) {       // zero header fields + 1..2 length bytes (sprintz_delta_rle.cpp:238-245)
             const uint32_t two = run_len > 0x7fu ? 1u : 0u;
@@ -301,7 +354,16 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
             ocur += kBlockRows * row_bytes;
             blk++;
         }
-        {   // my octet's 3 / 4 header bytes of this slot
+        if (PART) {     // my octet's fields start at bit (sl * D + 8 * t) * HB of the header: one or two words
+            if (h24) {
+                const uint32_t hb = ((uint32_t)((ob + hdr_off) - smem)) * 8u + (sl * D + 8u * t) * (uint32_t)HB;
+                uint32_t* hw = reinterpret_cast<uint32_t*>(smem) + (hb >> 5);
+                const uint32_t sh = hb & 31u;
+                atomicOr(hw, h24 << sh);
+                const uint32_t hi = __funnelshift_l(h24, 0u, sh);       // h24 >> (32 - sh), 0 when sh == 0
+                if (hi) atomicOr(hw + 1, hi);
+            }
+        } else {        // my octet's 3 / 4 header bytes of this slot
             uint8_t* hp = ob + hdr_off + sl * SH + (uint32_t)HB * t;
             hp[0] = (uint8_t)h24; hp[1] = (uint8_t)(h24 >> 8); hp[2] = (uint8_t)(h24 >> 16);
             if (W == 16) hp[HB - 1] = (uint8_t)(h24 >> 24);
@@ -613,20 +675,23 @@ cudaError_t launch_encode_wide(int elem_sz, int predictor, EncParams p, cudaStre
 {
     if (get_force_path() == 1) return cudaErrorNotSupported;
     if ((elem_sz != 1 && elem_sz != 2) || (predictor != 0 && predictor != 1) || p.variant != 0) return cudaErrorNotSupported;
-    if (p.ndims < 16u || p.ndims > 256 || (p.ndims & 7u)) return cudaErrorNotSupported;
+    // high-dim layouts only (sprintz.cpp:44-71: up to 4 / 2 dims use the low-dim codecs)
+    if (p.ndims < (elem_sz == 1 ? 5u : 3u) || p.ndims > 256) return cudaErrorNotSupported;
+    if (p.ndims == 8u) return cudaErrorNotSupported;                    // lane kernels, else the team kernel
     if (p.chunk_len > 0x30000000ull) return cudaErrorNotSupported;      // 32-bit cursors inside one chunk
-    // 64 / 128-bit row loads: every octet row of every chunk must start 8 / 16-byte aligned
+    // whole octets and 64 / 128-bit aligned octet rows in every chunk: the aligned form; anything else: the PART form
     const uint32_t esz = (uint32_t)elem_sz, amask = 8u * esz - 1u;
-    if (((uintptr_t)p.src & amask) || (p.nchunks > 1 && ((p.chunk_len * esz) & amask))) return cudaErrorNotSupported;
-    const uint32_t NP = p.ndims / 8u, TPW = 32u / NP, NPC = NP * esz;
-    const uint32_t H = (2u * p.ndims * (esz == 1 ? 3u : 4u)) / 8u;
+    const bool part = (p.ndims & 7u) || ((uintptr_t)p.src & amask) || (p.nchunks > 1 && ((p.chunk_len * esz) & amask));
+    const uint32_t NP = (p.ndims + 7u) / 8u, TPW = 32u / NP, NPC = NP * esz;
+    const uint32_t H = (2u * p.ndims * (esz == 1 ? 3u : 4u) + 7u) / 8u;
     p.team = NP; p.dpl = TPW;
     const uint32_t grp = H + 16u * p.ndims * esz + 4u;
     const uint32_t teams_per_cta = (kWideEncThreads / 32) * TPW;
     p.teams_per_cta = teams_per_cta;
     const uint32_t nbuf = esz == 2u ? 1u : 2u;
     const uint32_t NPS = NPC + ((NPC & 15u) ? 0u : 1u);            // padded row stride of the piece buffer (see the kernel)
-    p.out_off = up16w(nbuf * (64u * NPS + 32u * esz + 64u * esz));  // piece buffers | piece widths | row bit offsets
+    const uint32_t wcap = (NPC + 3u) & ~3u;
+    p.out_off = up16w(nbuf * (64u * NPS + wcap + 2u * wcap));       // piece buffers | piece widths | row bit offsets
     // the staging tile holds up to 4 groups, fewer when that would cost occupancy (6 CTAs per SM need <= 36 KB each; the
     // 16-bit and FIRE forms run 4 CTAs per SM: <= 56 KB)
     const uint32_t budget = (esz == 2 || predictor == 1) ? 56u * 1024u : 36u * 1024u;
@@ -654,28 +719,24 @@ cudaError_t launch_encode_wide(int elem_sz, int predictor, EncParams p, cudaStre
         kernel<<<(uint32_t)grid64, kWideEncThreads, smem, stream>>>(p);
         return cudaGetLastError();
     };
-    if (esz == 2u) {         // twice the registers per row: 4 CTAs per SM
-        if (predictor == 1) {
-            if (TPW == 1u) return go(spz_encode_wide_kernel<16, true, 4, 2, false>);
-            if (TPW == 2u) return go(spz_encode_wide_kernel<16, true, 4, 1, false>);
-            if (TPW == 3u) return go(spz_encode_wide_kernel<16, true, 4, 0, true>);
-            return go(spz_encode_wide_kernel<16, true, 4, 0, false>);
-        }
-        if (TPW == 1u) return go(spz_encode_wide_kernel<16, false, 4, 2, false>);
-        if (TPW == 2u) return go(spz_encode_wide_kernel<16, false, 4, 1, false>);
-        if (TPW == 3u) return go(spz_encode_wide_kernel<16, false, 4, 0, true>);
-        return go(spz_encode_wide_kernel<16, false, 4, 0, false>);
+#define SPZ_WIDE_GO(Wv, Fv, Mv) \
+    if (part) { \
+        if (TPW == 1u) return go(spz_encode_wide_kernel<Wv, Fv, 4, 2, false, true>); \
+        if (TPW == 2u) return go(spz_encode_wide_kernel<Wv, Fv, 4, 1, false, true>); \
+        return go(spz_encode_wide_kernel<Wv, Fv, 4, 0, false, true>); \
+    } \
+    if (TPW == 1u) return go(spz_encode_wide_kernel<Wv, Fv, Mv, 2, false, false>); \
+    if (TPW == 2u) return go(spz_encode_wide_kernel<Wv, Fv, Mv, 1, false, false>); \
+    if (TPW == 3u) return go(spz_encode_wide_kernel<Wv, Fv, Mv, 0, true, false>); \
+    return go(spz_encode_wide_kernel<Wv, Fv, Mv, 0, false, false>);
+    // 16-bit rows are twice the registers, FIRE keeps 24 more registers of state per lane: 4 CTAs per SM
+    if (esz == 2u) {
+        if (predictor == 1) { SPZ_WIDE_GO(16, true, 4) }
+        SPZ_WIDE_GO(16, false, 4)
     }
-    if (predictor == 1) {    // FIRE keeps 24 more registers of state per lane: 4 CTAs per SM
-        if (TPW == 1u) return go(spz_encode_wide_kernel<8, true, 4, 2, false>);
-        if (TPW == 2u) return go(spz_encode_wide_kernel<8, true, 4, 1, false>);
-        if (TPW == 3u) return go(spz_encode_wide_kernel<8, true, 4, 0, true>);
-        return go(spz_encode_wide_kernel<8, true, 4, 0, false>);
-    }
-    if (TPW == 1u) return go(spz_encode_wide_kernel<8, false, 5, 2, false>);
-    if (TPW == 2u) return go(spz_encode_wide_kernel<8, false, 5, 1, false>);
-    if (TPW == 3u) return go(spz_encode_wide_kernel<8, false, 5, 0, true>);
-    return go(spz_encode_wide_kernel<8, false, 5, 0, false>);
+    if (predictor == 1) { SPZ_WIDE_GO(8, true, 4) }
+    SPZ_WIDE_GO(8, false, 5)
+#undef SPZ_WIDE_GO
 }
 
 }  // namespace spz

@@ -11,7 +11,9 @@ from test_gpu_parity import _check_case
 
 pytestmark = pytest.mark.gpu
 
-WIDE_DIMS = (16, 24, 32, 40, 56, 64, 80, 96, 128, 200, 256)
+# partial octets / unaligned rows (the PART form of the kernels): any ndims of the high-dim layout
+PART_DIMS = (5, 6, 7, 9, 12, 15, 17, 20, 30, 33, 100, 255)
+WIDE_DIMS = PART_DIMS + (16, 24, 32, 40, 56, 64, 80, 96, 128, 200, 256)
 FAMILY_WIDE = 3
 
 
@@ -24,6 +26,10 @@ def spz():
 
 def _ran_wide(spz, D=80, esz=1):
     L = spz.lib()
+    if D % 8:
+        assert L.spz_last_kernel_family(0) == FAMILY_WIDE, "wide-row encoder did not run"
+        assert L.spz_last_kernel_family(1) == FAMILY_WIDE, "wide-row decoder did not run"
+        return
     if D == 16:                                               # decoded by the lane kernels; 16-bit frames are encoded by them too
         assert esz == 2 or L.spz_last_kernel_family(0) == FAMILY_WIDE, "wide-row encoder did not run"
         return
@@ -72,14 +78,14 @@ def test_wide_adversarial_and_runs(spz, oracle, pred, esz):
         steps[::7, :] = -amp[None, :] - (nb > 0)
         x = ((1 << (8 * esz - 1)) + np.cumsum(steps, axis=0)) & ((1 << (8 * esz)) - 1)
         _check_case(spz, oracle, pred, esz, D, x.astype(_dt(esz)).reshape(-1), bad, "mixed widths")
-    for D in (24, 80, 256):
+    for D in (7, 24, 33, 80, 256):
         B = 8 * D
         for k in (2, 3, 18):                                   # RLE termination edges
             for j in list(range(0, 2 * B + 1, 37)) + [B - 1, B, B + 1, 2 * B - 1, 2 * B]:
                 L = k * B + j
                 _check_case(spz, oracle, pred, esz, D, np.zeros(L, _dt(esz)), bad, "zeros")
                 _check_case(spz, oracle, pred, esz, D, inputs.const_then_data(L, esz, (k - 1) * B), bad, "const+data")
-    for D in (24, 80):
+    for D in (6, 24, 80, 100):
         B = 8 * D
         for nblocks in (0x7f, 0x80, 0x7fff, 0x8000):           # run-length byte edges
             x = np.full((nblocks + 3) * B, 9, _dt(esz))
@@ -88,7 +94,7 @@ def test_wide_adversarial_and_runs(spz, oracle, pred, esz):
     fams = {}
     n = 256 * 1024 + 7
     fams.update(inputs.fuzz(n, esz)); fams.update(inputs.sparse(n, esz))
-    for D in (24, 80, 256):
+    for D in (5, 24, 30, 80, 256):
         for tag in ("fuzz256", "fuzz16", "fuzz2", "sparse6", "sparse2"):
             _check_case(spz, oracle, pred, esz, D, fams[tag], bad, tag)
     assert not bad, (len(bad), bad[:5])
