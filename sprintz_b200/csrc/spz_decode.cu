@@ -271,7 +271,7 @@ cudaError_t launch_decode(int elem_sz, int predictor, DecParams p, cudaStream_t 
         if (e != cudaErrorNotSupported) { g_last_decode_family = 2; return e; }
     }
     if (p.variant == 0)
-    {   // wide rows (ndims a multiple of 8, 16..256), 8- and 16-bit, delta and FIRE: octet teams (spz_decode_wide.cu)
+    {   // wide rows (ndims a multiple of 8, 32..256), 8- and 16-bit, delta and FIRE: octet teams (spz_decode_wide.cu)
         const cudaError_t e = launch_decode_wide(elem_sz, predictor, p, stream);
         if (e != cudaErrorNotSupported) { g_last_decode_family = 3; return e; }
     }

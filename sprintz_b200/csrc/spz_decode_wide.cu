@@ -72,10 +72,8 @@ __device__ __forceinline__ uint32_t octet_width16(uint32_t fw)
 // left-aligned values exactly like the lane kernel's (spz_decode_lane.cu: one window per quad, one shift per field,
 // zigzag^-1 and icopysign as multiply-adds) and the row is re-packed four samples to a word; stream ring, header scan,
 // tiles and control are shared with the delta form.
-// PART: any ndims -- the last lane of a team owns a partial octet (its missing fields are masked to width 0), rows are
-// stored into the tile element by element and the tile leaves in 64-bit units.
-template <int W, bool FIRE, bool HALF, bool PART>
-__global__ void __launch_bounds__(kWideThreads, (FIRE || W == 16 || PART) ? 4 : 1) spz_decode_wide_kernel(const DecParams p)
+template <int W, bool FIRE, bool HALF>
+__global__ void __launch_bounds__(kWideThreads, (FIRE || W == 16) ? 4 : 1) spz_decode_wide_kernel(const DecParams p)
 {
     static_assert(W == 8 || W == 16, "8- and 16-bit elements");
     constexpr int HB = Traits<W>::HB;
@@ -83,7 +81,7 @@ __global__ void __launch_bounds__(kWideThreads, (FIRE || W == 16 || PART) ? 4 : 
     constexpr int UP = 32 - W;
     constexpr uint32_t ESZ = W / 8;
     constexpr uint32_t FMASK = (1u << HB) - 1u;
-    constexpr bool ELEM = FIRE || W == 16 || PART;      // data slots are decoded per element (left-aligned values)
+    constexpr bool ELEM = FIRE || W == 16;              // data slots are decoded per element (left-aligned values)
     extern __shared__ __align__(16) uint8_t smem[];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -95,16 +93,14 @@ __global__ void __launch_bounds__(kWideThreads, (FIRE || W == 16 || PART) ? 4 : 
     const uint64_t c64 = ((uint64_t)blockIdx.x * (kWideThreads / 32) + warp) * TPW + tw;
     const bool valid = lane_on && c64 < p.nchunks;
     const uint64_t c = valid ? c64 : 0;
-    const uint32_t D = PART ? p.ndims : NP * 8u;
-    const uint32_t dl = PART ? (D - 8u * t < 8u ? D - 8u * t : 8u) : 8u;     // dims of my octet
-    const uint32_t hmask = (PART && dl * HB < 32u) ? ((1u << (dl * HB)) - 1u) : 0xffffffffu;   // my header fields
+    const uint32_t D = NP * 8u;
     const uint32_t last_lane = tw * NP + NP - 1u;       // the lane holding my team's inclusive totals
 
     const uint32_t team_slot = (uint32_t)warp * TPW + tw;
     const uint32_t ring_off = team_slot * p.team_smem;  // team_smem is a multiple of ring_cap: wrap + base is one LOP3
     uint8_t* const ring = smem + ring_off;
     const uint32_t RCAP = p.ring_cap, RMASK = RCAP - 1u;
-    const uint32_t TILE = 8u * D * ESZ;                 // 8 rows x D elements
+    const uint32_t TILE = 64u * NP * ESZ;               // 8 rows x D elements
     // two output tiles; team k's rows start where team k-1's end (mod the banks) so the 64-bit row stores of the
     // warp's teams fall into different banks
     uint8_t* const tile0 = ring + RCAP + 32 + ((tw * D * ESZ) & 112u);
@@ -186,15 +182,7 @@ __global__ void __launch_bounds__(kWideThreads, (FIRE || W == 16 || PART) ? 4 : 
     for (int j = 0; j < (FIRE ? 8 : 1); j++) { pdh[j] = 0; ct[j] = 0; }
     constexpr int E1 = ELEM ? 1 : 0;
     auto store_row = [&](uint8_t* dst) {                // the top W bits of my 8 left-aligned values
-        if (PART) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                if ((uint32_t)j < dl) {
-                    if (W == 8) dst[j] = (uint8_t)(pvh[j * E1] >> 24);
-                    else reinterpret_cast<uint16_t*>(dst)[j] = (uint16_t)(pvh[j * E1] >> 16);
-                }
-            }
-        } else if (W == 8) {
+        if (W == 8) {
             const uint32_t a0 = __byte_perm(pvh[0], pvh[1 * E1], 0x0073), a1 = __byte_perm(pvh[2 * E1], pvh[3 * E1], 0x0073);
             const uint32_t b0 = __byte_perm(pvh[4 * E1], pvh[5 * E1], 0x0073), b1 = __byte_perm(pvh[6 * E1], pvh[7 * E1], 0x0073);
             *reinterpret_cast<uint2*>(dst) = make_uint2(__byte_perm(a0, a1, 0x5410), __byte_perm(b0, b1, 0x5410));
@@ -304,16 +292,10 @@ __global__ void __launch_bounds__(kWideThreads, (FIRE || W == 16 || PART) ? 4 : 
             }
             __syncwarp();                               // the tile is complete
             if (doit) {
-                if (PART) {     // 8 * D * ESZ bytes: D * ESZ 64-bit units
-                    const uint2* s2 = reinterpret_cast<const uint2*>(tile);
-                    uint2* g2 = reinterpret_cast<uint2*>(out + (size_t)o * ESZ);
-                    for (uint32_t u = t; u < D * ESZ; u += NP) g2[u] = s2[u];
-                } else {
-                    const uint4* s4 = reinterpret_cast<const uint4*>(tile);
-                    uint4* g4 = reinterpret_cast<uint4*>(out + (size_t)o * ESZ);
+                const uint4* s4 = reinterpret_cast<const uint4*>(tile);
+                uint4* g4 = reinterpret_cast<uint4*>(out + (size_t)o * ESZ);
 #pragma unroll
-                    for (uint32_t i = 0; i < 4u * ESZ; i++) g4[t + i * NP] = s4[t + i * NP];
-                }
+                for (uint32_t i = 0; i < 4u * ESZ; i++) g4[t + i * NP] = s4[t + i * NP];
                 pos += row_bytes * 8u;
                 o += B;
             }
@@ -371,8 +353,8 @@ __global__ void __launch_bounds__(kWideThreads, (FIRE || W == 16 || PART) ? 4 : 
 
         // ---- both slots' widths: my octet's fields, one packed scan over the team for the bit offsets
         const uint32_t hbit = (pos & RMASK) * 8u;
-        const uint32_t fw0 = ring_bits(hbit + (8u * t) * HB) & hmask;
-        const uint32_t fw1 = ring_bits(hbit + (D + 8u * t) * HB) & hmask;
+        const uint32_t fw0 = ring_bits(hbit + (8u * t) * HB);
+        const uint32_t fw1 = ring_bits(hbit + (D + 8u * t) * HB);
         const uint32_t mine = W == 8 ? (octet_width8(fw0) | (octet_width8(fw1) << 16)) : (octet_width16(fw0) | (octet_width16(fw1) << 16));
         uint32_t incl = mine;
         for (uint32_t s = 1; s < NP; s <<= 1) {
@@ -467,23 +449,18 @@ cudaError_t launch_decode_wide(int elem_sz, int predictor, DecParams p, cudaStre
 {
     if (get_force_path() == 1) return cudaErrorNotSupported;
     if ((elem_sz != 1 && elem_sz != 2) || (predictor != 0 && predictor != 1) || p.variant != 0 || p.qop != 0) return cudaErrorNotSupported;
-    // high-dim layouts only (sprintz.cpp:44-71: up to 4 / 2 dims use the low-dim codecs)
-    if (p.ndims < (elem_sz == 1 ? 5u : 3u) || p.ndims > 256) return cudaErrorNotSupported;
+    // 24 dims (three lanes per chunk, shared memory limits the occupancy): the team kernel measured faster (8-bit delta 1952
+    // vs 1720 GB/s, FIRE 1328 vs 1287; 16-bit delta 1712 vs 840)
+    if (p.ndims < 32u || p.ndims > 256 || (p.ndims & 7u)) return cudaErrorNotSupported;
+    if (elem_sz == 2 && p.ndims == 32u) return cudaErrorNotSupported;   // one dim per lane of a full warp: team kernel 2739 vs 2060 GB/s
     if (p.src_end == nullptr || p.src_end <= p.src) return cudaErrorNotSupported;
+    const uint32_t esz = (uint32_t)elem_sz;
+    // 128-bit tile flushes: every block of every chunk must start 16-byte aligned in the output
+    if (((uintptr_t)p.dst & 15) != 0) return cudaErrorNotSupported;
+    if (p.nchunks > 1 && ((p.chunk_len * esz) & 15) != 0) return cudaErrorNotSupported;
     if (p.chunk_len % p.ndims != 0 && p.nchunks > 1) return cudaErrorNotSupported;
     if (p.chunk_len > 0x30000000ull) return cudaErrorNotSupported;      // 32-bit cursors inside one chunk
-    const uint32_t esz = (uint32_t)elem_sz;
-    // whole octets and 128-bit tile flushes (every block of every chunk starts 16-byte aligned in the output): the aligned
-    // form; anything else: the PART form, whose tiles leave in 64-bit units
-    const bool part = (p.ndims & 7u) || ((uintptr_t)p.dst & 15) || (p.nchunks > 1 && ((p.chunk_len * esz) & 15));
-    if (part && (((uintptr_t)p.dst & 7) || (p.nchunks > 1 && ((p.chunk_len * esz) & 7)))) return cudaErrorNotSupported;
-    if (!part) {
-        // 24 dims (three lanes per chunk, shared memory limits the occupancy): the team kernel measured faster (8-bit delta
-        // 1952 vs 1720 GB/s, FIRE 1328 vs 1287; 16-bit delta 1712 vs 840); 8 / 16 dims: lane kernels, else the team kernel
-        if (p.ndims < 32u) return cudaErrorNotSupported;
-        if (elem_sz == 2 && p.ndims == 32u) return cudaErrorNotSupported;   // one dim per lane of a full warp: team kernel 2739 vs 2060 GB/s
-    }
-    const uint32_t NP = (p.ndims + 7u) / 8u, TPW = 32u / NP;
+    const uint32_t NP = p.ndims / 8u, TPW = 32u / NP;
     const uint32_t H = (2u * p.ndims * (esz == 1 ? 3u : 4u) + 7u) / 8u;
     // 16-bit delta slots are staged in two halves (D = 80: 2165 -> 2456 GB/s, D = 256: 1986 -> 2865); the FIRE form would spill
     // the state it has to hold across the refill (1961 -> 1344 at D = 80)
@@ -493,8 +470,8 @@ cudaError_t launch_decode_wide(int elem_sz, int predictor, DecParams p, cudaStre
     p.team = NP; p.dpl = TPW;
     p.ring_cap = pow2_ceil_w(max_need + NP * 32u + 32u);
     p.ring_mask4 = (p.ring_cap - 1u) & ~3u;
-    const uint32_t tile = (8u * p.ndims * esz + 15u) & ~15u;
-    const uint32_t ntiles = (esz == 2u || predictor == 1 || part) ? 1u : 2u;  // the per-element forms synchronise instead of alternating tiles
+    const uint32_t tile = 64u * NP * esz;
+    const uint32_t ntiles = (esz == 2u || predictor == 1) ? 1u : 2u;  // the per-element forms synchronise instead of alternating tiles
     p.team_smem = ((p.ring_cap + 32u + 128u + ntiles * (tile + 128u) + p.ring_cap - 1u) / p.ring_cap) * p.ring_cap;
     const uint32_t teams_per_cta = (kWideThreads / 32) * TPW;
     const size_t smem = (size_t)teams_per_cta * p.team_smem;
@@ -508,12 +485,9 @@ cudaError_t launch_decode_wide(int elem_sz, int predictor, DecParams p, cudaStre
         kernel<<<(uint32_t)grid64, kWideThreads, smem, stream>>>(p);
         return cudaGetLastError();
     };
-    if (part) {
-        if (esz == 2u) return predictor == 1 ? go(spz_decode_wide_kernel<16, true, false, true>) : go(spz_decode_wide_kernel<16, false, true, true>);
-        return predictor == 1 ? go(spz_decode_wide_kernel<8, true, false, true>) : go(spz_decode_wide_kernel<8, false, false, true>);
-    }
-    if (esz == 2u) return predictor == 1 ? go(spz_decode_wide_kernel<16, true, false, false>) : go(spz_decode_wide_kernel<16, false, true, false>);
-    return predictor == 1 ? go(spz_decode_wide_kernel<8, true, false, false>) : go(spz_decode_wide_kernel<8, false, false, false>);
+    if (esz == 2u && half) return predictor == 1 ? go(spz_decode_wide_kernel<16, true, true>) : go(spz_decode_wide_kernel<16, false, true>);
+    if (esz == 2u) return predictor == 1 ? go(spz_decode_wide_kernel<16, true, false>) : go(spz_decode_wide_kernel<16, false, false>);
+    return predictor == 1 ? go(spz_decode_wide_kernel<8, true, false>) : go(spz_decode_wide_kernel<8, false, false>);
 }
 
 }  // namespace spz

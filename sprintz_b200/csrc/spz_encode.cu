@@ -446,7 +446,7 @@ cudaError_t launch_encode(int elem_sz, int predictor, EncParams p, cudaStream_t 
         if (e != cudaErrorNotSupported) { g_last_encode_family = 2; return e; }
     }
     if (p.variant == 0 && (pin == 0 || pin == 4))
-    {   // wide rows (ndims a multiple of 8, 16..256), 8- and 16-bit, delta and FIRE: octet teams (spz_encode_wide.cu)
+    {   // wide rows (ndims 5..256), 8- and 16-bit, delta and FIRE: octet teams (spz_encode_wide.cu)
         const cudaError_t e = launch_encode_wide(elem_sz, predictor, p, stream);
         if (e != cudaErrorNotSupported) { g_last_encode_family = 3; return e; }
     }

@@ -1,5 +1,5 @@
-// spz_encode_wide.cu -- wide-row ("octet team") encode kernel: ndims a multiple of 8, 16..256; 8- and 16-bit elements,
-// delta and FIRE.  The text below describes the 8-bit delta form (SIMD within a register); the FIRE and 16-bit forms share
+// spz_encode_wide.cu -- wide-row ("octet team") encode kernel: ndims 5..256 (whole octets in the aligned form, any ndims
+// in the PART form); 8- and 16-bit elements, delta and FIRE.  The text below describes the 8-bit delta form (SIMD within a register); the FIRE and 16-bit forms share
 // everything but the arithmetic of pass 1 and the field packing (see the comment at the kernel).
 //
 // BASELINE config 4 (int8 x 80 dims, delta) ran on the team kernel of spz_encode_hd.cu at 0.23 of the roofline: ncu
@@ -676,7 +676,8 @@ cudaError_t launch_encode_wide(int elem_sz, int predictor, EncParams p, cudaStre
     if (get_force_path() == 1) return cudaErrorNotSupported;
     if ((elem_sz != 1 && elem_sz != 2) || (predictor != 0 && predictor != 1) || p.variant != 0) return cudaErrorNotSupported;
     // high-dim layouts only (sprintz.cpp:44-71: up to 4 / 2 dims use the low-dim codecs)
-    if (p.ndims < (elem_sz == 1 ? 5u : 3u) || p.ndims > 256) return cudaErrorNotSupported;
+    if (p.ndims < 5u || p.ndims > 256) return cudaErrorNotSupported;
+    if (elem_sz == 2 && p.ndims == 6u) return cudaErrorNotSupported;    // team kernel 684 vs 621 GB/s (and 3 / 4 dims: 663 / 779 vs 430 / 504)
     if (p.ndims == 8u) return cudaErrorNotSupported;                    // lane kernels, else the team kernel
     if (p.chunk_len > 0x30000000ull) return cudaErrorNotSupported;      // 32-bit cursors inside one chunk
     // whole octets and 64 / 128-bit aligned octet rows in every chunk: the aligned form; anything else: the PART form
