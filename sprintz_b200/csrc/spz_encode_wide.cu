@@ -314,6 +314,31 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
             if (t == 0) ob[ocur] = 0;
             ocur += 1u;
         } else {
+            // SOLO (a one-lane team, ndims <= 8 in the PART form): the lane holds every piece of its rows, so it appends the 8
+            // byte-padded rows itself with a scalar bit writer -- no piece buffer, no row jobs (int8 x 5 dims: 463 -> 606 GB/s, int16 x 5: 508 -> 809)
+            const bool solo = PART && NP == 1u;
+            uint32_t s_waddr = 0, s_fill = 0, s_a0 = 0;
+            if (solo) {
+                const uint32_t bit0 = (uint32_t)((ob + ocur) - smem) * 8u;
+                s_waddr = (bit0 >> 5) << 2; s_fill = bit0 & 31u;
+                if (s_fill) s_a0 = *reinterpret_cast<const uint32_t*>(smem + s_waddr) & ((1u << s_fill) - 1u);
+            }
+            auto append = [&](uint32_t x, uint32_t y, uint32_t w) {      // w <= 64 bits of (x, y), clean above w
+                s_a0 |= x << s_fill;
+                const uint32_t a1 = __funnelshift_l(x, y, s_fill), a2 = __funnelshift_l(y, 0u, s_fill);
+                s_fill += w;
+                const bool p1 = s_fill >= 32u, p2 = s_fill >= 64u;
+                if (p1) *reinterpret_cast<uint32_t*>(smem + s_waddr) = s_a0;
+                if (p2) *reinterpret_cast<uint32_t*>(smem + s_waddr + 4u) = a1;
+                s_a0 = p2 ? a2 : (p1 ? a1 : s_a0);
+                s_waddr += (s_fill >> 5) * 4u;
+                s_fill &= 31u;
+            };
+            auto pad_bits = [&](uint32_t n) {                            // n < 8 zero bits: rows are byte-padded
+                s_fill += n;
+                if (s_fill >= 32u) { *reinterpret_cast<uint32_t*>(smem + s_waddr) = s_a0; s_a0 = 0; s_waddr += 4u; s_fill -= 32u; }
+            };
+            const uint32_t row_pad = row_bytes * 8u - wo;
             if (W == 8) {
                 h24 = header12(nA) | (header12(nB) << 12);
                 PackC qa, qb;
@@ -324,10 +349,14 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
                 for (int r = 0; r < kBlockRows; r++) {
                     const uint32_t va = pack_quad(zz[r][0], qa), vb = pack_quad(zz[r][1], qb);
                     // octet piece = va | vb << wA (wA <= 32: the clamping funnel shifts give 0 / vb at 32)
-                    pb[(uint32_t)r * NPS] = make_uint2(va | __funnelshift_lc(0u, vb, wA), __funnelshift_lc(vb, 0u, wA));
+                    const uint2 piece = make_uint2(va | __funnelshift_lc(0u, vb, wA), __funnelshift_lc(vb, 0u, wA));
+                    if (solo) { append(piece.x, piece.y, wo); pad_bits(row_pad); }
+                    else pb[(uint32_t)r * NPS] = piece;
                 }
-                sm[wid_off + pbsel * WCAP + t] = (uint8_t)wo;
-                if (SEG > 1u) reinterpret_cast<uint16_t*>(sm + pre_off)[pbsel * WCAP + t] = (uint16_t)excl;
+                if (!solo) {
+                    sm[wid_off + pbsel * WCAP + t] = (uint8_t)wo;
+                    if (SEG > 1u) reinterpret_cast<uint16_t*>(sm + pre_off)[pbsel * WCAP + t] = (uint16_t)excl;
+                }
             } else {
                 h24 = header16(nA) | (header16(nB) << 16);
                 // a pair of fields p = lo | hi << 16 closes up as p + (p >> 16) * (2^n_lo - 2^16); two pairs make a quad's
@@ -340,17 +369,22 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
                 for (int r = 0; r < kBlockRows; r++) {
                     const uint32_t a0 = zz[r][0] + (zz[r][0] >> 16) * mA0, a1 = zz[r][1] + (zz[r][1] >> 16) * mA1;
                     const uint32_t b0 = zz[r][NXW - 2] + (zz[r][NXW - 2] >> 16) * mB0, b1 = zz[r][NXW - 1] + (zz[r][NXW - 1] >> 16) * mB1;
-                    pb[(uint32_t)r * NPS] = make_uint2(a0 | __funnelshift_lc(0u, a1, cA0), __funnelshift_lc(a1, 0u, cA0));
-                    pb[(uint32_t)r * NPS + 1u] = make_uint2(b0 | __funnelshift_lc(0u, b1, cB0), __funnelshift_lc(b1, 0u, cB0));
+                    const uint2 pa = make_uint2(a0 | __funnelshift_lc(0u, a1, cA0), __funnelshift_lc(a1, 0u, cA0));
+                    const uint2 pq = make_uint2(b0 | __funnelshift_lc(0u, b1, cB0), __funnelshift_lc(b1, 0u, cB0));
+                    if (solo) { append(pa.x, pa.y, wA); append(pq.x, pq.y, wo - wA); pad_bits(row_pad); }
+                    else { pb[(uint32_t)r * NPS] = pa; pb[(uint32_t)r * NPS + 1u] = pq; }
                 }
-                sm[wid_off + pbsel * WCAP + 2u * t] = (uint8_t)wA;
-                sm[wid_off + pbsel * WCAP + 2u * t + 1u] = (uint8_t)(wo - wA);
-                if (SEG > 1u) {
+                if (!solo) {
+                    sm[wid_off + pbsel * WCAP + 2u * t] = (uint8_t)wA;
+                    sm[wid_off + pbsel * WCAP + 2u * t + 1u] = (uint8_t)(wo - wA);
+                }
+                if (!solo && SEG > 1u) {
                     uint16_t* pre = reinterpret_cast<uint16_t*>(sm + pre_off) + pbsel * WCAP + 2u * t;
                     pre[0] = (uint16_t)excl; pre[1] = (uint16_t)(excl + wA);
                 }
             }
-            info = 1u | (row_bytes << 1) | ((uint32_t)((ob + ocur) - smem) << 11);
+            if (solo) { if (s_fill) *reinterpret_cast<uint32_t*>(smem + s_waddr) = s_a0; }     // zeros behind the payload: written later
+            else info = 1u | (row_bytes << 1) | ((uint32_t)((ob + ocur) - smem) << 11);
             ocur += kBlockRows * row_bytes;
             blk++;
         }
@@ -598,7 +632,7 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
             bool gc = false;
             if (on) { gc = emit_slot(WACT_DATA, 0u, pbsel); outer = gc; }
             if (W == 16) prefetch(it + 1u);
-            emit_rows(on, pbsel);
+            if (!(PART && NP == 1u)) emit_rows(on, pbsel);
             if (__any_sync(kFullWE, gc)) close_group(gc);
             continue;
         }
@@ -629,7 +663,7 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
                 gc = emit_slot(act, run_len, pbsel);
                 if (act == WACT_DATA) outer = gc;
             }
-            if (__any_sync(kFullWE, act == WACT_DATA)) emit_rows(act == WACT_DATA, pbsel);
+            if (!(PART && NP == 1u) && __any_sync(kFullWE, act == WACT_DATA)) emit_rows(act == WACT_DATA, pbsel);
             if (__any_sync(kFullWE, gc)) close_group(gc);
         }
         if (W == 16) prefetch(it + 1u);
@@ -676,8 +710,8 @@ cudaError_t launch_encode_wide(int elem_sz, int predictor, EncParams p, cudaStre
     if (get_force_path() == 1) return cudaErrorNotSupported;
     if ((elem_sz != 1 && elem_sz != 2) || (predictor != 0 && predictor != 1) || p.variant != 0) return cudaErrorNotSupported;
     // high-dim layouts only (sprintz.cpp:44-71: up to 4 / 2 dims use the low-dim codecs)
+    // (int16 x 3 / 4 dims are high-dim too, but the team kernel measured faster: 663 / 782 vs 603 / 649 GB/s)
     if (p.ndims < 5u || p.ndims > 256) return cudaErrorNotSupported;
-    if (elem_sz == 2 && p.ndims == 6u) return cudaErrorNotSupported;    // team kernel 684 vs 621 GB/s (and 3 / 4 dims: 663 / 779 vs 430 / 504)
     if (p.ndims == 8u) return cudaErrorNotSupported;                    // lane kernels, else the team kernel
     if (p.chunk_len > 0x30000000ull) return cudaErrorNotSupported;      // 32-bit cursors inside one chunk
     // whole octets and 64 / 128-bit aligned octet rows in every chunk: the aligned form; anything else: the PART form
