@@ -72,8 +72,10 @@ __device__ __forceinline__ uint32_t octet_width16(uint32_t fw)
 // left-aligned values exactly like the lane kernel's (spz_decode_lane.cu: one window per quad, one shift per field,
 // zigzag^-1 and icopysign as multiply-adds) and the row is re-packed four samples to a word; stream ring, header scan,
 // tiles and control are shared with the delta form.
+// Registers: the 8-bit delta form is held to 80 (6 CTAs per SM, which is also what its shared memory allows): without a bound
+// the compiler took 102 (5 CTAs, c4 decode 1.77 -> 1.82 ms), with 72 it schedules worse (1.88 ms); measured 1.79 ms.
 template <int W, bool FIRE, bool HALF>
-__global__ void __launch_bounds__(kWideThreads, (FIRE || W == 16) ? 4 : 1) spz_decode_wide_kernel(const DecParams p)
+__global__ void __launch_bounds__(kWideThreads, (FIRE || W == 16) ? 4 : 6) spz_decode_wide_kernel(const DecParams p)
 {
     static_assert(W == 8 || W == 16, "8- and 16-bit elements");
     constexpr int HB = Traits<W>::HB;
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(kWideThreads, (FIRE || W == 16) ? 4 : 1) spz_d
     // stream bytes a data slot of `tot` bits per row needs staged before data_slot(): the slot plus the window over-read;
     // 16-bit slots are staged in two halves (the second inside data_slot)
     auto slot_need = [&](uint32_t tot) -> uint32_t {
-        return HALF ? ((tot + 7u) >> 3) * 4u + 16u : ((tot + 7u) & ~7u) + 16u;
+        return HALF ? ((tot + 7u) >> 3) * 4u + 16u : ((tot + 7u) & ~7u) + (W == 16 ? 16u : 8u);     // 32-bit windows over-read < 8 bytes, 64-bit ones < 12
     };
     const uint32_t gmax = __reduce_max_sync(kFullW, ngroups);
     for (uint32_t g = 0; g < gmax; g++) {
@@ -485,7 +487,7 @@ cudaError_t launch_decode_wide(int elem_sz, int predictor, DecParams p, cudaStre
         kernel<<<(uint32_t)grid64, kWideThreads, smem, stream>>>(p);
         return cudaGetLastError();
     };
-    if (esz == 2u && half) return predictor == 1 ? go(spz_decode_wide_kernel<16, true, true>) : go(spz_decode_wide_kernel<16, false, true>);
+    if (half) return go(spz_decode_wide_kernel<16, false, true>);
     if (esz == 2u) return predictor == 1 ? go(spz_decode_wide_kernel<16, true, false>) : go(spz_decode_wide_kernel<16, false, false>);
     return predictor == 1 ? go(spz_decode_wide_kernel<8, true, false>) : go(spz_decode_wide_kernel<8, false, false>);
 }

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
     const uint32_t warp_base = (uint32_t)warp * TPW * TS;
     uint8_t* const sm = smem + warp_base + tw * TS;
     const uint32_t NPC = NP * NQ;                       // pieces of a row
-    const uint32_t WCAP = (NPC + 3u) & ~3u;             // entries of a width / offset array
+    const uint32_t WCAP = PART ? ((NPC + 3u) & ~3u) : 32u * NQ;     // entries of a width / offset array (a constant in the aligned form)
     // row stride of the piece buffer, in pieces: a multiple of 16 pieces (128 bytes) would put the 8 row jobs of a team on
     // the same banks, so such rows are padded by one piece
     const uint32_t NPS = NPC + ((NPC & 15u) ? 0u : 1u);
@@ -725,7 +725,7 @@ cudaError_t launch_encode_wide(int elem_sz, int predictor, EncParams p, cudaStre
     p.teams_per_cta = teams_per_cta;
     const uint32_t nbuf = esz == 2u ? 1u : 2u;
     const uint32_t NPS = NPC + ((NPC & 15u) ? 0u : 1u);            // padded row stride of the piece buffer (see the kernel)
-    const uint32_t wcap = (NPC + 3u) & ~3u;
+    const uint32_t wcap = part ? ((NPC + 3u) & ~3u) : 32u * esz;
     p.out_off = up16w(nbuf * (64u * NPS + wcap + 2u * wcap));       // piece buffers | piece widths | row bit offsets
     // the staging tile holds up to 4 groups, fewer when that would cost occupancy (6 CTAs per SM need <= 36 KB each; the
     // 16-bit and FIRE forms run 4 CTAs per SM: <= 56 KB)
