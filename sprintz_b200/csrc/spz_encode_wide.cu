@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
     // Rows are byte aligned, the writer stores whole words: a row's first word is stored with ZERO low bytes (they
     // belong to the previous row), so after a barrier the previous row's lane ORs its last partial word into it.  Row 0
     // saves the bytes in front of the payload before and restores them after; row 7 stores its tail with zeros behind
-    // the payload (bytes that are only written later).  Rows shorter than 8 bytes (which may not own a whole word) take
+    // the payload (bytes that are only written later).  Rows shorter than 4 bytes (which may not complete a word) take
     // a byte-wise path.
     auto emit_rows = [&](bool doit, uint32_t pbsel) {
         if (!doit) info = 0;
@@ -454,7 +454,9 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
                     seg = 0u;
                 }
             }
-            const bool fast = act && mine && rb >= 8u;
+            // a row of >= 4 bytes completes the word it starts in, which is all the hand-over below needs (every word then has
+            // exactly one job that stores it whole; a shorter row could share one word with BOTH neighbours)
+            const bool fast = act && mine && rb >= 4u;
             const uint32_t bit0 = rowaddr * 8u + s0;
             uint32_t waddr = (bit0 >> 5) << 2;
             const uint32_t fill0 = bit0 & 31u;
