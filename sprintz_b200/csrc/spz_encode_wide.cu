@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
     const uint32_t WCAP = PART ? ((NPC + 3u) & ~3u) : 32u * NQ;     // entries of a width / offset array (a constant in the aligned form)
     // row stride of the piece buffer, in pieces: a multiple of 16 pieces (128 bytes) would put the 8 row jobs of a team on
     // the same banks, so such rows are padded by one piece
-    const uint32_t NPS = NPC + ((NPC & 15u) ? 0u : 1u);
+    // (16-bit: by two, so that an octet's two pieces stay one aligned 128-bit store)
+    const uint32_t NPS = NPC + ((NPC & 15u) ? 0u : NQ);
     const uint32_t PB = 64u * NPS;                      // one piece buffer: [8 rows][NPS] x 8 bytes
     // 8-bit: two piece buffers used in turn; 16-bit: one (emit_rows() ends with a barrier, and shared memory bounds the
     // occupancy of the 16-bit form: 80 dims 3 -> 4 CTAs per SM)
@@ -372,7 +373,7 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
                     const uint2 pa = make_uint2(a0 | __funnelshift_lc(0u, a1, cA0), __funnelshift_lc(a1, 0u, cA0));
                     const uint2 pq = make_uint2(b0 | __funnelshift_lc(0u, b1, cB0), __funnelshift_lc(b1, 0u, cB0));
                     if (solo) { append(pa.x, pa.y, wA); append(pq.x, pq.y, wo - wA); pad_bits(row_pad); }
-                    else { pb[(uint32_t)r * NPS] = pa; pb[(uint32_t)r * NPS + 1u] = pq; }
+                    else *reinterpret_cast<uint4*>(pb + (uint32_t)r * NPS) = make_uint4(pa.x, pa.y, pq.x, pq.y);
                 }
                 if (!solo) {
                     sm[wid_off + pbsel * WCAP + 2u * t] = (uint8_t)wA;
@@ -726,7 +727,7 @@ cudaError_t launch_encode_wide(int elem_sz, int predictor, EncParams p, cudaStre
     const uint32_t teams_per_cta = (kWideEncThreads / 32) * TPW;
     p.teams_per_cta = teams_per_cta;
     const uint32_t nbuf = esz == 2u ? 1u : 2u;
-    const uint32_t NPS = NPC + ((NPC & 15u) ? 0u : 1u);            // padded row stride of the piece buffer (see the kernel)
+    const uint32_t NPS = NPC + ((NPC & 15u) ? 0u : esz);           // padded row stride of the piece buffer (see the kernel)
     const uint32_t wcap = part ? ((NPC + 3u) & ~3u) : 32u * esz;
     p.out_off = up16w(nbuf * (64u * NPS + wcap + 2u * wcap));       // piece buffers | piece widths | row bit offsets
     // the staging tile holds up to 4 groups, fewer when that would cost occupancy (6 CTAs per SM need <= 36 KB each; the
