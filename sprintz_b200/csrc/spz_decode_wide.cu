@@ -21,7 +21,8 @@
 //   output   8 rows x ndims bytes are staged in a shared tile (one 64-bit store per lane per row) and leave as
 //            coalesced 128-bit stores that complete whole 32-byte sectors
 //
-// Reference behaviour restated: sprintz_delta_rle.cpp:417-772 (high-dim delta + RLE decode).
+// Reference behaviour restated: sprintz_delta_rle.cpp:417-772 (high-dim delta + RLE decode), sprintz_xff_rle.cpp:569-1179
+// (high-dim FIRE + RLE decode).
 #include "spz_host.h"
 
 namespace spz {

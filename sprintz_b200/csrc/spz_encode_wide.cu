@@ -1,6 +1,7 @@
 // spz_encode_wide.cu -- wide-row ("octet team") encode kernel: ndims 5..256 (whole octets in the aligned form, any ndims
-// in the PART form); 8- and 16-bit elements, delta and FIRE.  The text below describes the 8-bit delta form (SIMD within a register); the FIRE and 16-bit forms share
-// everything but the arithmetic of pass 1 and the field packing (see the comment at the kernel).
+// in the PART form); 8- and 16-bit elements, delta and FIRE.  The text below describes the 8-bit delta form (SIMD within a
+// register); the FIRE and 16-bit forms share everything but the arithmetic of pass 1 and the field packing (see the
+// comments at the kernel).
 //
 // BASELINE config 4 (int8 x 80 dims, delta) ran on the team kernel of spz_encode_hd.cu at 0.23 of the roofline: ncu
 // showed 26 thread instructions per sample (lane-per-dim forecasting of single bytes, a cluster multiply-add bit
@@ -27,7 +28,8 @@
 //            of spz_encode_hd.cu, executed in lock-step passes
 //   output   shared staging tile, flushed with 128-bit stores
 //
-// Reference behaviour restated: sprintz_delta_rle.cpp:54-404 (high-dim delta + RLE encode).
+// Reference behaviour restated: sprintz_delta_rle.cpp:54-404 (high-dim delta + RLE encode), sprintz_xff_rle.cpp:61-555
+// (high-dim FIRE + RLE encode).
 #include "spz_host.h"
 #include "spz_swar.cuh"
 
