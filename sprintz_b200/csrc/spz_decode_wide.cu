@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kWideThreads, (FIRE || W == 16) ? 4 : 6) spz_d
     uint32_t tsel = 0;                                  // which tile the next data slot uses
 
     uint32_t xA = 0, xB = 0;                            // the previous row's values of my 8 dims (4 bytes per word)
-    uint32_t pvh[ELEM ? 8 : 1];                         // per-element form: previous values / deltas left-aligned, FIRE counters (sprintz_xff_rle.cpp:505-520)
+    uint32_t pvh[ELEM ? 8 : 1];                         // per-element form: previous values / deltas left-aligned, FIRE counters (sprintz_xff_rle.cpp:683-688)
     int32_t pdh[FIRE ? 8 : 1], ct[FIRE ? 8 : 1];
 #pragma unroll
     for (int j = 0; j < (ELEM ? 8 : 1); j++) pvh[j] = 0;
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(kWideThreads, (FIRE || W == 16) ? 4 : 6) spz_d
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     const uint32_t f = (fw >> (j * HB)) & FMASK;
-                    const uint32_t n = f + (f == FMASK ? 1u : 0u);   // W - 1 is stored for W (sprintz_xff_rle.cpp:287)
+                    const uint32_t n = f + (f == FMASK ? 1u : 0u);   // W - 1 is stored for W (sprintz_xff_rle.cpp:296)
                     nb[j] = n;
                     if (j < 4) wA += n;
                     fm[j] = (1u << n) - 1u;

@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kWideEncThreads, MINB) spz_encode_wide_kernel(
 
     // ---- team-uniform encoder state (sprintz_delta_rle.cpp:132-158)
     uint32_t xA = 0, xB = 0;                            // the previous row's values of my 8 dims
-    uint32_t xprev[ELEM ? 8 : 1];                       // per-element form: previous values / deltas left-aligned, FIRE counters (sprintz_xff_rle.cpp:150-158)
+    uint32_t xprev[ELEM ? 8 : 1];                       // per-element form: previous values / deltas left-aligned, FIRE counters (sprintz_xff_rle.cpp:148-152)
     int32_t dprev[FIRE ? 8 : 1], ct[FIRE ? 8 : 1];
 #pragma unroll
     for (int e = 0; e < (ELEM ? 8 : 1); e++) xprev[e] = 0;
